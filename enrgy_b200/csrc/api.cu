@@ -1,0 +1,740 @@
+// C ABI of enrgy_b200 (include/enrgy_b200.h): context, device memory, launches.  No CPU fallback:
+// every entry point that computes needs a CUDA device and fails with ENRGY_ERR_NODEVICE /
+// ENRGY_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/enrgy_b200.h"
+#include "common.cuh"
+#include "kernels.cuh"
+#include "prepass.cuh"
+
+using namespace enrgy;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                      \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return fail(ENRGY_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                  __FILE__, __LINE__);                                                    \
+  } while (0)
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    release();
+    cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+}  // namespace
+
+struct enrgy_ctx {
+  int device = 0, rows = 0, cols = 0, precision = ENRGY_F32;
+  int sm_count = 148;
+  enrgy_params p{};
+  bool have_params = false, have_dem = false, have_forcing = false, prepass_done = false;
+  bool state_advanced = false;
+  // geometry
+  int pitch = 0, rows_pad_full = 0, band_row0 = 0, band_rows = 0, band_rows_pad = 0;
+  int tile_h = 8, tiles_r = 0, tiles_c = 0, n_tiles = 0;
+  double n_valid = 0.0;
+  size_t band_elems = 0;  // band_rows_pad * pitch
+  // host copies
+  std::vector<float> h_dem;
+  std::vector<double> forcing;
+  int n_steps = 0;
+  std::vector<double> pot_aws;
+  PrepassOutput pre;
+  // device rasters
+  DevBuf<float> d_dem, d_albedo, d_pot, d_tmp32;
+  DevBuf<unsigned char> d_nx, d_ny, d_nz, d_swe, d_ts, d_ti, d_dump, d_stage;
+  int n_maps = 0;
+  int pot_t0 = 0, pot_n = 0;
+  // tables
+  DevBuf<unsigned char> d_steps, d_subs;
+  DevBuf<StepRec<double>> d_steps64;
+  DevBuf<ShadeRec> d_shades;
+  DevBuf<TimeBlock> d_blocks;
+  DevBuf<int2> d_tiles;
+  DevBuf<int> d_counts;
+  DevBuf<double> d_partials, d_stats, d_small;
+  DevBuf<unsigned long long> d_counters;
+  DevBuf<unsigned> d_masks;
+  // SWE statistics of the initial raster (first CSV row)
+  double swe0_sum = 0.0, swe0_nsnow = 0.0, swe0_nvalid = 0.0;
+  // runtime
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_pending = false;
+  int64_t launches = 0;
+  double last_ms = 0.0;
+  LaunchInfo info{};
+};
+
+namespace {
+
+size_t rsize(const enrgy_ctx* c) { return c->precision == ENRGY_F32 ? 4 : 8; }
+
+int use_device(enrgy_ctx* c) {
+  if (!c) return fail(ENRGY_ERR_ARG, "null context");
+  CU_TRY(cudaSetDevice(c->device));
+  return ENRGY_OK;
+}
+
+// host [rows][cols] float -> device padded [rows_pad][pitch] float (padding = NaN)
+int upload_padded(enrgy_ctx* c, const float* src, int rows, float* dst, int rows_pad) {
+  CU_TRY(cudaMemsetAsync(dst, 0xFF, (size_t)rows_pad * c->pitch * sizeof(float), c->stream));
+  CU_TRY(cudaMemcpy2DAsync(dst, (size_t)c->pitch * sizeof(float), src, (size_t)c->cols * sizeof(float),
+                           (size_t)c->cols * sizeof(float), rows, cudaMemcpyHostToDevice, c->stream));
+  return ENRGY_OK;
+}
+
+template <typename R>
+int convert_state(enrgy_ctx* c, const float* d_src32, unsigned char* dst) {
+  CU_TRY(launch_pad_convert<R>(d_src32, (R*)dst, c->band_elems, c->stream));
+  c->launches++;
+  return ENRGY_OK;
+}
+
+int check_mask(enrgy_ctx* c, const float* d_other, const char* what, bool strict_other_valid) {
+  CU_TRY(c->d_counters.alloc(2));
+  CU_TRY(cudaMemsetAsync(c->d_counters.p, 0, 2 * sizeof(unsigned long long), c->stream));
+  CU_TRY(launch_mask_check(c->d_dem.p, d_other, c->pitch, c->band_row0, c->band_rows, c->cols,
+                           c->d_counters.p, c->stream));
+  c->launches++;
+  unsigned long long h[2];
+  CU_TRY(cudaMemcpyAsync(h, c->d_counters.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  if (h[0] != 0) {
+    return fail(ENRGY_ERR_MASK,
+                "%s is NaN at %llu cells where the DEM is valid; the reference would propagate NaN "
+                "into only some of its area means there -- not supported",
+                what, h[0]);
+  }
+  if (strict_other_valid && h[1] != 0) {
+    return fail(ENRGY_ERR_MASK, "%s is valid at %llu cells where the DEM is NaN -- not supported", what,
+                h[1]);
+  }
+  return ENRGY_OK;
+}
+
+template <typename R>
+int upload_tables(enrgy_ctx* c) {
+  const PrepassOutput& o = c->pre;
+  const int T = c->n_steps;
+  std::vector<StepRec<R>> st(T);
+  for (int i = 0; i < T; ++i) {
+    const StepRec<double>& s = o.steps[i];
+    StepRec<R>& d = st[i];
+    d.t_air = (R)s.t_air; d.lapse = (R)s.lapse; d.p_hpa = (R)s.p_hpa; d.e_aws = (R)s.e_aws;
+    d.c_sens = (R)s.c_sens; d.c_lat = (R)s.c_lat; d.c_lwd = (R)s.c_lwd; d.c_lwu = (R)s.c_lwu;
+    d.c_sw = (R)s.c_sw; d.c_melt = (R)s.c_melt; d.alb_w = (R)s.alb_w; d.snow_alb = (R)s.snow_alb;
+    d.dsum = (R)s.dsum; d.dt = (R)s.dt; d.alb_pair = (R)s.alb_pair; d.sub = (R)s.sub;
+  }
+  const size_t ns = o.subs.size();
+  std::vector<SubRec<R>> sb(std::max<size_t>(ns, 1));
+  std::vector<ShadeRec> sh(std::max<size_t>(ns, 1));
+  for (size_t i = 0; i < ns; ++i) {
+    sb[i].e = (R)o.subs[i].e; sb[i].n = (R)o.subs[i].n; sb[i].u = (R)o.subs[i].u; sb[i].b = (R)o.subs[i].b;
+    sh[i] = o.subs[i].shade;
+  }
+  CU_TRY(c->d_steps.alloc(std::max<size_t>(T, 1) * sizeof(StepRec<R>)));
+  CU_TRY(c->d_steps64.alloc(std::max<size_t>(T, 1)));
+  CU_TRY(c->d_subs.alloc(sb.size() * sizeof(SubRec<R>)));
+  CU_TRY(c->d_shades.alloc(sh.size()));
+  CU_TRY(c->d_blocks.alloc(std::max<size_t>(o.blocks.size(), 1)));
+  if (T) {
+    CU_TRY(cudaMemcpyAsync(c->d_steps.p, st.data(), (size_t)T * sizeof(StepRec<R>), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(c->d_steps64.p, o.steps.data(), (size_t)T * sizeof(StepRec<double>), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(c->d_blocks.p, o.blocks.data(), o.blocks.size() * sizeof(TimeBlock), cudaMemcpyHostToDevice, c->stream));
+  }
+  if (ns) {
+    CU_TRY(cudaMemcpyAsync(c->d_subs.p, sb.data(), ns * sizeof(SubRec<R>), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(c->d_shades.p, sh.data(), ns * sizeof(ShadeRec), cudaMemcpyHostToDevice, c->stream));
+  }
+  CU_TRY(cudaStreamSynchronize(c->stream));   // host vectors go out of scope
+  return ENRGY_OK;
+}
+
+template <typename R>
+int fill_args(enrgy_ctx* c, int t0, int t1, KernelArgs<R>& a) {
+  a = KernelArgs<R>{};
+  a.rows_full = c->rows; a.cols = c->cols; a.pitch = c->pitch;
+  a.band_row0 = c->band_row0; a.band_rows = c->band_rows; a.rows_pad_full = c->rows_pad_full;
+  a.dem = c->d_dem.p;
+  a.nx = (const R*)c->d_nx.p; a.ny = (const R*)c->d_ny.p; a.nz = (const R*)c->d_nz.p;
+  a.albedo = c->d_albedo.p;
+  a.map_stride = c->band_elems;
+  a.albedo_const = c->p.albedo_const;
+  a.albedo_ice = (R)c->p.albedo_ice; a.albedo_snow = (R)c->p.albedo_snow;
+  a.max_ice_albedo = (R)c->p.max_ice_albedo;
+  a.elev_aws = (R)c->p.elev_aws;
+  a.zmax = (R)c->pre.zmax;
+  a.swe = (R*)c->d_swe.p; a.total_snow = (R*)c->d_ts.p; a.total_ice = (R*)c->d_ti.p;
+  a.pot = c->d_pot.p; a.pot_stride = c->band_elems; a.pot_t0 = c->pot_t0;
+  a.steps = (const StepRec<R>*)c->d_steps.p;
+  a.subs = (const SubRec<R>*)c->d_subs.p;
+  a.shades = c->d_shades.p;
+  a.blocks = c->d_blocks.p;
+  int b0 = 0;
+  const auto& bl = c->pre.blocks;
+  while (b0 < (int)bl.size() && bl[b0].t_end <= t0) ++b0;
+  int b1 = b0;
+  while (b1 < (int)bl.size() && bl[b1].t_begin < t1) ++b1;
+  a.block_begin = b0; a.block_end = b1;
+  a.t0 = t0; a.t1 = t1;
+  a.tiles = c->d_tiles.p; a.n_tiles = c->n_tiles;
+  return ENRGY_OK;
+}
+
+int insol_variant(const enrgy_ctx* c) {
+  if (c->p.insol_mode == ENRGY_INSOL_STREAMED) return kInsolStreamed;
+  return c->p.shadow ? kInsolShadow : kInsolComputed;
+}
+
+int check_run_ready(enrgy_ctx* c, int t0, int t1) {
+  if (!c->have_dem || !c->prepass_done) return fail(ENRGY_ERR_ARG, "set_dem / set_forcing / prepass must precede run");
+  if (t0 < 0 || t1 > c->n_steps || t0 > t1) return fail(ENRGY_ERR_ARG, "step range [%d, %d) outside [0, %d)", t0, t1, c->n_steps);
+  if (!c->p.albedo_const && c->n_maps == 0) return fail(ENRGY_ERR_ARG, "albedo maps not set");
+  if (c->p.insol_mode == ENRGY_INSOL_STREAMED && t1 > t0 &&
+      (t0 < c->pot_t0 || t1 > c->pot_t0 + c->pot_n)) {
+    return fail(ENRGY_ERR_ARG, "insolation rasters resident for steps [%d, %d), run asks [%d, %d)",
+                c->pot_t0, c->pot_t0 + c->pot_n, t0, t1);
+  }
+  return ENRGY_OK;
+}
+
+template <typename R>
+int run_typed(enrgy_ctx* c, int t0, int t1, double* d_stats, cudaStream_t stream) {
+  KernelArgs<R> a;
+  fill_args<R>(c, t0, t1, a);
+  const int insol = insol_variant(c);
+  LaunchInfo li;
+  CU_TRY(energy_balance_grid<R>(insol, false, c->sm_count, &li));
+  int grid = std::min(li.grid, std::max(c->n_tiles, 1));
+  const int n = t1 - t0;
+  CU_TRY(c->d_partials.alloc((size_t)grid * std::max(n, 1) * kStatsK));
+  CU_TRY(cudaMemsetAsync(c->d_partials.p, 0, (size_t)grid * std::max(n, 1) * kStatsK * sizeof(double), stream));
+  a.partials = c->d_partials.p;
+  if (n > 0 && !c->state_advanced) {
+    CU_TRY(launch_nan_offglacier<R>(c->d_dem.p, c->pitch, c->band_row0, c->band_rows, c->cols, a.swe,
+                                    a.total_snow, a.total_ice, stream));
+    c->launches++;
+  }
+  CU_TRY(cudaEventRecord(c->ev0, stream));
+  CU_TRY(launch_energy_balance<R>(a, insol, false, c->sm_count, grid, &c->info, stream));
+  CU_TRY(cudaEventRecord(c->ev1, stream));
+  c->ev_pending = true;
+  c->launches++;
+  if (d_stats && n > 0) {
+    FinalizeArgs f{};
+    f.partials = c->d_partials.p; f.n_ctas = grid; f.n_steps = n; f.t0 = t0;
+    f.n_valid = c->n_valid; f.f32_mode = c->precision == ENRGY_F32;
+    f.steps64 = c->d_steps64.p; f.stats = d_stats;
+    f.override_first = (t0 == 0 && !c->state_advanced) ? 1 : 0;
+    f.swe0_sum = c->swe0_sum; f.swe0_nsnow = c->swe0_nsnow; f.swe0_nvalid = c->swe0_nvalid;
+    CU_TRY(launch_finalize(f, stream));
+    c->launches++;
+  }
+  if (n > 0) c->state_advanced = true;
+  return ENRGY_OK;
+}
+
+template <typename R>
+int dump_typed(enrgy_ctx* c, int t0, int t1, double* out, unsigned* mask_host, int max_sub, int* n_sub_out) {
+  KernelArgs<R> a;
+  fill_args<R>(c, t0, t1, a);
+  const int insol = insol_variant(c);
+  const int n = t1 - t0;
+  const size_t per_step = (size_t)ENRGY_D_COUNT * c->band_elems;
+  int n_sub = 0;
+  if (mask_host) {
+    if (insol != kInsolShadow) return fail(ENRGY_ERR_ARG, "shade masks need insol_mode = COMPUTED with shadow = 1");
+    n_sub = c->pre.sub_count[t0];
+    if (n_sub > max_sub) return fail(ENRGY_ERR_ARG, "step has %d sunlit sub-steps, buffer holds %d", n_sub, max_sub);
+    a.mask_words = (c->cols + 31) / 32;
+    const size_t words = (size_t)std::max(n_sub, 1) * c->band_rows * a.mask_words;
+    CU_TRY(c->d_masks.alloc(words));
+    CU_TRY(cudaMemsetAsync(c->d_masks.p, 0, words * sizeof(unsigned), c->stream));
+    a.mask_out = c->d_masks.p;
+  } else {
+    CU_TRY(c->d_dump.alloc((size_t)n * per_step * sizeof(R)));
+    CU_TRY(cudaMemsetAsync(c->d_dump.p, 0xFF, (size_t)n * per_step * sizeof(R), c->stream));
+    a.dump = (R*)c->d_dump.p;
+    a.dump_field_stride = c->band_elems;
+  }
+  CU_TRY(launch_energy_balance<R>(a, insol, true, c->sm_count, 0, nullptr, c->stream));
+  c->launches++;
+  if (mask_host) {
+    const size_t words = (size_t)n_sub * c->band_rows * a.mask_words;
+    if (words) CU_TRY(cudaMemcpyAsync(mask_host, c->d_masks.p, words * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (n_sub_out) *n_sub_out = n_sub;
+    return ENRGY_OK;
+  }
+  std::vector<R> h((size_t)n * per_step);
+  CU_TRY(cudaMemcpyAsync(h.data(), c->d_dump.p, h.size() * sizeof(R), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  for (int s = 0; s < n; ++s)
+    for (int fld = 0; fld < ENRGY_D_COUNT; ++fld)
+      for (int r = 0; r < c->band_rows; ++r) {
+        const R* src = h.data() + ((size_t)s * ENRGY_D_COUNT + fld) * c->band_elems + (size_t)r * c->pitch;
+        double* dst = out + (((size_t)s * ENRGY_D_COUNT + fld) * c->band_rows + r) * c->cols;
+        for (int x = 0; x < c->cols; ++x) dst[x] = (double)src[x];
+      }
+  return ENRGY_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int enrgy_abi_version(void) { return ENRGY_ABI_VERSION; }
+const char* enrgy_last_error(void) { return g_err.c_str(); }
+
+int enrgy_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int enrgy_create(int device, int rows, int cols, int precision, enrgy_ctx** out) {
+  if (!out) return fail(ENRGY_ERR_ARG, "out is null");
+  *out = nullptr;
+  if (rows <= 0 || cols <= 0 || rows > 32767 || cols > 32767)
+    return fail(ENRGY_ERR_ARG, "raster %d x %d outside 1..32767", rows, cols);
+  if (precision != ENRGY_F32 && precision != ENRGY_F64) return fail(ENRGY_ERR_ARG, "precision must be 32 or 64");
+  const int n = enrgy_device_count();
+  if (n <= 0) return fail(ENRGY_ERR_NODEVICE, "no CUDA device visible; enrgy_b200 has no CPU fallback");
+  if (device < 0 || device >= n) return fail(ENRGY_ERR_ARG, "device %d outside 0..%d", device, n - 1);
+  CU_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    return fail(ENRGY_ERR_NODEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device,
+                prop.major, prop.minor);
+  }
+  enrgy_ctx* c = new enrgy_ctx();
+  c->device = device; c->rows = rows; c->cols = cols; c->precision = precision;
+  c->sm_count = prop.multiProcessorCount;
+  c->pitch = round_up(cols, kTileW);
+  c->rows_pad_full = round_up(rows, 16);
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+    delete c;
+    return fail(ENRGY_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  *out = c;
+  return ENRGY_OK;
+}
+
+int enrgy_destroy(enrgy_ctx* c) {
+  if (!c) return ENRGY_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->d_dem.release(); c->d_albedo.release(); c->d_pot.release(); c->d_tmp32.release();
+  c->d_nx.release(); c->d_ny.release(); c->d_nz.release(); c->d_swe.release(); c->d_ts.release();
+  c->d_ti.release(); c->d_dump.release(); c->d_stage.release(); c->d_steps.release(); c->d_subs.release();
+  c->d_steps64.release(); c->d_shades.release(); c->d_blocks.release(); c->d_tiles.release();
+  c->d_counts.release(); c->d_partials.release(); c->d_stats.release(); c->d_small.release();
+  c->d_counters.release(); c->d_masks.release();
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return ENRGY_OK;
+}
+
+int enrgy_set_params(enrgy_ctx* c, const enrgy_params* pin) {
+  if (int e = use_device(c)) return e;
+  if (!pin) return fail(ENRGY_ERR_ARG, "params is null");
+  if (c->have_dem) return fail(ENRGY_ERR_ARG, "set_params must precede set_dem");
+  enrgy_params p = *pin;
+  auto dflt = [](double& v, double d) { if (std::isnan(v)) v = d; };
+  dflt(p.zm, 0.001);                 // turbo.py:273-274
+  dflt(p.z_h_or_e, p.zm / 10);       // turbo.py:275-277
+  dflt(p.emissivity, 0.98);          // model.py:541-542
+  dflt(p.max_ice_albedo, 0.45);      // model.py:325-326
+  dflt(p.snow_density, 387.0);       // var_classes.py:9
+  dflt(p.ice_density, 900.0);
+  dflt(p.solar_const, 1367.0);       // saga_lighting.py:42
+  dflt(p.transmittance, 0.70);       // saga_lighting.py:44
+  dflt(p.hour_step, 0.25);           // saga_lighting.py:43
+  dflt(p.sensible_corr, 1.0);
+  dflt(p.latent_corr, 1.0);
+  if (!(p.cell_size > 0)) return fail(ENRGY_ERR_ARG, "cell_size must be > 0");
+  if (!(p.sensor_z > 0) || !(p.zm > 0) || !(p.z_h_or_e > 0)) return fail(ENRGY_ERR_ARG, "sensor_z, zm, z_h_or_e must be > 0");
+  if (p.msm_layers < 0 || p.msm_layers > ENRGY_MAX_LAYERS - 1) return fail(ENRGY_ERR_ARG, "msm_layers outside 0..%d", ENRGY_MAX_LAYERS - 1);
+  if (p.msm_layers > 0) return fail(ENRGY_ERR_ARG, "sub-surface model (msm) is not built into this round's kernels");
+  if (p.insol_mode != ENRGY_INSOL_STREAMED && p.insol_mode != ENRGY_INSOL_COMPUTED) return fail(ENRGY_ERR_ARG, "bad insol_mode");
+  if (p.band_rows == 0) { p.band_row0 = 0; p.band_rows = c->rows; }
+  if (p.band_row0 < 0 || p.band_rows < 0 || p.band_row0 + p.band_rows > c->rows) return fail(ENRGY_ERR_ARG, "row band outside the raster");
+  c->p = p;
+  c->band_row0 = p.band_row0;
+  c->band_rows = p.band_rows;
+  c->tile_h = c->precision == ENRGY_F32 ? energy_balance_tile_h<float>(0) : energy_balance_tile_h<double>(0);
+  c->band_rows_pad = round_up(std::max(c->band_rows, 1), 16);
+  c->band_elems = (size_t)c->band_rows_pad * c->pitch;
+  c->have_params = true;
+  return ENRGY_OK;
+}
+
+int enrgy_set_dem(enrgy_ctx* c, const float* dem) {
+  if (int e = use_device(c)) return e;
+  if (!c->have_params) return fail(ENRGY_ERR_ARG, "set_params must precede set_dem");
+  if (!dem) return fail(ENRGY_ERR_ARG, "dem is null");
+  c->h_dem.assign(dem, dem + (size_t)c->rows * c->cols);
+  CU_TRY(c->d_dem.alloc((size_t)c->rows_pad_full * c->pitch));
+  if (int e = upload_padded(c, dem, c->rows, c->d_dem.p, c->rows_pad_full)) return e;
+  // active tiles of the band
+  c->tiles_r = (c->band_rows + c->tile_h - 1) / c->tile_h;
+  c->tiles_c = c->pitch / kTileW;
+  const int nt = c->tiles_r * c->tiles_c;
+  CU_TRY(c->d_counts.alloc(std::max(nt, 1)));
+  std::vector<int> counts(std::max(nt, 1), 0);
+  if (nt > 0) {
+    CU_TRY(launch_tile_scan(c->d_dem.p, c->pitch, c->band_row0, c->band_rows, c->cols, c->tile_h, c->tiles_r,
+                            c->tiles_c, c->d_counts.p, c->stream));
+    c->launches++;
+    CU_TRY(cudaMemcpyAsync(counts.data(), c->d_counts.p, (size_t)nt * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+  }
+  std::vector<int2> tiles;
+  double nv = 0.0;
+  for (int tr = 0; tr < c->tiles_r; ++tr)
+    for (int tc = 0; tc < c->tiles_c; ++tc) {
+      const int n = counts[tr * c->tiles_c + tc];
+      if (n > 0) {
+        tiles.push_back(make_int2(tr, tc));
+        nv += n;
+      }
+    }
+  c->n_tiles = (int)tiles.size();
+  c->n_valid = nv;
+  CU_TRY(c->d_tiles.alloc(std::max<size_t>(tiles.size(), 1)));
+  if (!tiles.empty()) CU_TRY(cudaMemcpyAsync(c->d_tiles.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+  // state rasters: zeros (model.py:76-80)
+  const size_t rs = rsize(c);
+  CU_TRY(c->d_swe.alloc(c->band_elems * rs));
+  CU_TRY(c->d_ts.alloc(c->band_elems * rs));
+  CU_TRY(c->d_ti.alloc(c->band_elems * rs));
+  CU_TRY(cudaMemsetAsync(c->d_swe.p, 0, c->band_elems * rs, c->stream));
+  CU_TRY(cudaMemsetAsync(c->d_ts.p, 0, c->band_elems * rs, c->stream));
+  CU_TRY(cudaMemsetAsync(c->d_ti.p, 0, c->band_elems * rs, c->stream));
+  c->swe0_sum = 0.0; c->swe0_nsnow = 0.0; c->swe0_nvalid = (double)c->band_rows * c->cols;
+  c->state_advanced = false;
+  // terrain normals for the in-kernel insolation
+  if (c->p.insol_mode == ENRGY_INSOL_COMPUTED) {
+    CU_TRY(c->d_nx.alloc(c->band_elems * rs));
+    CU_TRY(c->d_ny.alloc(c->band_elems * rs));
+    CU_TRY(c->d_nz.alloc(c->band_elems * rs));
+    if (c->precision == ENRGY_F32) {
+      CU_TRY(launch_terrain<float>(c->d_dem.p, c->rows, c->cols, c->pitch, c->band_row0, c->band_rows_pad,
+                                   c->p.cell_size, (float*)c->d_nx.p, (float*)c->d_ny.p, (float*)c->d_nz.p, c->stream));
+    } else {
+      CU_TRY(launch_terrain<double>(c->d_dem.p, c->rows, c->cols, c->pitch, c->band_row0, c->band_rows_pad,
+                                    c->p.cell_size, (double*)c->d_nx.p, (double*)c->d_ny.p, (double*)c->d_nz.p, c->stream));
+    }
+    c->launches++;
+  }
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  c->have_dem = true;
+  c->prepass_done = false;
+  return ENRGY_OK;
+}
+
+int enrgy_set_albedo_maps(enrgy_ctx* c, int n_maps, const float* const* maps) {
+  if (int e = use_device(c)) return e;
+  if (!c->have_dem) return fail(ENRGY_ERR_ARG, "set_dem must precede set_albedo_maps");
+  if (n_maps < 1 || n_maps > 255 || !maps) return fail(ENRGY_ERR_ARG, "n_maps outside 1..255");
+  CU_TRY(c->d_albedo.alloc((size_t)n_maps * c->band_elems));
+  for (int m = 0; m < n_maps; ++m) {
+    if (!maps[m]) return fail(ENRGY_ERR_ARG, "albedo map %d is null", m);
+    float* dst = c->d_albedo.p + (size_t)m * c->band_elems;
+    if (int e = upload_padded(c, maps[m], c->band_rows, dst, c->band_rows_pad)) return e;
+    if (int e = check_mask(c, dst, "albedo map", false)) return e;
+  }
+  c->n_maps = n_maps;
+  return ENRGY_OK;
+}
+
+int enrgy_set_swe(enrgy_ctx* c, const float* swe) {
+  if (int e = use_device(c)) return e;
+  if (!c->have_dem) return fail(ENRGY_ERR_ARG, "set_dem must precede set_swe");
+  const size_t rs = rsize(c);
+  if (!swe) {
+    CU_TRY(cudaMemsetAsync(c->d_swe.p, 0, c->band_elems * rs, c->stream));
+    c->swe0_sum = 0.0; c->swe0_nsnow = 0.0; c->swe0_nvalid = (double)c->band_rows * c->cols;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return ENRGY_OK;
+  }
+  CU_TRY(c->d_tmp32.alloc(c->band_elems));
+  if (int e = upload_padded(c, swe, c->band_rows, c->d_tmp32.p, c->band_rows_pad)) return e;
+  if (int e = check_mask(c, c->d_tmp32.p, "SWE raster", false)) return e;
+  const int blocks = 296;
+  CU_TRY(c->d_small.alloc((size_t)blocks * 3));
+  CU_TRY(launch_swe0_stats(c->d_tmp32.p, c->pitch, c->band_rows, c->cols, c->d_small.p, blocks, c->stream));
+  c->launches++;
+  std::vector<double> h((size_t)blocks * 3);
+  CU_TRY(cudaMemcpyAsync(h.data(), c->d_small.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (c->precision == ENRGY_F32) {
+    if (int e = convert_state<float>(c, c->d_tmp32.p, c->d_swe.p)) return e;
+  } else {
+    if (int e = convert_state<double>(c, c->d_tmp32.p, c->d_swe.p)) return e;
+  }
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  c->swe0_sum = c->swe0_nsnow = c->swe0_nvalid = 0.0;
+  for (int b = 0; b < blocks; ++b) {
+    c->swe0_sum += h[b * 3 + 0]; c->swe0_nsnow += h[b * 3 + 1]; c->swe0_nvalid += h[b * 3 + 2];
+  }
+  c->state_advanced = false;
+  return ENRGY_OK;
+}
+
+int enrgy_set_msm(enrgy_ctx* c, const double* temps, double elev) {
+  (void)temps; (void)elev;
+  if (int e = use_device(c)) return e;
+  return fail(ENRGY_ERR_ARG, "sub-surface model (msm) is not built into this round's kernels");
+}
+
+int enrgy_set_forcing(enrgy_ctx* c, int n_steps, const double* forcing) {
+  if (int e = use_device(c)) return e;
+  if (n_steps < 0 || (n_steps > 0 && !forcing)) return fail(ENRGY_ERR_ARG, "bad forcing table");
+  for (int i = 0; i < n_steps; ++i) {
+    const double* f = forcing + (size_t)i * ENRGY_F_COUNT;
+    if (!(f[ENRGY_F_RH] <= 1.0)) return fail(ENRGY_ERR_RANGE, "row %d: HUMID must be a 0..1 fraction here (helpers.py:74-87)", i);
+    if (!(f[ENRGY_F_DT] > 0)) return fail(ENRGY_ERR_RANGE, "row %d: time step must be > 0", i);
+  }
+  c->forcing.assign(forcing, forcing + (size_t)n_steps * ENRGY_F_COUNT);
+  c->n_steps = n_steps;
+  c->pot_aws.assign(n_steps, std::numeric_limits<double>::quiet_NaN());
+  c->have_forcing = true;
+  c->prepass_done = false;
+  return ENRGY_OK;
+}
+
+int enrgy_set_insolation(enrgy_ctx* c, int t0, int n, const float* pot) {
+  if (int e = use_device(c)) return e;
+  if (!c->have_dem || !c->have_forcing) return fail(ENRGY_ERR_ARG, "set_dem and set_forcing must precede set_insolation");
+  if (c->p.insol_mode != ENRGY_INSOL_STREAMED) return fail(ENRGY_ERR_ARG, "insol_mode is not STREAMED");
+  if (t0 < 0 || n < 0 || t0 + n > c->n_steps || (n > 0 && !pot)) return fail(ENRGY_ERR_ARG, "bad insolation window");
+  CU_TRY(c->d_pot.alloc((size_t)std::max(n, 1) * c->band_elems));
+  const size_t per = (size_t)c->band_rows * c->cols;
+  const int ar = c->p.aws_row - c->band_row0;
+  for (int i = 0; i < n; ++i) {
+    float* dst = c->d_pot.p + (size_t)i * c->band_elems;
+    if (int e = upload_padded(c, pot + (size_t)i * per, c->band_rows, dst, c->band_rows_pad)) return e;
+    if (ar >= 0 && ar < c->band_rows) c->pot_aws[t0 + i] = (double)pot[(size_t)i * per + (size_t)ar * c->cols + c->p.aws_col];
+  }
+  // NaN masks: checked on the first raster of the window (the reference writes them all with one cutline)
+  if (n > 0) {
+    if (int e = check_mask(c, c->d_pot.p, "insolation raster", false)) return e;
+  }
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  c->pot_t0 = t0;
+  c->pot_n = n;
+  c->prepass_done = false;
+  return ENRGY_OK;
+}
+
+int enrgy_prepass(enrgy_ctx* c) {
+  if (int e = use_device(c)) return e;
+  if (!c->have_dem || !c->have_forcing) return fail(ENRGY_ERR_ARG, "set_dem and set_forcing must precede prepass");
+  PrepassInput in;
+  in.p = c->p; in.precision = c->precision; in.rows = c->rows; in.cols = c->cols;
+  in.dem = c->h_dem.data(); in.n_steps = c->n_steps; in.forcing = c->forcing.data();
+  in.pot_aws = c->pot_aws.data();
+  std::string err;
+  const int rc = run_prepass(in, c->pre, err);
+  if (rc != ENRGY_OK) return fail(rc, "%s", err.c_str());
+  const int urc = c->precision == ENRGY_F32 ? upload_tables<float>(c) : upload_tables<double>(c);
+  if (urc != ENRGY_OK) return urc;
+  c->prepass_done = true;
+  return ENRGY_OK;
+}
+
+int enrgy_get_point_scalars(enrgy_ctx* c, double* out) {
+  if (!c || !out) return fail(ENRGY_ERR_ARG, "null argument");
+  if (!c->prepass_done) return fail(ENRGY_ERR_ARG, "prepass has not run");
+  std::memcpy(out, c->pre.point.data(), c->pre.point.size() * sizeof(double));
+  return ENRGY_OK;
+}
+
+int enrgy_run_async(enrgy_ctx* c, int t0, int t1, double* d_stats, void* stream) {
+  if (int e = use_device(c)) return e;
+  if (int e = check_run_ready(c, t0, t1)) return e;
+  cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+  return c->precision == ENRGY_F32 ? run_typed<float>(c, t0, t1, d_stats, s) : run_typed<double>(c, t0, t1, d_stats, s);
+}
+
+int enrgy_run(enrgy_ctx* c, int t0, int t1, double* stats_out) {
+  if (int e = use_device(c)) return e;
+  if (int e = check_run_ready(c, t0, t1)) return e;
+  const int n = t1 - t0;
+  double* d_stats = nullptr;
+  if (stats_out && n > 0) {
+    CU_TRY(c->d_stats.alloc((size_t)n * ENRGY_S_COUNT));
+    d_stats = c->d_stats.p;
+  }
+  const int rc = c->precision == ENRGY_F32 ? run_typed<float>(c, t0, t1, d_stats, c->stream)
+                                           : run_typed<double>(c, t0, t1, d_stats, c->stream);
+  if (rc != ENRGY_OK) return rc;
+  if (d_stats) CU_TRY(cudaMemcpyAsync(stats_out, d_stats, (size_t)n * ENRGY_S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return ENRGY_OK;
+}
+
+int enrgy_synchronize(enrgy_ctx* c) {
+  if (int e = use_device(c)) return e;
+  CU_TRY(cudaDeviceSynchronize());
+  return ENRGY_OK;
+}
+
+int enrgy_dump_steps(enrgy_ctx* c, int t0, int t1, double* out) {
+  if (int e = use_device(c)) return e;
+  if (int e = check_run_ready(c, t0, t1)) return e;
+  if (!out) return fail(ENRGY_ERR_ARG, "out is null");
+  if (t1 == t0) return ENRGY_OK;
+  return c->precision == ENRGY_F32 ? dump_typed<float>(c, t0, t1, out, nullptr, 0, nullptr)
+                                   : dump_typed<double>(c, t0, t1, out, nullptr, 0, nullptr);
+}
+
+int enrgy_shade_masks(enrgy_ctx* c, int step, int max_sub, uint32_t* out, int* n_sub_out) {
+  if (int e = use_device(c)) return e;
+  if (int e = check_run_ready(c, step, step + 1)) return e;
+  if (!out) return fail(ENRGY_ERR_ARG, "out is null");
+  return c->precision == ENRGY_F32 ? dump_typed<float>(c, step, step + 1, nullptr, out, max_sub, n_sub_out)
+                                   : dump_typed<double>(c, step, step + 1, nullptr, out, max_sub, n_sub_out);
+}
+
+int enrgy_potential_insolation(enrgy_ctx* c, int step, double* out) {
+  if (int e = use_device(c)) return e;
+  if (!out) return fail(ENRGY_ERR_ARG, "out is null");
+  std::vector<double> tmp((size_t)ENRGY_D_COUNT * c->band_rows * c->cols);
+  if (int e = enrgy_dump_steps(c, step, step + 1, tmp.data())) return e;
+  std::memcpy(out, tmp.data() + (size_t)ENRGY_D_POT * c->band_rows * c->cols, (size_t)c->band_rows * c->cols * sizeof(double));
+  return ENRGY_OK;
+}
+
+int enrgy_get_state(enrgy_ctx* c, int dtype, void* swe, void* total_snow, void* total_ice) {
+  if (int e = use_device(c)) return e;
+  if (!c->have_dem) return fail(ENRGY_ERR_ARG, "no state before set_dem");
+  if (dtype != 32 && dtype != 64) return fail(ENRGY_ERR_ARG, "dtype must be 32 or 64");
+  const size_t n = (size_t)c->band_rows * c->cols;
+  const size_t osz = dtype == 32 ? 4 : 8;
+  CU_TRY(c->d_stage.alloc(n * osz));
+  void* dsts[3] = {swe, total_snow, total_ice};
+  unsigned char* srcs[3] = {c->d_swe.p, c->d_ts.p, c->d_ti.p};
+  for (int q = 0; q < 3; ++q) {
+    if (!dsts[q]) continue;
+    if (c->precision == ENRGY_F32) {
+      CU_TRY(launch_unpad_state<float>((const float*)srcs[q], c->pitch, c->band_rows, c->cols, dtype, c->d_stage.p, c->stream));
+    } else {
+      CU_TRY(launch_unpad_state<double>((const double*)srcs[q], c->pitch, c->band_rows, c->cols, dtype, c->d_stage.p, c->stream));
+    }
+    c->launches++;
+    CU_TRY(cudaMemcpyAsync(dsts[q], c->d_stage.p, n * osz, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+  }
+  return ENRGY_OK;
+}
+
+int enrgy_set_state(enrgy_ctx* c, int dtype, const void* swe, const void* total_snow, const void* total_ice) {
+  if (int e = use_device(c)) return e;
+  if (!c->have_dem) return fail(ENRGY_ERR_ARG, "set_dem must precede set_state");
+  if (dtype != 32 && dtype != 64) return fail(ENRGY_ERR_ARG, "dtype must be 32 or 64");
+  const void* srcs[3] = {swe, total_snow, total_ice};
+  unsigned char* dsts[3] = {c->d_swe.p, c->d_ts.p, c->d_ti.p};
+  const size_t rs = rsize(c);
+  std::vector<unsigned char> host(c->band_elems * rs);
+  for (int q = 0; q < 3; ++q) {
+    if (!srcs[q]) continue;
+    // host-side pad + convert (restart path, not on the hot path)
+    for (size_t i = 0; i < c->band_elems; ++i) {
+      if (rs == 4) ((float*)host.data())[i] = std::numeric_limits<float>::quiet_NaN();
+      else ((double*)host.data())[i] = std::numeric_limits<double>::quiet_NaN();
+    }
+    for (int r = 0; r < c->band_rows; ++r)
+      for (int x = 0; x < c->cols; ++x) {
+        const size_t si = (size_t)r * c->cols + x, di = (size_t)r * c->pitch + x;
+        const double v = dtype == 32 ? (double)((const float*)srcs[q])[si] : ((const double*)srcs[q])[si];
+        if (rs == 4) ((float*)host.data())[di] = (float)v;
+        else ((double*)host.data())[di] = v;
+      }
+    CU_TRY(cudaMemcpyAsync(dsts[q], host.data(), host.size(), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+  }
+  c->state_advanced = true;   // a restart: the first-row SWE quirk no longer applies
+  return ENRGY_OK;
+}
+
+int enrgy_get_layer_temps(enrgy_ctx* c, double* out) {
+  (void)out;
+  if (int e = use_device(c)) return e;
+  return fail(ENRGY_ERR_ARG, "sub-surface model (msm) is not built into this round's kernels");
+}
+
+int64_t enrgy_launch_count(enrgy_ctx* c) { return c ? c->launches : 0; }
+
+double enrgy_last_kernel_ms(enrgy_ctx* c) {
+  if (!c) return 0.0;
+  if (c->ev_pending) {
+    cudaSetDevice(c->device);
+    if (cudaEventSynchronize(c->ev1) == cudaSuccess) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_ms = ms;
+    }
+    c->ev_pending = false;
+  }
+  return c->last_ms;
+}
+
+int enrgy_kernel_info(enrgy_ctx* c, int* regs, int* smem_bytes, int* ctas_per_sm, int* grid) {
+  if (!c) return fail(ENRGY_ERR_ARG, "null context");
+  if (regs) *regs = c->info.regs;
+  if (smem_bytes) *smem_bytes = c->info.smem_bytes;
+  if (ctas_per_sm) *ctas_per_sm = c->info.ctas_per_sm;
+  if (grid) *grid = c->info.grid;
+  return ENRGY_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,11 @@
+#!/bin/bash
+# Builds libenrgy_b200.so in-tree for sm_100a.  Used by __graft_entry__.build().
+set -e
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-ffp-contract=off,-Wall,-Wno-unused-function"
+$NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c kernels.cu -o kernels.o
+$NVCC $FLAGS -c prepass.cu -o prepass.o
+$NVCC $FLAGS -c api.cu -o api.o
+$NVCC -shared -o libenrgy_b200.so kernels.o prepass.o api.o -cudart static
+echo built $(pwd)/libenrgy_b200.so

@@ -1,0 +1,87 @@
+// Shared between the host pre-pass (prepass.cu) and the device kernels (kernels.cu):
+// record layouts of the per-step / per-sub-step scalar tables and the physical constants.
+//
+// Reference (tepextepex/ENRGY) citations are file:line into the upstream checkout.
+#pragma once
+#include <cstdint>
+#include <cmath>
+
+#if defined(__CUDACC__)
+#define ENRGY_HD __host__ __device__ __forceinline__
+#else
+#define ENRGY_HD inline
+#endif
+
+namespace enrgy {
+
+// ---- constants (turbo.py:30-40, var_classes.py:7-15, model.py:540) ----------------------------
+constexpr double kRair = 287.058;
+constexpr double kKarman = 0.4;
+constexpr double kGrav = 9.81;
+constexpr double kCpAir = 1010.0;
+constexpr double kLv = 2.514 * 1e6;
+constexpr double kSigma = 5.70 * 1e-8;        // sic: the reference uses 5.70e-8
+constexpr double kLf = 3.34 * 1e5;
+constexpr double kCice = 2097.0;
+constexpr double kKappaIce = 1.16 * 1e-6;
+constexpr double kKappaSnow = 0.40 * 1e-6;
+constexpr double kPressureLapse = -0.1145;    // hPa per m, var_classes.py:152
+constexpr double kVapourScale = 6300.0;       // e = e0 * 10**(-dz/6300), var_classes.py:162
+constexpr double kMsmInitLapse = -0.006;      // model.py:137
+
+// ---- tiling -----------------------------------------------------------------------------------
+constexpr int kThreads = 256;                 // 8 warps per CTA
+constexpr int kWarps = kThreads / 32;
+constexpr int kTileW = 128;                   // one warp row = 32 lanes x float4
+constexpr int kStatsK = 8;                    // statistics reduced in the kernel (see StatK)
+constexpr int kMaxStepsPerBlock = 64;         // time block: per-step records staged in smem
+constexpr int kMaxSubsPerBlock = 256;         // ... and their sunlit sub-steps
+
+// Statistics the kernel reduces per step (the rest of ENRGY_S_* is derived from these by
+// linearity in finalize_stats_kernel; DESIGN.md "Statistics").
+enum StatK { K_RS = 0, K_LWD, K_SENS, K_LAT, K_MELT, K_SNOW, K_SWE, K_NSNOW };
+// extra statistics when the sub-surface model is on
+enum StatM { M_LWU = 0, M_G, kStatsM };
+
+// ---- per-step record (16 values, staged per time block by a TMA bulk copy) ---------------------
+template <typename R>
+struct alignas(16) StepRec {
+  R t_air;     // T_AIR at the AWS [deg C]
+  R lapse;     // air-temperature lapse rate [K/m]
+  R p_hpa;     // PRESSURE at the AWS [hPa]
+  R e_aws;     // vapour pressure at the AWS [Pa]               var_classes.py:85
+  R c_sens;    // CH * Cp * uz * sensible_corr                   turbo.py:156, model.py:386
+  R c_lat;     // CE * uz * 0.622 * Lv * latent_corr             turbo.py:182, model.py:387
+  R c_lwd;     // (0.765 + 0.22 cld^3) * sigma                   model.py:544
+  R c_lwu;     // no MSM: eps*sigma*273.15^4 (the flux itself); MSM: eps*sigma   model.py:543
+  R c_sw;      // 3.6e6 / dt * (SWD / potential at AWS)          model.py:483-489
+  R c_melt;    // dt / Lf / 1000                                 msm.py:194-197
+  R alb_w;     // whole days since map i0 / whole days between i0 and i1  interpolator.py:18
+  R snow_alb;  // aged snow albedo, < 0 = off                    model.py:318-320
+  R dsum;      // sum of the diffuse coefficients of the step's sub-steps (computed insolation)
+  R dt;        // time step [s]
+  R alb_pair;  // i0 * 256 + i1 (exact small integer)
+  R sub;       // (first sub-step index relative to the time block) * 256 + number of sub-steps
+};
+
+// ---- per-sub-step record (sun above the horizon only) ------------------------------------------
+template <typename R>
+struct alignas(16) SubRec {
+  R e, n, u;   // unit vector toward the sun (east, north, up)
+  R b;         // S0 * tau^(1/u) * width_h / 1000   [kWh m-2 per unit cos(incidence)]
+};
+// shading direction of a sub-step (precision independent: the mask spec is float32 + integers)
+struct alignas(16) ShadeRec {
+  int32_t dc_fix;  // Q16 column step per ray step (east = +col)
+  int32_t dr_fix;  // Q16 row step per ray step (north = -row)
+  float dz;        // rise of the ray per step [m] (float32 of cell * u / max(|e|,|n|))
+  int32_t kmax;    // last ray step that can still be inside the grid
+};
+
+// time block = consecutive steps whose records and sub-steps fit the smem staging buffers
+struct TimeBlock {
+  int32_t t_begin, t_end;      // steps [t_begin, t_end)
+  int32_t sub_begin, sub_end;  // sub-step records [sub_begin, sub_end)
+};
+
+}  // namespace enrgy

@@ -1,0 +1,809 @@
+// Fused surface-energy-balance kernels for sm_100a (B200).
+//
+// One persistent CTA per resident slot walks a static list of raster tiles.  For each tile every
+// thread owns K cells for the WHOLE time range: SWE and the two melt totals live in registers, the
+// per-step AWS scalars are staged per time block in shared memory by TMA bulk copies
+// (cp.async.bulk + mbarrier, double buffered), and the only global traffic inside the time loop is
+// the optional streamed insolation raster (4 B per cell-step) and the shading ray samples.
+//
+// Reference arithmetic being replaced (tepextepex/ENRGY, file:line):
+//   var_classes.py:113-125  lapse-rate distribution of T, p, e            -> cell_step()
+//   turbo.py:140-196        distributed sensible / latent flux            -> cell_step()
+//   turbo.py:368-379        Magnus saturation vapour pressure             -> surface vapour term
+//   model.py:533-545        longwave                                      -> cell_step()
+//   model.py:298-337        albedo                                        -> cell_step()
+//   model.py:464-497        shortwave from potential insolation           -> cell_step()
+//   saga_lighting.py:42-44  potential insolation incl. shadows (SAGA)     -> insolation()/march()
+//   model.py:411, :434-438  flux sum and clamp                            -> cell_step()
+//   msm.py:193-203          melt partition                                -> cell_step()
+//   model.py:258-261        state update                                  -> cell_step()
+//   var_classes.py:45-56, model.py:246-252  per-step area statistics      -> warp_reduce8 + slots
+#include "kernels.cuh"
+
+#include <cstdio>
+
+#include "../../include/enrgy_b200.h"
+
+namespace enrgy {
+
+// =================================================================================================
+// small device helpers
+// =================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// arithmetic traits ------------------------------------------------------------------------------
+template <typename R>
+struct Num;
+template <>
+struct Num<float> {
+  static __device__ __forceinline__ float rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+  }
+  // T + delta * lapse exactly as NumPy float32 evaluates it (rounded product, rounded sum)
+  static __device__ __forceinline__ float lapse(float t, float delta, float g) {
+    return __fadd_rn(t, __fmul_rn(delta, g));
+  }
+  static __device__ __forceinline__ float pow10(float x) { return powf(10.0f, x); }
+  static __device__ __forceinline__ float rsqrt_(float x) { return 1.0f / sqrtf(x); }
+};
+template <>
+struct Num<double> {
+  static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+  static __device__ __forceinline__ double lapse(double t, double delta, double g) {
+    return t + delta * g;
+  }
+  static __device__ __forceinline__ double pow10(double x) { return pow(10.0, x); }
+  static __device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }
+};
+
+template <typename R>
+__device__ __forceinline__ R fmax_(R a, R b) {
+  return a > b ? a : b;
+}
+template <typename R>
+__device__ __forceinline__ R fmin_(R a, R b) {
+  return a < b ? a : b;
+}
+
+// Sum of 8 per-thread values over the 32 lanes with 15 shuffles instead of 40: each butterfly stage
+// halves the number of values a lane still carries.  Returns the total of statistic
+// stat_of_lane(lane) = 4*bit4 + 2*bit3 + bit2; fixed order, hence deterministic.
+template <typename R>
+__device__ __forceinline__ R warp_reduce8(const R (&v)[8], int lane) {
+  const unsigned full = 0xffffffffu;
+  R a[4], b[2], c;
+  bool hi = (lane & 16) != 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const R send = hi ? v[i] : v[i + 4];
+    const R keep = hi ? v[i + 4] : v[i];
+    a[i] = keep + __shfl_xor_sync(full, send, 16);
+  }
+  hi = (lane & 8) != 0;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const R send = hi ? a[i] : a[i + 2];
+    const R keep = hi ? a[i + 2] : a[i];
+    b[i] = keep + __shfl_xor_sync(full, send, 8);
+  }
+  hi = (lane & 4) != 0;
+  {
+    const R send = hi ? b[0] : b[1];
+    const R keep = hi ? b[1] : b[0];
+    c = keep + __shfl_xor_sync(full, send, 4);
+  }
+  c += __shfl_xor_sync(full, c, 2);
+  c += __shfl_xor_sync(full, c, 1);
+  return c;
+}
+__device__ __forceinline__ int stat_of_lane(int lane) {
+  return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+}
+
+// =================================================================================================
+// set-up kernels
+// =================================================================================================
+// terrain normal from the 4-neighbourhood; a missing neighbour is mirrored from the opposite one
+// (DESIGN.md "Insolation specification"; oracle/insolation_oracle.py:terrain_normals)
+template <typename R>
+__global__ void terrain_kernel(const float* __restrict__ dem, int rows_full, int cols, int pitch,
+                               int band_row0, int band_rows_pad, R inv2cell, R* __restrict__ nx,
+                               R* __restrict__ ny, R* __restrict__ nz) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int rb = blockIdx.y;
+  if (c >= pitch || rb >= band_rows_pad) return;
+  const int r = rb + band_row0;
+  const size_t o = (size_t)rb * pitch + c;
+  const float qnan = __int_as_float(0x7fc00000);
+  auto at = [&](int rr, int cc) -> float {
+    if (rr < 0 || rr >= rows_full || cc < 0 || cc >= cols) return qnan;
+    return dem[(size_t)rr * pitch + cc];
+  };
+  const float zf = at(r, c);
+  if (!(zf == zf)) {
+    nx[o] = (R)qnan; ny[o] = (R)qnan; nz[o] = (R)qnan;
+    return;
+  }
+  const R z = (R)zf;
+  auto one_sided = [&](float a, float b) -> R {
+    if (a == a) return (R)a - z;
+    if (b == b) return z - (R)b;
+    return (R)0;
+  };
+  const float zn = at(r - 1, c), zs = at(r + 1, c), ze = at(r, c + 1), zw = at(r, c - 1);
+  const R gy = (one_sided(zn, zs) - one_sided(zs, zn)) * inv2cell;
+  const R gx = (one_sided(ze, zw) - one_sided(zw, ze)) * inv2cell;
+  const R inv = Num<R>::rsqrt_((R)1 + gx * gx + gy * gy);
+  nx[o] = -gx * inv;
+  ny[o] = -gy * inv;
+  nz[o] = inv;
+}
+
+template <typename R>
+cudaError_t launch_terrain(const float* dem, int rows_full, int cols, int pitch, int band_row0,
+                           int band_rows_pad, double cell, R* nx, R* ny, R* nz, cudaStream_t stream) {
+  dim3 grid((pitch + 255) / 256, band_rows_pad);
+  terrain_kernel<R><<<grid, 256, 0, stream>>>(dem, rows_full, cols, pitch, band_row0, band_rows_pad,
+                                              (R)(1.0 / (2.0 * cell)), nx, ny, nz);
+  return cudaGetLastError();
+}
+template cudaError_t launch_terrain<float>(const float*, int, int, int, int, int, double, float*, float*, float*, cudaStream_t);
+template cudaError_t launch_terrain<double>(const float*, int, int, int, int, int, double, double*, double*, double*, cudaStream_t);
+
+// valid (non-NaN DEM) cells per tile
+__global__ void tile_scan_kernel(const float* __restrict__ dem, int pitch, int band_row0,
+                                 int band_rows, int cols, int tile_h, int tiles_c,
+                                 int* __restrict__ counts) {
+  const int tr = blockIdx.y, tc = blockIdx.x;
+  int n = 0;
+  for (int i = threadIdx.x; i < tile_h * kTileW; i += blockDim.x) {
+    const int rb = tr * tile_h + i / kTileW;
+    const int c = tc * kTileW + i % kTileW;
+    if (rb < band_rows && c < cols) {
+      const float z = dem[(size_t)(rb + band_row0) * pitch + c];
+      n += (z == z) ? 1 : 0;
+    }
+  }
+  n = __reduce_add_sync(0xffffffffu, n);
+  __shared__ int s[32];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s[w];
+    counts[tr * tiles_c + tc] = tot;
+  }
+}
+cudaError_t launch_tile_scan(const float* dem, int pitch, int band_row0, int band_rows, int cols,
+                             int tile_h, int tiles_r, int tiles_c, int* counts, cudaStream_t stream) {
+  tile_scan_kernel<<<dim3(tiles_c, tiles_r), 256, 0, stream>>>(dem, pitch, band_row0, band_rows, cols,
+                                                               tile_h, tiles_c, counts);
+  return cudaGetLastError();
+}
+
+// counters[0] += cells valid in the DEM but NaN in `other`; counters[1] += the opposite
+__global__ void mask_check_kernel(const float* __restrict__ dem, const float* __restrict__ other,
+                                  int pitch, int band_row0, int band_rows, int cols,
+                                  unsigned long long* counters) {
+  unsigned a = 0, b = 0;
+  const size_t n = (size_t)band_rows * cols;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int rb = (int)(i / cols), c = (int)(i % cols);
+    const float z = dem[(size_t)(rb + band_row0) * pitch + c];
+    const float o = other[(size_t)rb * pitch + c];
+    const bool vz = z == z, vo = o == o;
+    a += (vz && !vo) ? 1u : 0u;
+    b += (!vz && vo) ? 1u : 0u;
+  }
+  a = __reduce_add_sync(0xffffffffu, a);
+  b = __reduce_add_sync(0xffffffffu, b);
+  if ((threadIdx.x & 31) == 0) {
+    if (a) atomicAdd(&counters[0], (unsigned long long)a);
+    if (b) atomicAdd(&counters[1], (unsigned long long)b);
+  }
+}
+cudaError_t launch_mask_check(const float* dem, const float* other, int pitch, int band_row0,
+                              int band_rows, int cols, unsigned long long* counters,
+                              cudaStream_t stream) {
+  mask_check_kernel<<<592, 256, 0, stream>>>(dem, other, pitch, band_row0, band_rows, cols, counters);
+  return cudaGetLastError();
+}
+
+// SWE statistics of the initial raster over ALL its non-NaN cells (first CSV row quirk).
+// block_out[b] = {sum, count(swe > 0), count(non-NaN)}; summed on the host in block order.
+__global__ void swe0_stats_kernel(const float* __restrict__ swe, int pitch, int band_rows, int cols,
+                                  double* __restrict__ block_out) {
+  double s = 0.0, ns = 0.0, nv = 0.0;
+  const size_t n = (size_t)band_rows * cols;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int rb = (int)(i / cols), c = (int)(i % cols);
+    const float v = swe[(size_t)rb * pitch + c];
+    if (v == v) {
+      s += (double)v;
+      nv += 1.0;
+      if (v > 0.f) ns += 1.0;
+    }
+  }
+  __shared__ double sh[3][kThreads];
+  sh[0][threadIdx.x] = s; sh[1][threadIdx.x] = ns; sh[2][threadIdx.x] = nv;
+  __syncthreads();
+  for (int off = kThreads / 2; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) {
+      for (int q = 0; q < 3; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + off];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < 3; ++q) block_out[blockIdx.x * 3 + q] = sh[q][0];
+  }
+}
+cudaError_t launch_swe0_stats(const float* swe, int pitch, int band_rows, int cols, double* block_out,
+                              int blocks, cudaStream_t stream) {
+  swe0_stats_kernel<<<blocks, kThreads, 0, stream>>>(swe, pitch, band_rows, cols, block_out);
+  return cudaGetLastError();
+}
+
+template <typename R>
+__global__ void pad_convert_kernel(const float* __restrict__ src, R* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    dst[i] = (R)src[i];
+  }
+}
+template <typename R>
+cudaError_t launch_pad_convert(const float* src, R* dst, size_t n, cudaStream_t stream) {
+  pad_convert_kernel<R><<<1184, 256, 0, stream>>>(src, dst, n);
+  return cudaGetLastError();
+}
+template cudaError_t launch_pad_convert<float>(const float*, float*, size_t, cudaStream_t);
+template cudaError_t launch_pad_convert<double>(const float*, double*, size_t, cudaStream_t);
+
+template <typename R, typename O>
+__global__ void unpad_kernel(const R* __restrict__ src, int pitch, int rows, int cols, O* __restrict__ dst) {
+  const size_t n = (size_t)rows * cols;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    dst[i] = (O)src[(size_t)r * pitch + c];
+  }
+}
+template <typename R>
+cudaError_t launch_unpad_state(const R* src, int pitch, int rows, int cols, int dtype, void* dst,
+                               cudaStream_t stream) {
+  if (dtype == 32) {
+    unpad_kernel<R, float><<<1184, 256, 0, stream>>>(src, pitch, rows, cols, (float*)dst);
+  } else {
+    unpad_kernel<R, double><<<1184, 256, 0, stream>>>(src, pitch, rows, cols, (double*)dst);
+  }
+  return cudaGetLastError();
+}
+template cudaError_t launch_unpad_state<float>(const float*, int, int, int, int, void*, cudaStream_t);
+template cudaError_t launch_unpad_state<double>(const double*, int, int, int, int, void*, cudaStream_t);
+
+// off-glacier cells of the state rasters become NaN with the first step (model.py:258: swe -= NaN);
+// the fused kernel only visits tiles that hold glacier cells, this covers the rest.
+template <typename R>
+__global__ void nan_offglacier_kernel(const float* __restrict__ dem, int pitch, int band_row0,
+                                      int band_rows, int cols, R* __restrict__ swe,
+                                      R* __restrict__ tsn, R* __restrict__ tic) {
+  const size_t n = (size_t)band_rows * cols;
+  const R qnan = (R)__int_as_float(0x7fc00000);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int rb = (int)(i / cols), c = (int)(i % cols);
+    const float z = dem[(size_t)(rb + band_row0) * pitch + c];
+    if (!(z == z)) {
+      const size_t o = (size_t)rb * pitch + c;
+      swe[o] = qnan; tsn[o] = qnan; tic[o] = qnan;
+    }
+  }
+}
+template <typename R>
+cudaError_t launch_nan_offglacier(const float* dem, int pitch, int band_row0, int band_rows, int cols,
+                                  R* swe, R* tsn, R* tic, cudaStream_t stream) {
+  nan_offglacier_kernel<R><<<1184, 256, 0, stream>>>(dem, pitch, band_row0, band_rows, cols, swe, tsn, tic);
+  return cudaGetLastError();
+}
+template cudaError_t launch_nan_offglacier<float>(const float*, int, int, int, int, float*, float*, float*, cudaStream_t);
+template cudaError_t launch_nan_offglacier<double>(const float*, int, int, int, int, double*, double*, double*, cudaStream_t);
+
+// =================================================================================================
+// shading ray march (DESIGN.md "Shading"; oracle/insolation_oracle.py:shadow_mask)
+// =================================================================================================
+// All K cells of a thread and all 32 lanes step together; bit i of the returned mask = cell i is
+// sunlit.  float32 + integer arithmetic only, non-fused multiply/add, so the mask is bit-identical
+// to the NumPy statement whatever the precision of the energy balance.
+template <int K>
+__device__ __forceinline__ unsigned march(const float* __restrict__ dem, int pitch, int rows_full,
+                                          int cols, const int (&row)[K], const int (&col)[K],
+                                          const float (&z0)[K], unsigned valid_bits,
+                                          const ShadeRec s, float zmax) {
+  unsigned lit = (1u << K) - 1u;
+  if (!(s.dz < 3.0e38f)) return lit;   // sun at the zenith
+  unsigned active = valid_bits;
+  for (int k = 1; __any_sync(0xffffffffu, active != 0u); ++k) {
+    const int ro = (k * s.dr_fix + 32768) >> 16;
+    const int co = (k * s.dc_fix + 32768) >> 16;
+    const float kdz = __fmul_rn((float)k, s.dz);
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      const unsigned bit = 1u << i;
+      if (active & bit) {
+        const int rr = row[i] + ro, cc = col[i] + co;
+        const float zk = __fadd_rn(z0[i], kdz);
+        if ((unsigned)rr >= (unsigned)rows_full || (unsigned)cc >= (unsigned)cols || zk > zmax) {
+          active &= ~bit;
+        } else {
+          const float smp = __ldg(dem + (size_t)rr * pitch + cc);
+          if (smp > zk) {
+            lit &= ~bit;
+            active &= ~bit;
+          }
+        }
+      }
+    }
+  }
+  return lit;
+}
+
+// =================================================================================================
+// the fused energy-balance kernel
+// =================================================================================================
+template <typename R>
+struct SmemLayout {
+  StepRec<R> steps[2][kMaxStepsPerBlock];
+  SubRec<R> subs[2][kMaxSubsPerBlock];
+  ShadeRec shades[2][kMaxSubsPerBlock];
+  R slots[kWarps][kMaxStepsPerBlock][kStatsK];
+  uint64_t full[2];
+};
+
+template <typename R, int K, int INSOL, bool DUMP>
+__global__ void __launch_bounds__(kThreads, (sizeof(R) == 4 && K <= 4) ? 2 : 1)
+energy_balance_kernel(const KernelArgs<R> a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemLayout<R>& sm = *reinterpret_cast<SmemLayout<R>*>(smem_raw);
+  constexpr int TILE_H = kWarps * (K / 4);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const R qnan = (R)__int_as_float(0x7fc00000);
+
+  if (tid == 0) {
+    mbar_init(&sm.full[0], 1);
+    mbar_init(&sm.full[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  unsigned phase[2] = {0u, 0u};
+
+  const bool use_shades = INSOL == kInsolShadow;
+  auto issue_block = [&](int b, int buf) {
+    // one elected thread: stage the per-step records (and sub-step records) of time block b
+    const TimeBlock tb = a.blocks[b];
+    const unsigned n_steps = (unsigned)(tb.t_end - tb.t_begin);
+    const unsigned n_subs = (unsigned)(tb.sub_end - tb.sub_begin);
+    unsigned bytes = n_steps * (unsigned)sizeof(StepRec<R>);
+    if (INSOL != kInsolStreamed) bytes += n_subs * (unsigned)sizeof(SubRec<R>);
+    if (use_shades) bytes += n_subs * (unsigned)sizeof(ShadeRec);
+    fence_proxy_async();
+    mbar_expect_tx(&sm.full[buf], bytes);
+    tma_bulk_g2s(&sm.steps[buf][0], a.steps + tb.t_begin, n_steps * (unsigned)sizeof(StepRec<R>),
+                 &sm.full[buf]);
+    if (INSOL != kInsolStreamed && n_subs) {
+      tma_bulk_g2s(&sm.subs[buf][0], a.subs + tb.sub_begin, n_subs * (unsigned)sizeof(SubRec<R>),
+                   &sm.full[buf]);
+      if (use_shades) {
+        tma_bulk_g2s(&sm.shades[buf][0], a.shades + tb.sub_begin, n_subs * (unsigned)sizeof(ShadeRec),
+                     &sm.full[buf]);
+      }
+    }
+  };
+
+  const int n_steps_run = a.t1 - a.t0;
+  double* my_partials = a.partials ? a.partials + (size_t)blockIdx.x * n_steps_run * kStatsK : nullptr;
+
+  for (int ti = blockIdx.x; ti < a.n_tiles; ti += gridDim.x) {
+    const int2 tile = a.tiles[ti];
+    // ---- prologue: per-cell invariants and state into registers --------------------------------
+    int rowb[K], col[K];           // band-local row, column
+    R delta[K], pw[K], a0[K], da[K], nxv[K], nyv[K], nzv[K], swe[K], tsn[K], tic[K], wgt[K];
+    float z0[K];
+    int rowf[K];
+    unsigned valid_bits = 0;
+    int cur_pair = -1;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      rowb[i] = tile.x * TILE_H + warp + kWarps * (i >> 2);
+      col[i] = tile.y * kTileW + lane + 32 * (i & 3);
+      rowf[i] = rowb[i] + a.band_row0;
+      const size_t o = (size_t)rowb[i] * a.pitch + col[i];
+      const bool inside = rowb[i] < a.band_rows && col[i] < a.cols;
+      float z = inside ? __ldg(a.dem + (size_t)rowf[i] * a.pitch + col[i]) : __int_as_float(0x7fc00000);
+      const bool v = z == z;
+      valid_bits |= v ? (1u << i) : 0u;
+      wgt[i] = v ? (R)1 : (R)0;
+      z0[i] = z;
+      if (!v) z = (float)a.elev_aws;           // keep the arithmetic of masked cells finite
+      delta[i] = (R)z - a.elev_aws;            // var_classes.py:114
+      pw[i] = Num<R>::pow10(-delta[i] / (R)kVapourScale);   // var_classes.py:162
+      if (INSOL != kInsolStreamed) {
+        nxv[i] = v ? a.nx[o] : (R)0;
+        nyv[i] = v ? a.ny[o] : (R)0;
+        nzv[i] = v ? a.nz[o] : (R)1;
+      } else {
+        nxv[i] = nyv[i] = (R)0; nzv[i] = (R)1;
+      }
+      swe[i] = v ? a.swe[o] : (R)0;
+      tsn[i] = v ? a.total_snow[o] : (R)0;
+      tic[i] = v ? a.total_ice[o] : (R)0;
+      a0[i] = (R)0.5; da[i] = (R)0;
+    }
+
+    int buf = 0;
+    if (tid == 0) issue_block(a.block_begin, 0);
+
+    for (int b = a.block_begin; b < a.block_end; ++b, buf ^= 1) {
+      if (tid == 0 && b + 1 < a.block_end) issue_block(b + 1, buf ^ 1);
+      mbar_wait(&sm.full[buf], phase[buf]);
+      phase[buf] ^= 1u;
+      const TimeBlock tb = a.blocks[b];
+      const int ts = max(tb.t_begin, a.t0), te = min(tb.t_end, a.t1);
+
+      // streamed insolation: first step's values, then one step ahead
+      float pot_next[K];
+      if (INSOL == kInsolStreamed) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          const size_t o = (size_t)(ts - a.pot_t0) * a.pot_stride + (size_t)rowb[i] * a.pitch + col[i];
+          pot_next[i] = (valid_bits >> i) & 1u ? __ldg(a.pot + o) : 0.f;
+        }
+      }
+
+      for (int t = ts; t < te; ++t) {
+        const StepRec<R> s = sm.steps[buf][t - tb.t_begin];
+        // ---- albedo maps of this step's bracket (interpolator.py:12-18) -------------------------
+        if (!a.albedo_const) {
+          const int pair = (int)s.alb_pair;
+          if (pair != cur_pair) {      // uniform across the CTA: a few times per season
+            cur_pair = pair;
+            const float* m0 = a.albedo + (size_t)(pair >> 8) * a.map_stride;
+            const float* m1 = a.albedo + (size_t)(pair & 255) * a.map_stride;
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+              const size_t o = (size_t)rowb[i] * a.pitch + col[i];
+              const bool v = (valid_bits >> i) & 1u;
+              const R x0 = v ? (R)__ldg(m0 + o) : (R)0.5;
+              const R x1 = v ? (R)__ldg(m1 + o) : (R)0.5;
+              a0[i] = x0;
+              da[i] = x1 - x0;
+            }
+          }
+        }
+        float pot_cur[K];
+        if (INSOL == kInsolStreamed) {
+#pragma unroll
+          for (int i = 0; i < K; ++i) pot_cur[i] = pot_next[i];
+          if (t + 1 < te) {
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+              const size_t o = (size_t)(t + 1 - a.pot_t0) * a.pot_stride + (size_t)rowb[i] * a.pitch + col[i];
+              pot_next[i] = (valid_bits >> i) & 1u ? __ldg(a.pot + o) : 0.f;
+            }
+          }
+        }
+
+        // ---- potential insolation of the step [kWh m-2] -----------------------------------------
+        R pot[K];
+        if (INSOL == kInsolStreamed) {
+#pragma unroll
+          for (int i = 0; i < K; ++i) pot[i] = (R)pot_cur[i];
+        } else {
+          R direct[K];
+#pragma unroll
+          for (int i = 0; i < K; ++i) direct[i] = (R)0;
+          const int sub_code = (int)s.sub;
+          const int j0 = sub_code >> 8, nj = sub_code & 255;
+          for (int j = j0; j < j0 + nj; ++j) {
+            const SubRec<R> sb = sm.subs[buf][j];
+            unsigned lit = 0xffffffffu;
+            if (INSOL == kInsolShadow) {
+              lit = march<K>(a.dem, a.pitch, a.rows_full, a.cols, rowf, col, z0, valid_bits,
+                             sm.shades[buf][j], (float)a.zmax);
+              if (DUMP && a.mask_out != nullptr && t == a.t0) {
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                  const unsigned word = __ballot_sync(0xffffffffu, (lit >> i) & 1u);
+                  if (lane == 0 && rowb[i] < a.band_rows && col[i] < a.cols) {
+                    a.mask_out[((size_t)(j - j0) * a.band_rows + rowb[i]) * a.mask_words + (col[i] >> 5)] = word;
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+              R c = nxv[i] * sb.e + nyv[i] * sb.n + nzv[i] * sb.u;
+              c = fmax_(c, (R)0);
+              if (INSOL == kInsolShadow) c = ((lit >> i) & 1u) ? c : (R)0;
+              direct[i] += sb.b * c;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < K; ++i) pot[i] = direct[i] + s.dsum * ((R)1 + nzv[i]);
+        }
+
+        // ---- per-cell energy balance -------------------------------------------------------------
+        R acc[kStatsK];
+#pragma unroll
+        for (int q = 0; q < kStatsK; ++q) acc[q] = (R)0;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          // lapse-rate distribution, var_classes.py:113-125
+          const R t_air = Num<R>::lapse(s.t_air, delta[i], s.lapse);
+          const R tz = t_air + (R)273.15;
+          const R d_t = tz - (R)273.15;                     // Tz - Ts, Ts = 0 degC + 273.15
+          const R p_hpa = s.p_hpa + delta[i] * (R)kPressureLapse;
+          const R p_pa = p_hpa * (R)100;
+          const R e = s.e_aws * pw[i];
+          // bulk fluxes, turbo.py:140-196 with rho = P / (R Tz), rho / P = 1 / (R Tz)
+          const R r_rt = Num<R>::rcp((R)kRair * tz);
+          const R rho = p_pa * r_rt;
+          const R sens = s.c_sens * rho * d_t;
+          // saturation vapour pressure of the melting surface, turbo.py:368-379 with t = 0:
+          // exp(0) = 1 exactly, so es = 611.2 * f(p).  ez = e_max * (e / e_max) = e (one rounding).
+          const R f_p = (R)1.0016 + (R)(3.15 * 1e-6) * p_hpa - (R)0.074 * Num<R>::rcp(p_hpa);
+          const R es = (R)611.2 * f_p;
+          const R lat = s.c_lat * r_rt * (e - es);
+          // longwave, model.py:533-545
+          const R tz2 = tz * tz;
+          const R lwd = s.c_lwd * (tz2 * tz2);
+          const R lwu = s.c_lwu;
+          // albedo, model.py:298-337
+          R alb;
+          if (a.albedo_const) {
+            alb = swe[i] > (R)0 ? a.albedo_snow : a.albedo_ice;
+          } else {
+            alb = a0[i] + s.alb_w * da[i];
+            if (s.snow_alb >= (R)0) alb = swe[i] > (R)0 ? s.snow_alb : alb;
+            alb = (swe[i] <= (R)0 && alb > a.max_ice_albedo) ? a.max_ice_albedo : alb;
+          }
+          // shortwave, model.py:483-497
+          const R rs = pot[i] * s.c_sw * ((R)1 - alb);
+          // balance, clamp, melt partition: model.py:411, :434-438, msm.py:193-203
+          const R atmo = rs + lwd - lwu + sens + lat;
+          const R mf = fmax_(atmo, (R)0);
+          const R we = mf * s.c_melt;
+          const R snow = fmin_(we, swe[i]);
+          const R ice = we - snow;
+          const R w = wgt[i];
+          acc[K_RS] += w * rs;
+          acc[K_LWD] += w * lwd;
+          acc[K_SENS] += w * sens;
+          acc[K_LAT] += w * lat;
+          acc[K_MELT] += w * mf;
+          acc[K_SNOW] += w * snow;
+          acc[K_SWE] += w * swe[i];
+          acc[K_NSNOW] += swe[i] > (R)0 ? w : (R)0;
+          if (DUMP && a.dump != nullptr) {
+            if ((valid_bits >> i) & 1u) {
+              R* d = a.dump + (size_t)(t - a.t0) * ENRGY_D_COUNT * a.dump_field_stride +
+                     (size_t)rowb[i] * a.pitch + col[i];
+              d[ENRGY_D_RS * a.dump_field_stride] = rs;
+              d[ENRGY_D_LWD * a.dump_field_stride] = lwd;
+              d[ENRGY_D_LWU * a.dump_field_stride] = lwu;
+              d[ENRGY_D_SENS * a.dump_field_stride] = sens;
+              d[ENRGY_D_LAT * a.dump_field_stride] = lat;
+              d[ENRGY_D_ATMO * a.dump_field_stride] = atmo;
+              d[ENRGY_D_MELT * a.dump_field_stride] = mf;
+              d[ENRGY_D_SNOW * a.dump_field_stride] = snow;
+              d[ENRGY_D_ICE * a.dump_field_stride] = ice;
+              d[ENRGY_D_ALBEDO * a.dump_field_stride] = alb;
+              d[ENRGY_D_POT * a.dump_field_stride] = pot[i];
+              d[ENRGY_D_G * a.dump_field_stride] = (R)0;
+            }
+          }
+          // state update, model.py:258-261
+          swe[i] -= snow;
+          tsn[i] += snow;
+          tic[i] += ice;
+        }
+        // ---- per-step statistics: warp butterfly, one slot per warp --------------------------------
+        if (!DUMP) {
+          const R tot = warp_reduce8<R>(acc, lane);
+          if ((lane & 3) == 0) sm.slots[warp][t - tb.t_begin][stat_of_lane(lane)] = tot;
+        }
+      }  // steps of the time block
+
+      // ---- flush the block's statistics into this CTA's partial rows (fixed order) ---------------
+      __syncthreads();
+      if (!DUMP && my_partials != nullptr) {
+        const int n = (te - ts) * kStatsK;
+        for (int idx = tid; idx < n; idx += kThreads) {
+          const int tl = ts - tb.t_begin + idx / kStatsK, q = idx % kStatsK;
+          double sum = 0.0;
+#pragma unroll
+          for (int w = 0; w < kWarps; ++w) sum += (double)sm.slots[w][tl][q];
+          my_partials[(size_t)(ts - a.t0) * kStatsK + idx] += sum;
+        }
+      }
+      __syncthreads();
+    }  // time blocks
+
+    // ---- epilogue: state back to HBM (off-glacier cells become NaN, model.py:258) ---------------
+    if (!DUMP) {
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        if (rowb[i] < a.band_rows && col[i] < a.cols) {
+          const size_t o = (size_t)rowb[i] * a.pitch + col[i];
+          const bool v = (valid_bits >> i) & 1u;
+          a.swe[o] = v ? swe[i] : qnan;
+          a.total_snow[o] = v ? tsn[i] : qnan;
+          a.total_ice[o] = v ? tic[i] : qnan;
+        }
+      }
+    }
+  }  // tiles
+}
+
+template <typename R, int INSOL>
+struct CellsPerThread {
+  static constexpr int value = sizeof(R) == 4 ? 8 : 4;
+};
+
+template <typename R>
+int energy_balance_tile_h(int insol) {
+  (void)insol;
+  return kWarps * (CellsPerThread<R, 0>::value / 4);
+}
+template int energy_balance_tile_h<float>(int);
+template int energy_balance_tile_h<double>(int);
+
+template <typename R, int INSOL, bool DUMP>
+static cudaError_t configure(int sm_count, LaunchInfo* info) {
+  constexpr int K = CellsPerThread<R, INSOL>::value;
+  auto kern = energy_balance_kernel<R, K, INSOL, DUMP>;
+  const int smem = (int)sizeof(SmemLayout<R>);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
+  if (e != cudaSuccess) return e;
+  cudaFuncAttributes fa;
+  e = cudaFuncGetAttributes(&fa, kern);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  info->regs = fa.numRegs;
+  info->smem_bytes = smem;
+  info->ctas_per_sm = per_sm;
+  info->grid = per_sm * sm_count;
+  info->cells_per_thread = K;
+  return cudaSuccess;
+}
+
+template <typename R, int INSOL, bool DUMP>
+static cudaError_t launch_one(const KernelArgs<R>& a, int sm_count, int forced_grid, LaunchInfo* info,
+                              cudaStream_t stream) {
+  constexpr int K = CellsPerThread<R, INSOL>::value;
+  LaunchInfo li;
+  cudaError_t e = configure<R, INSOL, DUMP>(sm_count, &li);
+  if (e != cudaSuccess) return e;
+  int grid = forced_grid > 0 ? forced_grid : li.grid;
+  li.grid = grid;
+  if (info) *info = li;
+  if (a.n_tiles == 0 || a.t1 <= a.t0) return cudaSuccess;
+  energy_balance_kernel<R, K, INSOL, DUMP><<<grid, kThreads, li.smem_bytes, stream>>>(a);
+  return cudaGetLastError();
+}
+
+template <typename R>
+cudaError_t energy_balance_grid(int insol, bool dump, int sm_count, LaunchInfo* info) {
+  if (dump) {
+    if (insol == 0) return configure<R, 0, true>(sm_count, info);
+    if (insol == 1) return configure<R, 1, true>(sm_count, info);
+    return configure<R, 2, true>(sm_count, info);
+  }
+  if (insol == 0) return configure<R, 0, false>(sm_count, info);
+  if (insol == 1) return configure<R, 1, false>(sm_count, info);
+  return configure<R, 2, false>(sm_count, info);
+}
+template cudaError_t energy_balance_grid<float>(int, bool, int, LaunchInfo*);
+template cudaError_t energy_balance_grid<double>(int, bool, int, LaunchInfo*);
+
+template <typename R>
+cudaError_t launch_energy_balance(const KernelArgs<R>& a, int insol, bool dump, int sm_count,
+                                  int forced_grid, LaunchInfo* info, cudaStream_t stream) {
+  if (dump) {
+    if (insol == 0) return launch_one<R, 0, true>(a, sm_count, forced_grid, info, stream);
+    if (insol == 1) return launch_one<R, 1, true>(a, sm_count, forced_grid, info, stream);
+    return launch_one<R, 2, true>(a, sm_count, forced_grid, info, stream);
+  }
+  if (insol == 0) return launch_one<R, 0, false>(a, sm_count, forced_grid, info, stream);
+  if (insol == 1) return launch_one<R, 1, false>(a, sm_count, forced_grid, info, stream);
+  return launch_one<R, 2, false>(a, sm_count, forced_grid, info, stream);
+}
+template cudaError_t launch_energy_balance<float>(const KernelArgs<float>&, int, bool, int, int, LaunchInfo*, cudaStream_t);
+template cudaError_t launch_energy_balance<double>(const KernelArgs<double>&, int, bool, int, int, LaunchInfo*, cudaStream_t);
+
+// =================================================================================================
+// statistics: cross-CTA sum in fixed order + the derived columns
+// =================================================================================================
+__global__ void finalize_stats_kernel(const FinalizeArgs f) {
+  const int f32_mode = f.f32_mode;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= f.n_steps) return;
+  double k[kStatsK];
+  for (int q = 0; q < kStatsK; ++q) k[q] = 0.0;
+  for (int c = 0; c < f.n_ctas; ++c) {
+    const double* p = f.partials + ((size_t)c * f.n_steps + t) * kStatsK;
+    for (int q = 0; q < kStatsK; ++q) k[q] += p[q];
+  }
+  const StepRec<double> s = f.steps64[f.t0 + t];
+  const double lwu_cell = f32_mode ? (double)(float)s.c_lwu : s.c_lwu;
+  const double c_melt = f32_mode ? (double)(float)s.c_melt : s.c_melt;
+  double* o = f.stats + (size_t)t * ENRGY_S_COUNT;
+  const double lwu = f.n_valid * lwu_cell;
+  o[ENRGY_S_RS] = k[K_RS];
+  o[ENRGY_S_LWD] = k[K_LWD];
+  o[ENRGY_S_LWU] = lwu;
+  o[ENRGY_S_SENS] = k[K_SENS];
+  o[ENRGY_S_LAT] = k[K_LAT];
+  // linear in the cell values: sum(atmo) = sum(rs) + sum(lwd) - sum(lwu) + sum(sens) + sum(lat)
+  o[ENRGY_S_ATMO] = k[K_RS] + k[K_LWD] - lwu + k[K_SENS] + k[K_LAT];
+  o[ENRGY_S_G] = 0.0;
+  o[ENRGY_S_MELT] = k[K_MELT];
+  o[ENRGY_S_SNOW] = k[K_SNOW];
+  // ice = we - snow with we = mf * c_melt
+  o[ENRGY_S_ICE] = k[K_MELT] * c_melt - k[K_SNOW];
+  o[ENRGY_S_SWE] = k[K_SWE];
+  o[ENRGY_S_NSNOW] = k[K_NSNOW];
+  o[ENRGY_S_NSWE] = f.n_valid;
+  o[ENRGY_S_NVALID] = f.n_valid;
+  if (f.override_first && f.t0 + t == 0) {
+    o[ENRGY_S_SWE] = f.swe0_sum;
+    o[ENRGY_S_NSNOW] = f.swe0_nsnow;
+    o[ENRGY_S_NSWE] = f.swe0_nvalid;
+  }
+}
+
+cudaError_t launch_finalize(const FinalizeArgs& f, cudaStream_t stream) {
+  if (f.n_steps <= 0) return cudaSuccess;
+  finalize_stats_kernel<<<(f.n_steps + 127) / 128, 128, 0, stream>>>(f);
+  return cudaGetLastError();
+}
+
+}  // namespace enrgy

@@ -1,0 +1,105 @@
+// Device-side interface of the fused energy-balance kernels (kernels.cu), used by api.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace enrgy {
+
+// insolation source of the fused kernel (template parameter)
+constexpr int kInsolStreamed = 0;  // per-step kWh m-2 raster streamed from HBM
+constexpr int kInsolComputed = 1;  // terrain normal . sun vector per sub-step, no shadows
+constexpr int kInsolShadow = 2;    // ... with the ray-marched sunlit mask
+
+template <typename R>
+struct KernelArgs {
+  // geometry (padded device rasters; pitch is a multiple of kTileW, padding cells hold NaN)
+  int rows_full, cols, pitch;     // full DEM
+  int band_row0, band_rows;       // this handle's row band (rasters below are band-local)
+  int rows_pad_full;              // padded row count of the full DEM buffer
+  const float* dem;               // [rows_pad_full][pitch] full DEM (replicated for shading)
+  const R* nx;                    // [band_rows_pad][pitch] terrain normal (computed insolation)
+  const R* ny;
+  const R* nz;
+  const float* albedo;            // [n_maps][band_rows_pad][pitch]
+  size_t map_stride;              // elements between consecutive albedo maps
+  int albedo_const;
+  R albedo_ice, albedo_snow, max_ice_albedo;
+  R elev_aws;
+  R zmax;                         // max of the valid DEM, as float exactly
+  // state, band-local [band_rows_pad][pitch]
+  R* swe;
+  R* total_snow;
+  R* total_ice;
+  // streamed insolation [n_steps_resident][band_rows_pad][pitch], step index relative to pot_t0
+  const float* pot;
+  size_t pot_stride;
+  int pot_t0;
+  // tables
+  const StepRec<R>* steps;        // [n_steps]
+  const SubRec<R>* subs;          // [n_subs]
+  const ShadeRec* shades;         // [n_subs]
+  const TimeBlock* blocks;        // [n_blocks] covering at least [t0, t1)
+  int block_begin, block_end;     // blocks to process
+  int t0, t1;                     // steps to process (clip of the first/last block)
+  // work list
+  const int2* tiles;              // active tiles (tile row, tile col) of the band
+  int n_tiles;
+  // statistics: per-CTA partial sums [gridDim.x][t1 - t0][kStatsK] float64
+  double* partials;
+  // dump mode: [t1 - t0][ENRGY_D_COUNT][band_rows_pad][pitch] R (may be null)
+  R* dump;
+  size_t dump_field_stride;
+  // shade-mask dump: [n_sub][band_rows][words] bit masks of step t0 (may be null)
+  unsigned* mask_out;
+  int mask_words;
+};
+
+struct FinalizeArgs {
+  const double* partials;   // [n_ctas][n_steps][kStatsK]
+  int n_ctas, n_steps, t0;
+  double n_valid;           // valid cells of the band
+  int f32_mode;             // round the per-step constants the way the float32 kernel saw them
+  const StepRec<double>* steps64;  // master copy of the per-step records (float64)
+  double* stats;            // [n_steps][ENRGY_S_COUNT]
+  // first-row quirk of the reference (model.py:248-252): SWE statistics of step 0 run over every
+  // non-NaN cell of the INITIAL raster, including off-glacier cells
+  int override_first;
+  double swe0_sum, swe0_nsnow, swe0_nvalid;
+};
+
+// launch helpers (defined in kernels.cu); all asynchronous on `stream`
+template <typename R>
+cudaError_t launch_terrain(const float* dem, int rows_full, int cols, int pitch, int band_row0,
+                           int band_rows_pad, double cell, R* nx, R* ny, R* nz, cudaStream_t stream);
+cudaError_t launch_tile_scan(const float* dem, int pitch, int band_row0, int band_rows, int cols,
+                             int tile_h, int tiles_r, int tiles_c, int* counts, cudaStream_t stream);
+cudaError_t launch_mask_check(const float* dem, const float* other, int pitch, int band_row0,
+                              int band_rows, int cols, unsigned long long* counters /*[2]*/,
+                              cudaStream_t stream);
+cudaError_t launch_swe0_stats(const float* swe, int pitch, int band_rows, int cols,
+                              double* block_out /*[blocks][3]*/, int blocks, cudaStream_t stream);
+template <typename R>
+cudaError_t launch_pad_convert(const float* src_pitched, R* dst, size_t n, cudaStream_t stream);
+template <typename R>
+cudaError_t launch_unpad_state(const R* src, int pitch, int rows, int cols, int dtype, void* dst,
+                               cudaStream_t stream);
+
+template <typename R>
+cudaError_t launch_nan_offglacier(const float* dem, int pitch, int band_row0, int band_rows, int cols,
+                                  R* swe, R* tsn, R* tic, cudaStream_t stream);
+
+struct LaunchInfo {
+  int regs, smem_bytes, ctas_per_sm, grid, cells_per_thread;
+};
+template <typename R>
+cudaError_t launch_energy_balance(const KernelArgs<R>& a, int insol, bool dump, int sm_count,
+                                  int forced_grid, LaunchInfo* info, cudaStream_t stream);
+template <typename R>
+int energy_balance_tile_h(int insol);
+template <typename R>
+cudaError_t energy_balance_grid(int insol, bool dump, int sm_count, LaunchInfo* info);
+
+cudaError_t launch_finalize(const FinalizeArgs& f, cudaStream_t stream);
+
+}  // namespace enrgy

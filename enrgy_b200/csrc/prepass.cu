@@ -1,0 +1,374 @@
+// Host pre-pass (see prepass.cuh).  Host-only translation unit; compiled with -ffp-contract=off.
+#include "prepass.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <limits>
+
+namespace enrgy {
+
+namespace {
+
+constexpr double kDeg = 0.017453292519943295;
+constexpr double kPi = 3.141592653589793;
+
+// Beljaars & Holtslag (1991) stable / Dyer unstable integrated stability functions,
+// scalar branch of turbo.py:308-361 (the model path only ever takes the scalar branch because z
+// and L are scalars).
+constexpr double kA = 0.7, kB = 0.75, kC = 5.0, kD = 0.35;
+
+double minus_psi_m(double z, double l) {
+  const double zeta = z / l;
+  if (zeta >= 0) {
+    return kA * zeta + kB * (zeta - kC / kD) * std::exp(-kD * zeta) + kB * kC / kD;
+  }
+  const double x = std::pow(1 - 16 * zeta, 0.25);
+  return -(2 * std::log((1 + x) / 2) + std::log((1 + x * x) / 2) - 2 * std::atan(x) + kPi / 2);
+}
+
+double minus_psi_h(double z, double l) {
+  const double zeta = z / l;
+  if (zeta >= 0) {
+    return std::pow(1 + 2 * kA * zeta / 3, 1.5) + kB * (zeta - kC / kD) * std::exp(-kD * zeta) +
+           kB * kC / kD - 1;
+  }
+  const double x = std::pow(1 - 16 * zeta, 0.25);
+  return -(2 * std::log((1 + x * x) / 2));
+}
+
+// turbo.py:293-305.  `k_uz` is the already formed product k*uz (its rounding differs between the
+// point call, float64, and the distributed call, float32 array * weak Python float).
+double friction_velocity(double k_uz, double z, bool have_l, double l, double zm) {
+  double den = std::log(z / zm);
+  if (have_l) den = den + minus_psi_m(z, l);
+  return k_uz / den;
+}
+
+// turbo.py:199-261
+double andreas_z0(double k_uz, double z, double zm, bool have_l, double l) {
+  const double ustar = friction_velocity(k_uz, z, have_l, l, zm);
+  const double re = ustar * zm / 1.5e-5;
+  double b0, b1, b2;
+  if (re <= 0.135) {
+    b0 = 1.25; b1 = 0; b2 = 0;
+  } else if (re <= 2.5) {
+    b0 = 0.149; b1 = -0.55; b2 = 0;
+  } else {
+    b0 = 0.317; b1 = -0.565; b2 = -0.183;
+  }
+  const double ln_re = std::log(re);
+  return zm * std::exp(b0 + b1 * ln_re + b2 * (ln_re * ln_re));
+}
+
+}  // namespace
+
+double sat_vapour_pressure(double t_kelvin, double p_pa) {
+  const double t = t_kelvin - 273.15;
+  const double p = p_pa / 100;
+  const double ew = 611.2 * std::exp((17.62 * t) / (243.12 + t));
+  const double fp = 1.0016 + 3.15 * 1e-6 * p - 0.074 / p;
+  return fp * ew;
+}
+
+// turbo.py:264-290 with zh already resolved (constant or Andreas).
+double exchange_coefficient(double z, bool have_l, double l, double zm, double zh) {
+  const double num = kKarman * kKarman;
+  double den;
+  if (have_l) {
+    const double pm = minus_psi_m(z, l);
+    const double ph = minus_psi_h(z, l);
+    den = (std::log(z / zm) + pm * (z / l)) * (std::log(z / zh) + ph * (z / l));
+  } else {
+    den = std::log(z / zm) * std::log(z / zh);
+  }
+  return num / den;
+}
+
+// turbo.py:88-137: neutral first guess, then exactly five updates of (u*, Qh, L).
+void point_turbulence(double z, double uz, double tz, double p, double ts, bool ts_f32, double zm,
+                      double zh_const, bool andreas, double* qh_out, double* l_out) {
+  // (Tz - Ts): Python float minus np.float32 scalar is a float32 operation under NEP 50 when the
+  // surface temperature was sampled from a float32 raster (as shipped), model.py:347-350.
+  double d_t;
+  if (ts_f32) {
+    d_t = (double)((float)tz - (float)ts);
+  } else {
+    d_t = tz - ts;
+  }
+  const double rho = p / (kRair * tz);
+  const double k_uz = kKarman * uz;
+  bool have_l = false;
+  double l = 0.0, qh = 0.0;
+  for (int it = 0; it < 6; ++it) {
+    const double ustar = friction_velocity(k_uz, z, have_l, l, zm);
+    const double zh = andreas ? andreas_z0(k_uz, z, zm, have_l, l) : zh_const;
+    const double ch = exchange_coefficient(z, have_l, l, zm, zh);
+    qh = ch * kCpAir * rho * uz * d_t;
+    const double num = rho * kCpAir * std::pow(ustar, 3.0) * tz;
+    const double den = kKarman * kGrav * qh;
+    l = num / den;
+    have_l = true;
+  }
+  *qh_out = qh;
+  *l_out = l;
+}
+
+void sun_vector(double t_unix, double lat_deg, double lon_deg, double* e, double* n, double* u) {
+  // low-precision almanac ephemeris; the same expression order as oracle/insolation_oracle.py
+  const double d = t_unix / 86400.0 + 2440587.5 - 2451545.0;
+  const double mean_lon = std::fmod(280.460 + 0.9856474 * d, 360.0);
+  const double g = std::fmod(357.528 + 0.9856003 * d, 360.0) * kDeg;
+  const double lam = (mean_lon + 1.915 * std::sin(g) + 0.020 * std::sin(2.0 * g)) * kDeg;
+  const double eps = (23.439 - 0.0000004 * d) * kDeg;
+  const double ra = std::atan2(std::cos(eps) * std::sin(lam), std::cos(lam));
+  const double dec = std::asin(std::sin(eps) * std::sin(lam));
+  const double gmst = std::fmod(280.46061837 + 360.98564736629 * d, 360.0);
+  const double ha = (gmst + lon_deg) * kDeg - ra;
+  const double phi = lat_deg * kDeg;
+  const double sd = std::sin(dec), cd = std::cos(dec);
+  const double sp = std::sin(phi), cp = std::cos(phi);
+  const double sh = std::sin(ha), ch = std::cos(ha);
+  *u = sp * sd + cp * cd * ch;
+  *e = -cd * sh;
+  *n = sd * cp - cd * sp * ch;
+}
+
+namespace {
+
+inline bool valid(float z) { return z == z; }
+
+// terrain normal of one cell on the host (double), same rule as terrain_kernel
+void host_normal(const float* dem, int rows, int cols, int r, int c, double cell, double* nx,
+                 double* ny, double* nz) {
+  auto at = [&](int rr, int cc) -> float {
+    if (rr < 0 || rr >= rows || cc < 0 || cc >= cols) return std::numeric_limits<float>::quiet_NaN();
+    return dem[(size_t)rr * cols + cc];
+  };
+  const double z = dem[(size_t)r * cols + c];
+  auto one_sided = [&](float a, float b) -> double {
+    if (valid(a)) return (double)a - z;
+    if (valid(b)) return z - (double)b;
+    return 0.0;
+  };
+  const float zn = at(r - 1, c), zs = at(r + 1, c), ze = at(r, c + 1), zw = at(r, c - 1);
+  const double gy = (one_sided(zn, zs) - one_sided(zs, zn)) / (2.0 * cell);
+  const double gx = (one_sided(ze, zw) - one_sided(zw, ze)) / (2.0 * cell);
+  const double inv = 1.0 / std::sqrt(1.0 + gx * gx + gy * gy);
+  *nx = -gx * inv;
+  *ny = -gy * inv;
+  *nz = inv;
+}
+
+// the shading specification for ONE cell on the host (float32 + integers, see common.cuh)
+bool host_lit(const float* dem, int rows, int cols, int r, int c, const ShadeRec& s, float zmax) {
+  if (!std::isfinite(s.dz)) return true;
+  const float z0 = dem[(size_t)r * cols + c];
+  for (int k = 1;; ++k) {
+    const int rr = r + ((k * s.dr_fix + 32768) >> 16);
+    const int cc = c + ((k * s.dc_fix + 32768) >> 16);
+    if (rr < 0 || rr >= rows || cc < 0 || cc >= cols) return true;
+    volatile float prod = (float)k * s.dz;   // one rounded multiply, one rounded add
+    const float zk = z0 + prod;
+    if (zk > zmax) return true;
+    const float smp = dem[(size_t)rr * cols + cc];
+    if (smp > zk) return false;
+  }
+}
+
+}  // namespace
+
+int run_prepass(const PrepassInput& in, PrepassOutput& out, std::string& err) {
+  const enrgy_params& p = in.p;
+  const int T = in.n_steps;
+  const bool mirror32 = in.precision == ENRGY_F32;
+  const bool computed = p.insol_mode == ENRGY_INSOL_COMPUTED;
+  out.steps.assign(T, StepRec<double>{});
+  out.subs.clear();
+  out.sub_first.assign(T, 0);
+  out.sub_count.assign(T, 0);
+  out.blocks.clear();
+  out.point.assign((size_t)T * ENRGY_P_COUNT, 0.0);
+
+  // zmax of the valid DEM
+  float zmax = -std::numeric_limits<float>::infinity();
+  for (size_t i = 0, n = (size_t)in.rows * in.cols; i < n; ++i) {
+    const float z = in.dem[i];
+    if (z == z && z > zmax) zmax = z;
+  }
+  out.zmax = zmax;
+
+  if (p.aws_row < 0 || p.aws_row >= in.rows || p.aws_col < 0 || p.aws_col >= in.cols) {
+    err = "AWS cell outside the raster";
+    return ENRGY_ERR_ARG;
+  }
+  double nx = 0, ny = 0, nz = 1;
+  if (computed) host_normal(in.dem, in.rows, in.cols, p.aws_row, p.aws_col, p.cell_size, &nx, &ny, &nz);
+
+  const double zm = p.zm;
+  const double zh_const = p.z_h_or_e;
+  const double ts_aws_c = 0.0;   // no sub-surface model: layer_temperatures[0] is all zeros (F9)
+
+  for (int i = 0; i < T; ++i) {
+    const double* f = in.forcing + (size_t)i * ENRGY_F_COUNT;
+    StepRec<double>& s = out.steps[i];
+    double* pt = &out.point[(size_t)i * ENRGY_P_COUNT];
+    const double dt = f[ENRGY_F_DT];
+    if (!(dt > 0)) {
+      err = "time step <= 0 (a one-row AWS file divides by zero in the reference too, helpers.py:67-70)";
+      return ENRGY_ERR_RANGE;
+    }
+    // AwsVars.__post_init__, var_classes.py:80-85
+    double wind = f[ENRGY_F_WIND];
+    if (wind == 0) wind = 0.1;
+    const double t_air = f[ENRGY_F_T_AIR];
+    const double tz = t_air + 273.15;
+    const double p_hpa = f[ENRGY_F_PRESSURE];
+    const double p_pa = p_hpa * 100;
+    const double rh = f[ENRGY_F_RH];
+    const double e_aws = rh * sat_vapour_pressure(tz, p_pa);
+
+    // point solve for L, model.py:347-358
+    double ts_k;
+    if (mirror32) {
+      ts_k = (double)((float)ts_aws_c + 273.15f);
+    } else {
+      ts_k = ts_aws_c + 273.15;
+    }
+    double qh, l;
+    point_turbulence(p.sensor_z, wind, tz, p_pa, ts_k, mirror32, zm, zh_const, p.andreas != 0, &qh, &l);
+
+    // distributed exchange coefficient, model.py:372-381 -> turbo.py:154,180.  The wind raster
+    // is float32 (var_classes.py:170); with Andreas its product with k is a float32 product.
+    const float wind32 = (float)wind;
+    double zh = zh_const;
+    if (p.andreas) {
+      const double k_uz32 = (double)(0.4f * wind32);
+      zh = andreas_z0(k_uz32, p.sensor_z, zm, true, l);
+    }
+    const double ch = exchange_coefficient(p.sensor_z, true, l, zm, zh);
+    const double uz = (double)wind32;
+
+    s.t_air = t_air;
+    s.lapse = f[ENRGY_F_LAPSE];
+    s.p_hpa = p_hpa;
+    s.e_aws = e_aws;
+    s.c_sens = ch * kCpAir * uz * p.sensible_corr;
+    s.c_lat = ch * uz * 0.622 * kLv * p.latent_corr;
+    const double cld = f[ENRGY_F_CLOUD];
+    s.c_lwd = (0.765 + 0.22 * std::pow(cld, 3.0)) * kSigma;
+    if (p.msm_layers > 0) {
+      s.c_lwu = p.emissivity * kSigma;
+    } else {
+      s.c_lwu = p.emissivity * kSigma * std::pow(ts_k, 4.0);
+    }
+    s.c_melt = dt / kLf / 1000;
+    s.dt = dt;
+
+    // albedo schedule, interpolator.py:5-20 and model.py:311-320
+    const int i0 = (int)f[ENRGY_F_ALB_I0], i1 = (int)f[ENRGY_F_ALB_I1];
+    const double span = f[ENRGY_F_ALB_SPAN];
+    s.alb_pair = (double)(i0 * 256 + i1);
+    s.alb_w = span > 0 ? f[ENRGY_F_ALB_DAYS] / span : 0.0;
+    const double snow_days = f[ENRGY_F_SNOW_DAYS];
+    s.snow_alb = snow_days > 0 ? 0.40 + 0.44 * std::exp(-0.12 * snow_days) : -1.0;
+
+    // insolation sub-steps, saga_lighting.py:24-44
+    double pot_aws_kwh = 0.0;
+    out.sub_first[i] = (int)out.subs.size();
+    if (computed) {
+      const double dt_h = dt / 3600.0;
+      const double hs = p.hour_step;
+      int n_sub = (int)std::ceil(dt_h / hs - 1e-9);
+      if (n_sub < 1) n_sub = 1;
+      double direct = 0.0, dsum = 0.0;
+      for (int j = 0; j < n_sub; ++j) {
+        const double w = std::min(hs, dt_h - j * hs);
+        const double t_mid = f[ENRGY_F_TIME] + (j * hs + 0.5 * w) * 3600.0;
+        SubHost sb;
+        sun_vector(t_mid, p.lat_deg, p.lon_deg, &sb.e, &sb.n, &sb.u);
+        if (!(sb.u > 0.0)) continue;
+        const double tb = std::pow(p.transmittance, 1.0 / sb.u);
+        sb.b = p.solar_const * tb * w / 1000.0;
+        sb.d = p.solar_const * (0.271 - 0.294 * tb) * sb.u * w / 1000.0 * 0.5;
+        const double m = std::max(std::fabs(sb.e), std::fabs(sb.n));
+        if (m > 0.0) {
+          sb.shade.dc_fix = (int32_t)std::floor(sb.e / m * 65536.0 + 0.5);
+          sb.shade.dr_fix = (int32_t)std::floor(-sb.n / m * 65536.0 + 0.5);
+          sb.shade.dz = (float)(p.cell_size * sb.u / m);
+        } else {
+          sb.shade.dc_fix = 0;
+          sb.shade.dr_fix = 0;
+          sb.shade.dz = std::numeric_limits<float>::infinity();
+        }
+        sb.shade.kmax = std::max(in.rows, in.cols);
+        out.subs.push_back(sb);
+        const double cosi = nx * sb.e + ny * sb.n + nz * sb.u;
+        double term = sb.b * std::max(cosi, 0.0);
+        if (p.shadow && !host_lit(in.dem, in.rows, in.cols, p.aws_row, p.aws_col, sb.shade, zmax)) {
+          term = 0.0;
+        }
+        direct = direct + term;
+        dsum = dsum + sb.d;
+      }
+      s.dsum = dsum;
+      pot_aws_kwh = direct + dsum * (1.0 + nz);
+    } else {
+      s.dsum = 0.0;
+      pot_aws_kwh = in.pot_aws ? in.pot_aws[i] : 0.0;
+    }
+    out.sub_count[i] = (int)out.subs.size() - out.sub_first[i];
+    if (out.sub_count[i] > 255) {
+      err = "more than 255 insolation sub-steps in one time step";
+      return ENRGY_ERR_RANGE;
+    }
+
+    // kWh -> W and the observed/potential factor, helpers.py:27-60, model.py:512-526
+    double pot_w, factor;
+    const double swd = f[ENRGY_F_SWD];
+    if (mirror32 && !computed) {
+      const float pw32 = (((float)pot_aws_kwh * 3.6f) * 1000000.0f) / (float)dt;
+      pot_w = (double)pw32;
+      factor = pw32 == 0.0f ? 1.0 : (double)((float)swd / pw32);
+    } else {
+      pot_w = pot_aws_kwh * 3.6 * 1000000 / dt;
+      factor = pot_w == 0 ? 1.0 : swd / pot_w;
+    }
+    s.c_sw = 3.6 * 1000000 / dt * factor;
+
+    pt[ENRGY_P_L] = l;
+    pt[ENRGY_P_CH] = ch;
+    pt[ENRGY_P_POT_AWS] = pot_w;
+    pt[ENRGY_P_SW_FACTOR] = factor;
+    pt[ENRGY_P_TSURF_AWS] = mirror32 ? (double)((float)ts_k - 273.15f) : ts_k - 273.15;
+    pt[ENRGY_P_QH_AWS] = qh;
+    pt[ENRGY_P_NSUB] = out.sub_count[i];
+  }
+
+  // time blocks: as many consecutive steps as fit the smem staging buffers
+  int t = 0;
+  while (t < T) {
+    TimeBlock b;
+    b.t_begin = t;
+    b.sub_begin = out.sub_first[t];
+    int n_sub = 0;
+    int e = t;
+    while (e < T && e - t < kMaxStepsPerBlock && n_sub + out.sub_count[e] <= kMaxSubsPerBlock) {
+      n_sub += out.sub_count[e];
+      ++e;
+    }
+    b.t_end = e;
+    b.sub_end = b.sub_begin + n_sub;
+    out.blocks.push_back(b);
+    t = e;
+  }
+  // sub-step index of each step relative to its time block
+  for (const TimeBlock& b : out.blocks) {
+    for (int i = b.t_begin; i < b.t_end; ++i) {
+      out.steps[i].sub = (double)((out.sub_first[i] - b.sub_begin) * 256 + out.sub_count[i]);
+    }
+  }
+  return ENRGY_OK;
+}
+
+}  // namespace enrgy

@@ -1,0 +1,171 @@
+"""Thin object wrapper over the C ABI: one Engine = one enrgy_ctx = one GPU (row band)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Params, check
+
+
+def _f32c(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a
+
+
+class Engine:
+    def __init__(self, rows, cols, precision=_lib.F32, device=0):
+        self.lib = _lib.load()
+        self.rows, self.cols, self.precision, self.device = int(rows), int(cols), int(precision), int(device)
+        h = C.c_void_p()
+        check(self.lib.enrgy_create(self.device, self.rows, self.cols, self.precision, C.byref(h)))
+        self.h = h
+        self.band_row0, self.band_rows = 0, self.rows
+        self.n_steps = 0
+        self._keep = []
+
+    # ---- configuration ------------------------------------------------------------------------
+    def set_params(self, *, cell_size, elev_aws, aws_row, aws_col, sensor_z=2.0, zm=None, z_h_or_e=None,
+                   andreas=False, sensible_corr=1.0, latent_corr=1.0, emissivity=None,
+                   const_albedo=None, max_ice_albedo=None, snow_density=None, ice_density=None,
+                   insol_mode=_lib.INSOL_STREAMED, shadow=False, lat=0.0, lon=0.0, solar_const=None,
+                   transmittance=None, hour_step=None, band_row0=0, band_rows=0):
+        nan = float("nan")
+        p = Params()
+        p.cell_size = cell_size
+        p.elev_aws = elev_aws
+        p.aws_row, p.aws_col = int(aws_row), int(aws_col)
+        p.sensor_z = sensor_z
+        p.zm = nan if zm is None else zm
+        p.z_h_or_e = nan if z_h_or_e is None else z_h_or_e
+        p.andreas = 1 if andreas else 0
+        p.sensible_corr, p.latent_corr = float(sensible_corr), float(latent_corr)
+        p.emissivity = nan if emissivity is None else emissivity
+        if const_albedo is not None:
+            p.albedo_const = 1
+            p.albedo_ice, p.albedo_snow = float(const_albedo[0]), float(const_albedo[1])
+        p.max_ice_albedo = nan if max_ice_albedo is None else max_ice_albedo
+        p.snow_density = nan if snow_density is None else snow_density
+        p.ice_density = nan if ice_density is None else ice_density
+        p.insol_mode = int(insol_mode)
+        p.shadow = 1 if shadow else 0
+        p.lat_deg, p.lon_deg = float(lat), float(lon)
+        p.solar_const = nan if solar_const is None else solar_const
+        p.transmittance = nan if transmittance is None else transmittance
+        p.hour_step = nan if hour_step is None else hour_step
+        p.band_row0, p.band_rows = int(band_row0), int(band_rows)
+        check(self.lib.enrgy_set_params(self.h, C.byref(p)))
+        self.band_row0 = int(band_row0)
+        self.band_rows = int(band_rows) if band_rows else self.rows
+        self.params = p
+
+    def set_dem(self, dem):
+        dem = _f32c(dem)
+        assert dem.shape == (self.rows, self.cols), dem.shape
+        check(self.lib.enrgy_set_dem(self.h, dem.ctypes.data))
+
+    def set_albedo_maps(self, maps):
+        maps = [_f32c(m) for m in maps]
+        for m in maps:
+            assert m.shape == (self.band_rows, self.cols), m.shape
+        arr = (C.c_void_p * len(maps))(*[m.ctypes.data for m in maps])
+        check(self.lib.enrgy_set_albedo_maps(self.h, len(maps), arr))
+
+    def set_swe(self, swe):
+        if swe is None:
+            check(self.lib.enrgy_set_swe(self.h, None))
+            return
+        swe = _f32c(swe)
+        assert swe.shape == (self.band_rows, self.cols), swe.shape
+        check(self.lib.enrgy_set_swe(self.h, swe.ctypes.data))
+
+    def set_forcing(self, table):
+        table = np.ascontiguousarray(table, dtype=np.float64)
+        assert table.ndim == 2 and table.shape[1] == _lib.F_COUNT
+        self.n_steps = table.shape[0]
+        check(self.lib.enrgy_set_forcing(self.h, self.n_steps, table.ctypes.data))
+
+    def set_insolation(self, t0, pot):
+        pot = _f32c(pot)
+        assert pot.ndim == 3 and pot.shape[1:] == (self.band_rows, self.cols), pot.shape
+        check(self.lib.enrgy_set_insolation(self.h, int(t0), pot.shape[0], pot.ctypes.data))
+
+    def prepass(self):
+        check(self.lib.enrgy_prepass(self.h))
+
+    def point_scalars(self):
+        out = np.empty((self.n_steps, _lib.P_COUNT), dtype=np.float64)
+        check(self.lib.enrgy_get_point_scalars(self.h, out.ctypes.data))
+        return out
+
+    # ---- the hot path -------------------------------------------------------------------------
+    def run(self, t0=0, t1=None, want_stats=True):
+        t1 = self.n_steps if t1 is None else t1
+        if want_stats:
+            stats = np.empty((t1 - t0, _lib.S_COUNT), dtype=np.float64)
+            check(self.lib.enrgy_run(self.h, int(t0), int(t1), stats.ctypes.data))
+            return stats
+        check(self.lib.enrgy_run(self.h, int(t0), int(t1), None))
+        return None
+
+    def run_async(self, t0, t1, d_stats_ptr=None, stream_ptr=None):
+        check(self.lib.enrgy_run_async(self.h, int(t0), int(t1), d_stats_ptr, stream_ptr))
+
+    def synchronize(self):
+        check(self.lib.enrgy_synchronize(self.h))
+
+    # ---- debug views --------------------------------------------------------------------------
+    def dump_steps(self, t0, t1):
+        out = np.empty((t1 - t0, _lib.D_COUNT, self.band_rows, self.cols), dtype=np.float64)
+        check(self.lib.enrgy_dump_steps(self.h, int(t0), int(t1), out.ctypes.data))
+        return out
+
+    def shade_masks(self, step, max_sub=256):
+        words = (self.cols + 31) // 32
+        buf = np.zeros((max_sub, self.band_rows, words), dtype=np.uint32)
+        n = C.c_int(0)
+        check(self.lib.enrgy_shade_masks(self.h, int(step), max_sub, buf.ctypes.data, C.byref(n)))
+        bits = np.unpackbits(buf[:n.value].view(np.uint8), axis=-1, bitorder="little")
+        return bits[:, :, :self.cols].astype(bool)
+
+    def potential_insolation(self, step):
+        out = np.empty((self.band_rows, self.cols), dtype=np.float64)
+        check(self.lib.enrgy_potential_insolation(self.h, int(step), out.ctypes.data))
+        return out
+
+    # ---- state --------------------------------------------------------------------------------
+    def state(self, dtype=np.float32):
+        dt = np.dtype(dtype)
+        code = 32 if dt == np.float32 else 64
+        outs = [np.empty((self.band_rows, self.cols), dtype=dt) for _ in range(3)]
+        check(self.lib.enrgy_get_state(self.h, code, *[o.ctypes.data for o in outs]))
+        return tuple(outs)
+
+    def set_state(self, swe=None, total_snow=None, total_ice=None):
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+                for a in (swe, total_snow, total_ice)]
+        check(self.lib.enrgy_set_state(self.h, 64, *[None if a is None else a.ctypes.data for a in arrs]))
+
+    # ---- introspection ------------------------------------------------------------------------
+    def launch_count(self):
+        return int(self.lib.enrgy_launch_count(self.h))
+
+    def last_kernel_ms(self):
+        return float(self.lib.enrgy_last_kernel_ms(self.h))
+
+    def kernel_info(self):
+        v = [C.c_int(0) for _ in range(4)]
+        check(self.lib.enrgy_kernel_info(self.h, *[C.byref(x) for x in v]))
+        return dict(regs=v[0].value, smem_bytes=v[1].value, ctas_per_sm=v[2].value, grid=v[3].value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.enrgy_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
