@@ -80,6 +80,9 @@ _PROTOTYPES = {
     "enrgy_get_state": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "enrgy_set_state": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "enrgy_get_layer_temps": (C.c_int, [_P, _P]),
+    "enrgy_set_stream": (C.c_int, [_P, _P]),
+    "enrgy_snapshot": (C.c_int, [_P, C.c_int]),
+    "enrgy_microbench": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
     "enrgy_launch_count": (C.c_int64, [_P]),
     "enrgy_last_kernel_ms": (C.c_double, [_P]),
     "enrgy_kernel_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),

@@ -82,7 +82,8 @@ struct enrgy_ctx {
   PrepassOutput pre;
   // device rasters
   DevBuf<float> d_dem, d_albedo, d_pot, d_tmp32;
-  DevBuf<unsigned char> d_nx, d_ny, d_nz, d_swe, d_ts, d_ti, d_dump, d_stage;
+  DevBuf<unsigned char> d_nx, d_ny, d_nz, d_swe, d_ts, d_ti, d_dump, d_stage, d_snap;
+  bool snap_valid = false, snap_advanced = false;
   int n_maps = 0;
   int pot_t0 = 0, pot_n = 0;
   // tables
@@ -99,6 +100,7 @@ struct enrgy_ctx {
   double swe0_sum = 0.0, swe0_nsnow = 0.0, swe0_nvalid = 0.0;
   // runtime
   cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_pending = false;
   int64_t launches = 0;
@@ -358,11 +360,12 @@ int enrgy_create(int device, int rows, int cols, int precision, enrgy_ctx** out)
   c->sm_count = prop.multiProcessorCount;
   c->pitch = round_up(cols, kTileW);
   c->rows_pad_full = round_up(rows, 16);
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
     delete c;
     return fail(ENRGY_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
+  c->stream = c->own_stream;
   *out = c;
   return ENRGY_OK;
 }
@@ -376,10 +379,10 @@ int enrgy_destroy(enrgy_ctx* c) {
   c->d_ti.release(); c->d_dump.release(); c->d_stage.release(); c->d_steps.release(); c->d_subs.release();
   c->d_steps64.release(); c->d_shades.release(); c->d_blocks.release(); c->d_tiles.release();
   c->d_counts.release(); c->d_partials.release(); c->d_stats.release(); c->d_small.release();
-  c->d_counters.release(); c->d_masks.release();
+  c->d_counters.release(); c->d_masks.release(); c->d_snap.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
-  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return ENRGY_OK;
 }
@@ -711,6 +714,53 @@ int enrgy_get_layer_temps(enrgy_ctx* c, double* out) {
   (void)out;
   if (int e = use_device(c)) return e;
   return fail(ENRGY_ERR_ARG, "sub-surface model (msm) is not built into this round's kernels");
+}
+
+int enrgy_snapshot(enrgy_ctx* c, int save) {
+  if (int e = use_device(c)) return e;
+  if (!c->have_dem) return fail(ENRGY_ERR_ARG, "no state before set_dem");
+  const size_t bytes = c->band_elems * rsize(c);
+  unsigned char* st[3] = {c->d_swe.p, c->d_ts.p, c->d_ti.p};
+  if (save) {
+    CU_TRY(c->d_snap.alloc(3 * bytes));
+    for (int q = 0; q < 3; ++q)
+      CU_TRY(cudaMemcpyAsync(c->d_snap.p + q * bytes, st[q], bytes, cudaMemcpyDeviceToDevice, c->stream));
+    c->snap_valid = true;
+    c->snap_advanced = c->state_advanced;
+  } else {
+    if (!c->snap_valid) return fail(ENRGY_ERR_ARG, "no snapshot to restore");
+    for (int q = 0; q < 3; ++q)
+      CU_TRY(cudaMemcpyAsync(st[q], c->d_snap.p + q * bytes, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    c->state_advanced = c->snap_advanced;
+  }
+  return ENRGY_OK;
+}
+
+int enrgy_set_stream(enrgy_ctx* c, void* stream) {
+  if (int e = use_device(c)) return e;
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+  return ENRGY_OK;
+}
+
+int enrgy_microbench(enrgy_ctx* c, int kind, double* result) {
+  if (int e = use_device(c)) return e;
+  if (!result || kind < 0 || kind > 3) return fail(ENRGY_ERR_ARG, "bad microbench request");
+  CU_TRY(c->d_stage.alloc((size_t)c->sm_count * 8 * 256 * 8));
+  const int iters = kind == 1 ? 2000 : 4000;
+  double ops = 0.0, best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU_TRY(cudaEventRecord(c->ev0, c->stream));
+    CU_TRY(launch_microbench(kind, c->sm_count, iters, c->d_stage.p, &ops, c->stream));
+    CU_TRY(cudaEventRecord(c->ev1, c->stream));
+    CU_TRY(cudaEventSynchronize(c->ev1));
+    c->launches++;
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    if (rep > 0 && ms > 0.f) best = std::max(best, ops / (ms * 1e-3));
+  }
+  *result = (kind <= 1) ? best / 1e12 : best / 1e9;
+  return ENRGY_OK;
 }
 
 int64_t enrgy_launch_count(enrgy_ctx* c) { return c ? c->launches : 0; }

@@ -760,6 +760,82 @@ template cudaError_t launch_energy_balance<float>(const KernelArgs<float>&, int,
 template cudaError_t launch_energy_balance<double>(const KernelArgs<double>&, int, bool, int, int, LaunchInfo*, cudaStream_t);
 
 // =================================================================================================
+// micro-benchmarks: the pipe peaks the roofline is quoted against
+// =================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T b) {
+  T x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = (T)(threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = x[i] * a + b;
+    }
+  }
+  T s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i];
+  if (s == (T)-1.2345) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) mufu_peak_kernel(float* out, int iters) {
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = 1.0f + threadIdx.x + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
+    }
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i];
+  if (s == -1.2345f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) lds_peak_kernel(float* out, int iters) {
+  __shared__ float buf[4096];
+  for (int i = threadIdx.x; i < 4096; i += 256) buf[i] = (float)i;
+  __syncthreads();
+  float s = 0;
+  int idx = threadIdx.x;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 64; ++r) {
+      s += buf[(idx + r * 32) & 4095];
+    }
+    idx += 1;
+  }
+  if (s == -1.2345f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+cudaError_t launch_microbench(int kind, int sm_count, int iters, void* scratch, double* ops_per_launch,
+                              cudaStream_t stream) {
+  const int grid = sm_count * 8;
+  const double threads = (double)grid * 256;
+  switch (kind) {
+    case 0:
+      fma_peak_kernel<float><<<grid, 256, 0, stream>>>((float*)scratch, iters, 1.0000001f, 1e-9f);
+      *ops_per_launch = threads * iters * 64.0 * 2.0;
+      break;
+    case 1:
+      fma_peak_kernel<double><<<grid, 256, 0, stream>>>((double*)scratch, iters, 1.0000001, 1e-9);
+      *ops_per_launch = threads * iters * 64.0 * 2.0;
+      break;
+    case 2:
+      mufu_peak_kernel<<<grid, 256, 0, stream>>>((float*)scratch, iters);
+      *ops_per_launch = threads * iters * 64.0;
+      break;
+    default:
+      lds_peak_kernel<<<grid, 256, 0, stream>>>((float*)scratch, iters);
+      *ops_per_launch = threads * iters * 64.0;
+      break;
+  }
+  return cudaGetLastError();
+}
+
+// =================================================================================================
 // statistics: cross-CTA sum in fixed order + the derived columns
 // =================================================================================================
 __global__ void finalize_stats_kernel(const FinalizeArgs f) {

@@ -101,5 +101,7 @@ template <typename R>
 cudaError_t energy_balance_grid(int insol, bool dump, int sm_count, LaunchInfo* info);
 
 cudaError_t launch_finalize(const FinalizeArgs& f, cudaStream_t stream);
+cudaError_t launch_microbench(int kind, int sm_count, int iters, void* scratch, double* ops_per_launch,
+                              cudaStream_t stream);
 
 }  // namespace enrgy

@@ -147,6 +147,17 @@ class Engine:
                 for a in (swe, total_snow, total_ice)]
         check(self.lib.enrgy_set_state(self.h, 64, *[None if a is None else a.ctypes.data for a in arrs]))
 
+    def set_stream(self, stream_ptr):
+        check(self.lib.enrgy_set_stream(self.h, stream_ptr))
+
+    def snapshot(self, save=True):
+        check(self.lib.enrgy_snapshot(self.h, 1 if save else 0))
+
+    def microbench(self, kind):
+        v = C.c_double(0.0)
+        check(self.lib.enrgy_microbench(self.h, int(kind), C.byref(v)))
+        return v.value
+
     # ---- introspection ------------------------------------------------------------------------
     def launch_count(self):
         return int(self.lib.enrgy_launch_count(self.h))

@@ -177,3 +177,35 @@ def make_case(n=256, n_steps=24, seed=0, cell=10.0, glacier_mask=True, albedo_da
     return SyntheticCase(dem=dem, geotransform=gt, cell=cell, albedo_maps=albedo, swe=swe,
                          aws_rows=aws, elev_aws=elev_aws, xy_aws=(x, y), aws_rc=(r, c),
                          meta={"n": n, "n_steps": n_steps, "seed": seed, "step_s": step_s})
+
+
+def make_band_case(n, n_steps, world=1, rank=0, seed=0, cell=10.0, glacier_mask=True,
+                   albedo_dates=None, step_s=3600, start="20220601 00:00:00"):
+    """Weak-scaling workload: a (world*n) x n raster split into `world` row bands of n rows.
+
+    Returns (case, dem_full): `case` holds the band-local albedo maps / SWE of `rank` and the AWS
+    description of the FULL raster (aws_rc in full-raster coordinates); `dem_full` is the whole DEM
+    (replicated on every rank)."""
+    rows_full = n * world
+    dem_full = make_dem(rows_full, n, seed=seed, cell=cell, glacier_mask=glacier_mask)
+    r0 = rank * n
+    band = dem_full[r0:r0 + n]
+    gt = (DEFAULT_ULX, cell, 0.0, DEFAULT_ULY, 0.0, -cell)
+    if albedo_dates is None:
+        albedo_dates = ["20220520", "20220615", "20220710", "20220805", "20220915"]
+    albedo = make_albedo_maps(n, n, albedo_dates, seed=seed + 1, nan_like=band, row0=r0)
+    zmin, zmax = float(np.nanmin(dem_full)), float(np.nanmax(dem_full))
+    rel = (band.astype(np.float64) - zmin) / max(zmax - zmin, 1.0)
+    swe = np.where(0.5 * rel - 0.05 < 0.0, 0.0, 0.5 * rel - 0.05).astype(np.float32)
+    swe[np.isnan(band)] = np.nan
+    aws = make_aws_rows(n_steps, start=start, step_s=step_s, seed=seed + 3)
+    r, c = rows_full // 2, n // 2
+    if np.isnan(dem_full[r, c]):
+        raise ValueError("AWS cell is off-glacier")
+    x = gt[0] + (c + 0.5) * cell
+    y = gt[3] - (r + 0.5) * cell
+    case = SyntheticCase(dem=band, geotransform=gt, cell=cell, albedo_maps=albedo, swe=swe,
+                         aws_rows=aws, elev_aws=float(np.float32(dem_full[r, c])), xy_aws=(x, y),
+                         aws_rc=(r, c), meta={"n": n, "n_steps": n_steps, "world": world, "rank": rank,
+                                              "band_row0": r0, "rows_full": rows_full})
+    return case, dem_full

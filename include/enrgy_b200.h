@@ -205,6 +205,20 @@ int enrgy_set_state(enrgy_ctx* ctx, int dtype, const void* swe, const void* tota
 /* sub-surface boundary temperatures, host [msm_layers + 1][rows][cols] float64 */
 int enrgy_get_layer_temps(enrgy_ctx* ctx, double* out);
 
+/* run every subsequent operation of this handle on the caller's stream (cudaStream_t as void*;
+ * NULL = back to the handle's own stream).  Lets a host framework (torch) order its collectives
+ * and events with the kernels. */
+int enrgy_set_stream(enrgy_ctx* ctx, void* stream);
+
+/* device-side snapshot of the state rasters: save != 0 stores a copy, save == 0 restores it
+ * (bench.py rewinds the season between timed passes without touching the host) */
+int enrgy_snapshot(enrgy_ctx* ctx, int save);
+
+/* micro-benchmarks for the roofline denominators MEASURED_PEAKS.json lacks:
+ * kind 0 = FP32 FMA [TFLOP/s], 1 = FP64 FMA [TFLOP/s], 2 = MUFU.RCP [Gop/s], 3 = shared-memory
+ * 4-byte loads [Gop/s]; runs ~ms on the context's device, CUDA-event timed. */
+int enrgy_microbench(enrgy_ctx* ctx, int kind, double* result);
+
 /* introspection for bench.py / tests: kernels launched so far, device time of the last run [ms] */
 int64_t enrgy_launch_count(enrgy_ctx* ctx);
 double enrgy_last_kernel_ms(enrgy_ctx* ctx);
