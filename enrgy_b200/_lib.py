@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libenrgy_b200.so")
+LIB_PATH = os.environ.get("ENRGY_B200_LIB") or os.path.join(_HERE, "csrc", "libenrgy_b200.so")
 
 F32, F64 = 32, 64
 INSOL_STREAMED, INSOL_COMPUTED = 0, 1

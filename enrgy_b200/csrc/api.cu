@@ -204,7 +204,7 @@ int fill_args(enrgy_ctx* c, int t0, int t1, KernelArgs<R>& a) {
   a.map_stride = c->band_elems;
   a.albedo_const = c->p.albedo_const;
   a.albedo_ice = (R)c->p.albedo_ice; a.albedo_snow = (R)c->p.albedo_snow;
-  a.max_ice_albedo = (R)c->p.max_ice_albedo;
+  a.max_ice_albedo = c->p.albedo_const ? (R)INFINITY : (R)c->p.max_ice_albedo;
   a.elev_aws = (R)c->p.elev_aws;
   a.zmax = (R)c->pre.zmax;
   a.swe = (R*)c->d_swe.p; a.total_snow = (R*)c->d_ts.p; a.total_ice = (R*)c->d_ti.p;

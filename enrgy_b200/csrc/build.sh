@@ -4,8 +4,9 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-ffp-contract=off,-Wall,-Wno-unused-function"
-$NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c kernels.cu -o kernels.o
+$NVCC $FLAGS $EXTRA ${PTXAS_V:+-Xptxas -v} -c kernels.cu -o kernels.o
 $NVCC $FLAGS -c prepass.cu -o prepass.o
 $NVCC $FLAGS -c api.cu -o api.o
-$NVCC -shared -o libenrgy_b200.so kernels.o prepass.o api.o -cudart static
-echo built $(pwd)/libenrgy_b200.so
+OUT=${OUT:-libenrgy_b200.so}
+$NVCC -shared -o $OUT kernels.o prepass.o api.o -cudart static
+echo built $(pwd)/$OUT

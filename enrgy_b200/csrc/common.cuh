@@ -50,7 +50,7 @@ struct alignas(16) StepRec {
   R lapse;     // air-temperature lapse rate [K/m]
   R p_hpa;     // PRESSURE at the AWS [hPa]
   R e_aws;     // vapour pressure at the AWS [Pa]               var_classes.py:85
-  R c_sens;    // CH * Cp * uz * sensible_corr                   turbo.py:156, model.py:386
+  R c_sens;    // CH * Cp * uz * sensible_corr * 100 Pa/hPa      turbo.py:156, model.py:386
   R c_lat;     // CE * uz * 0.622 * Lv * latent_corr             turbo.py:182, model.py:387
   R c_lwd;     // (0.765 + 0.22 cld^3) * sigma                   model.py:544
   R c_lwu;     // no MSM: eps*sigma*273.15^4 (the flux itself); MSM: eps*sigma   model.py:543

@@ -173,9 +173,11 @@ __global__ void terrain_kernel(const float* __restrict__ dem, int rows_full, int
   const float zn = at(r - 1, c), zs = at(r + 1, c), ze = at(r, c + 1), zw = at(r, c - 1);
   const R gy = (one_sided(zn, zs) - one_sided(zs, zn)) * inv2cell;
   const R gx = (one_sided(ze, zw) - one_sided(zw, ze)) * inv2cell;
+  // stored as (nx/nz, ny/nz, nz) = (-gx, -gy, nz): cos(incidence) = nz * (u + px*e + py*n), which
+  // costs the time loop two FMAs per sub-step instead of three
   const R inv = Num<R>::rsqrt_((R)1 + gx * gx + gy * gy);
-  nx[o] = -gx * inv;
-  ny[o] = -gy * inv;
+  nx[o] = -gx;
+  ny[o] = -gy;
   nz[o] = inv;
 }
 
@@ -395,8 +397,22 @@ struct SmemLayout {
   uint64_t full[2];
 };
 
+// tuning knobs (cells per thread, minimum resident CTAs per SM), overridable at build time
+#ifndef ENRGY_K32
+#define ENRGY_K32 8
+#endif
+#ifndef ENRGY_K64
+#define ENRGY_K64 4
+#endif
+#ifndef ENRGY_MINB32
+#define ENRGY_MINB32 2
+#endif
+#ifndef ENRGY_MINB64
+#define ENRGY_MINB64 1
+#endif
+
 template <typename R, int K, int INSOL, bool DUMP>
-__global__ void __launch_bounds__(kThreads, (sizeof(R) == 4 && K <= 4) ? 2 : 1)
+__global__ void __launch_bounds__(kThreads, sizeof(R) == 4 ? ENRGY_MINB32 : ENRGY_MINB64)
 energy_balance_kernel(const KernelArgs<R> a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemLayout<R>& sm = *reinterpret_cast<SmemLayout<R>*>(smem_raw);
@@ -470,9 +486,10 @@ energy_balance_kernel(const KernelArgs<R> a) {
         nxv[i] = nyv[i] = (R)0; nzv[i] = (R)1;
       }
       swe[i] = v ? a.swe[o] : (R)0;
-      tsn[i] = v ? a.total_snow[o] : (R)0;
+      tsn[i] = swe[i];               // SWE at the start of the run, for total_snow in the epilogue
       tic[i] = v ? a.total_ice[o] : (R)0;
-      a0[i] = (R)0.5; da[i] = (R)0;
+      a0[i] = a.albedo_const ? a.albedo_ice : (R)0.5;
+      da[i] = (R)0;
     }
 
     int buf = 0;
@@ -557,20 +574,26 @@ energy_balance_kernel(const KernelArgs<R> a) {
             }
 #pragma unroll
             for (int i = 0; i < K; ++i) {
-              R c = nxv[i] * sb.e + nyv[i] * sb.n + nzv[i] * sb.u;
+              // cos(incidence) / nz; nxv, nyv hold nx/nz, ny/nz (terrain_kernel)
+              R c = sb.u + nxv[i] * sb.e + nyv[i] * sb.n;
               c = fmax_(c, (R)0);
               if (INSOL == kInsolShadow) c = ((lit >> i) & 1u) ? c : (R)0;
               direct[i] += sb.b * c;
             }
           }
 #pragma unroll
-          for (int i = 0; i < K; ++i) pot[i] = direct[i] + s.dsum * ((R)1 + nzv[i]);
+          for (int i = 0; i < K; ++i) pot[i] = direct[i] * nzv[i] + s.dsum * ((R)1 + nzv[i]);
         }
 
         // ---- per-cell energy balance -------------------------------------------------------------
         R acc[kStatsK];
 #pragma unroll
         for (int q = 0; q < kStatsK; ++q) acc[q] = (R)0;
+        int n_snow = 0;
+        // albedo of snow-covered cells: the aged value when ageing is on, else the blended map
+        // (uniform per step): alb_snow = alb * keep_map + snow_const
+        const R keep_map = s.snow_alb >= (R)0 ? (R)0 : (R)1;
+        const R snow_const = s.snow_alb >= (R)0 ? s.snow_alb : (R)0;
 #pragma unroll
         for (int i = 0; i < K; ++i) {
           // lapse-rate distribution, var_classes.py:113-125
@@ -578,30 +601,26 @@ energy_balance_kernel(const KernelArgs<R> a) {
           const R tz = t_air + (R)273.15;
           const R d_t = tz - (R)273.15;                     // Tz - Ts, Ts = 0 degC + 273.15
           const R p_hpa = s.p_hpa + delta[i] * (R)kPressureLapse;
-          const R p_pa = p_hpa * (R)100;
           const R e = s.e_aws * pw[i];
-          // bulk fluxes, turbo.py:140-196 with rho = P / (R Tz), rho / P = 1 / (R Tz)
+          // bulk fluxes, turbo.py:140-196 with rho = P / (R Tz) and rho / P = 1 / (R Tz);
+          // c_sens carries CH * Cp * uz * 100 (Pa per hPa), c_lat carries CE * uz * 0.622 * Lv
           const R r_rt = Num<R>::rcp((R)kRair * tz);
-          const R rho = p_pa * r_rt;
-          const R sens = s.c_sens * rho * d_t;
+          const R sens = (s.c_sens * p_hpa) * (r_rt * d_t);
           // saturation vapour pressure of the melting surface, turbo.py:368-379 with t = 0:
           // exp(0) = 1 exactly, so es = 611.2 * f(p).  ez = e_max * (e / e_max) = e (one rounding).
           const R f_p = (R)1.0016 + (R)(3.15 * 1e-6) * p_hpa - (R)0.074 * Num<R>::rcp(p_hpa);
-          const R es = (R)611.2 * f_p;
-          const R lat = s.c_lat * r_rt * (e - es);
+          const R lat = (s.c_lat * r_rt) * (e - (R)611.2 * f_p);
           // longwave, model.py:533-545
           const R tz2 = tz * tz;
           const R lwd = s.c_lwd * (tz2 * tz2);
           const R lwu = s.c_lwu;
           // albedo, model.py:298-337
-          R alb;
-          if (a.albedo_const) {
-            alb = swe[i] > (R)0 ? a.albedo_snow : a.albedo_ice;
-          } else {
-            alb = a0[i] + s.alb_w * da[i];
-            if (s.snow_alb >= (R)0) alb = swe[i] > (R)0 ? s.snow_alb : alb;
-            alb = (swe[i] <= (R)0 && alb > a.max_ice_albedo) ? a.max_ice_albedo : alb;
-          }
+          const bool has_snow = swe[i] > (R)0;
+          // maps: blend of the bracketing maps; snow cells take the aged snow albedo when ageing
+          // is on; ice cells are capped.  Constant albedo rides the same formula: a0 = ice,
+          // da = 0, snow_alb = snow (so keep_map = 0), cap = +inf (set up by the host).
+          const R blend = a0[i] + s.alb_w * da[i];
+          const R alb = has_snow ? blend * keep_map + snow_const : fmin_(blend, a.max_ice_albedo);
           // shortwave, model.py:483-497
           const R rs = pot[i] * s.c_sw * ((R)1 - alb);
           // balance, clamp, melt partition: model.py:411, :434-438, msm.py:193-203
@@ -616,9 +635,9 @@ energy_balance_kernel(const KernelArgs<R> a) {
           acc[K_SENS] += w * sens;
           acc[K_LAT] += w * lat;
           acc[K_MELT] += w * mf;
-          acc[K_SNOW] += w * snow;
-          acc[K_SWE] += w * swe[i];
-          acc[K_NSNOW] += swe[i] > (R)0 ? w : (R)0;
+          acc[K_SNOW] += snow;          // masked cells: swe = 0 -> snow = 0
+          acc[K_SWE] += swe[i];
+          n_snow += has_snow ? 1 : 0;
           if (DUMP && a.dump != nullptr) {
             if ((valid_bits >> i) & 1u) {
               R* d = a.dump + (size_t)(t - a.t0) * ENRGY_D_COUNT * a.dump_field_stride +
@@ -637,11 +656,12 @@ energy_balance_kernel(const KernelArgs<R> a) {
               d[ENRGY_D_G * a.dump_field_stride] = (R)0;
             }
           }
-          // state update, model.py:258-261
+          // state update, model.py:258-261.  total_snow is not accumulated here: it equals
+          // swe(start) - swe(end) and is added once in the epilogue.
           swe[i] -= snow;
-          tsn[i] += snow;
           tic[i] += ice;
         }
+        acc[K_NSNOW] = (R)n_snow;
         // ---- per-step statistics: warp butterfly, one slot per warp --------------------------------
         if (!DUMP) {
           const R tot = warp_reduce8<R>(acc, lane);
@@ -672,7 +692,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
           const size_t o = (size_t)rowb[i] * a.pitch + col[i];
           const bool v = (valid_bits >> i) & 1u;
           a.swe[o] = v ? swe[i] : qnan;
-          a.total_snow[o] = v ? tsn[i] : qnan;
+          a.total_snow[o] = v ? a.total_snow[o] + (tsn[i] - swe[i]) : qnan;
           a.total_ice[o] = v ? tic[i] : qnan;
         }
       }
@@ -682,7 +702,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
 
 template <typename R, int INSOL>
 struct CellsPerThread {
-  static constexpr int value = sizeof(R) == 4 ? 8 : 4;
+  static constexpr int value = sizeof(R) == 4 ? ENRGY_K32 : ENRGY_K64;
 };
 
 template <typename R>

@@ -253,7 +253,7 @@ int run_prepass(const PrepassInput& in, PrepassOutput& out, std::string& err) {
     s.lapse = f[ENRGY_F_LAPSE];
     s.p_hpa = p_hpa;
     s.e_aws = e_aws;
-    s.c_sens = ch * kCpAir * uz * p.sensible_corr;
+    s.c_sens = ch * kCpAir * uz * p.sensible_corr * 100;   // x100: the kernel multiplies by hPa
     s.c_lat = ch * uz * 0.622 * kLv * p.latent_corr;
     const double cld = f[ENRGY_F_CLOUD];
     s.c_lwd = (0.765 + 0.22 * std::pow(cld, 3.0)) * kSigma;
@@ -272,6 +272,11 @@ int run_prepass(const PrepassInput& in, PrepassOutput& out, std::string& err) {
     s.alb_w = span > 0 ? f[ENRGY_F_ALB_DAYS] / span : 0.0;
     const double snow_days = f[ENRGY_F_SNOW_DAYS];
     s.snow_alb = snow_days > 0 ? 0.40 + 0.44 * std::exp(-0.12 * snow_days) : -1.0;
+    if (p.albedo_const) {             // model.py:329-332: where(swe > 0, snow, ice)
+      s.snow_alb = p.albedo_snow;
+      s.alb_w = 0.0;
+      s.alb_pair = 0.0;
+    }
 
     // insolation sub-steps, saga_lighting.py:24-44
     double pot_aws_kwh = 0.0;
