@@ -75,6 +75,7 @@ _PROTOTYPES = {
     "enrgy_run_async": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "enrgy_synchronize": (C.c_int, [_P]),
     "enrgy_dump_steps": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "enrgy_get_substeps": (C.c_int, [_P, C.c_int, C.c_int, _P, C.POINTER(C.c_int)]),
     "enrgy_shade_masks": (C.c_int, [_P, C.c_int, C.c_int, _P, C.POINTER(C.c_int)]),
     "enrgy_potential_insolation": (C.c_int, [_P, C.c_int, _P]),
     "enrgy_get_state": (C.c_int, [_P, C.c_int, _P, _P, _P]),

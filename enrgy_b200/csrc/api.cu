@@ -602,6 +602,22 @@ int enrgy_get_point_scalars(enrgy_ctx* c, double* out) {
   return ENRGY_OK;
 }
 
+int enrgy_get_substeps(enrgy_ctx* c, int step, int max_sub, double* out, int* n_out) {
+  if (!c || !out || !n_out) return fail(ENRGY_ERR_ARG, "null argument");
+  if (!c->prepass_done) return fail(ENRGY_ERR_ARG, "prepass has not run");
+  if (step < 0 || step >= c->n_steps) return fail(ENRGY_ERR_ARG, "step outside the forcing table");
+  const int n = c->pre.sub_count[step], first = c->pre.sub_first[step];
+  if (n > max_sub) return fail(ENRGY_ERR_ARG, "step has %d sunlit sub-steps, buffer holds %d", n, max_sub);
+  for (int j = 0; j < n; ++j) {
+    const SubHost& s = c->pre.subs[first + j];
+    double* o = out + (size_t)j * 8;
+    o[0] = s.e; o[1] = s.n; o[2] = s.u; o[3] = s.b; o[4] = s.d;
+    o[5] = s.shade.dc_fix; o[6] = s.shade.dr_fix; o[7] = (double)s.shade.dz;
+  }
+  *n_out = n;
+  return ENRGY_OK;
+}
+
 int enrgy_run_async(enrgy_ctx* c, int t0, int t1, double* d_stats, void* stream) {
   if (int e = use_device(c)) return e;
   if (int e = check_run_ready(c, t0, t1)) return e;

@@ -121,6 +121,12 @@ class Engine:
         check(self.lib.enrgy_dump_steps(self.h, int(t0), int(t1), out.ctypes.data))
         return out
 
+    def substeps(self, step, max_sub=256):
+        buf = np.zeros((max_sub, 8), dtype=np.float64)
+        n = C.c_int(0)
+        check(self.lib.enrgy_get_substeps(self.h, int(step), max_sub, buf.ctypes.data, C.byref(n)))
+        return buf[:n.value].copy()
+
     def shade_masks(self, step, max_sub=256):
         words = (self.cols + 31) // 32
         buf = np.zeros((max_sub, self.band_rows, words), dtype=np.uint32)

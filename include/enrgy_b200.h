@@ -191,6 +191,9 @@ int enrgy_synchronize(enrgy_ctx* ctx);
  * (what OutputRow / calc_melt see, model.py:451-452, :245).  out: host
  * [t1 - t0][ENRGY_D_COUNT][rows][cols] float64. */
 int enrgy_dump_steps(enrgy_ctx* ctx, int t0, int t1, double* out);
+/* sunlit sub-steps of one step as the pre-pass derived them: out[n][8] =
+ * {east, north, up, B, D, dc_fix, dr_fix, dz}; n_out receives the count (<= max_sub). */
+int enrgy_get_substeps(enrgy_ctx* ctx, int step, int max_sub, double* out, int* n_out);
 /* bit-packed sunlit masks of one step's sub-steps (bit = 1: lit), [n_sub][rows][ceil(cols/32)];
  * n_sub_out receives the number of sunlit sub-steps (<= max_sub). */
 int enrgy_shade_masks(enrgy_ctx* ctx, int step, int max_sub, uint32_t* out, int* n_sub_out);

@@ -1,0 +1,96 @@
+"""Shading masks: bit-exact against the NumPy statement of the specification
+(oracle/insolation_oracle.py).  Upstream parity of this part is UNPINNED (SAGA GIS is an external
+binary); the masks are graded against this repo's own specification."""
+import numpy as np
+import pytest
+
+from enrgy_b200 import _lib
+from enrgy_b200.synthetic import make_case
+from oracle import insolation_oracle as I
+from oracle.enrgy_oracle import time_step_seconds
+from tests import parity as P
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(case, f64=False):
+    return P.make_engine(case, f64, computed=True, shadow=True)
+
+
+@pytest.mark.parametrize("shape", [(96, 160), (130, 70), (64, 300)])
+def test_masks_and_tables_bit_exact(shape):
+    case = make_case(shape[0], 24, w=shape[1], seed=shape[0])
+    eng = _engine(case)
+    try:
+        n_checked = 0
+        for step in (0, 5, 11, 17, 23):
+            row = case.aws_rows[step]
+            dt = time_step_seconds(case.aws_rows, step)
+            table = I.substep_table(I.to_unix(row["DATE"]), dt, case.lat, case.lon, case.cell)
+            subs = eng.substeps(step)
+            assert len(subs) == len(table)
+            for got, want in zip(subs, table):
+                # same libm, same expression order: the tables agree to the last bit
+                assert got[0] == want["E"] and got[1] == want["N"] and got[2] == want["U"]
+                assert got[3] == want["B"] and got[4] == want["D"]
+                assert int(got[5]) == want["dc_fix"] and int(got[6]) == want["dr_fix"]
+                assert np.float32(got[7]) == want["dz"]
+            masks = eng.shade_masks(step)
+            assert masks.shape[0] == len(table)
+            valid = ~np.isnan(case.dem)
+            for j, sub in enumerate(table):
+                lit = I.shadow_mask(case.dem, sub["dc_fix"], sub["dr_fix"], sub["dz"])
+                assert np.array_equal(masks[j][valid], lit[valid]), (step, j)
+                n_checked += int(valid.sum())
+        assert n_checked > 0
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("f64", [False, True])
+def test_potential_insolation_raster(f64):
+    case = make_case(100, 30, w=140, seed=3)
+    eng = _engine(case, f64)
+    try:
+        for step in (2, 13, 29):
+            row = case.aws_rows[step]
+            want = I.potential_insolation(case.dem, case.cell, case.lat, case.lon, I.to_unix(row["DATE"]),
+                                          time_step_seconds(case.aws_rows, step), shadow=True)
+            got = eng.potential_insolation(step)
+            err = P.max_rel_err(got, want, 1e-6)
+            assert err < (1e-9 if f64 else 1e-4), (step, err)
+    finally:
+        eng.close()
+
+
+def test_masks_independent_of_precision():
+    case = make_case(80, 12, w=96, seed=8)
+    e32, e64 = _engine(case, False), _engine(case, True)
+    try:
+        for step in (3, 9):
+            assert np.array_equal(e32.shade_masks(step), e64.shade_masks(step))
+    finally:
+        e32.close()
+        e64.close()
+
+
+def test_large_raster_spot_check():
+    """2048 x 1024: the full NumPy mask is too slow, so 20000 random cells are ray-traced one by one
+    with the same specification (oracle trace_cells)."""
+    case = make_case(2048, 14, w=1024, seed=5)
+    eng = _engine(case)
+    try:
+        step = 1                                         # 01:00 UTC: sun ~10 deg above the northern horizon
+        table = I.substep_table(I.to_unix(case.aws_rows[step]["DATE"]), 3600, case.lat, case.lon, case.cell)
+        masks = eng.shade_masks(step)
+        rng = np.random.default_rng(0)
+        rr = rng.integers(0, 2048, 20000)
+        cc = rng.integers(0, 1024, 20000)
+        ok = ~np.isnan(case.dem[rr, cc])
+        rr, cc = rr[ok], cc[ok]
+        for j, sub in enumerate(table):
+            lit = I.trace_cells(case.dem, rr, cc, sub["dc_fix"], sub["dr_fix"], sub["dz"])
+            assert np.array_equal(masks[j][rr, cc], lit), j
+            assert 0.005 < 1.0 - lit.mean() < 0.995    # the case really has both shade and light
+    finally:
+        eng.close()
