@@ -33,6 +33,7 @@ N_CELLS = 2048
 N_STEPS = 2200
 FLOP_PER_CELL_STEP = 88.0       # DESIGN.md "Algorithmic work": C2 = 4 sub-steps, albedo maps
 METRIC = "cell-timesteps/s"
+SHADOW = False                   # --shadow: C3-style run with the per-sub-step shading ray march
 
 
 def log(*a):
@@ -100,7 +101,7 @@ def build_engine(case, dem_full, precision, device, pinned=None):
     eng = Engine(m["rows_full"], case.dem.shape[1], precision=precision, device=device)
     eng.set_params(cell_size=case.cell, elev_aws=case.elev_aws, aws_row=case.aws_rc[0],
                    aws_col=case.aws_rc[1], sensor_z=1.6, zm=1e-3, z_h_or_e=1e-4, emissivity=0.98,
-                   insol_mode=_lib.INSOL_COMPUTED, shadow=False, lat=case.lat, lon=case.lon,
+                   insol_mode=_lib.INSOL_COMPUTED, shadow=SHADOW, lat=case.lat, lon=case.lon,
                    band_row0=m["band_row0"], band_rows=case.dem.shape[0])
     keys = list(case.albedo_maps)
     table = build_forcing(case.aws_rows, keys)
@@ -237,7 +238,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": "C2: %dx%d 10 m synthetic DEM + 5 albedo maps per GPU, %d hourly steps, "
-                                   "in-kernel insolation (4 sub-steps/step), no shading" % (n, n, T),
+                                   "in-kernel insolation (4 sub-steps/step), %s" % (n, n, T, "shading ray march" if SHADOW else "no shading"),
                        "raster": [n * world, n], "steps_per_pass": T, "parallelism": "row bands x%d" % world,
                        "l2": "per-pass inputs ~%.0f MB > 126 MB L2, no flush" % (bytes_per_launch / 1e6)},
             "roofline": {"bound": "fp32" if args.dtype == "f32" else "fp64", "achieved": achieved, "peak": peak,
@@ -386,7 +387,10 @@ def main():
     ap.add_argument("--t", type=int, default=N_STEPS, help="AWS rows per pass")
     ap.add_argument("--cpu-sample-steps", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--shadow", action="store_true", help="topographic shading ray march on (config C3)")
     args = ap.parse_args()
+    global SHADOW
+    SHADOW = bool(args.shadow)
     if args.warmup < 3 and args.impl == "ours":
         log("note: the timing rules ask for >= 3 warm-up passes")
     if args.impl == "reference":

@@ -408,7 +408,7 @@ struct SmemLayout {
 #define ENRGY_MINB32 2
 #endif
 #ifndef ENRGY_MINB64
-#define ENRGY_MINB64 1
+#define ENRGY_MINB64 2
 #endif
 
 template <typename R, int K, int INSOL, bool DUMP>
@@ -604,11 +604,21 @@ energy_balance_kernel(const KernelArgs<R> a) {
           const R e = s.e_aws * pw[i];
           // bulk fluxes, turbo.py:140-196 with rho = P / (R Tz) and rho / P = 1 / (R Tz);
           // c_sens carries CH * Cp * uz * 100 (Pa per hPa), c_lat carries CE * uz * 0.622 * Lv
-          const R r_rt = Num<R>::rcp((R)kRair * tz);
+          R r_rt, r_p;                                      // 1 / (R Tz) and 1 / p_hpa
+          if (sizeof(R) == 8) {
+            // float64: one division serves both reciprocals (a DP division is ~20 instructions)
+            const R rt = (R)kRair * tz;
+            const R inv = (R)1 / (rt * p_hpa);
+            r_rt = inv * p_hpa;
+            r_p = inv * rt;
+          } else {
+            r_rt = Num<R>::rcp((R)kRair * tz);
+            r_p = Num<R>::rcp(p_hpa);
+          }
           const R sens = (s.c_sens * p_hpa) * (r_rt * d_t);
           // saturation vapour pressure of the melting surface, turbo.py:368-379 with t = 0:
           // exp(0) = 1 exactly, so es = 611.2 * f(p).  ez = e_max * (e / e_max) = e (one rounding).
-          const R f_p = (R)1.0016 + (R)(3.15 * 1e-6) * p_hpa - (R)0.074 * Num<R>::rcp(p_hpa);
+          const R f_p = (R)1.0016 + (R)(3.15 * 1e-6) * p_hpa - (R)0.074 * r_p;
           const R lat = (s.c_lat * r_rt) * (e - (R)611.2 * f_p);
           // longwave, model.py:533-545
           const R tz2 = tz * tz;

@@ -1,0 +1,117 @@
+"""World-size-2 test of the N>1 host path on the CPU (gloo): row-band partition, per-band
+statistics as SUMS + counts, one all-reduce, means formed after -- must equal the single-process
+result on the whole raster.  The per-band numbers come from the NumPy oracle here (the CUDA kernel
+needs a GPU); what is under test is the partition and the reduction plumbing bench.py and
+Energy use on the GPUs."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from enrgy_b200 import _lib
+from enrgy_b200.parallel import allreduce_stats, means_from_sums, row_bands
+from enrgy_b200.synthetic import make_case
+from oracle import enrgy_oracle as O
+from tests import parity as P
+
+
+def _band_sums(case, pot, r0, n, kw):
+    """Oracle on rows [r0, r0+n) (+ the AWS row in front so the point sampling is unchanged)."""
+    ar = case.aws_rc[0]
+    sl = slice(r0, r0 + n)
+
+    def band(a):
+        return np.concatenate([a[ar:ar + 1], a[sl]], axis=0)
+    gt = list(case.geotransform)
+    gt[3] = case.xy_aws[1] + 0.5 * case.cell
+    cfg = P.oracle_config(case, **kw)
+    alb = {k: band(a) for k, a in P.clipped_albedo(case, np.float64).items()}
+    out = O.run_model(band(case.dem.astype(np.float64)), tuple(gt), case.aws_rows,
+                      np.concatenate([pot[:, ar:ar + 1], pot[:, sl]], axis=1).astype(np.float64), cfg,
+                      swe=band(case.swe.astype(np.float64)), albedo_arrays=alb, state_dtype=np.float64,
+                      keep_steps=None)
+    T = len(case.aws_rows)
+    s = np.zeros((T, _lib.S_COUNT))
+    for i in range(T):
+        row, melt = out["rows"][i], out["melt"][i]
+        cut = lambda a: np.asarray(a)[1:]          # drop the duplicated AWS row
+        s[i, _lib.S_RS] = np.nansum(cut(row["rs"]))
+        s[i, _lib.S_LWD] = np.nansum(cut(row["lwd"]))
+        s[i, _lib.S_LWU] = np.nansum(np.where(np.isnan(cut(row["lwd"])), np.nan, cut(row["lwu"])))
+        s[i, _lib.S_SENS] = np.nansum(cut(row["sens"]))
+        s[i, _lib.S_LAT] = np.nansum(cut(row["lat"]))
+        s[i, _lib.S_ATMO] = np.nansum(cut(row["atmo"]))
+        s[i, _lib.S_MELT] = np.nansum(cut(row["mf"]))
+        s[i, _lib.S_SNOW] = np.nansum(cut(melt[0]))
+        s[i, _lib.S_ICE] = np.nansum(cut(melt[1]))
+        swe = cut(melt[2])
+        s[i, _lib.S_SWE] = np.nansum(swe)
+        s[i, _lib.S_NSNOW] = np.sum(swe > 0)
+        s[i, _lib.S_NSWE] = np.count_nonzero(~np.isnan(swe))
+        s[i, _lib.S_NVALID] = np.count_nonzero(~np.isnan(cut(row["atmo"])))
+    return s
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        case = make_case(64, 6, seed=31, w=48)
+        pot = P.random_insolation(case, 6, seed=2)
+        valid_per_row = (~np.isnan(case.dem)).sum(axis=1)
+        bands = row_bands(case.dem.shape[0], world, align=8, valid_per_row=valid_per_row)
+        r0, n = bands[rank]
+        sums = torch.from_numpy(_band_sums(case, pot, r0, n, {}))
+        allreduce_stats(sums)
+        if rank == 0:
+            np.save(os.path.join(out_dir, "reduced.npy"), sums.numpy())
+            np.save(os.path.join(out_dir, "bands.npy"), np.array(bands))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_two_rank_band_reduction(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    reduced = np.load(tmp_path / "reduced.npy")
+    bands = np.load(tmp_path / "bands.npy")
+    assert bands[0][0] == 0 and bands[-1][0] + bands[-1][1] == 64 and bands[1][0] % 8 == 0
+    case = make_case(64, 6, seed=31, w=48)
+    pot = P.random_insolation(case, 6, seed=2)
+    whole = P.run_oracle(case, pot, True)
+    got = means_from_sums(reduced)
+    want = whole["means"]
+    # oracle means: rs, rl, lwd, sens, lat, atmo, g, melt, snow, ice, swe, n_snow, n_swe
+    assert np.allclose(got[1:, :11], want[1:, :11], rtol=1e-11, atol=1e-12)
+    cover = np.round(want[1:, 11] / want[1:, 12] * 100)
+    assert np.array_equal(got[1:, 11], cover)
+    # first row: the reference counts EVERY non-NaN SWE cell, off-glacier included -- identical here
+    # because the synthetic SWE raster is NaN off-glacier
+    assert np.allclose(got[0, :11], want[0, :11], rtol=1e-11, atol=1e-12)
+
+
+def test_row_bands_properties():
+    for rows, world in ((2048, 8), (100, 3), (16, 4), (8192, 8)):
+        b = row_bands(rows, world)
+        assert b[0][0] == 0 and sum(n for _, n in b) == rows
+        assert all(b[i][0] + b[i][1] == b[i + 1][0] for i in range(world - 1))
+    w = np.zeros(256)
+    w[64:192] = 1.0                                  # glacier only in the middle half
+    b = row_bands(256, 2, align=16, valid_per_row=w)
+    assert b[0] == (0, 128) and b[1] == (128, 128)
+    w[64:96] = 5.0
+    b = row_bands(256, 2, align=16, valid_per_row=w)
+    assert b[1][0] < 128                             # the heavy rows pull the cut north
