@@ -81,7 +81,9 @@ struct enrgy_ctx {
   std::vector<double> pot_aws;
   PrepassOutput pre;
   // device rasters
-  DevBuf<float> d_dem, d_albedo, d_pot, d_tmp32;
+  DevBuf<float> d_dem, d_albedo, d_pot, d_tmp32, d_blockmax;
+  int dem_pitch = 0, nbr = 0, nbc = 0;
+  float* dem0 = nullptr;          // cell (0, 0) inside the apron buffer
   DevBuf<unsigned char> d_nx, d_ny, d_nz, d_swe, d_ts, d_ti, d_dump, d_stage, d_snap;
   bool snap_valid = false, snap_advanced = false;
   int n_maps = 0;
@@ -136,7 +138,7 @@ int convert_state(enrgy_ctx* c, const float* d_src32, unsigned char* dst) {
 int check_mask(enrgy_ctx* c, const float* d_other, const char* what, bool strict_other_valid) {
   CU_TRY(c->d_counters.alloc(2));
   CU_TRY(cudaMemsetAsync(c->d_counters.p, 0, 2 * sizeof(unsigned long long), c->stream));
-  CU_TRY(launch_mask_check(c->d_dem.p, d_other, c->pitch, c->band_row0, c->band_rows, c->cols,
+  CU_TRY(launch_mask_check(c->dem0, c->dem_pitch, d_other, c->pitch, c->band_row0, c->band_rows, c->cols,
                            c->d_counters.p, c->stream));
   c->launches++;
   unsigned long long h[2];
@@ -198,7 +200,8 @@ int fill_args(enrgy_ctx* c, int t0, int t1, KernelArgs<R>& a) {
   a = KernelArgs<R>{};
   a.rows_full = c->rows; a.cols = c->cols; a.pitch = c->pitch;
   a.band_row0 = c->band_row0; a.band_rows = c->band_rows; a.rows_pad_full = c->rows_pad_full;
-  a.dem = c->d_dem.p;
+  a.dem = c->dem0; a.dem_pitch = c->dem_pitch;
+  a.blockmax = c->d_blockmax.p; a.nbr = c->nbr; a.nbc = c->nbc;
   a.nx = (const R*)c->d_nx.p; a.ny = (const R*)c->d_ny.p; a.nz = (const R*)c->d_nz.p;
   a.albedo = c->d_albedo.p;
   a.map_stride = c->band_elems;
@@ -254,7 +257,7 @@ int run_typed(enrgy_ctx* c, int t0, int t1, double* d_stats, cudaStream_t stream
   CU_TRY(cudaMemsetAsync(c->d_partials.p, 0, (size_t)grid * std::max(n, 1) * kStatsK * sizeof(double), stream));
   a.partials = c->d_partials.p;
   if (n > 0 && !c->state_advanced) {
-    CU_TRY(launch_nan_offglacier<R>(c->d_dem.p, c->pitch, c->band_row0, c->band_rows, c->cols, a.swe,
+    CU_TRY(launch_nan_offglacier<R>(c->dem0, c->dem_pitch, c->pitch, c->band_row0, c->band_rows, c->cols, a.swe,
                                     a.total_snow, a.total_ice, stream));
     c->launches++;
   }
@@ -379,7 +382,7 @@ int enrgy_destroy(enrgy_ctx* c) {
   c->d_ti.release(); c->d_dump.release(); c->d_stage.release(); c->d_steps.release(); c->d_subs.release();
   c->d_steps64.release(); c->d_shades.release(); c->d_blocks.release(); c->d_tiles.release();
   c->d_counts.release(); c->d_partials.release(); c->d_stats.release(); c->d_small.release();
-  c->d_counters.release(); c->d_masks.release(); c->d_snap.release();
+  c->d_counters.release(); c->d_masks.release(); c->d_snap.release(); c->d_blockmax.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -426,8 +429,19 @@ int enrgy_set_dem(enrgy_ctx* c, const float* dem) {
   if (!c->have_params) return fail(ENRGY_ERR_ARG, "set_params must precede set_dem");
   if (!dem) return fail(ENRGY_ERR_ARG, "dem is null");
   c->h_dem.assign(dem, dem + (size_t)c->rows * c->cols);
-  CU_TRY(c->d_dem.alloc((size_t)c->rows_pad_full * c->pitch));
-  if (int e = upload_padded(c, dem, c->rows, c->d_dem.p, c->rows_pad_full)) return e;
+  // DEM buffer with a NaN apron of kDemApron cells on every side (ray chunks never leave it)
+  c->dem_pitch = c->pitch + 2 * kDemApron;
+  const size_t dem_elems = (size_t)(c->rows_pad_full + 2 * kDemApron) * c->dem_pitch;
+  CU_TRY(c->d_dem.alloc(dem_elems));
+  c->dem0 = c->d_dem.p + (size_t)kDemApron * c->dem_pitch + kDemApron;
+  CU_TRY(cudaMemsetAsync(c->d_dem.p, 0xFF, dem_elems * sizeof(float), c->stream));
+  CU_TRY(cudaMemcpy2DAsync(c->dem0, (size_t)c->dem_pitch * sizeof(float), dem, (size_t)c->cols * sizeof(float),
+                           (size_t)c->cols * sizeof(float), c->rows, cudaMemcpyHostToDevice, c->stream));
+  c->nbr = (c->rows + kMaxBlock - 1) / kMaxBlock;
+  c->nbc = (c->cols + kMaxBlock - 1) / kMaxBlock;
+  CU_TRY(c->d_blockmax.alloc((size_t)(c->nbr + 2) * (c->nbc + 2)));
+  CU_TRY(launch_blockmax(c->dem0, c->dem_pitch, c->rows, c->cols, c->nbr, c->nbc, c->d_blockmax.p, c->stream));
+  c->launches++;
   // active tiles of the band
   c->tiles_r = (c->band_rows + c->tile_h - 1) / c->tile_h;
   c->tiles_c = c->pitch / kTileW;
@@ -435,7 +449,7 @@ int enrgy_set_dem(enrgy_ctx* c, const float* dem) {
   CU_TRY(c->d_counts.alloc(std::max(nt, 1)));
   std::vector<int> counts(std::max(nt, 1), 0);
   if (nt > 0) {
-    CU_TRY(launch_tile_scan(c->d_dem.p, c->pitch, c->band_row0, c->band_rows, c->cols, c->tile_h, c->tiles_r,
+    CU_TRY(launch_tile_scan(c->dem0, c->dem_pitch, c->band_row0, c->band_rows, c->cols, c->tile_h, c->tiles_r,
                             c->tiles_c, c->d_counts.p, c->stream));
     c->launches++;
     CU_TRY(cudaMemcpyAsync(counts.data(), c->d_counts.p, (size_t)nt * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -471,10 +485,10 @@ int enrgy_set_dem(enrgy_ctx* c, const float* dem) {
     CU_TRY(c->d_ny.alloc(c->band_elems * rs));
     CU_TRY(c->d_nz.alloc(c->band_elems * rs));
     if (c->precision == ENRGY_F32) {
-      CU_TRY(launch_terrain<float>(c->d_dem.p, c->rows, c->cols, c->pitch, c->band_row0, c->band_rows_pad,
+      CU_TRY(launch_terrain<float>(c->dem0, c->dem_pitch, c->rows, c->cols, c->pitch, c->band_row0, c->band_rows_pad,
                                    c->p.cell_size, (float*)c->d_nx.p, (float*)c->d_ny.p, (float*)c->d_nz.p, c->stream));
     } else {
-      CU_TRY(launch_terrain<double>(c->d_dem.p, c->rows, c->cols, c->pitch, c->band_row0, c->band_rows_pad,
+      CU_TRY(launch_terrain<double>(c->dem0, c->dem_pitch, c->rows, c->cols, c->pitch, c->band_row0, c->band_rows_pad,
                                     c->p.cell_size, (double*)c->d_nx.p, (double*)c->d_ny.p, (double*)c->d_nz.p, c->stream));
     }
     c->launches++;

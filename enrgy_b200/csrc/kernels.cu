@@ -146,8 +146,8 @@ __device__ __forceinline__ int stat_of_lane(int lane) {
 // terrain normal from the 4-neighbourhood; a missing neighbour is mirrored from the opposite one
 // (DESIGN.md "Insolation specification"; oracle/insolation_oracle.py:terrain_normals)
 template <typename R>
-__global__ void terrain_kernel(const float* __restrict__ dem, int rows_full, int cols, int pitch,
-                               int band_row0, int band_rows_pad, R inv2cell, R* __restrict__ nx,
+__global__ void terrain_kernel(const float* __restrict__ dem, int dem_pitch, int rows_full, int cols,
+                               int pitch, int band_row0, int band_rows_pad, R inv2cell, R* __restrict__ nx,
                                R* __restrict__ ny, R* __restrict__ nz) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int rb = blockIdx.y;
@@ -157,7 +157,7 @@ __global__ void terrain_kernel(const float* __restrict__ dem, int rows_full, int
   const float qnan = __int_as_float(0x7fc00000);
   auto at = [&](int rr, int cc) -> float {
     if (rr < 0 || rr >= rows_full || cc < 0 || cc >= cols) return qnan;
-    return dem[(size_t)rr * pitch + cc];
+    return dem[(size_t)rr * dem_pitch + cc];
   };
   const float zf = at(r, c);
   if (!(zf == zf)) {
@@ -182,15 +182,16 @@ __global__ void terrain_kernel(const float* __restrict__ dem, int rows_full, int
 }
 
 template <typename R>
-cudaError_t launch_terrain(const float* dem, int rows_full, int cols, int pitch, int band_row0,
-                           int band_rows_pad, double cell, R* nx, R* ny, R* nz, cudaStream_t stream) {
+cudaError_t launch_terrain(const float* dem, int dem_pitch, int rows_full, int cols, int pitch,
+                           int band_row0, int band_rows_pad, double cell, R* nx, R* ny, R* nz,
+                           cudaStream_t stream) {
   dim3 grid((pitch + 255) / 256, band_rows_pad);
-  terrain_kernel<R><<<grid, 256, 0, stream>>>(dem, rows_full, cols, pitch, band_row0, band_rows_pad,
+  terrain_kernel<R><<<grid, 256, 0, stream>>>(dem, dem_pitch, rows_full, cols, pitch, band_row0, band_rows_pad,
                                               (R)(1.0 / (2.0 * cell)), nx, ny, nz);
   return cudaGetLastError();
 }
-template cudaError_t launch_terrain<float>(const float*, int, int, int, int, int, double, float*, float*, float*, cudaStream_t);
-template cudaError_t launch_terrain<double>(const float*, int, int, int, int, int, double, double*, double*, double*, cudaStream_t);
+template cudaError_t launch_terrain<float>(const float*, int, int, int, int, int, int, double, float*, float*, float*, cudaStream_t);
+template cudaError_t launch_terrain<double>(const float*, int, int, int, int, int, int, double, double*, double*, double*, cudaStream_t);
 
 // valid (non-NaN DEM) cells per tile
 __global__ void tile_scan_kernel(const float* __restrict__ dem, int pitch, int band_row0,
@@ -224,14 +225,14 @@ cudaError_t launch_tile_scan(const float* dem, int pitch, int band_row0, int ban
 }
 
 // counters[0] += cells valid in the DEM but NaN in `other`; counters[1] += the opposite
-__global__ void mask_check_kernel(const float* __restrict__ dem, const float* __restrict__ other,
-                                  int pitch, int band_row0, int band_rows, int cols,
-                                  unsigned long long* counters) {
+__global__ void mask_check_kernel(const float* __restrict__ dem, int dem_pitch,
+                                  const float* __restrict__ other, int pitch, int band_row0,
+                                  int band_rows, int cols, unsigned long long* counters) {
   unsigned a = 0, b = 0;
   const size_t n = (size_t)band_rows * cols;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int rb = (int)(i / cols), c = (int)(i % cols);
-    const float z = dem[(size_t)(rb + band_row0) * pitch + c];
+    const float z = dem[(size_t)(rb + band_row0) * dem_pitch + c];
     const float o = other[(size_t)rb * pitch + c];
     const bool vz = z == z, vo = o == o;
     a += (vz && !vo) ? 1u : 0u;
@@ -244,10 +245,11 @@ __global__ void mask_check_kernel(const float* __restrict__ dem, const float* __
     if (b) atomicAdd(&counters[1], (unsigned long long)b);
   }
 }
-cudaError_t launch_mask_check(const float* dem, const float* other, int pitch, int band_row0,
-                              int band_rows, int cols, unsigned long long* counters,
+cudaError_t launch_mask_check(const float* dem, int dem_pitch, const float* other, int pitch,
+                              int band_row0, int band_rows, int cols, unsigned long long* counters,
                               cudaStream_t stream) {
-  mask_check_kernel<<<592, 256, 0, stream>>>(dem, other, pitch, band_row0, band_rows, cols, counters);
+  mask_check_kernel<<<592, 256, 0, stream>>>(dem, dem_pitch, other, pitch, band_row0, band_rows, cols,
+                                             counters);
   return cudaGetLastError();
 }
 
@@ -323,14 +325,14 @@ template cudaError_t launch_unpad_state<double>(const double*, int, int, int, in
 // off-glacier cells of the state rasters become NaN with the first step (model.py:258: swe -= NaN);
 // the fused kernel only visits tiles that hold glacier cells, this covers the rest.
 template <typename R>
-__global__ void nan_offglacier_kernel(const float* __restrict__ dem, int pitch, int band_row0,
-                                      int band_rows, int cols, R* __restrict__ swe,
+__global__ void nan_offglacier_kernel(const float* __restrict__ dem, int dem_pitch, int pitch,
+                                      int band_row0, int band_rows, int cols, R* __restrict__ swe,
                                       R* __restrict__ tsn, R* __restrict__ tic) {
   const size_t n = (size_t)band_rows * cols;
   const R qnan = (R)__int_as_float(0x7fc00000);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int rb = (int)(i / cols), c = (int)(i % cols);
-    const float z = dem[(size_t)(rb + band_row0) * pitch + c];
+    const float z = dem[(size_t)(rb + band_row0) * dem_pitch + c];
     if (!(z == z)) {
       const size_t o = (size_t)rb * pitch + c;
       swe[o] = qnan; tsn[o] = qnan; tic[o] = qnan;
@@ -338,49 +340,135 @@ __global__ void nan_offglacier_kernel(const float* __restrict__ dem, int pitch, 
   }
 }
 template <typename R>
-cudaError_t launch_nan_offglacier(const float* dem, int pitch, int band_row0, int band_rows, int cols,
-                                  R* swe, R* tsn, R* tic, cudaStream_t stream) {
-  nan_offglacier_kernel<R><<<1184, 256, 0, stream>>>(dem, pitch, band_row0, band_rows, cols, swe, tsn, tic);
+cudaError_t launch_nan_offglacier(const float* dem, int dem_pitch, int pitch, int band_row0,
+                                  int band_rows, int cols, R* swe, R* tsn, R* tic, cudaStream_t stream) {
+  nan_offglacier_kernel<R><<<1184, 256, 0, stream>>>(dem, dem_pitch, pitch, band_row0, band_rows, cols, swe,
+                                                     tsn, tic);
   return cudaGetLastError();
 }
-template cudaError_t launch_nan_offglacier<float>(const float*, int, int, int, int, float*, float*, float*, cudaStream_t);
-template cudaError_t launch_nan_offglacier<double>(const float*, int, int, int, int, double*, double*, double*, cudaStream_t);
+template cudaError_t launch_nan_offglacier<float>(const float*, int, int, int, int, int, float*, float*, float*, cudaStream_t);
+template cudaError_t launch_nan_offglacier<double>(const float*, int, int, int, int, int, double*, double*, double*, cudaStream_t);
 
 // =================================================================================================
 // shading ray march (DESIGN.md "Shading"; oracle/insolation_oracle.py:shadow_mask)
 // =================================================================================================
-// All K cells of a thread and all 32 lanes step together; bit i of the returned mask = cell i is
-// sunlit.  float32 + integer arithmetic only, non-fused multiply/add, so the mask is bit-identical
-// to the NumPy statement whatever the precision of the energy balance.
+// max of the valid DEM cells of every 32 x 32 block, with one ring of -inf blocks around the grid
+__global__ void blockmax_kernel(const float* __restrict__ dem, int dem_pitch, int rows_full, int cols,
+                                int nbr, int nbc, float* __restrict__ blockmax) {
+  const int bc = (int)blockIdx.x - 1, br = (int)blockIdx.y - 1;
+  float m = -INFINITY;
+  if (br >= 0 && br < nbr && bc >= 0 && bc < nbc) {
+    for (int i = threadIdx.x; i < kMaxBlock * kMaxBlock; i += blockDim.x) {
+      const int r = br * kMaxBlock + i / kMaxBlock, c = bc * kMaxBlock + i % kMaxBlock;
+      if (r < rows_full && c < cols) {
+        const float z = dem[(size_t)r * dem_pitch + c];
+        if (z == z) m = fmaxf(m, z);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, sh[w]);
+    blockmax[(size_t)blockIdx.y * (nbc + 2) + blockIdx.x] = m;
+  }
+}
+cudaError_t launch_blockmax(const float* dem, int dem_pitch, int rows_full, int cols, int nbr, int nbc,
+                            float* blockmax, cudaStream_t stream) {
+  blockmax_kernel<<<dim3(nbc + 2, nbr + 2), 256, 0, stream>>>(dem, dem_pitch, rows_full, cols, nbr, nbc, blockmax);
+  return cudaGetLastError();
+}
+
+// order-preserving float -> int key (for REDUX min/max on the integer pipe)
+__device__ __forceinline__ int float_key(float x) {
+  const int i = __float_as_int(x);
+  return i ^ ((i >> 31) & 0x7fffffff);
+}
+
+// All K cells of a thread and all 32 lanes step together, kRayChunk steps at a time; bit i of the
+// returned mask = cell i is sunlit.  float32 + integer arithmetic only, non-fused multiply/add, so
+// the mask is bit-identical to the NumPy statement whatever the precision of the energy balance.
+//
+// Per chunk the warp (a) retires rays that left the grid, were hit, or are above the DEM maximum,
+// (b) compares its LOWEST ray height at the chunk start with the maximum of the DEM blocks the
+// chunk can touch -- ray heights only grow, so if even that is above the terrain no sample of the
+// chunk can hit and the chunk is skipped without reading the DEM (result-preserving), else
+// (c) samples the chunk: one coalesced 128 B read of the replicated DEM per cell row and step.
+// The NaN apron of kDemApron = kRayChunk cells lets a chunk that starts inside the grid run
+// without per-sample bounds checks.
 template <int K>
-__device__ __forceinline__ unsigned march(const float* __restrict__ dem, int pitch, int rows_full,
-                                          int cols, const int (&row)[K], const int (&col)[K],
-                                          const float (&z0)[K], unsigned valid_bits,
-                                          const ShadeRec s, float zmax) {
+__device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem_pitch, int rows_full,
+                                          int cols, const float* __restrict__ blockmax, int nbr, int nbc,
+                                          const int (&row)[K], const int (&col)[K], const float (&z0)[K],
+                                          unsigned start_bits, const ShadeRec s, float zmax, int lane) {
+  const unsigned full = 0xffffffffu;
   unsigned lit = (1u << K) - 1u;
   if (!(s.dz < 3.0e38f)) return lit;   // sun at the zenith
-  unsigned active = valid_bits;
-  for (int k = 1; __any_sync(0xffffffffu, active != 0u); ++k) {
-    const int ro = (k * s.dr_fix + 32768) >> 16;
-    const int co = (k * s.dc_fix + 32768) >> 16;
-    const float kdz = __fmul_rn((float)k, s.dz);
+  unsigned active = start_bits;
+  // bounding box of the warp's cells (rows of cell 0 / cell K-1, 128 columns from the lane-0 column)
+  const int r_lo = __shfl_sync(full, row[0], 0), r_hi = __shfl_sync(full, row[K - 1], 0);
+  const int c_lo = __shfl_sync(full, col[0], 0), c_hi = c_lo + kTileW - 1;
+  int base[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) base[i] = row[i] * dem_pitch + col[i];
+  const int zmax_key = float_key(zmax);
+
+  for (int k = 1; k < 65536; k += kRayChunk) {
+    // offsets of this lane's step of the chunk
+    const int kl = k + lane;
+    const int ro_l = (kl * s.dr_fix + 32768) >> 16;
+    const int co_l = (kl * s.dc_fix + 32768) >> 16;
+    const int ro_a = __shfl_sync(full, ro_l, 0), ro_b = __shfl_sync(full, ro_l, kRayChunk - 1);
+    const int co_a = __shfl_sync(full, co_l, 0), co_b = __shfl_sync(full, co_l, kRayChunk - 1);
+    const float kdz_a = __fmul_rn((float)k, s.dz);
+    // (a) retire rays: outside the grid at the chunk's first step, or above the DEM maximum
+    float zl = INFINITY;
 #pragma unroll
     for (int i = 0; i < K; ++i) {
       const unsigned bit = 1u << i;
-      if (active & bit) {
-        const int rr = row[i] + ro, cc = col[i] + co;
-        const float zk = __fadd_rn(z0[i], kdz);
-        if ((unsigned)rr >= (unsigned)rows_full || (unsigned)cc >= (unsigned)cols || zk > zmax) {
-          active &= ~bit;
-        } else {
-          const float smp = __ldg(dem + (size_t)rr * pitch + cc);
-          if (smp > zk) {
-            lit &= ~bit;
-            active &= ~bit;
-          }
-        }
+      const float zk = __fadd_rn(z0[i], kdz_a);
+      const bool in = (unsigned)(row[i] + ro_a) < (unsigned)rows_full && (unsigned)(col[i] + co_a) < (unsigned)cols;
+      if (!in || zk > zmax) active &= ~bit;
+      if (active & bit) zl = fminf(zl, zk);
+    }
+    if (!__any_sync(full, active != 0u)) break;
+    const int zlow_key = __reduce_min_sync(full, float_key(zl));
+    // (b) can the chunk hit anything?  max of the DEM blocks under the chunk's swept bounding box
+    const int rmin = r_lo + min(ro_a, ro_b), rmax = r_hi + max(ro_a, ro_b);
+    const int cmin = c_lo + min(co_a, co_b), cmax = c_hi + max(co_a, co_b);
+    const int br0 = rmin >> 5, br1 = rmax >> 5, bc0 = cmin >> 5, bc1 = cmax >> 5;
+    float m = -INFINITY;
+    {
+      // up to 4 x 8 blocks, one per lane (a chunk of 32 steps spans at most 3 x 7)
+      const int br = br0 + (lane >> 3), bc = bc0 + (lane & 7);
+      if (br <= br1 && bc <= bc1) {
+        const int cr = min(max(br, -1), nbr), cc = min(max(bc, -1), nbc);
+        m = __ldg(blockmax + (size_t)(cr + 1) * (nbc + 2) + (cc + 1));
       }
     }
+    const int region_key = __reduce_max_sync(full, float_key(m));
+    if (zlow_key > region_key) continue;     // nothing in reach is as high as the lowest ray
+    // (c) sample the chunk
+    const int off_l = ro_l * dem_pitch + co_l;
+    unsigned hit = 0u;
+#pragma unroll 4
+    for (int j = 0; j < kRayChunk; ++j) {
+      const int off = __shfl_sync(full, off_l, j);
+      const float kdz = __fmul_rn((float)(k + j), s.dz);
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        const float smp = __ldg(dem + (base[i] + off));
+        const float zk = __fadd_rn(z0[i], kdz);
+        hit |= (smp > zk) ? (1u << i) : 0u;
+      }
+    }
+    // samples of a retired ray do not count: it left the grid or cleared the terrain before
+    hit &= active;
+    lit &= ~hit;
+    active &= ~hit;
   }
   return lit;
 }
@@ -470,7 +558,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
       rowf[i] = rowb[i] + a.band_row0;
       const size_t o = (size_t)rowb[i] * a.pitch + col[i];
       const bool inside = rowb[i] < a.band_rows && col[i] < a.cols;
-      float z = inside ? __ldg(a.dem + (size_t)rowf[i] * a.pitch + col[i]) : __int_as_float(0x7fc00000);
+      float z = inside ? __ldg(a.dem + (size_t)rowf[i] * a.dem_pitch + col[i]) : __int_as_float(0x7fc00000);
       const bool v = z == z;
       valid_bits |= v ? (1u << i) : 0u;
       wgt[i] = v ? (R)1 : (R)0;
@@ -560,8 +648,18 @@ energy_balance_kernel(const KernelArgs<R> a) {
             const SubRec<R> sb = sm.subs[buf][j];
             unsigned lit = 0xffffffffu;
             if (INSOL == kInsolShadow) {
-              lit = march<K>(a.dem, a.pitch, a.rows_full, a.cols, rowf, col, z0, valid_bits,
-                             sm.shades[buf][j], (float)a.zmax);
+              // production runs skip cells that face away from the sun (direct beam = 0 whatever
+              // the mask says); the mask dump marches every glacier cell
+              unsigned start_bits = valid_bits;
+              if (!(DUMP && a.mask_out != nullptr)) {
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                  const R c = sb.u + nxv[i] * sb.e + nyv[i] * sb.n;
+                  if (!(c > (R)0)) start_bits &= ~(1u << i);
+                }
+              }
+              lit = march<K>(a.dem, a.dem_pitch, a.rows_full, a.cols, a.blockmax, a.nbr, a.nbc, rowf, col,
+                             z0, start_bits, sm.shades[buf][j], (float)a.zmax, lane);
               if (DUMP && a.mask_out != nullptr && t == a.t0) {
 #pragma unroll
                 for (int i = 0; i < K; ++i) {

@@ -17,7 +17,11 @@ struct KernelArgs {
   int rows_full, cols, pitch;     // full DEM
   int band_row0, band_rows;       // this handle's row band (rasters below are band-local)
   int rows_pad_full;              // padded row count of the full DEM buffer
-  const float* dem;               // [rows_pad_full][pitch] full DEM (replicated for shading)
+  const float* dem;               // full DEM (replicated for shading), pointing at cell (0, 0) of a
+                                  // buffer with a NaN apron of kDemApron cells on every side
+  int dem_pitch;                  // row stride of the DEM buffer
+  const float* blockmax;          // max of the valid DEM per 32x32 block, [(nbr + 2)][(nbc + 2)],
+  int nbr, nbc;                   //   one ring of -inf blocks around it (shading early exit)
   const R* nx;                    // [band_rows_pad][pitch] terrain normal (computed insolation)
   const R* ny;
   const R* nz;
@@ -70,13 +74,16 @@ struct FinalizeArgs {
 
 // launch helpers (defined in kernels.cu); all asynchronous on `stream`
 template <typename R>
-cudaError_t launch_terrain(const float* dem, int rows_full, int cols, int pitch, int band_row0,
-                           int band_rows_pad, double cell, R* nx, R* ny, R* nz, cudaStream_t stream);
+cudaError_t launch_terrain(const float* dem, int dem_pitch, int rows_full, int cols, int pitch,
+                           int band_row0, int band_rows_pad, double cell, R* nx, R* ny, R* nz,
+                           cudaStream_t stream);
+cudaError_t launch_blockmax(const float* dem, int dem_pitch, int rows_full, int cols, int nbr, int nbc,
+                            float* blockmax, cudaStream_t stream);
 cudaError_t launch_tile_scan(const float* dem, int pitch, int band_row0, int band_rows, int cols,
                              int tile_h, int tiles_r, int tiles_c, int* counts, cudaStream_t stream);
-cudaError_t launch_mask_check(const float* dem, const float* other, int pitch, int band_row0,
-                              int band_rows, int cols, unsigned long long* counters /*[2]*/,
-                              cudaStream_t stream);
+cudaError_t launch_mask_check(const float* dem, int dem_pitch, const float* other, int pitch,
+                              int band_row0, int band_rows, int cols,
+                              unsigned long long* counters /*[2]*/, cudaStream_t stream);
 cudaError_t launch_swe0_stats(const float* swe, int pitch, int band_rows, int cols,
                               double* block_out /*[blocks][3]*/, int blocks, cudaStream_t stream);
 template <typename R>
@@ -86,8 +93,8 @@ cudaError_t launch_unpad_state(const R* src, int pitch, int rows, int cols, int 
                                cudaStream_t stream);
 
 template <typename R>
-cudaError_t launch_nan_offglacier(const float* dem, int pitch, int band_row0, int band_rows, int cols,
-                                  R* swe, R* tsn, R* tic, cudaStream_t stream);
+cudaError_t launch_nan_offglacier(const float* dem, int dem_pitch, int pitch, int band_row0,
+                                  int band_rows, int cols, R* swe, R* tsn, R* tic, cudaStream_t stream);
 
 struct LaunchInfo {
   int regs, smem_bytes, ctas_per_sm, grid, cells_per_thread;
