@@ -82,7 +82,8 @@ struct enrgy_ctx {
   PrepassOutput pre;
   // device rasters
   DevBuf<float> d_dem, d_albedo, d_pot, d_tmp32, d_blockmax;
-  int dem_pitch = 0, nbr = 0, nbc = 0;
+  int dem_pitch = 0;
+  MaxPyramid pyramid{};
   float* dem0 = nullptr;          // cell (0, 0) inside the apron buffer
   DevBuf<unsigned char> d_nx, d_ny, d_nz, d_swe, d_ts, d_ti, d_dump, d_stage, d_snap;
   bool snap_valid = false, snap_advanced = false;
@@ -201,7 +202,7 @@ int fill_args(enrgy_ctx* c, int t0, int t1, KernelArgs<R>& a) {
   a.rows_full = c->rows; a.cols = c->cols; a.pitch = c->pitch;
   a.band_row0 = c->band_row0; a.band_rows = c->band_rows; a.rows_pad_full = c->rows_pad_full;
   a.dem = c->dem0; a.dem_pitch = c->dem_pitch;
-  a.blockmax = c->d_blockmax.p; a.nbr = c->nbr; a.nbc = c->nbc;
+  a.blockmax = c->d_blockmax.p; a.pyramid = c->pyramid;
   a.nx = (const R*)c->d_nx.p; a.ny = (const R*)c->d_ny.p; a.nz = (const R*)c->d_nz.p;
   a.albedo = c->d_albedo.p;
   a.map_stride = c->band_elems;
@@ -262,7 +263,7 @@ int run_typed(enrgy_ctx* c, int t0, int t1, double* d_stats, cudaStream_t stream
     c->launches++;
   }
   CU_TRY(cudaEventRecord(c->ev0, stream));
-  CU_TRY(launch_energy_balance<R>(a, insol, false, c->sm_count, grid, &c->info, stream));
+  CU_TRY(launch_energy_balance<R>(a, nullptr, insol, false, c->sm_count, grid, &c->info, stream));
   CU_TRY(cudaEventRecord(c->ev1, stream));
   c->ev_pending = true;
   c->launches++;
@@ -303,7 +304,7 @@ int dump_typed(enrgy_ctx* c, int t0, int t1, double* out, unsigned* mask_host, i
     a.dump = (R*)c->d_dump.p;
     a.dump_field_stride = c->band_elems;
   }
-  CU_TRY(launch_energy_balance<R>(a, insol, true, c->sm_count, 0, nullptr, c->stream));
+  CU_TRY(launch_energy_balance<R>(a, nullptr, insol, true, c->sm_count, 0, nullptr, c->stream));
   c->launches++;
   if (mask_host) {
     const size_t words = (size_t)n_sub * c->band_rows * a.mask_words;
@@ -437,10 +438,20 @@ int enrgy_set_dem(enrgy_ctx* c, const float* dem) {
   CU_TRY(cudaMemsetAsync(c->d_dem.p, 0xFF, dem_elems * sizeof(float), c->stream));
   CU_TRY(cudaMemcpy2DAsync(c->dem0, (size_t)c->dem_pitch * sizeof(float), dem, (size_t)c->cols * sizeof(float),
                            (size_t)c->cols * sizeof(float), c->rows, cudaMemcpyHostToDevice, c->stream));
-  c->nbr = (c->rows + kMaxBlock - 1) / kMaxBlock;
-  c->nbc = (c->cols + kMaxBlock - 1) / kMaxBlock;
-  CU_TRY(c->d_blockmax.alloc((size_t)(c->nbr + 2) * (c->nbc + 2)));
-  CU_TRY(launch_blockmax(c->dem0, c->dem_pitch, c->rows, c->cols, c->nbr, c->nbc, c->d_blockmax.p, c->stream));
+  {
+    MaxPyramid& py = c->pyramid;
+    py = MaxPyramid{};
+    int nbr = (c->rows + kMaxBlock - 1) / kMaxBlock, nbc = (c->cols + kMaxBlock - 1) / kMaxBlock, off = 0;
+    for (int l = 0; l < kMaxPyramidLevels; ++l) {
+      py.nbr[l] = nbr; py.nbc[l] = nbc; py.off[l] = off;
+      off += (nbr + 2) * (nbc + 2);
+      py.levels = l + 1;
+      if (nbr <= 1 && nbc <= 1) break;
+      nbr = (nbr + 1) / 2; nbc = (nbc + 1) / 2;
+    }
+    CU_TRY(c->d_blockmax.alloc((size_t)off));
+    CU_TRY(launch_blockmax(c->dem0, c->dem_pitch, c->rows, c->cols, py, c->d_blockmax.p, c->stream));
+  }
   c->launches++;
   // active tiles of the band
   c->tiles_r = (c->band_rows + c->tile_h - 1) / c->tile_h;

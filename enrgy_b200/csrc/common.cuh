@@ -36,9 +36,10 @@ constexpr int kTileW = 128;                   // one warp row = 32 lanes x float
 constexpr int kStatsK = 8;                    // statistics reduced in the kernel (see StatK)
 constexpr int kMaxStepsPerBlock = 64;         // time block: per-step records staged in smem
 constexpr int kMaxSubsPerBlock = 256;         // ... and their sunlit sub-steps
-constexpr int kDemApron = 32;                 // NaN cells around the DEM buffer = one ray chunk
-constexpr int kRayChunk = 32;                 // ray steps marched (or skipped) at a time
-constexpr int kMaxBlock = 32;                 // edge of the blocks of the DEM max grid
+constexpr int kDemApron = 64;                 // NaN cells around the DEM buffer: a ray-chunk window of a warp
+                                              // whose last active ray is at the grid edge stays inside it
+constexpr int kRayChunk = 16;                 // ray steps marched (or skipped) at a time
+constexpr int kMaxBlock = 16;                 // edge of the blocks of the DEM max grid
 
 // Statistics the kernel reduces per step (the rest of ENRGY_S_* is derived from these by
 // linearity in finalize_stats_kernel; DESIGN.md "Statistics").

@@ -21,6 +21,7 @@
 #include "kernels.cuh"
 
 #include <cstdio>
+#include <cstring>
 
 #include "../../include/enrgy_b200.h"
 
@@ -352,7 +353,8 @@ template cudaError_t launch_nan_offglacier<double>(const float*, int, int, int, 
 // =================================================================================================
 // shading ray march (DESIGN.md "Shading"; oracle/insolation_oracle.py:shadow_mask)
 // =================================================================================================
-// max of the valid DEM cells of every 32 x 32 block, with one ring of -inf blocks around the grid
+// Max pyramid of the DEM: level 0 = max of the valid cells of every 16 x 16 block, level l = max of
+// 2 x 2 blocks of level l-1; every level carries one ring of -inf blocks around the grid.
 __global__ void blockmax_kernel(const float* __restrict__ dem, int dem_pitch, int rows_full, int cols,
                                 int nbr, int nbc, float* __restrict__ blockmax) {
   const int bc = (int)blockIdx.x - 1, br = (int)blockIdx.y - 1;
@@ -376,16 +378,43 @@ __global__ void blockmax_kernel(const float* __restrict__ dem, int dem_pitch, in
     blockmax[(size_t)blockIdx.y * (nbc + 2) + blockIdx.x] = m;
   }
 }
-cudaError_t launch_blockmax(const float* dem, int dem_pitch, int rows_full, int cols, int nbr, int nbc,
-                            float* blockmax, cudaStream_t stream) {
-  blockmax_kernel<<<dim3(nbc + 2, nbr + 2), 256, 0, stream>>>(dem, dem_pitch, rows_full, cols, nbr, nbc, blockmax);
+__global__ void blockmax_coarsen_kernel(const float* __restrict__ fine, int fnbr, int fnbc,
+                                        float* __restrict__ coarse, int nbr, int nbc) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= nbc + 2 || y >= nbr + 2) return;
+  const int bc = x - 1, br = y - 1;
+  float m = -INFINITY;
+  if (br >= 0 && br < nbr && bc >= 0 && bc < nbc) {
+    for (int dy = 0; dy < 2; ++dy)
+      for (int dx = 0; dx < 2; ++dx) {
+        const int fr = 2 * br + dy, fc = 2 * bc + dx;
+        if (fr < fnbr && fc < fnbc) m = fmaxf(m, fine[(size_t)(fr + 1) * (fnbc + 2) + (fc + 1)]);
+      }
+  }
+  coarse[(size_t)y * (nbc + 2) + x] = m;
+}
+cudaError_t launch_blockmax(const float* dem, int dem_pitch, int rows_full, int cols, const MaxPyramid& py,
+                            float* buffer, cudaStream_t stream) {
+  blockmax_kernel<<<dim3(py.nbc[0] + 2, py.nbr[0] + 2), 256, 0, stream>>>(dem, dem_pitch, rows_full, cols, py.nbr[0],
+                                                                         py.nbc[0], buffer + py.off[0]);
+  for (int l = 1; l < py.levels; ++l) {
+    blockmax_coarsen_kernel<<<dim3((py.nbc[l] + 2 + 127) / 128, py.nbr[l] + 2), 128, 0, stream>>>(
+        buffer + py.off[l - 1], py.nbr[l - 1], py.nbc[l - 1], buffer + py.off[l], py.nbr[l], py.nbc[l]);
+  }
   return cudaGetLastError();
 }
 
-// order-preserving float -> int key (for REDUX min/max on the integer pipe)
+constexpr int kWinW = 52;                       // DEM window of a ray chunk: 32 columns + 16 steps + 3 (alignment)
+constexpr int kWinH = 24;                       //                            K <= 8 rows + 16 steps
+constexpr int kWinBytes = kWinW * kWinH * 4;    // 4992 B = 39 x 128 B
+
+// order-preserving float <-> int key (for REDUX min/max on the integer pipe)
 __device__ __forceinline__ int float_key(float x) {
   const int i = __float_as_int(x);
   return i ^ ((i >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float key_float(int k) {
+  return __int_as_float(k ^ ((k >> 31) & 0x7fffffff));
 }
 
 // All K cells of a thread and all 32 lanes step together, kRayChunk steps at a time; bit i of the
@@ -400,75 +429,127 @@ __device__ __forceinline__ int float_key(float x) {
 // The NaN apron of kDemApron = kRayChunk cells lets a chunk that starts inside the grid run
 // without per-sample bounds checks.
 template <int K>
-__device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem_pitch, int rows_full,
-                                          int cols, const float* __restrict__ blockmax, int nbr, int nbc,
+__device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem_pitch, float* win,
+                                          uint64_t* win_bar, unsigned& win_phase, int rows_full, int cols,
+                                          const float* __restrict__ pyr, const MaxPyramid& py,
                                           const int (&row)[K], const int (&col)[K], const float (&z0)[K],
                                           unsigned start_bits, const ShadeRec s, float zmax, int lane) {
   const unsigned full = 0xffffffffu;
   unsigned lit = (1u << K) - 1u;
   if (!(s.dz < 3.0e38f)) return lit;   // sun at the zenith
   unsigned active = start_bits;
-  // bounding box of the warp's cells (rows of cell 0 / cell K-1, 128 columns from the lane-0 column)
-  const int r_lo = __shfl_sync(full, row[0], 0), r_hi = __shfl_sync(full, row[K - 1], 0);
-  const int c_lo = __shfl_sync(full, col[0], 0), c_hi = c_lo + kTileW - 1;
-  int base[K];
+  // the warp's patch: K consecutive rows x 32 columns (lane = column)
+  const int r_lo = __shfl_sync(full, row[0], 0), r_hi = r_lo + K - 1;
+  const int c_lo = __shfl_sync(full, col[0], 0), c_hi = c_lo + 31;
+  // lowest start height of the rays still marching.  Rounding is monotone, so the lowest ray at
+  // step k is exactly fl(z0min + fl(k * dz)); a stale (too large) active set only makes it lower.
+  auto lowest = [&](unsigned act) -> float {
+    float zl = INFINITY;
 #pragma unroll
-  for (int i = 0; i < K; ++i) base[i] = row[i] * dem_pitch + col[i];
-  const int zmax_key = float_key(zmax);
-
-  for (int k = 1; k < 65536; k += kRayChunk) {
-    // offsets of this lane's step of the chunk
+    for (int i = 0; i < K; ++i) zl = ((act >> i) & 1u) ? fminf(zl, z0[i]) : zl;
+    return key_float(__reduce_min_sync(full, float_key(zl)));
+  };
+  if (!__any_sync(full, active != 0u)) return lit;
+  float z0min = lowest(active);
+  int level = 0;
+  int k = 1;
+  while (k < 32768) {                                      // rasters are at most 32767 cells wide
+    const int n = kRayChunk << level;                      // steps covered by this test
+    const float zlow = __fadd_rn(z0min, __fmul_rn((float)k, s.dz));
+    if (zlow > zmax) break;                                // every ray is above the terrain maximum
+    const int ke = min(k + n - 1, 32767);                  // (k * Q16 step stays inside int32)
+    const int ro_a = (k * s.dr_fix + 32768) >> 16, ro_b = (ke * s.dr_fix + 32768) >> 16;
+    const int co_a = (k * s.dc_fix + 32768) >> 16, co_b = (ke * s.dc_fix + 32768) >> 16;
+    const int ro_min = min(ro_a, ro_b), co_min = min(co_a, co_b);
+    const int rmin = r_lo + ro_min, rmax = r_hi + max(ro_a, ro_b);
+    const int cmin = c_lo + co_min, cmax = c_hi + max(co_a, co_b);
+    // the patch left the grid for good (offsets are monotone in k)
+    if (r_hi + ro_a < 0 || r_lo + ro_a >= rows_full || c_hi + co_a < 0 || c_lo + co_a >= cols) break;
+    // (b) can these n steps hit anything?  max of the pyramid blocks (edge 16 << level) under the
+    // swept bounding box: at most 3 x 4 blocks, one per lane, one REDUX
+    {
+      const int sh = 4 + level;
+      const int br0 = rmin >> sh, br1 = rmax >> sh, bc0 = cmin >> sh, bc1 = cmax >> sh;
+      const int nbr = py.nbr[level], nbc = py.nbc[level];
+      float m = -INFINITY;
+      const int br = br0 + (lane >> 2), bc = bc0 + (lane & 3);
+      if (br <= br1 && bc <= bc1) {
+        const int cr = min(max(br, -1), nbr), cc = min(max(bc, -1), nbc);
+        m = __ldg(pyr + py.off[level] + (size_t)(cr + 1) * (nbc + 2) + (cc + 1));
+      }
+      const int region_key = __reduce_max_sync(full, float_key(m));
+      if (float_key(zlow) > region_key) {                  // nothing in reach is as high as the lowest ray
+        k += n;
+        level = min(level + 1, py.levels - 1);
+        continue;
+      }
+    }
+    if (level > 0) {                                       // look closer before touching the DEM
+      --level;
+      continue;
+    }
+    // (a) about to sample: retire rays that are outside the grid at step k or above the maximum
+    {
+      const float kdz_a = __fmul_rn((float)k, s.dz);
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        const float zk = __fadd_rn(z0[i], kdz_a);
+        const bool in = (unsigned)(row[i] + ro_a) < (unsigned)rows_full && (unsigned)(col[i] + co_a) < (unsigned)cols;
+        if (!in || zk > zmax) active &= ~(1u << i);
+      }
+      if (!__any_sync(full, active != 0u)) break;
+    }
+    // (c) stage the chunk's DEM window (kWinH rows x kWinW columns) in this warp's shared-memory
+    // buffer with TMA bulk copies -- one 208 B row per lane, all in flight together, completion on
+    // the warp's mbarrier -- then sample it: a sample is LDS [idx + i * row pitch].
+    // (Tensor-map TMA, UTMALDG, raises "illegal instruction" on this pool's driver even for the
+    // libcu++ reference example -- scratch/tma_tensor_repro.cu -- hence row-wise UBLKCP.)
+    const int x_buf = cmin + kDemApron;                    // column of the window origin in the buffer
+    const int x_al = x_buf & ~3;                           // 16-byte aligned source address
+    const int shift = x_buf - x_al;
+    __syncwarp();                                          // every lane is done with the previous window
+    if (lane == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(win_bar, kWinW * kWinH * (unsigned)sizeof(float));
+    }
+    __syncwarp();
+    if (lane < kWinH) {
+      const float* src = dem + ((long long)(rmin + lane) * dem_pitch + (x_al - kDemApron));
+      tma_bulk_g2s(win + lane * kWinW, src, kWinW * (unsigned)sizeof(float), win_bar);
+    }
+    // offsets of this lane's step of the chunk (lanes >= kRayChunk are not read)
     const int kl = k + lane;
     const int ro_l = (kl * s.dr_fix + 32768) >> 16;
     const int co_l = (kl * s.dc_fix + 32768) >> 16;
-    const int ro_a = __shfl_sync(full, ro_l, 0), ro_b = __shfl_sync(full, ro_l, kRayChunk - 1);
-    const int co_a = __shfl_sync(full, co_l, 0), co_b = __shfl_sync(full, co_l, kRayChunk - 1);
-    const float kdz_a = __fmul_rn((float)k, s.dz);
-    // (a) retire rays: outside the grid at the chunk's first step, or above the DEM maximum
-    float zl = INFINITY;
+    const int ab_l = (ro_l - ro_min) * kWinW + (co_l - co_min) + shift;
+    mbar_wait(win_bar, win_phase);
+    win_phase ^= 1u;
+    float over[K];                                         // max over the chunk of (sample - ray height)
 #pragma unroll
-    for (int i = 0; i < K; ++i) {
-      const unsigned bit = 1u << i;
-      const float zk = __fadd_rn(z0[i], kdz_a);
-      const bool in = (unsigned)(row[i] + ro_a) < (unsigned)rows_full && (unsigned)(col[i] + co_a) < (unsigned)cols;
-      if (!in || zk > zmax) active &= ~bit;
-      if (active & bit) zl = fminf(zl, zk);
-    }
-    if (!__any_sync(full, active != 0u)) break;
-    const int zlow_key = __reduce_min_sync(full, float_key(zl));
-    // (b) can the chunk hit anything?  max of the DEM blocks under the chunk's swept bounding box
-    const int rmin = r_lo + min(ro_a, ro_b), rmax = r_hi + max(ro_a, ro_b);
-    const int cmin = c_lo + min(co_a, co_b), cmax = c_hi + max(co_a, co_b);
-    const int br0 = rmin >> 5, br1 = rmax >> 5, bc0 = cmin >> 5, bc1 = cmax >> 5;
-    float m = -INFINITY;
-    {
-      // up to 4 x 8 blocks, one per lane (a chunk of 32 steps spans at most 3 x 7)
-      const int br = br0 + (lane >> 3), bc = bc0 + (lane & 7);
-      if (br <= br1 && bc <= bc1) {
-        const int cr = min(max(br, -1), nbr), cc = min(max(bc, -1), nbc);
-        m = __ldg(blockmax + (size_t)(cr + 1) * (nbc + 2) + (cc + 1));
-      }
-    }
-    const int region_key = __reduce_max_sync(full, float_key(m));
-    if (zlow_key > region_key) continue;     // nothing in reach is as high as the lowest ray
-    // (c) sample the chunk
-    const int off_l = ro_l * dem_pitch + co_l;
-    unsigned hit = 0u;
+    for (int i = 0; i < K; ++i) over[i] = -INFINITY;
 #pragma unroll 4
     for (int j = 0; j < kRayChunk; ++j) {
-      const int off = __shfl_sync(full, off_l, j);
+      const int ab = __shfl_sync(full, ab_l, j) + lane;
       const float kdz = __fmul_rn((float)(k + j), s.dz);
+      const float* p = win + ab;
 #pragma unroll
       for (int i = 0; i < K; ++i) {
-        const float smp = __ldg(dem + (base[i] + off));
+        const float smp = p[i * kWinW];
         const float zk = __fadd_rn(z0[i], kdz);
-        hit |= (smp > zk) ? (1u << i) : 0u;
+        // smp > zk  <=>  smp - zk > 0 (IEEE subtraction keeps the sign; NaN samples never count)
+        over[i] = fmaxf(over[i], __fsub_rn(smp, zk));
       }
     }
+    unsigned hit = 0u;
+#pragma unroll
+    for (int i = 0; i < K; ++i) hit |= (over[i] > 0.0f) ? (1u << i) : 0u;
     // samples of a retired ray do not count: it left the grid or cleared the terrain before
     hit &= active;
     lit &= ~hit;
     active &= ~hit;
+    if (!__any_sync(full, active != 0u)) break;
+    z0min = lowest(active);
+    k += kRayChunk;
   }
   return lit;
 }
@@ -499,22 +580,36 @@ struct SmemLayout {
 #define ENRGY_MINB64 2
 #endif
 
+template <typename R>
+constexpr int kSmemCommon = (int)((sizeof(SmemLayout<R>) + 127) / 128 * 128);
+template <typename R, int INSOL>
+constexpr int kSmemTotal = kSmemCommon<R> + (INSOL == kInsolShadow ? kWarps * kWinBytes + kWarps * 8 : 0);
+
 template <typename R, int K, int INSOL, bool DUMP>
 __global__ void __launch_bounds__(kThreads, sizeof(R) == 4 ? ENRGY_MINB32 : ENRGY_MINB64)
 energy_balance_kernel(const KernelArgs<R> a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemLayout<R>& sm = *reinterpret_cast<SmemLayout<R>*>(smem_raw);
-  constexpr int TILE_H = kWarps * (K / 4);
+  // shading only: one DEM window + one mbarrier per warp, behind the common layout
+  float* win_base = reinterpret_cast<float*>(smem_raw + kSmemCommon<R>);
+  uint64_t* win_bars = reinterpret_cast<uint64_t*>(smem_raw + kSmemCommon<R> + kWarps * kWinBytes);
+  constexpr int TILE_H = (kWarps / 4) * K;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const R qnan = (R)__int_as_float(0x7fc00000);
 
   if (tid == 0) {
     mbar_init(&sm.full[0], 1);
     mbar_init(&sm.full[1], 1);
+    if (INSOL == kInsolShadow) {
+      for (int w = 0; w < kWarps; ++w) mbar_init(&win_bars[w], 1);
+    }
     fence_mbar_init();
   }
   __syncthreads();
   unsigned phase[2] = {0u, 0u};
+  unsigned win_phase = 0u;
+  float* const my_win = win_base + (size_t)(tid >> 5) * (kWinBytes / sizeof(float));
+  uint64_t* const my_win_bar = &win_bars[tid >> 5];
 
   const bool use_shades = INSOL == kInsolShadow;
   auto issue_block = [&](int b, int buf) {
@@ -553,8 +648,10 @@ energy_balance_kernel(const KernelArgs<R> a) {
     int cur_pair = -1;
 #pragma unroll
     for (int i = 0; i < K; ++i) {
-      rowb[i] = tile.x * TILE_H + warp + kWarps * (i >> 2);
-      col[i] = tile.y * kTileW + lane + 32 * (i & 3);
+      // a warp owns a compact 32-column x K-row patch (lane = column): every raster access is one
+      // coalesced 128 B line per row, and the patch keeps the shading bounding box tight
+      rowb[i] = tile.x * TILE_H + (warp >> 2) * K + i;
+      col[i] = tile.y * kTileW + (warp & 3) * 32 + lane;
       rowf[i] = rowb[i] + a.band_row0;
       const size_t o = (size_t)rowb[i] * a.pitch + col[i];
       const bool inside = rowb[i] < a.band_rows && col[i] < a.cols;
@@ -658,8 +755,8 @@ energy_balance_kernel(const KernelArgs<R> a) {
                   if (!(c > (R)0)) start_bits &= ~(1u << i);
                 }
               }
-              lit = march<K>(a.dem, a.dem_pitch, a.rows_full, a.cols, a.blockmax, a.nbr, a.nbc, rowf, col,
-                             z0, start_bits, sm.shades[buf][j], (float)a.zmax, lane);
+              lit = march<K>(a.dem, a.dem_pitch, my_win, my_win_bar, win_phase, a.rows_full, a.cols, a.blockmax,
+                             a.pyramid, rowf, col, z0, start_bits, sm.shades[buf][j], (float)a.zmax, lane);
               if (DUMP && a.mask_out != nullptr && t == a.t0) {
 #pragma unroll
                 for (int i = 0; i < K; ++i) {
@@ -816,7 +913,7 @@ struct CellsPerThread {
 template <typename R>
 int energy_balance_tile_h(int insol) {
   (void)insol;
-  return kWarps * (CellsPerThread<R, 0>::value / 4);
+  return (kWarps / 4) * CellsPerThread<R, 0>::value;
 }
 template int energy_balance_tile_h<float>(int);
 template int energy_balance_tile_h<double>(int);
@@ -825,7 +922,7 @@ template <typename R, int INSOL, bool DUMP>
 static cudaError_t configure(int sm_count, LaunchInfo* info) {
   constexpr int K = CellsPerThread<R, INSOL>::value;
   auto kern = energy_balance_kernel<R, K, INSOL, DUMP>;
-  const int smem = (int)sizeof(SmemLayout<R>);
+  const int smem = kSmemTotal<R, INSOL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
@@ -844,8 +941,8 @@ static cudaError_t configure(int sm_count, LaunchInfo* info) {
 }
 
 template <typename R, int INSOL, bool DUMP>
-static cudaError_t launch_one(const KernelArgs<R>& a, int sm_count, int forced_grid, LaunchInfo* info,
-                              cudaStream_t stream) {
+static cudaError_t launch_one(const KernelArgs<R>& a, const void* dem_map, int sm_count, int forced_grid,
+                              LaunchInfo* info, cudaStream_t stream) {
   constexpr int K = CellsPerThread<R, INSOL>::value;
   LaunchInfo li;
   cudaError_t e = configure<R, INSOL, DUMP>(sm_count, &li);
@@ -854,6 +951,7 @@ static cudaError_t launch_one(const KernelArgs<R>& a, int sm_count, int forced_g
   li.grid = grid;
   if (info) *info = li;
   if (a.n_tiles == 0 || a.t1 <= a.t0) return cudaSuccess;
+  (void)dem_map;
   energy_balance_kernel<R, K, INSOL, DUMP><<<grid, kThreads, li.smem_bytes, stream>>>(a);
   return cudaGetLastError();
 }
@@ -873,19 +971,19 @@ template cudaError_t energy_balance_grid<float>(int, bool, int, LaunchInfo*);
 template cudaError_t energy_balance_grid<double>(int, bool, int, LaunchInfo*);
 
 template <typename R>
-cudaError_t launch_energy_balance(const KernelArgs<R>& a, int insol, bool dump, int sm_count,
-                                  int forced_grid, LaunchInfo* info, cudaStream_t stream) {
+cudaError_t launch_energy_balance(const KernelArgs<R>& a, const void* dem_map, int insol, bool dump,
+                                  int sm_count, int forced_grid, LaunchInfo* info, cudaStream_t stream) {
   if (dump) {
-    if (insol == 0) return launch_one<R, 0, true>(a, sm_count, forced_grid, info, stream);
-    if (insol == 1) return launch_one<R, 1, true>(a, sm_count, forced_grid, info, stream);
-    return launch_one<R, 2, true>(a, sm_count, forced_grid, info, stream);
+    if (insol == 0) return launch_one<R, 0, true>(a, dem_map, sm_count, forced_grid, info, stream);
+    if (insol == 1) return launch_one<R, 1, true>(a, dem_map, sm_count, forced_grid, info, stream);
+    return launch_one<R, 2, true>(a, dem_map, sm_count, forced_grid, info, stream);
   }
-  if (insol == 0) return launch_one<R, 0, false>(a, sm_count, forced_grid, info, stream);
-  if (insol == 1) return launch_one<R, 1, false>(a, sm_count, forced_grid, info, stream);
-  return launch_one<R, 2, false>(a, sm_count, forced_grid, info, stream);
+  if (insol == 0) return launch_one<R, 0, false>(a, dem_map, sm_count, forced_grid, info, stream);
+  if (insol == 1) return launch_one<R, 1, false>(a, dem_map, sm_count, forced_grid, info, stream);
+  return launch_one<R, 2, false>(a, dem_map, sm_count, forced_grid, info, stream);
 }
-template cudaError_t launch_energy_balance<float>(const KernelArgs<float>&, int, bool, int, int, LaunchInfo*, cudaStream_t);
-template cudaError_t launch_energy_balance<double>(const KernelArgs<double>&, int, bool, int, int, LaunchInfo*, cudaStream_t);
+template cudaError_t launch_energy_balance<float>(const KernelArgs<float>&, const void*, int, bool, int, int, LaunchInfo*, cudaStream_t);
+template cudaError_t launch_energy_balance<double>(const KernelArgs<double>&, const void*, int, bool, int, int, LaunchInfo*, cudaStream_t);
 
 // =================================================================================================
 // micro-benchmarks: the pipe peaks the roofline is quoted against

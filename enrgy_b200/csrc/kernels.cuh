@@ -11,6 +11,14 @@ constexpr int kInsolStreamed = 0;  // per-step kWh m-2 raster streamed from HBM
 constexpr int kInsolComputed = 1;  // terrain normal . sun vector per sub-step, no shadows
 constexpr int kInsolShadow = 2;    // ... with the ray-marched sunlit mask
 
+// Max pyramid of the DEM: level l holds the max of the valid cells of every (16 << l)^2 block as
+// [(nbr + 2)][(nbc + 2)] floats with one ring of -inf blocks, at offset off[l] of one buffer.
+constexpr int kMaxPyramidLevels = 10;
+struct MaxPyramid {
+  int levels;
+  int off[kMaxPyramidLevels], nbr[kMaxPyramidLevels], nbc[kMaxPyramidLevels];
+};
+
 template <typename R>
 struct KernelArgs {
   // geometry (padded device rasters; pitch is a multiple of kTileW, padding cells hold NaN)
@@ -20,8 +28,8 @@ struct KernelArgs {
   const float* dem;               // full DEM (replicated for shading), pointing at cell (0, 0) of a
                                   // buffer with a NaN apron of kDemApron cells on every side
   int dem_pitch;                  // row stride of the DEM buffer
-  const float* blockmax;          // max of the valid DEM per 32x32 block, [(nbr + 2)][(nbc + 2)],
-  int nbr, nbc;                   //   one ring of -inf blocks around it (shading early exit)
+  const float* blockmax;          // max pyramid of the DEM (shading early exit), see MaxPyramid
+  MaxPyramid pyramid;
   const R* nx;                    // [band_rows_pad][pitch] terrain normal (computed insolation)
   const R* ny;
   const R* nz;
@@ -77,8 +85,8 @@ template <typename R>
 cudaError_t launch_terrain(const float* dem, int dem_pitch, int rows_full, int cols, int pitch,
                            int band_row0, int band_rows_pad, double cell, R* nx, R* ny, R* nz,
                            cudaStream_t stream);
-cudaError_t launch_blockmax(const float* dem, int dem_pitch, int rows_full, int cols, int nbr, int nbc,
-                            float* blockmax, cudaStream_t stream);
+cudaError_t launch_blockmax(const float* dem, int dem_pitch, int rows_full, int cols, const MaxPyramid& py,
+                            float* buffer, cudaStream_t stream);
 cudaError_t launch_tile_scan(const float* dem, int pitch, int band_row0, int band_rows, int cols,
                              int tile_h, int tiles_r, int tiles_c, int* counts, cudaStream_t stream);
 cudaError_t launch_mask_check(const float* dem, int dem_pitch, const float* other, int pitch,
@@ -100,8 +108,8 @@ struct LaunchInfo {
   int regs, smem_bytes, ctas_per_sm, grid, cells_per_thread;
 };
 template <typename R>
-cudaError_t launch_energy_balance(const KernelArgs<R>& a, int insol, bool dump, int sm_count,
-                                  int forced_grid, LaunchInfo* info, cudaStream_t stream);
+cudaError_t launch_energy_balance(const KernelArgs<R>& a, const void* reserved, int insol, bool dump,
+                                  int sm_count, int forced_grid, LaunchInfo* info, cudaStream_t stream);
 template <typename R>
 int energy_balance_tile_h(int insol);
 template <typename R>

@@ -133,7 +133,7 @@ def compare_run(case, f64, pot=None, computed=False, shadow=False, **kw):
         point = eng.point_scalars()
     finally:
         eng.close()
-    ff, mfl, tfl = (1e-3, 1e-8, 1e-6) if f64 else (1.0, 1e-3, 1e-3)
+    ff, mfl, tfl = (1e-3, 1e-7, 1e-6) if f64 else (1.0, 1e-3, 1e-3)
     res = {}
     off = np.isnan(case.dem)
     for name in FLUX_FIELDS:

@@ -2,7 +2,7 @@
 
 Bars (BASELINE.json north_star): float64 mode 1e-9 relative, float32 mode 1e-4 relative, relative
 error taken against max(|ref|, floor) because fluxes cross zero:
-floor = 1e-3 W m-2 (f64) / 1 W m-2 (f32) for fluxes, 1e-8 / 1e-3 m w.e. for per-step melt (the
+floor = 1e-3 W m-2 (f64) / 1 W m-2 (f32) for fluxes, 1e-7 / 1e-3 m w.e. for per-step melt (the
 last snow of a cell melts as `swe` itself, a float32 state of magnitude 0.5 m whose spacing is
 3e-8 m), 1e-6 / 1e-3 m w.e. for season totals.
 """
