@@ -430,7 +430,7 @@ __device__ __forceinline__ float key_float(int k) {
 // without per-sample bounds checks.
 template <int K>
 __device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem_pitch, float* win,
-                                          uint64_t* win_bar, unsigned& win_phase, int rows_full, int cols,
+                                          int rows_full, int cols,
                                           const float* __restrict__ pyr, const MaxPyramid& py,
                                           const int (&row)[K], const int (&col)[K], const float (&z0)[K],
                                           unsigned start_bits, const ShadeRec s, float zmax, int lane) {
@@ -499,31 +499,39 @@ __device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem
       }
       if (!__any_sync(full, active != 0u)) break;
     }
-    // (c) stage the chunk's DEM window (kWinH rows x kWinW columns) in this warp's shared-memory
-    // buffer with TMA bulk copies -- one 208 B row per lane, all in flight together, completion on
-    // the warp's mbarrier -- then sample it: a sample is LDS [idx + i * row pitch].
-    // (Tensor-map TMA, UTMALDG, raises "illegal instruction" on this pool's driver even for the
-    // libcu++ reference example -- scratch/tma_tensor_repro.cu -- hence row-wise UBLKCP.)
+    // (c) stage the chunk's DEM window (kWinH rows x kWinW columns, 16-byte aligned origin) in this
+    // warp's shared-memory buffer with asynchronous 16 B copies (cp.async / LDGSTS: 10 per lane, no
+    // registers, all in flight together), then sample it: a sample is LDS [idx + i * row pitch].
+    // Measured alternatives (profiles/r01_summary.md): direct L1 loads cost 7 instructions per
+    // sample against 4 here; one TMA bulk copy per row (UBLKCP) serialises 24 single-lane issues
+    // per window; tensor-map TMA (UTMALDG) raises "illegal instruction" on this pool's driver even
+    // for the libcu++ reference example (scratch/tma_tensor_repro.cu).
     const int x_buf = cmin + kDemApron;                    // column of the window origin in the buffer
     const int x_al = x_buf & ~3;                           // 16-byte aligned source address
     const int shift = x_buf - x_al;
     __syncwarp();                                          // every lane is done with the previous window
-    if (lane == 0) {
-      fence_proxy_async();
-      mbar_expect_tx(win_bar, kWinW * kWinH * (unsigned)sizeof(float));
-    }
-    __syncwarp();
-    if (lane < kWinH) {
-      const float* src = dem + ((long long)(rmin + lane) * dem_pitch + (x_al - kDemApron));
-      tma_bulk_g2s(win + lane * kWinW, src, kWinW * (unsigned)sizeof(float), win_bar);
+    {
+      constexpr int kChunksPerRow = kWinW / 4;             // 13 x 16 B
+      const float* src0 = dem + ((long long)rmin * dem_pitch + (x_al - kDemApron));
+#pragma unroll
+      for (int q0 = 0; q0 < kWinH * kChunksPerRow; q0 += 32) {
+        const int q = q0 + lane;
+        if (q < kWinH * kChunksPerRow) {
+          const int r = q / kChunksPerRow, cc = q - r * kChunksPerRow;
+          const float* src = src0 + ((long long)r * dem_pitch + cc * 4);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(win + r * kWinW + cc * 4)), "l"(src)
+                       : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
     // offsets of this lane's step of the chunk (lanes >= kRayChunk are not read)
     const int kl = k + lane;
     const int ro_l = (kl * s.dr_fix + 32768) >> 16;
     const int co_l = (kl * s.dc_fix + 32768) >> 16;
     const int ab_l = (ro_l - ro_min) * kWinW + (co_l - co_min) + shift;
-    mbar_wait(win_bar, win_phase);
-    win_phase ^= 1u;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
     float over[K];                                         // max over the chunk of (sample - ray height)
 #pragma unroll
     for (int i = 0; i < K; ++i) over[i] = -INFINITY;
@@ -583,16 +591,16 @@ struct SmemLayout {
 template <typename R>
 constexpr int kSmemCommon = (int)((sizeof(SmemLayout<R>) + 127) / 128 * 128);
 template <typename R, int INSOL>
-constexpr int kSmemTotal = kSmemCommon<R> + (INSOL == kInsolShadow ? kWarps * kWinBytes + kWarps * 8 : 0);
+constexpr int kSmemTotal = kSmemCommon<R> + (INSOL == kInsolShadow ? kWarps * kWinBytes : 0);
 
 template <typename R, int K, int INSOL, bool DUMP>
 __global__ void __launch_bounds__(kThreads, sizeof(R) == 4 ? ENRGY_MINB32 : ENRGY_MINB64)
 energy_balance_kernel(const KernelArgs<R> a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemLayout<R>& sm = *reinterpret_cast<SmemLayout<R>*>(smem_raw);
-  // shading only: one DEM window + one mbarrier per warp, behind the common layout
+  // shading only: one DEM window per warp, behind the common layout
   float* win_base = reinterpret_cast<float*>(smem_raw + kSmemCommon<R>);
-  uint64_t* win_bars = reinterpret_cast<uint64_t*>(smem_raw + kSmemCommon<R> + kWarps * kWinBytes);
+
   constexpr int TILE_H = (kWarps / 4) * K;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const R qnan = (R)__int_as_float(0x7fc00000);
@@ -600,16 +608,11 @@ energy_balance_kernel(const KernelArgs<R> a) {
   if (tid == 0) {
     mbar_init(&sm.full[0], 1);
     mbar_init(&sm.full[1], 1);
-    if (INSOL == kInsolShadow) {
-      for (int w = 0; w < kWarps; ++w) mbar_init(&win_bars[w], 1);
-    }
     fence_mbar_init();
   }
   __syncthreads();
   unsigned phase[2] = {0u, 0u};
-  unsigned win_phase = 0u;
   float* const my_win = win_base + (size_t)(tid >> 5) * (kWinBytes / sizeof(float));
-  uint64_t* const my_win_bar = &win_bars[tid >> 5];
 
   const bool use_shades = INSOL == kInsolShadow;
   auto issue_block = [&](int b, int buf) {
@@ -755,7 +758,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
                   if (!(c > (R)0)) start_bits &= ~(1u << i);
                 }
               }
-              lit = march<K>(a.dem, a.dem_pitch, my_win, my_win_bar, win_phase, a.rows_full, a.cols, a.blockmax,
+              lit = march<K>(a.dem, a.dem_pitch, my_win, a.rows_full, a.cols, a.blockmax,
                              a.pyramid, rowf, col, z0, start_bits, sm.shades[buf][j], (float)a.zmax, lane);
               if (DUMP && a.mask_out != nullptr && t == a.t0) {
 #pragma unroll
