@@ -85,7 +85,10 @@ struct enrgy_ctx {
   int dem_pitch = 0;
   MaxPyramid pyramid{};
   float* dem0 = nullptr;          // cell (0, 0) inside the apron buffer
-  DevBuf<unsigned char> d_nx, d_ny, d_nz, d_swe, d_ts, d_ti, d_dump, d_stage, d_snap;
+  DevBuf<unsigned char> d_nx, d_ny, d_nz, d_swe, d_ts, d_ti, d_dump, d_stage, d_snap, d_layer_t;
+  bool have_msm = false;
+  std::vector<double> alb_aws, layer_t_aws;
+  double swe_aws = 0.0;
   bool snap_valid = false, snap_advanced = false;
   int n_maps = 0;
   int pot_t0 = 0, pot_n = 0;
@@ -213,6 +216,17 @@ int fill_args(enrgy_ctx* c, int t0, int t1, KernelArgs<R>& a) {
   a.zmax = (R)c->pre.zmax;
   a.swe = (R*)c->d_swe.p; a.total_snow = (R*)c->d_ts.p; a.total_ice = (R*)c->d_ti.p;
   a.pot = c->d_pot.p; a.pot_stride = c->band_elems; a.pot_t0 = c->pot_t0;
+  a.layer_t = (R*)c->d_layer_t.p;
+  a.layer_stride = c->band_elems;
+  a.msm.layers = c->p.msm_layers;
+  for (int l = 0; l < kMaxLayers; ++l) {
+    const double d = l < c->p.msm_layers ? c->p.msm_depths[l] : 1.0;
+    a.msm.d[l] = (R)d;
+    a.msm.inv_d[l] = (R)(1.0 / d);
+  }
+  a.msm.c_ice = (R)kCice; a.msm.k_ice = (R)kKappaIce; a.msm.k_snow = (R)kKappaSnow;
+  a.msm.rho_ice = (R)c->p.ice_density; a.msm.rho_snow = (R)c->p.snow_density;
+  a.msm.inv_snow_density = (R)(1.0 / c->p.snow_density);
   a.steps = (const StepRec<R>*)c->d_steps.p;
   a.subs = (const SubRec<R>*)c->d_subs.p;
   a.shades = c->d_shades.p;
@@ -237,6 +251,7 @@ int check_run_ready(enrgy_ctx* c, int t0, int t1) {
   if (!c->have_dem || !c->prepass_done) return fail(ENRGY_ERR_ARG, "set_dem / set_forcing / prepass must precede run");
   if (t0 < 0 || t1 > c->n_steps || t0 > t1) return fail(ENRGY_ERR_ARG, "step range [%d, %d) outside [0, %d)", t0, t1, c->n_steps);
   if (!c->p.albedo_const && c->n_maps == 0) return fail(ENRGY_ERR_ARG, "albedo maps not set");
+  if (c->p.msm_layers > 0 && !c->have_msm) return fail(ENRGY_ERR_ARG, "enrgy_set_msm must precede run when msm_layers > 0");
   if (c->p.insol_mode == ENRGY_INSOL_STREAMED && t1 > t0 &&
       (t0 < c->pot_t0 || t1 > c->pot_t0 + c->pot_n)) {
     return fail(ENRGY_ERR_ARG, "insolation rasters resident for steps [%d, %d), run asks [%d, %d)",
@@ -251,11 +266,12 @@ int run_typed(enrgy_ctx* c, int t0, int t1, double* d_stats, cudaStream_t stream
   fill_args<R>(c, t0, t1, a);
   const int insol = insol_variant(c);
   LaunchInfo li;
-  CU_TRY(energy_balance_grid<R>(insol, false, c->sm_count, &li));
+  const bool msm = c->p.msm_layers > 0;
+  CU_TRY(energy_balance_grid<R>(insol, msm, false, c->sm_count, &li));
   int grid = std::min(li.grid, std::max(c->n_tiles, 1));
   const int n = t1 - t0;
-  CU_TRY(c->d_partials.alloc((size_t)grid * std::max(n, 1) * kStatsK));
-  CU_TRY(cudaMemsetAsync(c->d_partials.p, 0, (size_t)grid * std::max(n, 1) * kStatsK * sizeof(double), stream));
+  CU_TRY(c->d_partials.alloc((size_t)grid * std::max(n, 1) * kStatsP));
+  CU_TRY(cudaMemsetAsync(c->d_partials.p, 0, (size_t)grid * std::max(n, 1) * kStatsP * sizeof(double), stream));
   a.partials = c->d_partials.p;
   if (n > 0 && !c->state_advanced) {
     CU_TRY(launch_nan_offglacier<R>(c->dem0, c->dem_pitch, c->pitch, c->band_row0, c->band_rows, c->cols, a.swe,
@@ -270,7 +286,7 @@ int run_typed(enrgy_ctx* c, int t0, int t1, double* d_stats, cudaStream_t stream
   if (d_stats && n > 0) {
     FinalizeArgs f{};
     f.partials = c->d_partials.p; f.n_ctas = grid; f.n_steps = n; f.t0 = t0;
-    f.n_valid = c->n_valid; f.f32_mode = c->precision == ENRGY_F32;
+    f.n_valid = c->n_valid; f.f32_mode = c->precision == ENRGY_F32; f.msm = msm ? 1 : 0;
     f.steps64 = c->d_steps64.p; f.stats = d_stats;
     f.override_first = (t0 == 0 && !c->state_advanced) ? 1 : 0;
     f.swe0_sum = c->swe0_sum; f.swe0_nsnow = c->swe0_nsnow; f.swe0_nvalid = c->swe0_nvalid;
@@ -383,7 +399,7 @@ int enrgy_destroy(enrgy_ctx* c) {
   c->d_ti.release(); c->d_dump.release(); c->d_stage.release(); c->d_steps.release(); c->d_subs.release();
   c->d_steps64.release(); c->d_shades.release(); c->d_blocks.release(); c->d_tiles.release();
   c->d_counts.release(); c->d_partials.release(); c->d_stats.release(); c->d_small.release();
-  c->d_counters.release(); c->d_masks.release(); c->d_snap.release(); c->d_blockmax.release();
+  c->d_counters.release(); c->d_masks.release(); c->d_snap.release(); c->d_blockmax.release(); c->d_layer_t.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -411,14 +427,19 @@ int enrgy_set_params(enrgy_ctx* c, const enrgy_params* pin) {
   if (!(p.cell_size > 0)) return fail(ENRGY_ERR_ARG, "cell_size must be > 0");
   if (!(p.sensor_z > 0) || !(p.zm > 0) || !(p.z_h_or_e > 0)) return fail(ENRGY_ERR_ARG, "sensor_z, zm, z_h_or_e must be > 0");
   if (p.msm_layers < 0 || p.msm_layers > ENRGY_MAX_LAYERS - 1) return fail(ENRGY_ERR_ARG, "msm_layers outside 0..%d", ENRGY_MAX_LAYERS - 1);
-  if (p.msm_layers > 0) return fail(ENRGY_ERR_ARG, "sub-surface model (msm) is not built into this round's kernels");
+  if (p.msm_layers > kMaxLayers) return fail(ENRGY_ERR_ARG, "msm_layers > %d", kMaxLayers);
+  for (int l = 0; l < p.msm_layers; ++l) {
+    if (!(p.msm_depths[l] > 0)) return fail(ENRGY_ERR_ARG, "msm layer %d: thickness must be > 0 (zero-thickness layers never occur in the reference's model path: update_layers is not called, msm.py:300)", l);
+  }
   if (p.insol_mode != ENRGY_INSOL_STREAMED && p.insol_mode != ENRGY_INSOL_COMPUTED) return fail(ENRGY_ERR_ARG, "bad insol_mode");
   if (p.band_rows == 0) { p.band_row0 = 0; p.band_rows = c->rows; }
   if (p.band_row0 < 0 || p.band_rows < 0 || p.band_row0 + p.band_rows > c->rows) return fail(ENRGY_ERR_ARG, "row band outside the raster");
   c->p = p;
   c->band_row0 = p.band_row0;
   c->band_rows = p.band_rows;
-  c->tile_h = c->precision == ENRGY_F32 ? energy_balance_tile_h<float>(0) : energy_balance_tile_h<double>(0);
+  c->tile_h = c->precision == ENRGY_F32 ? energy_balance_tile_h<float>(p.msm_layers > 0)
+                                        : energy_balance_tile_h<double>(p.msm_layers > 0);
+  c->have_msm = false;
   c->band_rows_pad = round_up(std::max(c->band_rows, 1), 16);
   c->band_elems = (size_t)c->band_rows_pad * c->pitch;
   c->have_params = true;
@@ -522,6 +543,14 @@ int enrgy_set_albedo_maps(enrgy_ctx* c, int n_maps, const float* const* maps) {
     if (int e = check_mask(c, dst, "albedo map", false)) return e;
   }
   c->n_maps = n_maps;
+  {
+    const int ar = c->p.aws_row - c->band_row0;
+    c->alb_aws.clear();
+    if (ar >= 0 && ar < c->band_rows) {
+      for (int m = 0; m < n_maps; ++m) c->alb_aws.push_back((double)maps[m][(size_t)ar * c->cols + c->p.aws_col]);
+    }
+  }
+  c->prepass_done = false;
   return ENRGY_OK;
 }
 
@@ -532,9 +561,16 @@ int enrgy_set_swe(enrgy_ctx* c, const float* swe) {
   if (!swe) {
     CU_TRY(cudaMemsetAsync(c->d_swe.p, 0, c->band_elems * rs, c->stream));
     c->swe0_sum = 0.0; c->swe0_nsnow = 0.0; c->swe0_nvalid = (double)c->band_rows * c->cols;
+    c->swe_aws = 0.0;
+    c->prepass_done = false;
     CU_TRY(cudaStreamSynchronize(c->stream));
     return ENRGY_OK;
   }
+  {
+    const int ar = c->p.aws_row - c->band_row0;
+    if (ar >= 0 && ar < c->band_rows) c->swe_aws = (double)swe[(size_t)ar * c->cols + c->p.aws_col];
+  }
+  c->prepass_done = false;
   CU_TRY(c->d_tmp32.alloc(c->band_elems));
   if (int e = upload_padded(c, swe, c->band_rows, c->d_tmp32.p, c->band_rows_pad)) return e;
   if (int e = check_mask(c, c->d_tmp32.p, "SWE raster", false)) return e;
@@ -559,9 +595,38 @@ int enrgy_set_swe(enrgy_ctx* c, const float* swe) {
 }
 
 int enrgy_set_msm(enrgy_ctx* c, const double* temps, double elev) {
-  (void)temps; (void)elev;
   if (int e = use_device(c)) return e;
-  return fail(ENRGY_ERR_ARG, "sub-surface model (msm) is not built into this round's kernels");
+  if (!c->have_dem) return fail(ENRGY_ERR_ARG, "set_dem must precede set_msm");
+  const int nl = c->p.msm_layers;
+  if (nl <= 0) return fail(ENRGY_ERR_ARG, "msm_layers is 0 in the parameters");
+  if (!temps) return fail(ENRGY_ERR_ARG, "temps is null");
+  const size_t rs = rsize(c);
+  CU_TRY(c->d_layer_t.alloc((size_t)(nl + 1) * c->band_elems * rs));
+  if (c->precision == ENRGY_F32) {
+    CU_TRY(launch_msm_init<float>(c->dem0, c->dem_pitch, c->pitch, c->band_row0, c->band_rows_pad, nl + 1, temps,
+                                  elev, (float*)c->d_layer_t.p, c->band_elems, c->stream));
+  } else {
+    CU_TRY(launch_msm_init<double>(c->dem0, c->dem_pitch, c->pitch, c->band_row0, c->band_rows_pad, nl + 1, temps,
+                                   elev, (double*)c->d_layer_t.p, c->band_elems, c->stream));
+  }
+  c->launches++;
+  // the AWS cell's own boundary temperatures for the serial pre-pass, model.py:133-143
+  const float z = c->h_dem[(size_t)c->p.aws_row * c->cols + c->p.aws_col];
+  c->layer_t_aws.assign(nl + 1, 0.0);
+  for (int l = 0; l <= nl; ++l) {
+    double t;
+    if (c->precision == ENRGY_F32) {
+      const float d = z - (float)elev;
+      volatile float prod = d * -0.006f;
+      t = (double)((float)temps[l] + prod);
+    } else {
+      t = temps[l] + ((double)z - elev) * -0.006;
+    }
+    c->layer_t_aws[l] = t > 0 ? 0.0 : t;
+  }
+  c->have_msm = true;
+  c->prepass_done = false;
+  return ENRGY_OK;
 }
 
 int enrgy_set_forcing(enrgy_ctx* c, int n_steps, const double* forcing) {
@@ -611,6 +676,10 @@ int enrgy_prepass(enrgy_ctx* c) {
   in.p = c->p; in.precision = c->precision; in.rows = c->rows; in.cols = c->cols;
   in.dem = c->h_dem.data(); in.n_steps = c->n_steps; in.forcing = c->forcing.data();
   in.pot_aws = c->pot_aws.data();
+  in.alb_aws = c->alb_aws; in.swe_aws = c->swe_aws; in.layer_t_aws = c->layer_t_aws;
+  if (c->p.msm_layers > 0 && !c->have_msm) return fail(ENRGY_ERR_ARG, "enrgy_set_msm must precede prepass when msm_layers > 0");
+  if (c->p.msm_layers > 0 && !c->p.albedo_const && (int)c->alb_aws.size() != c->n_maps)
+    return fail(ENRGY_ERR_ARG, "the AWS cell lies outside this handle's row band: its albedo/SWE are needed for the sub-surface pre-pass");
   std::string err;
   const int rc = run_prepass(in, c->pre, err);
   if (rc != ENRGY_OK) return fail(rc, "%s", err.c_str());
@@ -752,9 +821,22 @@ int enrgy_set_state(enrgy_ctx* c, int dtype, const void* swe, const void* total_
 }
 
 int enrgy_get_layer_temps(enrgy_ctx* c, double* out) {
-  (void)out;
   if (int e = use_device(c)) return e;
-  return fail(ENRGY_ERR_ARG, "sub-surface model (msm) is not built into this round's kernels");
+  if (!c->have_msm) return fail(ENRGY_ERR_ARG, "the sub-surface model is not set up");
+  if (!out) return fail(ENRGY_ERR_ARG, "out is null");
+  const int nb = c->p.msm_layers + 1;
+  const size_t rs = rsize(c);
+  std::vector<unsigned char> h((size_t)nb * c->band_elems * rs);
+  CU_TRY(cudaMemcpyAsync(h.data(), c->d_layer_t.p, h.size(), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  for (int l = 0; l < nb; ++l)
+    for (int r = 0; r < c->band_rows; ++r)
+      for (int x = 0; x < c->cols; ++x) {
+        const size_t si = (size_t)l * c->band_elems + (size_t)r * c->pitch + x;
+        const double v = rs == 4 ? (double)((const float*)h.data())[si] : ((const double*)h.data())[si];
+        out[((size_t)l * c->band_rows + r) * c->cols + x] = v;
+      }
+  return ENRGY_OK;
 }
 
 int enrgy_snapshot(enrgy_ctx* c, int save) {
@@ -762,14 +844,17 @@ int enrgy_snapshot(enrgy_ctx* c, int save) {
   if (!c->have_dem) return fail(ENRGY_ERR_ARG, "no state before set_dem");
   const size_t bytes = c->band_elems * rsize(c);
   unsigned char* st[3] = {c->d_swe.p, c->d_ts.p, c->d_ti.p};
+  const size_t lbytes = c->have_msm ? (size_t)(c->p.msm_layers + 1) * bytes : 0;
   if (save) {
-    CU_TRY(c->d_snap.alloc(3 * bytes));
+    CU_TRY(c->d_snap.alloc(3 * bytes + lbytes));
+    if (lbytes) CU_TRY(cudaMemcpyAsync(c->d_snap.p + 3 * bytes, c->d_layer_t.p, lbytes, cudaMemcpyDeviceToDevice, c->stream));
     for (int q = 0; q < 3; ++q)
       CU_TRY(cudaMemcpyAsync(c->d_snap.p + q * bytes, st[q], bytes, cudaMemcpyDeviceToDevice, c->stream));
     c->snap_valid = true;
     c->snap_advanced = c->state_advanced;
   } else {
     if (!c->snap_valid) return fail(ENRGY_ERR_ARG, "no snapshot to restore");
+    if (lbytes) CU_TRY(cudaMemcpyAsync(c->d_layer_t.p, c->d_snap.p + 3 * bytes, lbytes, cudaMemcpyDeviceToDevice, c->stream));
     for (int q = 0; q < 3; ++q)
       CU_TRY(cudaMemcpyAsync(st[q], c->d_snap.p + q * bytes, bytes, cudaMemcpyDeviceToDevice, c->stream));
     c->state_advanced = c->snap_advanced;

@@ -34,6 +34,8 @@ constexpr int kThreads = 256;                 // 8 warps per CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kTileW = 128;                   // one warp row = 32 lanes x float4
 constexpr int kStatsK = 8;                    // statistics reduced in the kernel (see StatK)
+constexpr int kStatsM = 2;                    // + upward longwave and in-glacier flux with the sub-surface model
+constexpr int kStatsP = kStatsK + kStatsM;    // columns of a per-CTA partial row
 constexpr int kMaxStepsPerBlock = 64;         // time block: per-step records staged in smem
 constexpr int kMaxSubsPerBlock = 256;         // ... and their sunlit sub-steps
 constexpr int kDemApron = 64;                 // NaN cells around the DEM buffer: a ray-chunk window of a warp
@@ -44,8 +46,18 @@ constexpr int kMaxBlock = 16;                 // edge of the blocks of the DEM m
 // Statistics the kernel reduces per step (the rest of ENRGY_S_* is derived from these by
 // linearity in finalize_stats_kernel; DESIGN.md "Statistics").
 enum StatK { K_RS = 0, K_LWD, K_SENS, K_LAT, K_MELT, K_SNOW, K_SWE, K_NSNOW };
-// extra statistics when the sub-surface model is on
-enum StatM { M_LWU = 0, M_G, kStatsM };
+// extra statistics when the sub-surface model is on (columns kStatsK + ... of a partial row)
+enum StatM { M_LWU = 0, M_G };
+
+// sub-surface model constants (msm.py:42-46, var_classes.py:7-15), per run
+constexpr int kMaxLayers = 7;                 // layer thicknesses; boundaries = layers + 1
+template <typename R>
+struct MsmParams {
+  int layers;                                 // 0 = sub-surface model off
+  R d[kMaxLayers], inv_d[kMaxLayers];         // layer thicknesses [m] and their reciprocals
+  R c_ice, k_ice, k_snow, rho_ice, rho_snow;  // heat capacity, diffusivities, densities
+  R inv_snow_density;                         // snow depth = swe / snow_density (model.py:428, sic)
+};
 
 // ---- per-step record (16 values, staged per time block by a TMA bulk copy) ---------------------
 template <typename R>

@@ -22,6 +22,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <type_traits>
 
 #include "../../include/enrgy_b200.h"
 
@@ -85,6 +86,7 @@ struct Num<float> {
     return __fadd_rn(t, __fmul_rn(delta, g));
   }
   static __device__ __forceinline__ float pow10(float x) { return powf(10.0f, x); }
+  static __device__ __forceinline__ float exp_(float x) { return expf(x); }
   static __device__ __forceinline__ float rsqrt_(float x) { return 1.0f / sqrtf(x); }
 };
 template <>
@@ -94,6 +96,7 @@ struct Num<double> {
     return t + delta * g;
   }
   static __device__ __forceinline__ double pow10(double x) { return pow(10.0, x); }
+  static __device__ __forceinline__ double exp_(double x) { return exp(x); }
   static __device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }
 };
 
@@ -571,6 +574,7 @@ struct SmemLayout {
   SubRec<R> subs[2][kMaxSubsPerBlock];
   ShadeRec shades[2][kMaxSubsPerBlock];
   R slots[kWarps][kMaxStepsPerBlock][kStatsK];
+  R slots_m[kWarps][kMaxStepsPerBlock][kStatsM];
   uint64_t full[2];
 };
 
@@ -593,7 +597,7 @@ constexpr int kSmemCommon = (int)((sizeof(SmemLayout<R>) + 127) / 128 * 128);
 template <typename R, int INSOL>
 constexpr int kSmemTotal = kSmemCommon<R> + (INSOL == kInsolShadow ? kWarps * kWinBytes : 0);
 
-template <typename R, int K, int INSOL, bool DUMP>
+template <typename R, int K, int INSOL, bool MSM, bool DUMP>
 __global__ void __launch_bounds__(kThreads, sizeof(R) == 4 ? ENRGY_MINB32 : ENRGY_MINB64)
 energy_balance_kernel(const KernelArgs<R> a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -638,7 +642,8 @@ energy_balance_kernel(const KernelArgs<R> a) {
   };
 
   const int n_steps_run = a.t1 - a.t0;
-  double* my_partials = a.partials ? a.partials + (size_t)blockIdx.x * n_steps_run * kStatsK : nullptr;
+  double* my_partials = a.partials ? a.partials + (size_t)blockIdx.x * n_steps_run * kStatsP : nullptr;
+  constexpr int NB = MSM ? kMaxLayers + 1 : 1;       // boundary temperatures kept per cell
 
   for (int ti = blockIdx.x; ti < a.n_tiles; ti += gridDim.x) {
     const int2 tile = a.tiles[ti];
@@ -647,6 +652,11 @@ energy_balance_kernel(const KernelArgs<R> a) {
     R delta[K], pw[K], a0[K], da[K], nxv[K], nyv[K], nzv[K], swe[K], tsn[K], tic[K], wgt[K];
     float z0[K];
     int rowf[K];
+    R tl[K][NB];                   // sub-surface boundary temperatures [deg C] (MSM)
+    // The reference's top boundary turns float64 after its first tick (NEP 50: float32 array +
+    // float64 increment), so its round-off does not random-walk at float32 spacing; the float32
+    // kernel keeps that one temperature per cell as a float64 accumulator of float32 increments.
+    double t0_acc[MSM ? K : 1];
     unsigned valid_bits = 0;
     int cur_pair = -1;
 #pragma unroll
@@ -678,6 +688,13 @@ energy_balance_kernel(const KernelArgs<R> a) {
       tic[i] = v ? a.total_ice[o] : (R)0;
       a0[i] = a.albedo_const ? a.albedo_ice : (R)0.5;
       da[i] = (R)0;
+      if (MSM) {
+#pragma unroll
+        for (int l = 0; l < NB; ++l) {
+          tl[i][l] = (v && l <= a.msm.layers) ? a.layer_t[(size_t)l * a.layer_stride + o] : (R)0;
+        }
+        t0_acc[i] = (double)tl[i][0];
+      }
     }
 
     int buf = 0;
@@ -788,6 +805,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
 #pragma unroll
         for (int q = 0; q < kStatsK; ++q) acc[q] = (R)0;
         int n_snow = 0;
+        R acc_m[kStatsM] = {(R)0, (R)0};
         // albedo of snow-covered cells: the aged value when ageing is on, else the blended map
         // (uniform per step): alb_snow = alb * keep_map + snow_const
         const R keep_map = s.snow_alb >= (R)0 ? (R)0 : (R)1;
@@ -797,7 +815,17 @@ energy_balance_kernel(const KernelArgs<R> a) {
           // lapse-rate distribution, var_classes.py:113-125
           const R t_air = Num<R>::lapse(s.t_air, delta[i], s.lapse);
           const R tz = t_air + (R)273.15;
-          const R d_t = tz - (R)273.15;                     // Tz - Ts, Ts = 0 degC + 273.15
+          // surface temperature: 0 degC without the sub-surface model, else the top
+          // boundary of the layer stack (model.py:207-210)
+          const R ts_k = MSM ? tl[i][0] + (R)273.15 : (R)273.15;
+          R d_t = tz - ts_k;                                // Tz - Ts
+          if (MSM && sizeof(R) == 4) {
+            // float32 + sub-surface model: the reference's surface temperature raster turns
+            // float64 after the first tick, so its Tz - Ts is float32(Tz) - (t0 + 273.15) without
+            // a Kelvin rounding of Ts.  tz - 273.15f is exact (same binade); the second constant
+            // is float(273.15) - 273.15.
+            d_t = ((tz - (R)273.15) + (R)-6.103515625e-06) - tl[i][0];
+          }
           const R p_hpa = s.p_hpa + delta[i] * (R)kPressureLapse;
           const R e = s.e_aws * pw[i];
           // bulk fluxes, turbo.py:140-196 with rho = P / (R Tz) and rho / P = 1 / (R Tz);
@@ -817,11 +845,28 @@ energy_balance_kernel(const KernelArgs<R> a) {
           // saturation vapour pressure of the melting surface, turbo.py:368-379 with t = 0:
           // exp(0) = 1 exactly, so es = 611.2 * f(p).  ez = e_max * (e / e_max) = e (one rounding).
           const R f_p = (R)1.0016 + (R)(3.15 * 1e-6) * p_hpa - (R)0.074 * r_p;
-          const R lat = (s.c_lat * r_rt) * (e - (R)611.2 * f_p);
+          R es_t = (R)611.2;
+          if (MSM) {                                        // Magnus term of the surface, turbo.py:377
+            const R t0 = tl[i][0];
+            es_t = (R)611.2 * Num<R>::exp_(((R)17.62 * t0) / ((R)243.12 + t0));
+          }
+          const R lat = (s.c_lat * r_rt) * (e - es_t * f_p);
           // longwave, model.py:533-545
           const R tz2 = tz * tz;
           const R lwd = s.c_lwd * (tz2 * tz2);
-          const R lwu = s.c_lwu;
+          R lwu = s.c_lwu;
+          if (MSM) {
+            if (sizeof(R) == 4) {
+              // (273.15 + t0)^4 = 273.15^4 (1 + x)^4, x = t0 / 273.15: keeps the low bits of t0 that
+              // a float32 Kelvin temperature would drop
+              const R x = tl[i][0] * (R)(1.0 / 273.15);
+              const R poly = (R)1 + x * ((R)4 + x * ((R)6 + x * ((R)4 + x)));
+              lwu = (s.c_lwu * (R)(273.15 * 273.15 * 273.15 * 273.15)) * poly;
+            } else {
+              const R ts2 = ts_k * ts_k;
+              lwu = s.c_lwu * (ts2 * ts2);
+            }
+          }
           // albedo, model.py:298-337
           const bool has_snow = swe[i] > (R)0;
           // maps: blend of the bracketing maps; snow cells take the aged snow albedo when ageing
@@ -833,7 +878,48 @@ energy_balance_kernel(const KernelArgs<R> a) {
           const R rs = pot[i] * s.c_sw * ((R)1 - alb);
           // balance, clamp, melt partition: model.py:411, :434-438, msm.py:193-203
           const R atmo = rs + lwd - lwu + sens + lat;
-          const R mf = fmax_(atmo, (R)0);
+          R mf, gfl = (R)0;
+          if (MSM) {
+            // explicit conduction through the layer stack and the surface-layer melt gate,
+            // msm.py:31-107 (snow depth = swe / snow_density, model.py:428)
+            const MsmParams<R>& m = a.msm;
+            R sd = swe[i] * m.inv_snow_density;
+            R grad_prev = (R)0, t_next = tl[i][0];
+            const R dt = s.dt;
+            mf = (R)0;
+#pragma unroll
+            for (int l = 0; l < kMaxLayers; ++l) {
+              if (l < m.layers) {
+                const R t_here = t_next;
+                t_next = tl[i][l + 1];
+                const R grad = (t_next - t_here) * m.inv_d[l];            // msm.py:18-28
+                const R ratio = sd > m.d[l] ? (R)1 : sd * m.inv_d[l];     // msm.py:63
+                const R kap = ratio * m.k_snow + ((R)1 - ratio) * m.k_ice;
+                const R rho = ratio * m.rho_snow + ((R)1 - ratio) * m.rho_ice;
+                sd = fmax_(sd - m.d[l], (R)0);
+                R delta;
+                if (l == 0) {                                             // surface layer, msm.py:80-101
+                  gfl = kap * grad * m.c_ice * rho;
+                  const R full = atmo + gfl;
+                  const R crd = m.c_ice * rho * m.d[0];
+                  const R q0 = -t_here * crd / dt;
+                  mf = fmax_(full - q0, (R)0);
+                  delta = (full - mf) / crd;
+                } else {
+                  delta = kap * (grad - grad_prev) * m.inv_d[l];          // msm.py:103
+                }
+                grad_prev = grad;
+                if (l == 0 && sizeof(R) == 4) {
+                  t0_acc[i] += (double)(delta * dt);
+                  tl[i][0] = (R)t0_acc[i];
+                } else {
+                  tl[i][l] = t_here + delta * dt;
+                }
+              }
+            }
+          } else {
+            mf = fmax_(atmo, (R)0);
+          }
           const R we = mf * s.c_melt;
           const R snow = fmin_(we, swe[i]);
           const R ice = we - snow;
@@ -845,6 +931,10 @@ energy_balance_kernel(const KernelArgs<R> a) {
           acc[K_MELT] += w * mf;
           acc[K_SNOW] += snow;          // masked cells: swe = 0 -> snow = 0
           acc[K_SWE] += swe[i];
+          if (MSM) {
+            acc_m[M_LWU] += w * lwu;
+            acc_m[M_G] += w * gfl;
+          }
           n_snow += has_snow ? 1 : 0;
           if (DUMP && a.dump != nullptr) {
             if ((valid_bits >> i) & 1u) {
@@ -861,7 +951,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
               d[ENRGY_D_ICE * a.dump_field_stride] = ice;
               d[ENRGY_D_ALBEDO * a.dump_field_stride] = alb;
               d[ENRGY_D_POT * a.dump_field_stride] = pot[i];
-              d[ENRGY_D_G * a.dump_field_stride] = (R)0;
+              d[ENRGY_D_G * a.dump_field_stride] = gfl;
             }
           }
           // state update, model.py:258-261.  total_snow is not accumulated here: it equals
@@ -874,19 +964,32 @@ energy_balance_kernel(const KernelArgs<R> a) {
         if (!DUMP) {
           const R tot = warp_reduce8<R>(acc, lane);
           if ((lane & 3) == 0) sm.slots[warp][t - tb.t_begin][stat_of_lane(lane)] = tot;
+          if (MSM) {
+#pragma unroll
+            for (int q = 0; q < kStatsM; ++q) {
+              R v = acc_m[q];
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+              if (lane == 0) sm.slots_m[warp][t - tb.t_begin][q] = v;
+            }
+          }
         }
       }  // steps of the time block
 
       // ---- flush the block's statistics into this CTA's partial rows (fixed order) ---------------
       __syncthreads();
       if (!DUMP && my_partials != nullptr) {
-        const int n = (te - ts) * kStatsK;
+        constexpr int NQ = MSM ? kStatsP : kStatsK;
+        const int n = (te - ts) * NQ;
         for (int idx = tid; idx < n; idx += kThreads) {
-          const int tl = ts - tb.t_begin + idx / kStatsK, q = idx % kStatsK;
+          const int step = idx / NQ, q = idx - step * NQ;
+          const int sl = ts - tb.t_begin + step;
           double sum = 0.0;
 #pragma unroll
-          for (int w = 0; w < kWarps; ++w) sum += (double)sm.slots[w][tl][q];
-          my_partials[(size_t)(ts - a.t0) * kStatsK + idx] += sum;
+          for (int w = 0; w < kWarps; ++w) {
+            sum += q < kStatsK ? (double)sm.slots[w][sl][q] : (double)sm.slots_m[w][sl][q - kStatsK];
+          }
+          my_partials[(size_t)(ts - a.t0 + step) * kStatsP + q] += sum;
         }
       }
       __syncthreads();
@@ -902,29 +1005,35 @@ energy_balance_kernel(const KernelArgs<R> a) {
           a.swe[o] = v ? swe[i] : qnan;
           a.total_snow[o] = v ? a.total_snow[o] + (tsn[i] - swe[i]) : qnan;
           a.total_ice[o] = v ? tic[i] : qnan;
+          if (MSM) {
+#pragma unroll
+            for (int l = 0; l < NB; ++l) {
+              if (l <= a.msm.layers && v) a.layer_t[(size_t)l * a.layer_stride + o] = tl[i][l];
+            }
+          }
         }
       }
     }
   }  // tiles
 }
 
-template <typename R, int INSOL>
+// cells per thread: the sub-surface model carries 8 more registers per cell
+template <typename R, bool MSM>
 struct CellsPerThread {
-  static constexpr int value = sizeof(R) == 4 ? ENRGY_K32 : ENRGY_K64;
+  static constexpr int value = (sizeof(R) == 4 ? ENRGY_K32 : ENRGY_K64) / (MSM ? 2 : 1);
 };
 
 template <typename R>
-int energy_balance_tile_h(int insol) {
-  (void)insol;
-  return (kWarps / 4) * CellsPerThread<R, 0>::value;
+int energy_balance_tile_h(bool msm) {
+  return (kWarps / 4) * (msm ? CellsPerThread<R, true>::value : CellsPerThread<R, false>::value);
 }
-template int energy_balance_tile_h<float>(int);
-template int energy_balance_tile_h<double>(int);
+template int energy_balance_tile_h<float>(bool);
+template int energy_balance_tile_h<double>(bool);
 
-template <typename R, int INSOL, bool DUMP>
+template <typename R, int INSOL, bool MSM, bool DUMP>
 static cudaError_t configure(int sm_count, LaunchInfo* info) {
-  constexpr int K = CellsPerThread<R, INSOL>::value;
-  auto kern = energy_balance_kernel<R, K, INSOL, DUMP>;
+  constexpr int K = CellsPerThread<R, MSM>::value;
+  auto kern = energy_balance_kernel<R, K, INSOL, MSM, DUMP>;
   const int smem = kSmemTotal<R, INSOL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
@@ -943,50 +1052,104 @@ static cudaError_t configure(int sm_count, LaunchInfo* info) {
   return cudaSuccess;
 }
 
-template <typename R, int INSOL, bool DUMP>
-static cudaError_t launch_one(const KernelArgs<R>& a, const void* dem_map, int sm_count, int forced_grid,
-                              LaunchInfo* info, cudaStream_t stream) {
-  constexpr int K = CellsPerThread<R, INSOL>::value;
+template <typename R, int INSOL, bool MSM, bool DUMP>
+static cudaError_t launch_one(const KernelArgs<R>& a, int sm_count, int forced_grid, LaunchInfo* info,
+                              cudaStream_t stream) {
+  constexpr int K = CellsPerThread<R, MSM>::value;
   LaunchInfo li;
-  cudaError_t e = configure<R, INSOL, DUMP>(sm_count, &li);
+  cudaError_t e = configure<R, INSOL, MSM, DUMP>(sm_count, &li);
   if (e != cudaSuccess) return e;
   int grid = forced_grid > 0 ? forced_grid : li.grid;
   li.grid = grid;
   if (info) *info = li;
   if (a.n_tiles == 0 || a.t1 <= a.t0) return cudaSuccess;
-  (void)dem_map;
-  energy_balance_kernel<R, K, INSOL, DUMP><<<grid, kThreads, li.smem_bytes, stream>>>(a);
+  energy_balance_kernel<R, K, INSOL, MSM, DUMP><<<grid, kThreads, li.smem_bytes, stream>>>(a);
   return cudaGetLastError();
 }
 
-template <typename R>
-cudaError_t energy_balance_grid(int insol, bool dump, int sm_count, LaunchInfo* info) {
-  if (dump) {
-    if (insol == 0) return configure<R, 0, true>(sm_count, info);
-    if (insol == 1) return configure<R, 1, true>(sm_count, info);
-    return configure<R, 2, true>(sm_count, info);
-  }
-  if (insol == 0) return configure<R, 0, false>(sm_count, info);
-  if (insol == 1) return configure<R, 1, false>(sm_count, info);
-  return configure<R, 2, false>(sm_count, info);
+// runtime (insol, msm, dump) -> template instance
+template <typename R, typename F>
+static cudaError_t dispatch(int insol, bool msm, bool dump, F&& f) {
+#define ENRGY_CASE(I, M, D) \
+  if (insol == I && msm == M && dump == D) return f(std::integral_constant<int, I>{}, std::integral_constant<bool, M>{}, std::integral_constant<bool, D>{});
+  ENRGY_CASE(0, false, false) ENRGY_CASE(1, false, false) ENRGY_CASE(2, false, false)
+  ENRGY_CASE(0, true, false) ENRGY_CASE(1, true, false) ENRGY_CASE(2, true, false)
+  ENRGY_CASE(0, false, true) ENRGY_CASE(1, false, true) ENRGY_CASE(2, false, true)
+  ENRGY_CASE(0, true, true) ENRGY_CASE(1, true, true) ENRGY_CASE(2, true, true)
+#undef ENRGY_CASE
+  return cudaErrorInvalidValue;
 }
-template cudaError_t energy_balance_grid<float>(int, bool, int, LaunchInfo*);
-template cudaError_t energy_balance_grid<double>(int, bool, int, LaunchInfo*);
 
 template <typename R>
-cudaError_t launch_energy_balance(const KernelArgs<R>& a, const void* dem_map, int insol, bool dump,
+cudaError_t energy_balance_grid(int insol, bool msm, bool dump, int sm_count, LaunchInfo* info) {
+  return dispatch<R>(insol, msm, dump, [&](auto i, auto m, auto d) {
+    return configure<R, decltype(i)::value, decltype(m)::value, decltype(d)::value>(sm_count, info);
+  });
+}
+template cudaError_t energy_balance_grid<float>(int, bool, bool, int, LaunchInfo*);
+template cudaError_t energy_balance_grid<double>(int, bool, bool, int, LaunchInfo*);
+
+template <typename R>
+cudaError_t launch_energy_balance(const KernelArgs<R>& a, const void* reserved, int insol, bool dump,
                                   int sm_count, int forced_grid, LaunchInfo* info, cudaStream_t stream) {
-  if (dump) {
-    if (insol == 0) return launch_one<R, 0, true>(a, dem_map, sm_count, forced_grid, info, stream);
-    if (insol == 1) return launch_one<R, 1, true>(a, dem_map, sm_count, forced_grid, info, stream);
-    return launch_one<R, 2, true>(a, dem_map, sm_count, forced_grid, info, stream);
-  }
-  if (insol == 0) return launch_one<R, 0, false>(a, dem_map, sm_count, forced_grid, info, stream);
-  if (insol == 1) return launch_one<R, 1, false>(a, dem_map, sm_count, forced_grid, info, stream);
-  return launch_one<R, 2, false>(a, dem_map, sm_count, forced_grid, info, stream);
+  (void)reserved;
+  const bool msm = a.msm.layers > 0;
+  return dispatch<R>(insol, msm, dump, [&](auto i, auto m, auto d) {
+    return launch_one<R, decltype(i)::value, decltype(m)::value, decltype(d)::value>(a, sm_count, forced_grid,
+                                                                                     info, stream);
+  });
 }
 template cudaError_t launch_energy_balance<float>(const KernelArgs<float>&, const void*, int, bool, int, int, LaunchInfo*, cudaStream_t);
 template cudaError_t launch_energy_balance<double>(const KernelArgs<double>&, const void*, int, bool, int, int, LaunchInfo*, cudaStream_t);
+
+// initial boundary temperatures of the sub-surface model, model.py:133-143
+template <typename R>
+__global__ void msm_init_kernel(const float* __restrict__ dem, int dem_pitch, int pitch, int band_row0,
+                                int band_rows_pad, int n_bounds, const R* __restrict__ t_point, R elev,
+                                R* __restrict__ layer_t, size_t layer_stride) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int rb = blockIdx.y;
+  if (c >= pitch || rb >= band_rows_pad) return;
+  const float z = dem[(size_t)(rb + band_row0) * dem_pitch + c];
+  const size_t o = (size_t)rb * pitch + c;
+  const R qnan = (R)__int_as_float(0x7fc00000);
+  for (int l = 0; l < n_bounds; ++l) {
+    R t = qnan;
+    if (z == z) {
+      // value + (dem - elev) * -0.006, rounded product and rounded sum like NumPy
+      const R d = (R)z - elev;
+      if (sizeof(R) == 4) {
+        t = (R)__fadd_rn((float)t_point[l], __fmul_rn((float)d, -0.006f));
+      } else {
+        t = (R)__dadd_rn((double)t_point[l], __dmul_rn((double)d, -0.006));
+      }
+      if (t > (R)0) t = (R)0;             // ice temperature is limited by the melting point
+    }
+    layer_t[(size_t)l * layer_stride + o] = t;
+  }
+}
+template <typename R>
+cudaError_t launch_msm_init(const float* dem, int dem_pitch, int pitch, int band_row0, int band_rows_pad,
+                            int n_bounds, const double* t_point, double elev, R* layer_t, size_t layer_stride,
+                            cudaStream_t stream) {
+  R h[kMaxLayers + 1];
+  for (int l = 0; l < n_bounds; ++l) h[l] = (R)t_point[l];
+  R* d = nullptr;
+  cudaError_t e = cudaMalloc((void**)&d, sizeof(h));
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyAsync(d, h, sizeof(R) * n_bounds, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) {
+    dim3 grid((pitch + 255) / 256, band_rows_pad);
+    msm_init_kernel<R><<<grid, 256, 0, stream>>>(dem, dem_pitch, pitch, band_row0, band_rows_pad, n_bounds, d,
+                                                 (R)elev, layer_t, layer_stride);
+    e = cudaGetLastError();
+  }
+  cudaStreamSynchronize(stream);
+  cudaFree(d);
+  return e;
+}
+template cudaError_t launch_msm_init<float>(const float*, int, int, int, int, int, const double*, double, float*, size_t, cudaStream_t);
+template cudaError_t launch_msm_init<double>(const float*, int, int, int, int, int, const double*, double, double*, size_t, cudaStream_t);
 
 // =================================================================================================
 // micro-benchmarks: the pipe peaks the roofline is quoted against
@@ -1071,17 +1234,17 @@ __global__ void finalize_stats_kernel(const FinalizeArgs f) {
   const int f32_mode = f.f32_mode;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= f.n_steps) return;
-  double k[kStatsK];
-  for (int q = 0; q < kStatsK; ++q) k[q] = 0.0;
+  double k[kStatsP];
+  for (int q = 0; q < kStatsP; ++q) k[q] = 0.0;
   for (int c = 0; c < f.n_ctas; ++c) {
-    const double* p = f.partials + ((size_t)c * f.n_steps + t) * kStatsK;
-    for (int q = 0; q < kStatsK; ++q) k[q] += p[q];
+    const double* p = f.partials + ((size_t)c * f.n_steps + t) * kStatsP;
+    for (int q = 0; q < kStatsP; ++q) k[q] += p[q];
   }
   const StepRec<double> s = f.steps64[f.t0 + t];
   const double lwu_cell = f32_mode ? (double)(float)s.c_lwu : s.c_lwu;
   const double c_melt = f32_mode ? (double)(float)s.c_melt : s.c_melt;
   double* o = f.stats + (size_t)t * ENRGY_S_COUNT;
-  const double lwu = f.n_valid * lwu_cell;
+  const double lwu = f.msm ? k[kStatsK + M_LWU] : f.n_valid * lwu_cell;
   o[ENRGY_S_RS] = k[K_RS];
   o[ENRGY_S_LWD] = k[K_LWD];
   o[ENRGY_S_LWU] = lwu;
@@ -1089,7 +1252,7 @@ __global__ void finalize_stats_kernel(const FinalizeArgs f) {
   o[ENRGY_S_LAT] = k[K_LAT];
   // linear in the cell values: sum(atmo) = sum(rs) + sum(lwd) - sum(lwu) + sum(sens) + sum(lat)
   o[ENRGY_S_ATMO] = k[K_RS] + k[K_LWD] - lwu + k[K_SENS] + k[K_LAT];
-  o[ENRGY_S_G] = 0.0;
+  o[ENRGY_S_G] = f.msm ? k[kStatsK + M_G] : 0.0;
   o[ENRGY_S_MELT] = k[K_MELT];
   o[ENRGY_S_SNOW] = k[K_SNOW];
   // ice = we - snow with we = mf * c_melt

@@ -43,6 +43,10 @@ struct KernelArgs {
   R* swe;
   R* total_snow;
   R* total_ice;
+  // sub-surface model: boundary temperatures [layers + 1][band_rows_pad][pitch] (deg C)
+  R* layer_t;
+  size_t layer_stride;
+  MsmParams<R> msm;
   // streamed insolation [n_steps_resident][band_rows_pad][pitch], step index relative to pot_t0
   const float* pot;
   size_t pot_stride;
@@ -57,7 +61,7 @@ struct KernelArgs {
   // work list
   const int2* tiles;              // active tiles (tile row, tile col) of the band
   int n_tiles;
-  // statistics: per-CTA partial sums [gridDim.x][t1 - t0][kStatsK] float64
+  // statistics: per-CTA partial sums [gridDim.x][t1 - t0][kStatsP] float64
   double* partials;
   // dump mode: [t1 - t0][ENRGY_D_COUNT][band_rows_pad][pitch] R (may be null)
   R* dump;
@@ -68,7 +72,8 @@ struct KernelArgs {
 };
 
 struct FinalizeArgs {
-  const double* partials;   // [n_ctas][n_steps][kStatsK]
+  const double* partials;   // [n_ctas][n_steps][kStatsP]
+  int msm;                  // sub-surface model on: lwu and g are summed per cell
   int n_ctas, n_steps, t0;
   double n_valid;           // valid cells of the band
   int f32_mode;             // round the per-step constants the way the float32 kernel saw them
@@ -111,9 +116,14 @@ template <typename R>
 cudaError_t launch_energy_balance(const KernelArgs<R>& a, const void* reserved, int insol, bool dump,
                                   int sm_count, int forced_grid, LaunchInfo* info, cudaStream_t stream);
 template <typename R>
-int energy_balance_tile_h(int insol);
+int energy_balance_tile_h(bool msm);
 template <typename R>
-cudaError_t energy_balance_grid(int insol, bool dump, int sm_count, LaunchInfo* info);
+cudaError_t energy_balance_grid(int insol, bool msm, bool dump, int sm_count, LaunchInfo* info);
+// initial boundary temperatures: min(0, t_point[l] + (dem - elev) * -0.006), model.py:133-143
+template <typename R>
+cudaError_t launch_msm_init(const float* dem, int dem_pitch, int pitch, int band_row0, int band_rows_pad,
+                            int n_bounds, const double* t_point /*host*/, double elev, R* layer_t,
+                            size_t layer_stride, cudaStream_t stream);
 
 cudaError_t launch_finalize(const FinalizeArgs& f, cudaStream_t stream);
 cudaError_t launch_microbench(int kind, int sm_count, int iters, void* scratch, double* ops_per_launch,

@@ -207,7 +207,23 @@ int run_prepass(const PrepassInput& in, PrepassOutput& out, std::string& err) {
 
   const double zm = p.zm;
   const double zh_const = p.z_h_or_e;
-  const double ts_aws_c = 0.0;   // no sub-surface model: layer_temperatures[0] is all zeros (F9)
+  // sub-surface model: the AWS cell is integrated serially here because its surface temperature
+  // feeds the Monin-Obukhov solve of the NEXT row (model.py:347-358)
+  const bool msm = p.msm_layers > 0;
+  const int nl = p.msm_layers;
+  const float z_aws = in.dem[(size_t)p.aws_row * in.cols + p.aws_col];
+  if (!(z_aws == z_aws)) {
+    err = "the AWS cell is off-glacier (NaN in the DEM)";
+    return ENRGY_ERR_ARG;
+  }
+  std::vector<double> tl(in.layer_t_aws);
+  if (msm && (int)tl.size() != nl + 1) {
+    err = "enrgy_set_msm must precede enrgy_prepass when msm_layers > 0";
+    return ENRGY_ERR_ARG;
+  }
+  double swe_cell = in.swe_aws;
+  const double delta_cell = (double)z_aws - p.elev_aws;
+  const double pw_cell = std::pow(10.0, -delta_cell / kVapourScale);
 
   for (int i = 0; i < T; ++i) {
     const double* f = in.forcing + (size_t)i * ENRGY_F_COUNT;
@@ -229,6 +245,7 @@ int run_prepass(const PrepassInput& in, PrepassOutput& out, std::string& err) {
     const double e_aws = rh * sat_vapour_pressure(tz, p_pa);
 
     // point solve for L, model.py:347-358
+    const double ts_aws_c = msm ? tl[0] : 0.0;     // no MSM: layer_temperatures[0] is all zeros (F9)
     double ts_k;
     if (mirror32) {
       ts_k = (double)((float)ts_aws_c + 273.15f);
@@ -340,6 +357,60 @@ int run_prepass(const PrepassInput& in, PrepassOutput& out, std::string& err) {
       factor = pot_w == 0 ? 1.0 : swd / pot_w;
     }
     s.c_sw = 3.6 * 1000000 / dt * factor;
+
+    if (msm) {
+      // the AWS cell's own energy balance and conduction step (same arithmetic as the kernel)
+      const double t_air_c = t_air + delta_cell * f[ENRGY_F_LAPSE];
+      const double tz_c = t_air_c + 273.15;
+      const double tsk = tl[0] + 273.15;
+      const double p_c = p_hpa + delta_cell * kPressureLapse;
+      const double r_rt = 1.0 / (kRair * tz_c);
+      const double sens = (s.c_sens * p_c) * (r_rt * (tz_c - tsk));
+      const double f_p = 1.0016 + 3.15 * 1e-6 * p_c - 0.074 / p_c;
+      const double es = 611.2 * std::exp((17.62 * tl[0]) / (243.12 + tl[0])) * f_p;
+      const double lat = (s.c_lat * r_rt) * (e_aws * pw_cell - es);
+      const double lwd = s.c_lwd * (tz_c * tz_c) * (tz_c * tz_c);
+      const double lwu = s.c_lwu * (tsk * tsk) * (tsk * tsk);
+      double alb;
+      const bool has_snow = swe_cell > 0;
+      if (p.albedo_const) {
+        alb = has_snow ? p.albedo_snow : p.albedo_ice;
+      } else {
+        const double x0 = in.alb_aws.empty() ? 0.5 : in.alb_aws[i0];
+        const double x1 = in.alb_aws.empty() ? 0.5 : in.alb_aws[i1];
+        const double blend = x0 + s.alb_w * (x1 - x0);
+        alb = has_snow ? (s.snow_alb >= 0 ? s.snow_alb : blend) : std::min(blend, p.max_ice_albedo);
+      }
+      const double rs = pot_aws_kwh * s.c_sw * (1.0 - alb);
+      const double atmo = rs + lwd - lwu + sens + lat;
+      double sd = swe_cell / p.snow_density;
+      double grad_prev = 0.0, mf = 0.0;
+      std::vector<double> tn(tl);
+      for (int lyr = 0; lyr < nl; ++lyr) {
+        const double d = p.msm_depths[lyr];
+        const double grad = (tl[lyr + 1] - tl[lyr]) / d;
+        const double ratio = sd > d ? 1.0 : sd / d;
+        const double kap = ratio * kKappaSnow + (1 - ratio) * kKappaIce;
+        const double rho = ratio * p.snow_density + (1 - ratio) * p.ice_density;
+        sd = std::max(sd - d, 0.0);
+        double dlt;
+        if (lyr == 0) {
+          const double gfl = kap * grad * kCice * rho;
+          const double full = atmo + gfl;
+          const double crd = kCice * rho * d;
+          const double q0 = -tl[0] * crd / dt;
+          mf = std::max(full - q0, 0.0);
+          dlt = (full - mf) / crd;
+        } else {
+          dlt = kap * (grad - grad_prev) / d;
+        }
+        grad_prev = grad;
+        tn[lyr] = tl[lyr] + dlt * dt;
+      }
+      tl = tn;
+      const double we = mf * s.c_melt;
+      swe_cell -= std::min(we, swe_cell);
+    }
 
     pt[ENRGY_P_L] = l;
     pt[ENRGY_P_CH] = ch;

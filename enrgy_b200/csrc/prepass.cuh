@@ -33,7 +33,7 @@ struct PrepassInput {
   const double* forcing;   // [n_steps][ENRGY_F_COUNT]
   const double* pot_aws;   // streamed mode: potential insolation at the AWS cell per step [kWh m-2]
   // state of the AWS cell for the serial sub-surface integration (MSM): albedo maps at the cell,
-  // initial SWE, initial boundary temperatures
+  // SWE and boundary temperatures at step 0 (the pre-pass always integrates from the first row)
   std::vector<double> alb_aws;
   double swe_aws = 0.0;
   std::vector<double> layer_t_aws;

@@ -30,7 +30,7 @@ class Engine:
                    andreas=False, sensible_corr=1.0, latent_corr=1.0, emissivity=None,
                    const_albedo=None, max_ice_albedo=None, snow_density=None, ice_density=None,
                    insol_mode=_lib.INSOL_STREAMED, shadow=False, lat=0.0, lon=0.0, solar_const=None,
-                   transmittance=None, hour_step=None, band_row0=0, band_rows=0):
+                   transmittance=None, hour_step=None, band_row0=0, band_rows=0, msm_depths=None):
         nan = float("nan")
         p = Params()
         p.cell_size = cell_size
@@ -55,6 +55,13 @@ class Engine:
         p.transmittance = nan if transmittance is None else transmittance
         p.hour_step = nan if hour_step is None else hour_step
         p.band_row0, p.band_rows = int(band_row0), int(band_rows)
+        if msm_depths is not None:
+            if len(msm_depths) > _lib.MAX_LAYERS - 1:
+                raise ValueError("at most %d sub-surface layers" % (_lib.MAX_LAYERS - 1))
+            p.msm_layers = len(msm_depths)
+            for i, d in enumerate(msm_depths):
+                p.msm_depths[i] = float(d)
+        self.msm_layers = int(p.msm_layers)
         check(self.lib.enrgy_set_params(self.h, C.byref(p)))
         self.band_row0 = int(band_row0)
         self.band_rows = int(band_rows) if band_rows else self.rows
@@ -79,6 +86,17 @@ class Engine:
         swe = _f32c(swe)
         assert swe.shape == (self.band_rows, self.cols), swe.shape
         check(self.lib.enrgy_set_swe(self.h, swe.ctypes.data))
+
+    def set_msm(self, temperatures, elev):
+        """Initial boundary temperatures at the reference elevation (reference model.py:126-143)."""
+        t = np.ascontiguousarray(temperatures, dtype=np.float64)
+        assert t.shape == (self.msm_layers + 1,), t.shape
+        check(self.lib.enrgy_set_msm(self.h, t.ctypes.data, float(elev)))
+
+    def layer_temps(self):
+        out = np.empty((self.msm_layers + 1, self.band_rows, self.cols), dtype=np.float64)
+        check(self.lib.enrgy_get_layer_temps(self.h, out.ctypes.data))
+        return out
 
     def set_forcing(self, table):
         table = np.ascontiguousarray(table, dtype=np.float64)

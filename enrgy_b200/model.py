@@ -156,9 +156,22 @@ class Energy:
         self._swe_given = True
 
     def add_msm(self, depths, temperatures, elev_aws):
-        raise NotImplementedError(
-            "the sub-surface model (reference model.py:126-149, msm.py:31-107) is the next scope row "
-            "(SURVEY.md 8f-2); this round's kernels run the no-MSM energy balance only")
+        """Sub-surface model set-up, reference model.py:126-149: `depths` are layer THICKNESSES,
+        `temperatures` the boundary temperatures at elevation `elev_aws`; they are distributed with
+        -0.006 K/m and capped at 0 degC on the device."""
+        print("Initializing subsurface model...")
+        self.use_msm = True
+        self.layer_depths = list(depths)
+        self._msm_point_temps = list(temperatures)
+        self._msm_elev = elev_aws
+        if len(self._msm_point_temps) != len(self.layer_depths) + 1:
+            raise ValueError("temperatures are layer BOUNDARIES: one more than depths")
+        delta = self.base_dem_array - elev_aws                     # host copy for callers that read it
+        self.layer_temperatures = []
+        for t_point in temperatures:
+            t = t_point + delta * -0.006
+            t[t > 0] = 0.0
+            self.layer_temperatures.append(t)
 
     def add_checkpoints(self, date_str_list):
         self.result_export_dates = [s + " 12:00:00" for s in date_str_list]
@@ -210,8 +223,11 @@ class Energy:
                            emissivity=emissivity, const_albedo=const_albedo, max_ice_albedo=max_ice_albedo,
                            snow_density=self.params["snow_density"], ice_density=self.params["ice_density"],
                            insol_mode=_lib.INSOL_STREAMED if streamed else _lib.INSOL_COMPUTED,
-                           shadow=self.shadow, lat=lat or 0.0, lon=lon or 0.0)
+                           shadow=self.shadow, lat=lat or 0.0, lon=lon or 0.0,
+                           msm_depths=self.layer_depths if self.use_msm else None)
             eng.set_dem(self.base_dem_array)
+            if self.use_msm:
+                eng.set_msm(self._msm_point_temps, self._msm_elev)
             if keys is not None:
                 eng.set_albedo_maps([self.albedo_arrays[k] for k in keys])
             if self._swe_given:
@@ -255,6 +271,8 @@ class Energy:
                         self.sample_stakes()
                         self.write_stakes(out_file)
             self._pull_state(eng)
+            if self.use_msm:
+                self.layer_temperatures = [t.astype(np.float32) for t in eng.layer_temps()]
             self.stats = stats
             self.point_scalars = point
         finally:

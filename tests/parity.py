@@ -9,7 +9,7 @@ from enrgy_b200.forcing import build_forcing
 from oracle import enrgy_oracle as O
 from oracle import insolation_oracle as I
 
-FLUX_FIELDS = ("rs", "lwd", "lwu", "sens", "lat", "atmo", "mf")
+FLUX_FIELDS = ("rs", "lwd", "lwu", "sens", "lat", "atmo", "mf", "g")
 
 
 def clipped_albedo(case, dtype):
@@ -30,7 +30,8 @@ def oracle_config(case, **kw):
                          temp_lapse_rate=kw.get("temp_lapse_rate", -0.006),
                          last_snowfall=kw.get("last_snowfall"), max_ice_albedo=kw.get("max_ice_albedo"),
                          emissivity=kw.get("emissivity", 0.98), cloud_corr=kw.get("cloud_corr"),
-                         sensible_corr=kw.get("sensible_corr", 1), latent_corr=kw.get("latent_corr", 1))
+                         sensible_corr=kw.get("sensible_corr", 1), latent_corr=kw.get("latent_corr", 1),
+                         msm=kw.get("msm"), snow_density=kw.get("snow_density"))
 
 
 def run_oracle(case, pot, f64, keep_steps=None, **kw):
@@ -51,10 +52,13 @@ def make_engine(case, f64, pot=None, computed=False, shadow=False, device=0, **k
                    z_h_or_e=kw.get("z_h_or_e", 1e-4), andreas=kw.get("andreas", False),
                    sensible_corr=kw.get("sensible_corr", 1), latent_corr=kw.get("latent_corr", 1),
                    emissivity=kw.get("emissivity", 0.98), const_albedo=kw.get("const_albedo"),
-                   max_ice_albedo=kw.get("max_ice_albedo"),
+                   max_ice_albedo=kw.get("max_ice_albedo"), snow_density=kw.get("snow_density"),
+                   msm_depths=kw["msm"]["depths"] if kw.get("msm") else None,
                    insol_mode=_lib.INSOL_COMPUTED if computed else _lib.INSOL_STREAMED,
                    shadow=shadow, lat=case.lat, lon=case.lon)
     eng.set_dem(case.dem)
+    if kw.get("msm"):
+        eng.set_msm(kw["msm"]["temperatures"], kw["msm"]["elev"])
     keys = None
     if not kw.get("const_albedo"):
         alb = clipped_albedo(case, np.float32)
@@ -131,6 +135,7 @@ def compare_run(case, f64, pot=None, computed=False, shadow=False, **kw):
         stats = eng.run(0, n)
         swe, tsn, tic = eng.state(np.float64)
         point = eng.point_scalars()
+        layers = eng.layer_temps() if kw.get("msm") else None
     finally:
         eng.close()
     ff, mfl, tfl = (1e-3, 1e-7, 1e-6) if f64 else (1.0, 1e-3, 1e-3)
@@ -141,12 +146,21 @@ def compare_run(case, f64, pot=None, computed=False, shadow=False, **kw):
         worst = 0.0
         for i in range(n):
             ref = np.array(ora["rows"][i][name], dtype=np.float64)
-            if name == "lwu":
+            if name == "g" and not kw.get("msm"):
+                ref[off] = np.nan       # np.zeros(atmo.shape): finite off-glacier (model.py:434)
+            if name == "lwu" and not kw.get("msm"):
                 # without the sub-surface model the reference's surface temperature raster is
                 # zeros EVERYWHERE (np.zeros_like(dem)), so its lwu is finite off-glacier
                 # too; the debug view only covers glacier cells.
                 ref[off] = np.nan
-            worst = max(worst, max_rel_err(dump[i, idx], ref, ff))
+            floor = ff
+            if kw.get("msm") and not f64 and name in ("mf", "g"):
+                # float32 + sub-surface model: the melt gate qm = full - q0 carries the cold content
+                # of the surface layer, which integrates the float32 round-off of every earlier
+                # step's fluxes (3e-5 W m-2 per term, in the as-shipped reference too): the
+                # per-step melt flux agrees to ~5e-4 W m-2, the melt TOTALS to 1e-4 relative.
+                floor = 5.0
+            worst = max(worst, max_rel_err(dump[i, idx], ref, floor))
         res[name] = worst
     worst = 0.0
     for i in range(n):
@@ -156,6 +170,9 @@ def compare_run(case, f64, pot=None, computed=False, shadow=False, **kw):
     res["albedo"] = worst
     res["snow"] = max(max_rel_err(dump[i, _lib.D_SNOW], ora["melt"][i][0], mfl) for i in range(n))
     res["ice"] = max(max_rel_err(dump[i, _lib.D_ICE], ora["melt"][i][1], mfl) for i in range(n))
+    if layers is not None:
+        res["layer_t"] = max(max_rel_err(layers[l], ora["layer_temperatures"][l], 1e-3 if f64 else 1.0)
+                             for l in range(layers.shape[0]))
     res["swe"] = max_rel_err(swe, ora["swe"], tfl)
     res["total_snow"] = max_rel_err(tsn, ora["total_snow"], tfl)
     res["total_ice"] = max_rel_err(tic, ora["total_ice"], tfl)

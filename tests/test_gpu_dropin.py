@@ -132,3 +132,54 @@ def test_error_behaviour(tmp_path):
     case.write_aws_csv(aws)
     with pytest.raises(ValueError):                             # helpers.py:87
         e.model(aws_file=aws, albedo_maps=bad, z=1.6, elev_aws=case.elev_aws, xy_aws=case.xy_aws, v=False)
+
+
+def test_insolation_cache_writer_roundtrip(tmp_path):
+    """GPU-computed insolation written in the reference's pickle layout (model.py:477-481) and read
+    back through the reference-shaped `use_precomputed` path reproduces the in-kernel run."""
+    from enrgy_b200.insolation_pickler import pickle_insolation_series
+    case = make_case(56, 14, w=72, seed=29)
+    d = str(tmp_path)
+    dem, swe, alb, aws = _write_case(case, d)
+    files = pickle_insolation_series(case.dem, case.geotransform, case.aws_rows, os.path.join(d, "pickle"), 10,
+                                     lat=case.lat, lon=case.lon, shadow=True, dtype=np.float64)
+    assert len(files) == 14 and all(os.path.isfile(f) for f in files)
+    want = I.potential_insolation(case.dem, case.cell, case.lat, case.lon, I.to_unix(case.aws_rows[9]["DATE"]), 3600)
+    assert P.max_rel_err(np.load(files[9]), want, 1e-6) < 1e-9
+    # the oracle (= the reference's arithmetic) on these files vs the fused in-kernel path
+    pot = np.stack([np.load(f) for f in files])
+    ora = P.run_oracle(case, pot, True)
+    res = P.compare_run(case, True, computed=True, shadow=True)
+    assert max(res.values()) < 1e-9
+    e = Energy(dem, None, os.path.join(d, "out"), res=10, precision="f64")
+    e.use_precomputed = True
+    e.add_pickle_dir(os.path.join(d, "pickle"))
+    e.add_snow(swe)
+    e.model(aws_file=aws, albedo_maps=alb, z=1.6, elev_aws=case.elev_aws, xy_aws=case.xy_aws, zm=1e-3,
+            z_h_or_e=1e-4, emissivity=0.98, v=False)
+    # streamed rasters are float32 on the device (SAGA .sdat is float32): 1e-7 class agreement
+    assert P.max_rel_err(e.total_ice_melt_array, ora["total_ice"], 1e-3) < 5e-7
+
+
+def test_add_msm_drop_in(tmp_path):
+    """add_msm + model(): the sub-surface model through the reference-shaped class."""
+    case = make_case(48, 16, w=60, seed=37)
+    d = str(tmp_path)
+    dem, swe, alb, aws = _write_case(case, d)
+    msm = dict(depths=[0.1, 0.1, 0.3, 0.5, 0.5, 0.5, 3.0],
+               temperatures=[-6.9, -6.93, -7.025, -7.31, -6.93, -7.12, -7.0, -5.57], elev=275.0)
+    e = Energy(dem, None, os.path.join(d, "out"), res=10, precision="f64")
+    e.lat, e.lon = case.lat, case.lon
+    e.add_snow(swe)
+    e.add_msm(msm["depths"], msm["temperatures"], msm["elev"])
+    assert len(e.layer_temperatures) == 8 and float(np.nanmax(e.layer_temperatures[0])) <= 0.0
+    e.model(aws_file=aws, albedo_maps=alb, z=1.6, elev_aws=case.elev_aws, xy_aws=case.xy_aws, zm=1e-3,
+            z_h_or_e=1e-4, emissivity=0.98, v=False)
+    pot = I.insolation_series(case, shadow=True, dtype=np.float64)
+    ora = P.run_oracle(case, pot, True, msm=msm)
+    assert P.max_rel_err(e.total_ice_melt_array, ora["total_ice"], 1e-3) < 2e-7
+    assert P.max_rel_err(e.layer_temperatures[0], ora["layer_temperatures"][0], 1e-2) < 1e-5
+    rows = _csv_numbers(open(os.path.join(d, "out", "heat_fluxes.csv")).read())
+    want = _csv_numbers(ora["stats_csv"])
+    for (_, a), (_, b) in zip(rows, want):
+        assert abs(a[6] - b[6]) <= 0.1001 and abs(a[8] - b[8]) <= 0.0101      # in-glacier flux, POINT_T_SURF

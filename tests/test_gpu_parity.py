@@ -22,6 +22,11 @@ VARIANTS = {
     "corr": dict(cloud_corr=0.2, sensible_corr=1.1, latent_corr=0.9, emissivity=None, zm=None,
                  z_h_or_e=None),
     "no_swe": dict(use_swe=False, const_albedo=(0.35, 0.75)),
+    "msm": dict(msm=dict(depths=[0.1, 0.1, 0.3, 0.5, 0.5, 0.5, 3.0],
+                         temperatures=[-6.9, -6.93, -7.025, -7.31, -6.93, -7.12, -7.0, -5.57], elev=275.0),
+                snow_density=350.0, last_snowfall="20220522"),
+    "msm_const": dict(msm=dict(depths=[0.25, 0.5, 1.0], temperatures=[-2.0, -3.0, -4.0, -5.0], elev=400.0),
+                      const_albedo=(0.35, 0.75)),
 }
 
 
@@ -43,6 +48,16 @@ def test_streamed_f32(variant):
     print(variant, res)
     for k, v in res.items():
         assert v < 1e-4, (k, v)
+
+
+@pytest.mark.parametrize("f64", [True, False])
+def test_msm_with_in_kernel_insolation(f64):
+    case = make_case(72, 30, w=100, seed=41)
+    res = P.compare_run(case, f64, computed=True, shadow=True, **VARIANTS["msm"])
+    print(f64, res)
+    tol = 1e-9 if f64 else 1e-4
+    for k, v in res.items():
+        assert v < tol, (k, v)
 
 
 @pytest.mark.parametrize("f64", [True, False])
