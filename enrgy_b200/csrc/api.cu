@@ -75,7 +75,9 @@ struct enrgy_ctx {
   double n_valid = 0.0;
   size_t band_elems = 0;  // band_rows_pad * pitch
   // host copies
-  std::vector<float> h_dem;
+  std::vector<float> h_dem;       // full host copy, kept only when the AWS-cell shading ray needs it
+  float aws_nbhd[9] = {};         // DEM at the AWS cell and its 8 neighbours
+  float zmax = 0.f;               // top of the device max pyramid
   std::vector<double> forcing;
   int n_steps = 0;
   std::vector<double> pot_aws;
@@ -450,7 +452,21 @@ int enrgy_set_dem(enrgy_ctx* c, const float* dem) {
   if (int e = use_device(c)) return e;
   if (!c->have_params) return fail(ENRGY_ERR_ARG, "set_params must precede set_dem");
   if (!dem) return fail(ENRGY_ERR_ARG, "dem is null");
-  c->h_dem.assign(dem, dem + (size_t)c->rows * c->cols);
+  if (c->p.aws_row < 0 || c->p.aws_row >= c->rows || c->p.aws_col < 0 || c->p.aws_col >= c->cols)
+    return fail(ENRGY_ERR_ARG, "AWS cell (%d, %d) outside the %d x %d raster", c->p.aws_row, c->p.aws_col, c->rows, c->cols);
+  for (int dr = -1; dr <= 1; ++dr)
+    for (int dc = -1; dc <= 1; ++dc) {
+      const int r = c->p.aws_row + dr, x = c->p.aws_col + dc;
+      c->aws_nbhd[(dr + 1) * 3 + (dc + 1)] = (r >= 0 && r < c->rows && x >= 0 && x < c->cols)
+                                                 ? dem[(size_t)r * c->cols + x]
+                                                 : std::numeric_limits<float>::quiet_NaN();
+    }
+  if (c->p.insol_mode == ENRGY_INSOL_COMPUTED && c->p.shadow) {
+    c->h_dem.assign(dem, dem + (size_t)c->rows * c->cols);
+  } else {
+    c->h_dem.clear();
+    c->h_dem.shrink_to_fit();
+  }
   // DEM buffer with a NaN apron of kDemApron cells on every side (ray chunks never leave it)
   c->dem_pitch = c->pitch + 2 * kDemApron;
   const size_t dem_elems = (size_t)(c->rows_pad_full + 2 * kDemApron) * c->dem_pitch;
@@ -472,6 +488,14 @@ int enrgy_set_dem(enrgy_ctx* c, const float* dem) {
     }
     CU_TRY(c->d_blockmax.alloc((size_t)off));
     CU_TRY(launch_blockmax(c->dem0, c->dem_pitch, c->rows, c->cols, py, c->d_blockmax.p, c->stream));
+    // the top level is one block: its value is the maximum of the valid DEM
+    const int top = py.levels - 1;
+    std::vector<float> tv((size_t)(py.nbr[top] + 2) * (py.nbc[top] + 2));
+    CU_TRY(cudaMemcpyAsync(tv.data(), c->d_blockmax.p + py.off[top], tv.size() * sizeof(float),
+                           cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    c->zmax = -std::numeric_limits<float>::infinity();
+    for (float v : tv) c->zmax = std::max(c->zmax, v);
   }
   c->launches++;
   // active tiles of the band
@@ -611,7 +635,7 @@ int enrgy_set_msm(enrgy_ctx* c, const double* temps, double elev) {
   }
   c->launches++;
   // the AWS cell's own boundary temperatures for the serial pre-pass, model.py:133-143
-  const float z = c->h_dem[(size_t)c->p.aws_row * c->cols + c->p.aws_col];
+  const float z = c->aws_nbhd[4];
   c->layer_t_aws.assign(nl + 1, 0.0);
   for (int l = 0; l <= nl; ++l) {
     double t;
@@ -674,7 +698,8 @@ int enrgy_prepass(enrgy_ctx* c) {
   if (!c->have_dem || !c->have_forcing) return fail(ENRGY_ERR_ARG, "set_dem and set_forcing must precede prepass");
   PrepassInput in;
   in.p = c->p; in.precision = c->precision; in.rows = c->rows; in.cols = c->cols;
-  in.dem = c->h_dem.data(); in.n_steps = c->n_steps; in.forcing = c->forcing.data();
+  in.dem = c->h_dem.empty() ? nullptr : c->h_dem.data(); in.n_steps = c->n_steps; in.forcing = c->forcing.data();
+  std::memcpy(in.nbhd, c->aws_nbhd, sizeof(in.nbhd)); in.zmax = c->zmax;
   in.pot_aws = c->pot_aws.data();
   in.alb_aws = c->alb_aws; in.swe_aws = c->swe_aws; in.layer_t_aws = c->layer_t_aws;
   if (c->p.msm_layers > 0 && !c->have_msm) return fail(ENRGY_ERR_ARG, "enrgy_set_msm must precede prepass when msm_layers > 0");

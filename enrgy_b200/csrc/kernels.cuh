@@ -13,7 +13,7 @@ constexpr int kInsolShadow = 2;    // ... with the ray-marched sunlit mask
 
 // Max pyramid of the DEM: level l holds the max of the valid cells of every (16 << l)^2 block as
 // [(nbr + 2)][(nbc + 2)] floats with one ring of -inf blocks, at offset off[l] of one buffer.
-constexpr int kMaxPyramidLevels = 10;
+constexpr int kMaxPyramidLevels = 12;   // 16 << 11 = 32768 >= the largest raster edge
 struct MaxPyramid {
   int levels;
   int off[kMaxPyramidLevels], nbr[kMaxPyramidLevels], nbc[kMaxPyramidLevels];

@@ -138,20 +138,16 @@ namespace {
 
 inline bool valid(float z) { return z == z; }
 
-// terrain normal of one cell on the host (double), same rule as terrain_kernel
-void host_normal(const float* dem, int rows, int cols, int r, int c, double cell, double* nx,
-                 double* ny, double* nz) {
-  auto at = [&](int rr, int cc) -> float {
-    if (rr < 0 || rr >= rows || cc < 0 || cc >= cols) return std::numeric_limits<float>::quiet_NaN();
-    return dem[(size_t)rr * cols + cc];
-  };
-  const double z = dem[(size_t)r * cols + c];
+// terrain normal of the AWS cell on the host (double), same rule as terrain_kernel; nb = 3 x 3
+// neighbourhood of the cell, NaN outside the grid
+void host_normal(const float* nb, double cell, double* nx, double* ny, double* nz) {
+  const double z = nb[4];
   auto one_sided = [&](float a, float b) -> double {
     if (valid(a)) return (double)a - z;
     if (valid(b)) return z - (double)b;
     return 0.0;
   };
-  const float zn = at(r - 1, c), zs = at(r + 1, c), ze = at(r, c + 1), zw = at(r, c - 1);
+  const float zn = nb[1], zs = nb[7], ze = nb[5], zw = nb[3];
   const double gy = (one_sided(zn, zs) - one_sided(zs, zn)) / (2.0 * cell);
   const double gx = (one_sided(ze, zw) - one_sided(zw, ze)) / (2.0 * cell);
   const double inv = 1.0 / std::sqrt(1.0 + gx * gx + gy * gy);
@@ -190,12 +186,7 @@ int run_prepass(const PrepassInput& in, PrepassOutput& out, std::string& err) {
   out.blocks.clear();
   out.point.assign((size_t)T * ENRGY_P_COUNT, 0.0);
 
-  // zmax of the valid DEM
-  float zmax = -std::numeric_limits<float>::infinity();
-  for (size_t i = 0, n = (size_t)in.rows * in.cols; i < n; ++i) {
-    const float z = in.dem[i];
-    if (z == z && z > zmax) zmax = z;
-  }
+  const float zmax = in.zmax;
   out.zmax = zmax;
 
   if (p.aws_row < 0 || p.aws_row >= in.rows || p.aws_col < 0 || p.aws_col >= in.cols) {
@@ -203,7 +194,11 @@ int run_prepass(const PrepassInput& in, PrepassOutput& out, std::string& err) {
     return ENRGY_ERR_ARG;
   }
   double nx = 0, ny = 0, nz = 1;
-  if (computed) host_normal(in.dem, in.rows, in.cols, p.aws_row, p.aws_col, p.cell_size, &nx, &ny, &nz);
+  if (computed) host_normal(in.nbhd, p.cell_size, &nx, &ny, &nz);
+  if (computed && p.shadow && in.dem == nullptr) {
+    err = "the host DEM copy is missing for the AWS-cell shading ray";
+    return ENRGY_ERR_ARG;
+  }
 
   const double zm = p.zm;
   const double zh_const = p.z_h_or_e;
@@ -211,7 +206,7 @@ int run_prepass(const PrepassInput& in, PrepassOutput& out, std::string& err) {
   // feeds the Monin-Obukhov solve of the NEXT row (model.py:347-358)
   const bool msm = p.msm_layers > 0;
   const int nl = p.msm_layers;
-  const float z_aws = in.dem[(size_t)p.aws_row * in.cols + p.aws_col];
+  const float z_aws = in.nbhd[4];
   if (!(z_aws == z_aws)) {
     err = "the AWS cell is off-glacier (NaN in the DEM)";
     return ENRGY_ERR_ARG;

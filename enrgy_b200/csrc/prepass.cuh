@@ -28,7 +28,9 @@ struct PrepassInput {
   enrgy_params p;          // defaults already resolved (no NaNs left)
   int precision;           // ENRGY_F32 mirrors the as-shipped float32 point operations
   int rows, cols;          // full raster
-  const float* dem;        // full host DEM [rows][cols]
+  const float* dem;        // full host DEM [rows][cols]; only needed (non-null) for the shading ray of the AWS cell
+  float nbhd[9];           // DEM at the AWS cell and its 8 neighbours (row-major 3 x 3, NaN outside the grid)
+  float zmax;              // max of the valid DEM (top of the device max pyramid)
   int n_steps;
   const double* forcing;   // [n_steps][ENRGY_F_COUNT]
   const double* pot_aws;   // streamed mode: potential insolation at the AWS cell per step [kWh m-2]
