@@ -41,6 +41,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Keeps fd 1 for the ONE JSON line: everything else written to stdout by this process or by
+    native libraries (NCCL prints its version banner there) is sent to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 # ---------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU through NVML during the timed region."""
@@ -133,6 +155,7 @@ def run_ours(args):
     import torch.distributed as dist
     from enrgy_b200 import _lib
 
+    claim_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -240,7 +263,8 @@ def run_ours(args):
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": "C2: %dx%d 10 m synthetic DEM + 5 albedo maps per GPU, %d hourly steps, "
                                    "in-kernel insolation (4 sub-steps/step), %s" % (n, n, T, "shading ray march" if SHADOW else "no shading"),
-                       "raster": [n * world, n], "steps_per_pass": T, "parallelism": "row bands x%d" % world,
+                       "raster": [n * world, n], "steps_per_pass": T, "parallelism": "row bands x%d, balanced by glacier cells" % world,
+                       "band_rows": [b[1] for b in case.meta["bands"]],
                        "l2": "per-pass inputs ~%.0f MB > 126 MB L2, no flush" % (bytes_per_launch / 1e6)},
             "roofline": {"bound": "fp32" if args.dtype == "f32" else "fp64", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
@@ -267,7 +291,7 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(result), flush=True)
+        emit(result)
 
 
 def issue_roofline(cell_steps, kernel_ms, clocks, dtype):
@@ -361,6 +385,7 @@ def cpu_baseline(n, steps, cores):
 
 def run_reference(args):
     """--impl reference: the CPU path on all host cores (rank 0 only)."""
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -378,7 +403,7 @@ def run_reference(args):
     value = float(np.mean(timed))
     cb = dict(last)
     cb["value"] = value
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "cell-timesteps/s",
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": len(timed), "warmup": min(args.warmup, len(vals) - len(timed)),
         "ms_per_step": float(n) * n * T / value * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -387,7 +412,7 @@ def run_reference(args):
                                % (n, n, T, args.cpu_sample_steps)},
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "cell-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def main():

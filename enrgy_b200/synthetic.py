@@ -180,20 +180,27 @@ def make_case(n=256, n_steps=24, seed=0, cell=10.0, glacier_mask=True, albedo_da
 
 
 def make_band_case(n, n_steps, world=1, rank=0, seed=0, cell=10.0, glacier_mask=True,
-                   albedo_dates=None, step_s=3600, start="20220601 00:00:00"):
-    """Weak-scaling workload: a (world*n) x n raster split into `world` row bands of n rows.
+                   albedo_dates=None, step_s=3600, start="20220601 00:00:00", balance=True):
+    """Weak-scaling workload: a (world*n) x n raster cut into `world` row bands.
 
-    Returns (case, dem_full): `case` holds the band-local albedo maps / SWE of `rank` and the AWS
-    description of the FULL raster (aws_rc in full-raster coordinates); `dem_full` is the whole DEM
-    (replicated on every rank)."""
+    With `balance` the band edges are placed so that every rank gets the same number of GLACIER
+    cells (off-glacier tiles cost nothing; SURVEY.md section 7 "load balance"), aligned to 16 rows;
+    otherwise every band has n rows.  Returns (case, dem_full): `case` holds the band-local albedo
+    maps / SWE of `rank` and the AWS description of the FULL raster (aws_rc in full-raster
+    coordinates); `dem_full` is the whole DEM (replicated on every rank)."""
+    from .parallel import row_bands
     rows_full = n * world
     dem_full = make_dem(rows_full, n, seed=seed, cell=cell, glacier_mask=glacier_mask)
-    r0 = rank * n
-    band = dem_full[r0:r0 + n]
+    if balance and world > 1:
+        bands = row_bands(rows_full, world, align=16, valid_per_row=(~np.isnan(dem_full)).sum(axis=1))
+    else:
+        bands = [(r * n, n) for r in range(world)]
+    r0, nrows = bands[rank]
+    band = dem_full[r0:r0 + nrows]
     gt = (DEFAULT_ULX, cell, 0.0, DEFAULT_ULY, 0.0, -cell)
     if albedo_dates is None:
         albedo_dates = ["20220520", "20220615", "20220710", "20220805", "20220915"]
-    albedo = make_albedo_maps(n, n, albedo_dates, seed=seed + 1, nan_like=band, row0=r0)
+    albedo = make_albedo_maps(nrows, n, albedo_dates, seed=seed + 1, nan_like=band, row0=r0)
     zmin, zmax = float(np.nanmin(dem_full)), float(np.nanmax(dem_full))
     rel = (band.astype(np.float64) - zmin) / max(zmax - zmin, 1.0)
     swe = np.where(0.5 * rel - 0.05 < 0.0, 0.0, 0.5 * rel - 0.05).astype(np.float32)
@@ -207,5 +214,6 @@ def make_band_case(n, n_steps, world=1, rank=0, seed=0, cell=10.0, glacier_mask=
     case = SyntheticCase(dem=band, geotransform=gt, cell=cell, albedo_maps=albedo, swe=swe,
                          aws_rows=aws, elev_aws=float(np.float32(dem_full[r, c])), xy_aws=(x, y),
                          aws_rc=(r, c), meta={"n": n, "n_steps": n_steps, "world": world, "rank": rank,
-                                              "band_row0": r0, "rows_full": rows_full})
+                                              "band_row0": r0, "band_rows": nrows, "rows_full": rows_full,
+                                              "bands": bands})
     return case, dem_full
