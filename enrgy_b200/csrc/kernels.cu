@@ -100,14 +100,11 @@ struct Num<double> {
   static __device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }
 };
 
-template <typename R>
-__device__ __forceinline__ R fmax_(R a, R b) {
-  return a > b ? a : b;
-}
-template <typename R>
-__device__ __forceinline__ R fmin_(R a, R b) {
-  return a < b ? a : b;
-}
+// single-instruction min / max (FMNMX / DMNMX); glacier cells never carry NaN here
+__device__ __forceinline__ float fmax_(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ float fmin_(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double fmax_(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ double fmin_(double a, double b) { return fmin(a, b); }
 
 // Sum of 8 per-thread values over the 32 lanes with 15 shuffles instead of 40: each butterfly stage
 // halves the number of values a lane still carries.  Returns the total of statistic
@@ -848,7 +845,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
           R es_t = (R)611.2;
           if (MSM) {                                        // Magnus term of the surface, turbo.py:377
             const R t0 = tl[i][0];
-            es_t = (R)611.2 * Num<R>::exp_(((R)17.62 * t0) / ((R)243.12 + t0));
+            es_t = (R)611.2 * Num<R>::exp_(((R)17.62 * t0) * Num<R>::rcp((R)243.12 + t0));
           }
           const R lat = (s.c_lat * r_rt) * (e - es_t * f_p);
           // longwave, model.py:533-545
@@ -886,6 +883,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
             R sd = swe[i] * m.inv_snow_density;
             R grad_prev = (R)0, t_next = tl[i][0];
             const R dt = s.dt;
+            const R inv_dt = (R)1 / dt;
             mf = (R)0;
 #pragma unroll
             for (int l = 0; l < kMaxLayers; ++l) {
@@ -902,9 +900,9 @@ energy_balance_kernel(const KernelArgs<R> a) {
                   gfl = kap * grad * m.c_ice * rho;
                   const R full = atmo + gfl;
                   const R crd = m.c_ice * rho * m.d[0];
-                  const R q0 = -t_here * crd / dt;
+                  const R q0 = -t_here * crd * inv_dt;
                   mf = fmax_(full - q0, (R)0);
-                  delta = (full - mf) / crd;
+                  delta = (full - mf) * Num<R>::rcp(crd);
                 } else {
                   delta = kap * (grad - grad_prev) * m.inv_d[l];          // msm.py:103
                 }
