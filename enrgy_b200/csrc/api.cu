@@ -67,6 +67,8 @@ struct enrgy_ctx {
   int device = 0, rows = 0, cols = 0, precision = ENRGY_F32;
   int sm_count = 148;
   enrgy_params p{};
+  double albedo_offset = 0.0;     // ensemble member
+  double base_albedo_ice = 0.0, base_albedo_snow = 0.0;
   bool have_params = false, have_dem = false, have_forcing = false, prepass_done = false;
   bool state_advanced = false;
   // geometry
@@ -213,6 +215,7 @@ int fill_args(enrgy_ctx* c, int t0, int t1, KernelArgs<R>& a) {
   a.map_stride = c->band_elems;
   a.albedo_const = c->p.albedo_const;
   a.albedo_ice = (R)c->p.albedo_ice; a.albedo_snow = (R)c->p.albedo_snow;
+  a.albedo_offset = (R)c->albedo_offset;
   a.max_ice_albedo = c->p.albedo_const ? (R)INFINITY : (R)c->p.max_ice_albedo;
   a.elev_aws = (R)c->p.elev_aws;
   a.zmax = (R)c->pre.zmax;
@@ -437,6 +440,8 @@ int enrgy_set_params(enrgy_ctx* c, const enrgy_params* pin) {
   if (p.band_rows == 0) { p.band_row0 = 0; p.band_rows = c->rows; }
   if (p.band_row0 < 0 || p.band_rows < 0 || p.band_row0 + p.band_rows > c->rows) return fail(ENRGY_ERR_ARG, "row band outside the raster");
   c->p = p;
+  c->albedo_offset = 0.0;
+  c->base_albedo_ice = p.albedo_ice; c->base_albedo_snow = p.albedo_snow;
   c->band_row0 = p.band_row0;
   c->band_rows = p.band_rows;
   c->tile_h = c->precision == ENRGY_F32 ? energy_balance_tile_h<float>(p.msm_layers > 0)
@@ -653,6 +658,28 @@ int enrgy_set_msm(enrgy_ctx* c, const double* temps, double elev) {
   return ENRGY_OK;
 }
 
+int enrgy_set_member(enrgy_ctx* c, double albedo_offset, double zm, double z_h_or_e) {
+  if (int e = use_device(c)) return e;
+  if (!c->have_params) return fail(ENRGY_ERR_ARG, "set_params must precede set_member");
+  if (std::isnan(albedo_offset)) albedo_offset = 0.0;
+  if (!std::isnan(zm)) {
+    if (!(zm > 0)) return fail(ENRGY_ERR_ARG, "zm must be > 0");
+    c->p.zm = zm;
+  }
+  if (!std::isnan(z_h_or_e)) {
+    if (!(z_h_or_e > 0)) return fail(ENRGY_ERR_ARG, "z_h_or_e must be > 0");
+    c->p.z_h_or_e = z_h_or_e;
+  }
+  c->albedo_offset = albedo_offset;
+  auto clip = [](double a) { return std::min(std::max(a, 0.001), 1.0); };
+  if (c->p.albedo_const) {
+    c->p.albedo_ice = albedo_offset != 0.0 ? clip(c->base_albedo_ice + albedo_offset) : c->base_albedo_ice;
+    c->p.albedo_snow = albedo_offset != 0.0 ? clip(c->base_albedo_snow + albedo_offset) : c->base_albedo_snow;
+  }
+  c->prepass_done = false;
+  return ENRGY_OK;
+}
+
 int enrgy_set_forcing(enrgy_ctx* c, int n_steps, const double* forcing) {
   if (int e = use_device(c)) return e;
   if (n_steps < 0 || (n_steps > 0 && !forcing)) return fail(ENRGY_ERR_ARG, "bad forcing table");
@@ -698,6 +725,7 @@ int enrgy_prepass(enrgy_ctx* c) {
   if (!c->have_dem || !c->have_forcing) return fail(ENRGY_ERR_ARG, "set_dem and set_forcing must precede prepass");
   PrepassInput in;
   in.p = c->p; in.precision = c->precision; in.rows = c->rows; in.cols = c->cols;
+  in.albedo_offset = c->albedo_offset;
   in.dem = c->h_dem.empty() ? nullptr : c->h_dem.data(); in.n_steps = c->n_steps; in.forcing = c->forcing.data();
   std::memcpy(in.nbhd, c->aws_nbhd, sizeof(in.nbhd)); in.zmax = c->zmax;
   in.pot_aws = c->pot_aws.data();

@@ -727,8 +727,9 @@ energy_balance_kernel(const KernelArgs<R> a) {
             for (int i = 0; i < K; ++i) {
               const size_t o = (size_t)rowb[i] * a.pitch + col[i];
               const bool v = (valid_bits >> i) & 1u;
-              const R x0 = v ? (R)__ldg(m0 + o) : (R)0.5;
-              const R x1 = v ? (R)__ldg(m1 + o) : (R)0.5;
+              // + ensemble offset, clipped like the loader clips a raster (identity for offset 0)
+              const R x0 = v ? fmin_(fmax_((R)__ldg(m0 + o) + a.albedo_offset, (R)0.001f), (R)1) : (R)0.5;
+              const R x1 = v ? fmin_(fmax_((R)__ldg(m1 + o) + a.albedo_offset, (R)0.001f), (R)1) : (R)0.5;
               a0[i] = x0;
               da[i] = x1 - x0;
             }

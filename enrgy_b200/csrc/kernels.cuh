@@ -37,6 +37,7 @@ struct KernelArgs {
   size_t map_stride;              // elements between consecutive albedo maps
   int albedo_const;
   R albedo_ice, albedo_snow, max_ice_albedo;
+  R albedo_offset;                // ensemble member: added to the map values, clipped to [0.001, 1]
   R elev_aws;
   R zmax;                         // max of the valid DEM, as float exactly
   // state, band-local [band_rows_pad][pitch]

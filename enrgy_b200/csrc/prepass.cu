@@ -371,8 +371,9 @@ int run_prepass(const PrepassInput& in, PrepassOutput& out, std::string& err) {
       if (p.albedo_const) {
         alb = has_snow ? p.albedo_snow : p.albedo_ice;
       } else {
-        const double x0 = in.alb_aws.empty() ? 0.5 : in.alb_aws[i0];
-        const double x1 = in.alb_aws.empty() ? 0.5 : in.alb_aws[i1];
+        auto member = [&](double a) { return std::min(std::max((double)(float)(a) + in.albedo_offset, (double)0.001f), 1.0); };
+        const double x0 = in.alb_aws.empty() ? 0.5 : member(in.alb_aws[i0]);
+        const double x1 = in.alb_aws.empty() ? 0.5 : member(in.alb_aws[i1]);
         const double blend = x0 + s.alb_w * (x1 - x0);
         alb = has_snow ? (s.snow_alb >= 0 ? s.snow_alb : blend) : std::min(blend, p.max_ice_albedo);
       }

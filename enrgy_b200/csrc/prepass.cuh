@@ -27,6 +27,7 @@ struct SubHost {
 struct PrepassInput {
   enrgy_params p;          // defaults already resolved (no NaNs left)
   int precision;           // ENRGY_F32 mirrors the as-shipped float32 point operations
+  double albedo_offset = 0.0;   // ensemble member (enrgy_set_member); p.albedo_ice/snow are already shifted
   int rows, cols;          // full raster
   const float* dem;        // full host DEM [rows][cols]; only needed (non-null) for the shading ray of the AWS cell
   float nbhd[9];           // DEM at the AWS cell and its 8 neighbours (row-major 3 x 3, NaN outside the grid)

@@ -98,6 +98,12 @@ class Engine:
         check(self.lib.enrgy_get_layer_temps(self.h, out.ctypes.data))
         return out
 
+    def set_member(self, albedo_offset=0.0, zm=None, z_h_or_e=None):
+        """Ensemble member on the resident handle (BASELINE config C5), see enrgy_set_member."""
+        nan = float("nan")
+        check(self.lib.enrgy_set_member(self.h, float(albedo_offset), nan if zm is None else float(zm),
+                                        nan if z_h_or_e is None else float(z_h_or_e)))
+
     def set_forcing(self, table):
         table = np.ascontiguousarray(table, dtype=np.float64)
         assert table.ndim == 2 and table.shape[1] == _lib.F_COUNT

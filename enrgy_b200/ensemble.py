@@ -1,0 +1,49 @@
+"""Parameter ensembles (BASELINE config C5): members share the DEM, terrain, albedo maps and forcing
+on the device and differ in an albedo offset and the roughness lengths.  Members are independent, so
+the ensemble axis shards over ranks with no collective except gathering the per-member totals.
+
+The reference has no ensemble code; a member is defined as the reference run on perturbed inputs
+(albedo maps / constants shifted by the offset and clipped to [0.001, 1] like raster_utils.py:48-50,
+`zm` / `z_h_or_e` replaced), which is what tests/test_gpu_ensemble.py checks against the oracle.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+
+def make_members(n, seed=0, albedo_sigma=0.03, zm_range=(3e-4, 3e-3)):
+    """Seeded perturbations of SURVEY.md 8(d) C5: albedo offset ~ N(0, sigma), zm log-uniform;
+    z_h_or_e = zm / 10 (the reference's default ratio, turbo.py:275-277)."""
+    rng = np.random.default_rng(seed)
+    off = albedo_sigma * rng.standard_normal(n)
+    zm = np.exp(rng.uniform(np.log(zm_range[0]), np.log(zm_range[1]), n))
+    return [dict(albedo_offset=float(o), zm=float(z), z_h_or_e=float(z) / 10.0) for o, z in zip(off, zm)]
+
+
+def shard(members, world, rank):
+    """Member indices of `rank` (round-robin)."""
+    return list(range(rank, len(members), world))
+
+
+def run_members(engine, members, indices=None, n_steps=None, keep_rasters=False):
+    """Runs the given members one after the other on a loaded Engine (DEM, albedo maps, SWE, forcing
+    set; state = initial).  Returns {index: dict(stats=[T, S_COUNT], mean_ice, mean_snow[, rasters])}."""
+    n_steps = engine.n_steps if n_steps is None else n_steps
+    indices = range(len(members)) if indices is None else indices
+    engine.snapshot(save=True)
+    out = {}
+    for i in indices:
+        m = members[i]
+        engine.snapshot(save=False)
+        engine.synchronize()
+        engine.set_member(m.get("albedo_offset", 0.0), m.get("zm"), m.get("z_h_or_e"))
+        engine.prepass()
+        stats = engine.run(0, n_steps)
+        swe, tsn, tic = engine.state(np.float32)
+        res = dict(stats=stats, mean_ice=float(np.nanmean(tic)), mean_snow=float(np.nanmean(tsn)))
+        if keep_rasters:
+            res.update(swe=swe, total_snow=tsn, total_ice=tic)
+        out[i] = res
+    return out

@@ -169,6 +169,14 @@ int enrgy_set_swe(enrgy_ctx* ctx, const float* swe);
  * temps[msm_layers + 1], distributed with -0.006 K/m from elev and capped at 0 inside. */
 int enrgy_set_msm(enrgy_ctx* ctx, const double* temps, double elev);
 
+/* ensemble member on an already loaded handle (BASELINE config C5; the reference has no ensemble
+ * code -- a member is "the reference run on perturbed inputs"): albedo_offset is added to every
+ * albedo map / constant albedo and the result clipped to [0.001, 1] exactly as the loader clips a
+ * raster (raster_utils.py:48-50); zm / z_h_or_e replace the roughness lengths (NaN = keep).  The
+ * DEM, terrain, albedo maps and forcing stay resident; call enrgy_set_swe (or enrgy_snapshot
+ * restore), enrgy_prepass and enrgy_run afterwards. */
+int enrgy_set_member(enrgy_ctx* ctx, double albedo_offset, double zm, double z_h_or_e);
+
 /* forcing table [n_steps][ENRGY_F_COUNT] (model.py:182-230) */
 int enrgy_set_forcing(enrgy_ctx* ctx, int n_steps, const double* forcing);
 

@@ -44,6 +44,15 @@ def run_oracle(case, pot, f64, keep_steps=None, **kw):
                        albedo_arrays=alb, state_dtype=dt, keep_steps=keep_steps, want_means=True)
 
 
+def run_oracle_arrays(case, pot, f64, **kw):
+    """Like run_oracle, but the case's albedo maps are taken as they are (already clipped)."""
+    dt = np.float64 if f64 else np.float32
+    cfg = oracle_config(case, **kw)
+    alb = None if kw.get("const_albedo") else {k: a.astype(dt) for k, a in case.albedo_maps.items()}
+    return O.run_model(case.dem.astype(dt), case.geotransform, case.aws_rows, np.asarray(pot, dtype=dt), cfg,
+                       swe=case.swe.astype(dt), albedo_arrays=alb, state_dtype=dt, want_means=True)
+
+
 def make_engine(case, f64, pot=None, computed=False, shadow=False, device=0, **kw):
     h, w = case.shape
     eng = Engine(h, w, precision=_lib.F64 if f64 else _lib.F32, device=device)
