@@ -75,6 +75,7 @@ struct enrgy_ctx {
   int pitch = 0, rows_pad_full = 0, band_row0 = 0, band_rows = 0, band_rows_pad = 0;
   int tile_h = 8, tiles_r = 0, tiles_c = 0, n_tiles = 0;
   double n_valid = 0.0;
+  double mom[5] = {0, 0, 0, 0, 0};   // moments of (dem - elev_aws) over the band's glacier cells
   size_t band_elems = 0;  // band_rows_pad * pitch
   // host copies
   std::vector<float> h_dem;       // full host copy, kept only when the AWS-cell shading ray needs it
@@ -292,6 +293,7 @@ int run_typed(enrgy_ctx* c, int t0, int t1, double* d_stats, cudaStream_t stream
     FinalizeArgs f{};
     f.partials = c->d_partials.p; f.n_ctas = grid; f.n_steps = n; f.t0 = t0;
     f.n_valid = c->n_valid; f.f32_mode = c->precision == ENRGY_F32; f.msm = msm ? 1 : 0;
+    for (int q = 0; q < 5; ++q) f.mom[q] = c->mom[q];
     f.steps64 = c->d_steps64.p; f.stats = d_stats;
     f.override_first = (t0 == 0 && !c->state_advanced) ? 1 : 0;
     f.swe0_sum = c->swe0_sum; f.swe0_nsnow = c->swe0_nsnow; f.swe0_nvalid = c->swe0_nvalid;
@@ -530,6 +532,26 @@ int enrgy_set_dem(enrgy_ctx* c, const float* dem) {
   c->n_valid = nv;
   CU_TRY(c->d_tiles.alloc(std::max<size_t>(tiles.size(), 1)));
   if (!tiles.empty()) CU_TRY(cudaMemcpyAsync(c->d_tiles.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+  // moments of the elevation difference (area sum of the downward longwave flux)
+  {
+    const int blocks = 296;
+    CU_TRY(c->d_small.alloc((size_t)blocks * 5));
+    if (c->precision == ENRGY_F32) {
+      CU_TRY(launch_moments<float>(c->dem0, c->dem_pitch, c->band_row0, c->band_rows, c->cols, c->p.elev_aws,
+                                   c->d_small.p, blocks, c->stream));
+    } else {
+      CU_TRY(launch_moments<double>(c->dem0, c->dem_pitch, c->band_row0, c->band_rows, c->cols, c->p.elev_aws,
+                                    c->d_small.p, blocks, c->stream));
+    }
+    c->launches++;
+    std::vector<double> h((size_t)blocks * 5);
+    CU_TRY(cudaMemcpyAsync(h.data(), c->d_small.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    for (int q = 0; q < 5; ++q) {
+      c->mom[q] = 0.0;
+      for (int b = 0; b < blocks; ++b) c->mom[q] += h[(size_t)b * 5 + q];
+    }
+  }
   // state rasters: zeros (model.py:76-80)
   const size_t rs = rsize(c);
   CU_TRY(c->d_swe.alloc(c->band_elems * rs));

@@ -323,6 +323,44 @@ cudaError_t launch_unpad_state(const R* src, int pitch, int rows, int cols, int 
 template cudaError_t launch_unpad_state<float>(const float*, int, int, int, int, void*, cudaStream_t);
 template cudaError_t launch_unpad_state<double>(const double*, int, int, int, int, void*, cudaStream_t);
 
+// sum over the glacier cells of (dem - elev_aws)^k, k = 0..4, per block (summed on the host in block
+// order): the area sum of the downward longwave flux is a quartic in the lapse-rate temperature
+template <typename R>
+__global__ void moments_kernel(const float* __restrict__ dem, int dem_pitch, int band_row0, int band_rows,
+                               int cols, R elev, double* __restrict__ block_out) {
+  double m[5] = {0, 0, 0, 0, 0};
+  const size_t n = (size_t)band_rows * cols;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int rb = (int)(i / cols), c = (int)(i % cols);
+    const float z = dem[(size_t)(rb + band_row0) * dem_pitch + c];
+    if (z == z) {
+      const double d = (double)((R)z - elev);       // the kernel's own delta (float32 in F32 mode)
+      const double d2 = d * d;
+      m[0] += 1.0; m[1] += d; m[2] += d2; m[3] += d2 * d; m[4] += d2 * d2;
+    }
+  }
+  __shared__ double sh[5][kThreads];
+  for (int q = 0; q < 5; ++q) sh[q][threadIdx.x] = m[q];
+  __syncthreads();
+  for (int off = kThreads / 2; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) {
+      for (int q = 0; q < 5; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + off];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < 5; ++q) block_out[blockIdx.x * 5 + q] = sh[q][0];
+  }
+}
+template <typename R>
+cudaError_t launch_moments(const float* dem, int dem_pitch, int band_row0, int band_rows, int cols, double elev,
+                           double* block_out, int blocks, cudaStream_t stream) {
+  moments_kernel<R><<<blocks, kThreads, 0, stream>>>(dem, dem_pitch, band_row0, band_rows, cols, (R)elev, block_out);
+  return cudaGetLastError();
+}
+template cudaError_t launch_moments<float>(const float*, int, int, int, int, double, double*, int, cudaStream_t);
+template cudaError_t launch_moments<double>(const float*, int, int, int, int, double, double*, int, cudaStream_t);
+
 // off-glacier cells of the state rasters become NaN with the first step (model.py:258: swe -= NaN);
 // the fused kernel only visits tiles that hold glacier cells, this covers the rest.
 template <typename R>
@@ -795,7 +833,8 @@ energy_balance_kernel(const KernelArgs<R> a) {
             }
           }
 #pragma unroll
-          for (int i = 0; i < K; ++i) pot[i] = direct[i] * nzv[i] + s.dsum * ((R)1 + nzv[i]);
+          // direct * nz + dsum * (1 + nz), two instructions
+          for (int i = 0; i < K; ++i) pot[i] = nzv[i] * (direct[i] + s.dsum) + s.dsum;
         }
 
         // ---- per-cell energy balance -------------------------------------------------------------
@@ -851,7 +890,8 @@ energy_balance_kernel(const KernelArgs<R> a) {
           const R lat = (s.c_lat * r_rt) * (e - es_t * f_p);
           // longwave, model.py:533-545
           const R tz2 = tz * tz;
-          const R lwd = s.c_lwd * (tz2 * tz2);
+          const R tz4 = tz2 * tz2;
+          const R lwd = s.c_lwd * tz4;                      // (only the dump needs it separately)
           R lwu = s.c_lwu;
           if (MSM) {
             if (sizeof(R) == 4) {
@@ -873,9 +913,13 @@ energy_balance_kernel(const KernelArgs<R> a) {
           const R blend = a0[i] + s.alb_w * da[i];
           const R alb = has_snow ? blend * keep_map + snow_const : fmin_(blend, a.max_ice_albedo);
           // shortwave, model.py:483-497
-          const R rs = pot[i] * s.c_sw * ((R)1 - alb);
+          const R sw_in = pot[i] * s.c_sw;
+          const R rs = sw_in - sw_in * alb;                 // incoming * (1 - albedo)
           // balance, clamp, melt partition: model.py:411, :434-438, msm.py:193-203
-          const R atmo = rs + lwd - lwu + sens + lat;
+          // rs + lwd - lwu + sens + lat with lwd = c_lwd * Tz^4 folded into one FMA; the area sum
+          // of lwd is not reduced here: Tz is linear in the elevation, so it follows from the first
+          // four moments of (dem - elev_aws), see finalize_stats_kernel
+          const R atmo = DUMP ? (rs + lwd - lwu + sens + lat) : (s.c_lwd * tz4 + (rs - lwu + sens + lat));
           R mf, gfl = (R)0;
           if (MSM) {
             // explicit conduction through the layer stack and the surface-layer melt gate,
@@ -924,7 +968,6 @@ energy_balance_kernel(const KernelArgs<R> a) {
           const R ice = we - snow;
           const R w = wgt[i];
           acc[K_RS] += w * rs;
-          acc[K_LWD] += w * lwd;
           acc[K_SENS] += w * sens;
           acc[K_LAT] += w * lat;
           acc[K_MELT] += w * mf;
@@ -1244,6 +1287,17 @@ __global__ void finalize_stats_kernel(const FinalizeArgs f) {
   const double c_melt = f32_mode ? (double)(float)s.c_melt : s.c_melt;
   double* o = f.stats + (size_t)t * ENRGY_S_COUNT;
   const double lwu = f.msm ? k[kStatsK + M_LWU] : f.n_valid * lwu_cell;
+  // sum over glacier cells of c_lwd * Tz^4 with Tz = a + g * delta: quartic in the moments of delta
+  double lwd_sum;
+  {
+    const double a = f32_mode ? (double)(float)s.t_air + (double)273.15f : s.t_air + 273.15;
+    const double g = f32_mode ? (double)(float)s.lapse : s.lapse;
+    const double c_lwd = f32_mode ? (double)(float)s.c_lwd : s.c_lwd;
+    const double a2 = a * a, g2 = g * g;
+    lwd_sum = c_lwd * (a2 * a2 * f.mom[0] + 4.0 * a2 * a * g * f.mom[1] + 6.0 * a2 * g2 * f.mom[2] +
+                       4.0 * a * g2 * g * f.mom[3] + g2 * g2 * f.mom[4]);
+  }
+  k[K_LWD] = lwd_sum;
   o[ENRGY_S_RS] = k[K_RS];
   o[ENRGY_S_LWD] = k[K_LWD];
   o[ENRGY_S_LWU] = lwu;

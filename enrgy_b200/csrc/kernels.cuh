@@ -77,6 +77,7 @@ struct FinalizeArgs {
   int msm;                  // sub-surface model on: lwu and g are summed per cell
   int n_ctas, n_steps, t0;
   double n_valid;           // valid cells of the band
+  double mom[5];            // sum over the band's glacier cells of (dem - elev_aws)^k, k = 0..4
   int f32_mode;             // round the per-step constants the way the float32 kernel saw them
   const StepRec<double>* steps64;  // master copy of the per-step records (float64)
   double* stats;            // [n_steps][ENRGY_S_COUNT]
@@ -98,6 +99,9 @@ cudaError_t launch_tile_scan(const float* dem, int pitch, int band_row0, int ban
 cudaError_t launch_mask_check(const float* dem, int dem_pitch, const float* other, int pitch,
                               int band_row0, int band_rows, int cols,
                               unsigned long long* counters /*[2]*/, cudaStream_t stream);
+template <typename R>
+cudaError_t launch_moments(const float* dem, int dem_pitch, int band_row0, int band_rows, int cols, double elev,
+                           double* block_out /*[blocks][5]*/, int blocks, cudaStream_t stream);
 cudaError_t launch_swe0_stats(const float* swe, int pitch, int band_rows, int cols,
                               double* block_out /*[blocks][3]*/, int blocks, cudaStream_t stream);
 template <typename R>

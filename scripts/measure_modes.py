@@ -34,12 +34,37 @@ def timed(eng, t, passes=3):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["streamed", "msm", "strong"])
+    ap.add_argument("mode", choices=["streamed", "msm", "strong", "ensemble"])
+    ap.add_argument("--members", type=int, default=8)
     ap.add_argument("--size", dest="n", type=int, default=2048)
     ap.add_argument("--nsteps", dest="t", type=int, default=256)
     ap.add_argument("--dtype", default="f32")
     a = ap.parse_args()
     prec = _lib.F32 if a.dtype == "f32" else _lib.F64
+    if a.mode == "ensemble":
+        # config C5: members share DEM / terrain / maps / forcing on the device
+        from enrgy_b200.ensemble import make_members, run_members
+        case, dem = make_band_case(a.n, a.t)
+        keys = list(case.albedo_maps)
+        eng = Engine(a.n, a.n, precision=prec)
+        eng.set_params(cell_size=10.0, elev_aws=case.elev_aws, aws_row=case.aws_rc[0], aws_col=case.aws_rc[1],
+                       sensor_z=1.6, zm=1e-3, z_h_or_e=1e-4, emissivity=0.98, lat=case.lat, lon=case.lon,
+                       insol_mode=_lib.INSOL_COMPUTED)
+        eng.set_dem(dem)
+        eng.set_albedo_maps([case.albedo_maps[k] for k in keys])
+        eng.set_swe(case.swe)
+        eng.set_forcing(build_forcing(case.aws_rows, keys))
+        members = make_members(a.members)
+        run_members(eng, members, indices=[0])                       # warm-up
+        t0 = time.perf_counter()
+        out = run_members(eng, members)
+        wall = time.perf_counter() - t0
+        cells = float(a.n) * a.n * a.t * a.members
+        print(json.dumps({"mode": "ensemble", "members": a.members, "n": a.n, "t": a.t, "wall_s": wall,
+                          "member_cell_steps_per_s": cells / wall,
+                          "mean_ice_spread": float(np.std([o["mean_ice"] for o in out.values()]))}))
+        eng.close()
+        return
     if a.mode in ("streamed", "msm"):
         case, dem = make_band_case(a.n, a.t)
         keys = list(case.albedo_maps)
