@@ -73,7 +73,7 @@ struct enrgy_ctx {
   bool state_advanced = false;
   // geometry
   int pitch = 0, rows_pad_full = 0, band_row0 = 0, band_rows = 0, band_rows_pad = 0;
-  int tile_h = 8, tiles_r = 0, tiles_c = 0, n_tiles = 0;
+  int tile_h = 8, tile_w = kTileW, tiles_r = 0, tiles_c = 0, n_tiles = 0;
   double n_valid = 0.0;
   double mom[5] = {0, 0, 0, 0, 0};   // moments of (dem - elev_aws) over the band's glacier cells
   size_t band_elems = 0;  // band_rows_pad * pitch
@@ -319,7 +319,9 @@ int dump_typed(enrgy_ctx* c, int t0, int t1, double* out, unsigned* mask_host, i
     a.mask_words = (c->cols + 31) / 32;
     const size_t words = (size_t)std::max(n_sub, 1) * c->band_rows * a.mask_words;
     CU_TRY(c->d_masks.alloc(words));
-    CU_TRY(cudaMemsetAsync(c->d_masks.p, 0, words * sizeof(unsigned), c->stream));
+    // off-glacier cells read "sunlit" (nothing marches from them); tiles without a glacier cell are
+    // never visited, so the buffer starts all-ones to give them the same value
+    CU_TRY(cudaMemsetAsync(c->d_masks.p, 0xFF, words * sizeof(unsigned), c->stream));
     a.mask_out = c->d_masks.p;
   } else {
     CU_TRY(c->d_dump.alloc((size_t)n * per_step * sizeof(R)));
@@ -446,8 +448,14 @@ int enrgy_set_params(enrgy_ctx* c, const enrgy_params* pin) {
   c->base_albedo_ice = p.albedo_ice; c->base_albedo_snow = p.albedo_snow;
   c->band_row0 = p.band_row0;
   c->band_rows = p.band_rows;
-  c->tile_h = c->precision == ENRGY_F32 ? energy_balance_tile_h<float>(p.msm_layers > 0)
-                                        : energy_balance_tile_h<double>(p.msm_layers > 0);
+  {
+    const int insol = p.insol_mode == ENRGY_INSOL_STREAMED ? kInsolStreamed : (p.shadow ? kInsolShadow : kInsolComputed);
+    if (c->precision == ENRGY_F32) {
+      energy_balance_tile<float>(p.msm_layers > 0, insol, &c->tile_h, &c->tile_w);
+    } else {
+      energy_balance_tile<double>(p.msm_layers > 0, insol, &c->tile_h, &c->tile_w);
+    }
+  }
   c->have_msm = false;
   c->band_rows_pad = round_up(std::max(c->band_rows, 1), 16);
   c->band_elems = (size_t)c->band_rows_pad * c->pitch;
@@ -507,13 +515,13 @@ int enrgy_set_dem(enrgy_ctx* c, const float* dem) {
   c->launches++;
   // active tiles of the band
   c->tiles_r = (c->band_rows + c->tile_h - 1) / c->tile_h;
-  c->tiles_c = c->pitch / kTileW;
+  c->tiles_c = c->pitch / c->tile_w;
   const int nt = c->tiles_r * c->tiles_c;
   CU_TRY(c->d_counts.alloc(std::max(nt, 1)));
   std::vector<int> counts(std::max(nt, 1), 0);
   if (nt > 0) {
-    CU_TRY(launch_tile_scan(c->dem0, c->dem_pitch, c->band_row0, c->band_rows, c->cols, c->tile_h, c->tiles_r,
-                            c->tiles_c, c->d_counts.p, c->stream));
+    CU_TRY(launch_tile_scan(c->dem0, c->dem_pitch, c->band_row0, c->band_rows, c->cols, c->tile_h, c->tile_w,
+                            c->tiles_r, c->tiles_c, c->d_counts.p, c->stream));
     c->launches++;
     CU_TRY(cudaMemcpyAsync(counts.data(), c->d_counts.p, (size_t)nt * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));

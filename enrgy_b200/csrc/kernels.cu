@@ -26,7 +26,13 @@
 
 #include "../../include/enrgy_b200.h"
 
+#ifndef ENRGY_RAY_UNROLL
+#define ENRGY_RAY_UNROLL 16
+#endif
+
 namespace enrgy {
+
+constexpr int kRayUnroll = ENRGY_RAY_UNROLL;   // ray steps in flight per thread in the sampling loop
 
 // =================================================================================================
 // small device helpers
@@ -196,13 +202,13 @@ template cudaError_t launch_terrain<double>(const float*, int, int, int, int, in
 
 // valid (non-NaN DEM) cells per tile
 __global__ void tile_scan_kernel(const float* __restrict__ dem, int pitch, int band_row0,
-                                 int band_rows, int cols, int tile_h, int tiles_c,
+                                 int band_rows, int cols, int tile_h, int tile_w, int tiles_c,
                                  int* __restrict__ counts) {
   const int tr = blockIdx.y, tc = blockIdx.x;
   int n = 0;
-  for (int i = threadIdx.x; i < tile_h * kTileW; i += blockDim.x) {
-    const int rb = tr * tile_h + i / kTileW;
-    const int c = tc * kTileW + i % kTileW;
+  for (int i = threadIdx.x; i < tile_h * tile_w; i += blockDim.x) {
+    const int rb = tr * tile_h + i / tile_w;
+    const int c = tc * tile_w + i % tile_w;
     if (rb < band_rows && c < cols) {
       const float z = dem[(size_t)(rb + band_row0) * pitch + c];
       n += (z == z) ? 1 : 0;
@@ -219,9 +225,10 @@ __global__ void tile_scan_kernel(const float* __restrict__ dem, int pitch, int b
   }
 }
 cudaError_t launch_tile_scan(const float* dem, int pitch, int band_row0, int band_rows, int cols,
-                             int tile_h, int tiles_r, int tiles_c, int* counts, cudaStream_t stream) {
+                             int tile_h, int tile_w, int tiles_r, int tiles_c, int* counts,
+                             cudaStream_t stream) {
   tile_scan_kernel<<<dim3(tiles_c, tiles_r), 256, 0, stream>>>(dem, pitch, band_row0, band_rows, cols,
-                                                               tile_h, tiles_c, counts);
+                                                               tile_h, tile_w, tiles_c, counts);
   return cudaGetLastError();
 }
 
@@ -573,7 +580,7 @@ __device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem
     float over[K];                                         // max over the chunk of (sample - ray height)
 #pragma unroll
     for (int i = 0; i < K; ++i) over[i] = -INFINITY;
-#pragma unroll 4
+#pragma unroll(kRayUnroll)
     for (int j = 0; j < kRayChunk; ++j) {
       const int ab = __shfl_sync(full, ab_l, j) + lane;
       const float kdz = __fmul_rn((float)(k + j), s.dz);
@@ -603,13 +610,25 @@ __device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem
 // =================================================================================================
 // the fused energy-balance kernel
 // =================================================================================================
-template <typename R>
+// Warps per CTA.  The energy balance alone runs 8 warps that share one staged copy of the AWS
+// records (their end-of-time-block barrier costs ~1 % there).  With the shading ray march the
+// warps of a CTA finish their rays at very different times and a quarter of all stall samples sat
+// at that barrier (profiles/r01_summary.md), so every warp is its own CTA there: no coupling at
+// all, 7-8 independent warps per SM at up to 255 registers.
+#ifndef ENRGY_SHADOW_WARPS
+#define ENRGY_SHADOW_WARPS 1
+#endif
+template <int INSOL>
+constexpr int kWarpsFor = (INSOL == kInsolShadow) ? ENRGY_SHADOW_WARPS : kWarps;
+__host__ __device__ constexpr int warps_x(int w) { return w >= 4 ? 4 : w; }          // patches side by side in a tile
+
+template <typename R, int W>
 struct SmemLayout {
   StepRec<R> steps[2][kMaxStepsPerBlock];
   SubRec<R> subs[2][kMaxSubsPerBlock];
   ShadeRec shades[2][kMaxSubsPerBlock];
-  R slots[kWarps][kMaxStepsPerBlock][kStatsK];
-  R slots_m[kWarps][kMaxStepsPerBlock][kStatsM];
+  R slots[W][kMaxStepsPerBlock][kStatsK];
+  R slots_m[W][kMaxStepsPerBlock][kStatsM];
   uint64_t full[2];
 };
 
@@ -627,20 +646,28 @@ struct SmemLayout {
 #define ENRGY_MINB64 2
 #endif
 
-template <typename R>
-constexpr int kSmemCommon = (int)((sizeof(SmemLayout<R>) + 127) / 128 * 128);
+template <typename R, int W>
+constexpr int kSmemCommon = (int)((sizeof(SmemLayout<R, W>) + 127) / 128 * 128);
 template <typename R, int INSOL>
-constexpr int kSmemTotal = kSmemCommon<R> + (INSOL == kInsolShadow ? kWarps * kWinBytes : 0);
+constexpr int kSmemTotal = kSmemCommon<R, kWarpsFor<INSOL>> + (INSOL == kInsolShadow ? kWarpsFor<INSOL> * kWinBytes : 0);
 
+#ifndef ENRGY_MINB_SHADOW
+#define ENRGY_MINB_SHADOW 1
+#endif
 template <typename R, int K, int INSOL, bool MSM, bool DUMP>
-__global__ void __launch_bounds__(kThreads, sizeof(R) == 4 ? ENRGY_MINB32 : ENRGY_MINB64)
+__global__ void __launch_bounds__(32 * kWarpsFor<INSOL>, INSOL == kInsolShadow
+                                                            ? ENRGY_MINB_SHADOW
+                                                            : (sizeof(R) == 4 ? ENRGY_MINB32 : ENRGY_MINB64))
 energy_balance_kernel(const KernelArgs<R> a) {
+  constexpr int W = kWarpsFor<INSOL>;              // warps per CTA
+  constexpr int WX = warps_x(W), WY = W / WX;      // patches of a tile: WX across, WY down
+  constexpr int NT = 32 * W;                       // threads per CTA
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  SmemLayout<R>& sm = *reinterpret_cast<SmemLayout<R>*>(smem_raw);
+  SmemLayout<R, W>& sm = *reinterpret_cast<SmemLayout<R, W>*>(smem_raw);
   // shading only: one DEM window per warp, behind the common layout
-  float* win_base = reinterpret_cast<float*>(smem_raw + kSmemCommon<R>);
+  float* win_base = reinterpret_cast<float*>(smem_raw + kSmemCommon<R, W>);
 
-  constexpr int TILE_H = (kWarps / 4) * K;
+  constexpr int TILE_H = WY * K, TILE_W = 32 * WX;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const R qnan = (R)__int_as_float(0x7fc00000);
 
@@ -698,8 +725,8 @@ energy_balance_kernel(const KernelArgs<R> a) {
     for (int i = 0; i < K; ++i) {
       // a warp owns a compact 32-column x K-row patch (lane = column): every raster access is one
       // coalesced 128 B line per row, and the patch keeps the shading bounding box tight
-      rowb[i] = tile.x * TILE_H + (warp >> 2) * K + i;
-      col[i] = tile.y * kTileW + (warp & 3) * 32 + lane;
+      rowb[i] = tile.x * TILE_H + (warp / WX) * K + i;
+      col[i] = tile.y * TILE_W + (warp % WX) * 32 + lane;
       rowf[i] = rowb[i] + a.band_row0;
       const size_t o = (size_t)rowb[i] * a.pitch + col[i];
       const bool inside = rowb[i] < a.band_rows && col[i] < a.cols;
@@ -1023,12 +1050,12 @@ energy_balance_kernel(const KernelArgs<R> a) {
       if (!DUMP && my_partials != nullptr) {
         constexpr int NQ = MSM ? kStatsP : kStatsK;
         const int n = (te - ts) * NQ;
-        for (int idx = tid; idx < n; idx += kThreads) {
+        for (int idx = tid; idx < n; idx += NT) {
           const int step = idx / NQ, q = idx - step * NQ;
           const int sl = ts - tb.t_begin + step;
           double sum = 0.0;
 #pragma unroll
-          for (int w = 0; w < kWarps; ++w) {
+          for (int w = 0; w < W; ++w) {
             sum += q < kStatsK ? (double)sm.slots[w][sl][q] : (double)sm.slots_m[w][sl][q - kStatsK];
           }
           my_partials[(size_t)(ts - a.t0 + step) * kStatsP + q] += sum;
@@ -1066,11 +1093,14 @@ struct CellsPerThread {
 };
 
 template <typename R>
-int energy_balance_tile_h(bool msm) {
-  return (kWarps / 4) * (msm ? CellsPerThread<R, true>::value : CellsPerThread<R, false>::value);
+void energy_balance_tile(bool msm, int insol, int* tile_h, int* tile_w) {
+  const int k = msm ? CellsPerThread<R, true>::value : CellsPerThread<R, false>::value;
+  const int w = insol == kInsolShadow ? kWarpsFor<kInsolShadow> : kWarpsFor<kInsolComputed>;
+  *tile_w = 32 * warps_x(w);
+  *tile_h = (w / warps_x(w)) * k;
 }
-template int energy_balance_tile_h<float>(bool);
-template int energy_balance_tile_h<double>(bool);
+template void energy_balance_tile<float>(bool, int, int*, int*);
+template void energy_balance_tile<double>(bool, int, int*, int*);
 
 template <typename R, int INSOL, bool MSM, bool DUMP>
 static cudaError_t configure(int sm_count, LaunchInfo* info) {
@@ -1080,7 +1110,7 @@ static cudaError_t configure(int sm_count, LaunchInfo* info) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * kWarpsFor<INSOL>, smem);
   if (e != cudaSuccess) return e;
   cudaFuncAttributes fa;
   e = cudaFuncGetAttributes(&fa, kern);
@@ -1105,7 +1135,7 @@ static cudaError_t launch_one(const KernelArgs<R>& a, int sm_count, int forced_g
   li.grid = grid;
   if (info) *info = li;
   if (a.n_tiles == 0 || a.t1 <= a.t0) return cudaSuccess;
-  energy_balance_kernel<R, K, INSOL, MSM, DUMP><<<grid, kThreads, li.smem_bytes, stream>>>(a);
+  energy_balance_kernel<R, K, INSOL, MSM, DUMP><<<grid, 32 * kWarpsFor<INSOL>, li.smem_bytes, stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -95,7 +95,8 @@ cudaError_t launch_terrain(const float* dem, int dem_pitch, int rows_full, int c
 cudaError_t launch_blockmax(const float* dem, int dem_pitch, int rows_full, int cols, const MaxPyramid& py,
                             float* buffer, cudaStream_t stream);
 cudaError_t launch_tile_scan(const float* dem, int pitch, int band_row0, int band_rows, int cols,
-                             int tile_h, int tiles_r, int tiles_c, int* counts, cudaStream_t stream);
+                             int tile_h, int tile_w, int tiles_r, int tiles_c, int* counts,
+                             cudaStream_t stream);
 cudaError_t launch_mask_check(const float* dem, int dem_pitch, const float* other, int pitch,
                               int band_row0, int band_rows, int cols,
                               unsigned long long* counters /*[2]*/, cudaStream_t stream);
@@ -121,7 +122,7 @@ template <typename R>
 cudaError_t launch_energy_balance(const KernelArgs<R>& a, const void* reserved, int insol, bool dump,
                                   int sm_count, int forced_grid, LaunchInfo* info, cudaStream_t stream);
 template <typename R>
-int energy_balance_tile_h(bool msm);
+void energy_balance_tile(bool msm, int insol, int* tile_h, int* tile_w);
 template <typename R>
 cudaError_t energy_balance_grid(int insol, bool msm, bool dump, int sm_count, LaunchInfo* info);
 // initial boundary temperatures: min(0, t_point[l] + (dem - elev) * -0.006), model.py:133-143
