@@ -237,6 +237,7 @@ int fill_args(enrgy_ctx* c, int t0, int t1, KernelArgs<R>& a) {
   a.subs = (const SubRec<R>*)c->d_subs.p;
   a.shades = c->d_shades.p;
   a.blocks = c->d_blocks.p;
+  a.cap_steps = c->pre.cap_steps; a.cap_subs = c->pre.cap_subs;
   int b0 = 0;
   const auto& bl = c->pre.blocks;
   while (b0 < (int)bl.size() && bl[b0].t_end <= t0) ++b0;
@@ -273,7 +274,7 @@ int run_typed(enrgy_ctx* c, int t0, int t1, double* d_stats, cudaStream_t stream
   const int insol = insol_variant(c);
   LaunchInfo li;
   const bool msm = c->p.msm_layers > 0;
-  CU_TRY(energy_balance_grid<R>(insol, msm, false, c->sm_count, &li));
+  CU_TRY(energy_balance_grid<R>(insol, msm, false, c->sm_count, a.cap_steps, a.cap_subs, &li));
   int grid = std::min(li.grid, std::max(c->n_tiles, 1));
   const int n = t1 - t0;
   CU_TRY(c->d_partials.alloc((size_t)grid * std::max(n, 1) * kStatsP));
@@ -759,6 +760,7 @@ int enrgy_prepass(enrgy_ctx* c) {
   in.dem = c->h_dem.empty() ? nullptr : c->h_dem.data(); in.n_steps = c->n_steps; in.forcing = c->forcing.data();
   std::memcpy(in.nbhd, c->aws_nbhd, sizeof(in.nbhd)); in.zmax = c->zmax;
   in.pot_aws = c->pot_aws.data();
+  if (insol_variant(c) == kInsolShadow) { in.cap_steps = kShadowStepsPerBlock; in.cap_subs = kShadowSubsPerBlock; }
   in.alb_aws = c->alb_aws; in.swe_aws = c->swe_aws; in.layer_t_aws = c->layer_t_aws;
   if (c->p.msm_layers > 0 && !c->have_msm) return fail(ENRGY_ERR_ARG, "enrgy_set_msm must precede prepass when msm_layers > 0");
   if (c->p.msm_layers > 0 && !c->p.albedo_const && (int)c->alb_aws.size() != c->n_maps)

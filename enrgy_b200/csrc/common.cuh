@@ -36,8 +36,19 @@ constexpr int kTileW = 128;                   // one warp row = 32 lanes x float
 constexpr int kStatsK = 8;                    // statistics reduced in the kernel (see StatK)
 constexpr int kStatsM = 2;                    // + upward longwave and in-glacier flux with the sub-surface model
 constexpr int kStatsP = kStatsK + kStatsM;    // columns of a per-CTA partial row
-constexpr int kMaxStepsPerBlock = 64;         // time block: per-step records staged in smem
-constexpr int kMaxSubsPerBlock = 256;         // ... and their sunlit sub-steps
+// time block = steps whose records (and sunlit sub-step records) are staged in smem together.  The
+// capacities are run-time values (KernelArgs::cap_steps / cap_subs); a block always holds at least
+// one whole step, so cap_subs grows to the largest sub-step count of any step (<= 255).
+#ifndef ENRGY_STEPS_PER_BLOCK
+#define ENRGY_STEPS_PER_BLOCK 64
+#endif
+#ifndef ENRGY_SHADOW_STEPS_PER_BLOCK
+#define ENRGY_SHADOW_STEPS_PER_BLOCK 16
+#endif
+constexpr int kStepsPerBlock = ENRGY_STEPS_PER_BLOCK;               // energy balance alone
+constexpr int kSubsPerBlock = 256;
+constexpr int kShadowStepsPerBlock = ENRGY_SHADOW_STEPS_PER_BLOCK;  // with the shading ray march (one-warp CTAs)
+constexpr int kShadowSubsPerBlock = 4 * kShadowStepsPerBlock;
 constexpr int kDemApron = 64;                 // NaN cells around the DEM buffer: a ray-chunk window of a warp
                                               // whose last active ray is at the grid edge stays inside it
 constexpr int kRayChunk = 16;                 // ray steps marched (or skipped) at a time

@@ -622,15 +622,30 @@ template <int INSOL>
 constexpr int kWarpsFor = (INSOL == kInsolShadow) ? ENRGY_SHADOW_WARPS : kWarps;
 __host__ __device__ constexpr int warps_x(int w) { return w >= 4 ? 4 : w; }          // patches side by side in a tile
 
-template <typename R, int W>
-struct SmemLayout {
-  StepRec<R> steps[2][kMaxStepsPerBlock];
-  SubRec<R> subs[2][kMaxSubsPerBlock];
-  ShadeRec shades[2][kMaxSubsPerBlock];
-  R slots[W][kMaxStepsPerBlock][kStatsK];
-  R slots_m[W][kMaxStepsPerBlock][kStatsM];
-  uint64_t full[2];
+// Shared-memory carve-up of a CTA.  The capacities of a time block (steps, sunlit sub-steps) are
+// run-time values chosen by the host: 64 / 256 for the energy balance alone, 16 / >= 64 with the
+// shading ray march, whose one-warp CTAs want many residents per SM rather than long time blocks.
+template <typename R>
+struct SmemPlan {
+  int steps, subs, shades, slots, slots_m, full, win, total;   // byte offsets and the total size
 };
+template <typename R>
+__host__ __device__ inline SmemPlan<R> smem_plan(int warps, int cap_steps, int cap_subs, bool with_subs,
+                                                 bool with_shades, bool msm) {
+  SmemPlan<R> p;
+  int o = 0;
+  p.steps = o;   o += 2 * cap_steps * (int)sizeof(StepRec<R>);
+  p.subs = o;    o += with_subs ? 2 * cap_subs * (int)sizeof(SubRec<R>) : 0;
+  p.shades = o;  o += with_shades ? 2 * cap_subs * (int)sizeof(ShadeRec) : 0;
+  p.slots = o;   o += warps * cap_steps * kStatsK * (int)sizeof(R);
+  p.slots_m = o; o += msm ? warps * cap_steps * kStatsM * (int)sizeof(R) : 0;
+  o = (o + 15) / 16 * 16;
+  p.full = o;    o += 16;
+  o = (o + 127) / 128 * 128;
+  p.win = o;     o += with_shades ? warps * kWinBytes : 0;
+  p.total = o;
+  return p;
+}
 
 // tuning knobs (cells per thread, minimum resident CTAs per SM), overridable at build time
 #ifndef ENRGY_K32
@@ -646,13 +661,8 @@ struct SmemLayout {
 #define ENRGY_MINB64 2
 #endif
 
-template <typename R, int W>
-constexpr int kSmemCommon = (int)((sizeof(SmemLayout<R, W>) + 127) / 128 * 128);
-template <typename R, int INSOL>
-constexpr int kSmemTotal = kSmemCommon<R, kWarpsFor<INSOL>> + (INSOL == kInsolShadow ? kWarpsFor<INSOL> * kWinBytes : 0);
-
 #ifndef ENRGY_MINB_SHADOW
-#define ENRGY_MINB_SHADOW 1
+#define ENRGY_MINB_SHADOW 12
 #endif
 template <typename R, int K, int INSOL, bool MSM, bool DUMP>
 __global__ void __launch_bounds__(32 * kWarpsFor<INSOL>, INSOL == kInsolShadow
@@ -663,17 +673,24 @@ energy_balance_kernel(const KernelArgs<R> a) {
   constexpr int WX = warps_x(W), WY = W / WX;      // patches of a tile: WX across, WY down
   constexpr int NT = 32 * W;                       // threads per CTA
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  SmemLayout<R, W>& sm = *reinterpret_cast<SmemLayout<R, W>*>(smem_raw);
+  const int cap_steps = a.cap_steps, cap_subs = a.cap_subs;
+  const SmemPlan<R> plan = smem_plan<R>(W, cap_steps, cap_subs, INSOL != kInsolStreamed, INSOL == kInsolShadow, MSM);
+  StepRec<R>* const sm_steps = reinterpret_cast<StepRec<R>*>(smem_raw + plan.steps);     // [2][cap_steps]
+  SubRec<R>* const sm_subs = reinterpret_cast<SubRec<R>*>(smem_raw + plan.subs);         // [2][cap_subs]
+  ShadeRec* const sm_shades = reinterpret_cast<ShadeRec*>(smem_raw + plan.shades);       // [2][cap_subs]
+  R* const sm_slots = reinterpret_cast<R*>(smem_raw + plan.slots);                       // [W][cap_steps][kStatsK]
+  R* const sm_slots_m = reinterpret_cast<R*>(smem_raw + plan.slots_m);                   // [W][cap_steps][kStatsM]
+  uint64_t* const sm_full = reinterpret_cast<uint64_t*>(smem_raw + plan.full);           // [2]
   // shading only: one DEM window per warp, behind the common layout
-  float* win_base = reinterpret_cast<float*>(smem_raw + kSmemCommon<R, W>);
+  float* win_base = reinterpret_cast<float*>(smem_raw + plan.win);
 
   constexpr int TILE_H = WY * K, TILE_W = 32 * WX;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const R qnan = (R)__int_as_float(0x7fc00000);
 
   if (tid == 0) {
-    mbar_init(&sm.full[0], 1);
-    mbar_init(&sm.full[1], 1);
+    mbar_init(&sm_full[0], 1);
+    mbar_init(&sm_full[1], 1);
     fence_mbar_init();
   }
   __syncthreads();
@@ -690,15 +707,15 @@ energy_balance_kernel(const KernelArgs<R> a) {
     if (INSOL != kInsolStreamed) bytes += n_subs * (unsigned)sizeof(SubRec<R>);
     if (use_shades) bytes += n_subs * (unsigned)sizeof(ShadeRec);
     fence_proxy_async();
-    mbar_expect_tx(&sm.full[buf], bytes);
-    tma_bulk_g2s(&sm.steps[buf][0], a.steps + tb.t_begin, n_steps * (unsigned)sizeof(StepRec<R>),
-                 &sm.full[buf]);
+    mbar_expect_tx(&sm_full[buf], bytes);
+    tma_bulk_g2s(sm_steps + buf * cap_steps, a.steps + tb.t_begin, n_steps * (unsigned)sizeof(StepRec<R>),
+                 &sm_full[buf]);
     if (INSOL != kInsolStreamed && n_subs) {
-      tma_bulk_g2s(&sm.subs[buf][0], a.subs + tb.sub_begin, n_subs * (unsigned)sizeof(SubRec<R>),
-                   &sm.full[buf]);
+      tma_bulk_g2s(sm_subs + buf * cap_subs, a.subs + tb.sub_begin, n_subs * (unsigned)sizeof(SubRec<R>),
+                   &sm_full[buf]);
       if (use_shades) {
-        tma_bulk_g2s(&sm.shades[buf][0], a.shades + tb.sub_begin, n_subs * (unsigned)sizeof(ShadeRec),
-                     &sm.full[buf]);
+        tma_bulk_g2s(sm_shades + buf * cap_subs, a.shades + tb.sub_begin, n_subs * (unsigned)sizeof(ShadeRec),
+                     &sm_full[buf]);
       }
     }
   };
@@ -764,7 +781,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
 
     for (int b = a.block_begin; b < a.block_end; ++b, buf ^= 1) {
       if (tid == 0 && b + 1 < a.block_end) issue_block(b + 1, buf ^ 1);
-      mbar_wait(&sm.full[buf], phase[buf]);
+      mbar_wait(&sm_full[buf], phase[buf]);
       phase[buf] ^= 1u;
       const TimeBlock tb = a.blocks[b];
       const int ts = max(tb.t_begin, a.t0), te = min(tb.t_end, a.t1);
@@ -780,7 +797,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
       }
 
       for (int t = ts; t < te; ++t) {
-        const StepRec<R> s = sm.steps[buf][t - tb.t_begin];
+        const StepRec<R> s = sm_steps[buf * cap_steps + (t - tb.t_begin)];
         // ---- albedo maps of this step's bracket (interpolator.py:12-18) -------------------------
         if (!a.albedo_const) {
           const int pair = (int)s.alb_pair;
@@ -825,7 +842,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
           const int sub_code = (int)s.sub;
           const int j0 = sub_code >> 8, nj = sub_code & 255;
           for (int j = j0; j < j0 + nj; ++j) {
-            const SubRec<R> sb = sm.subs[buf][j];
+            const SubRec<R> sb = sm_subs[buf * cap_subs + j];
             unsigned lit = 0xffffffffu;
             if (INSOL == kInsolShadow) {
               // production runs skip cells that face away from the sun (direct beam = 0 whatever
@@ -839,7 +856,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
                 }
               }
               lit = march<K>(a.dem, a.dem_pitch, my_win, a.rows_full, a.cols, a.blockmax,
-                             a.pyramid, rowf, col, z0, start_bits, sm.shades[buf][j], (float)a.zmax, lane);
+                             a.pyramid, rowf, col, z0, start_bits, sm_shades[buf * cap_subs + j], (float)a.zmax, lane);
               if (DUMP && a.mask_out != nullptr && t == a.t0) {
 #pragma unroll
                 for (int i = 0; i < K; ++i) {
@@ -1032,14 +1049,14 @@ energy_balance_kernel(const KernelArgs<R> a) {
         // ---- per-step statistics: warp butterfly, one slot per warp --------------------------------
         if (!DUMP) {
           const R tot = warp_reduce8<R>(acc, lane);
-          if ((lane & 3) == 0) sm.slots[warp][t - tb.t_begin][stat_of_lane(lane)] = tot;
+          if ((lane & 3) == 0) sm_slots[(warp * cap_steps + (t - tb.t_begin)) * kStatsK + stat_of_lane(lane)] = tot;
           if (MSM) {
 #pragma unroll
             for (int q = 0; q < kStatsM; ++q) {
               R v = acc_m[q];
 #pragma unroll
               for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-              if (lane == 0) sm.slots_m[warp][t - tb.t_begin][q] = v;
+              if (lane == 0) sm_slots_m[(warp * cap_steps + (t - tb.t_begin)) * kStatsM + q] = v;
             }
           }
         }
@@ -1056,7 +1073,8 @@ energy_balance_kernel(const KernelArgs<R> a) {
           double sum = 0.0;
 #pragma unroll
           for (int w = 0; w < W; ++w) {
-            sum += q < kStatsK ? (double)sm.slots[w][sl][q] : (double)sm.slots_m[w][sl][q - kStatsK];
+            sum += q < kStatsK ? (double)sm_slots[(w * cap_steps + sl) * kStatsK + q]
+                           : (double)sm_slots_m[(w * cap_steps + sl) * kStatsM + (q - kStatsK)];
           }
           my_partials[(size_t)(ts - a.t0 + step) * kStatsP + q] += sum;
         }
@@ -1103,10 +1121,11 @@ template void energy_balance_tile<float>(bool, int, int*, int*);
 template void energy_balance_tile<double>(bool, int, int*, int*);
 
 template <typename R, int INSOL, bool MSM, bool DUMP>
-static cudaError_t configure(int sm_count, LaunchInfo* info) {
+static cudaError_t configure(int sm_count, int cap_steps, int cap_subs, LaunchInfo* info) {
   constexpr int K = CellsPerThread<R, MSM>::value;
   auto kern = energy_balance_kernel<R, K, INSOL, MSM, DUMP>;
-  const int smem = kSmemTotal<R, INSOL>;
+  const int smem = smem_plan<R>(kWarpsFor<INSOL>, cap_steps, cap_subs, INSOL != kInsolStreamed,
+                                INSOL == kInsolShadow, MSM).total;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
@@ -1129,7 +1148,7 @@ static cudaError_t launch_one(const KernelArgs<R>& a, int sm_count, int forced_g
                               cudaStream_t stream) {
   constexpr int K = CellsPerThread<R, MSM>::value;
   LaunchInfo li;
-  cudaError_t e = configure<R, INSOL, MSM, DUMP>(sm_count, &li);
+  cudaError_t e = configure<R, INSOL, MSM, DUMP>(sm_count, a.cap_steps, a.cap_subs, &li);
   if (e != cudaSuccess) return e;
   int grid = forced_grid > 0 ? forced_grid : li.grid;
   li.grid = grid;
@@ -1153,13 +1172,15 @@ static cudaError_t dispatch(int insol, bool msm, bool dump, F&& f) {
 }
 
 template <typename R>
-cudaError_t energy_balance_grid(int insol, bool msm, bool dump, int sm_count, LaunchInfo* info) {
+cudaError_t energy_balance_grid(int insol, bool msm, bool dump, int sm_count, int cap_steps, int cap_subs,
+                                LaunchInfo* info) {
   return dispatch<R>(insol, msm, dump, [&](auto i, auto m, auto d) {
-    return configure<R, decltype(i)::value, decltype(m)::value, decltype(d)::value>(sm_count, info);
+    return configure<R, decltype(i)::value, decltype(m)::value, decltype(d)::value>(sm_count, cap_steps, cap_subs,
+                                                                                    info);
   });
 }
-template cudaError_t energy_balance_grid<float>(int, bool, bool, int, LaunchInfo*);
-template cudaError_t energy_balance_grid<double>(int, bool, bool, int, LaunchInfo*);
+template cudaError_t energy_balance_grid<float>(int, bool, bool, int, int, int, LaunchInfo*);
+template cudaError_t energy_balance_grid<double>(int, bool, bool, int, int, int, LaunchInfo*);
 
 template <typename R>
 cudaError_t launch_energy_balance(const KernelArgs<R>& a, const void* reserved, int insol, bool dump,

@@ -57,6 +57,7 @@ struct KernelArgs {
   const SubRec<R>* subs;          // [n_subs]
   const ShadeRec* shades;         // [n_subs]
   const TimeBlock* blocks;        // [n_blocks] covering at least [t0, t1)
+  int cap_steps, cap_subs;        // capacities the time blocks were cut for (smem staging buffers)
   int block_begin, block_end;     // blocks to process
   int t0, t1;                     // steps to process (clip of the first/last block)
   // work list
@@ -124,7 +125,8 @@ cudaError_t launch_energy_balance(const KernelArgs<R>& a, const void* reserved, 
 template <typename R>
 void energy_balance_tile(bool msm, int insol, int* tile_h, int* tile_w);
 template <typename R>
-cudaError_t energy_balance_grid(int insol, bool msm, bool dump, int sm_count, LaunchInfo* info);
+cudaError_t energy_balance_grid(int insol, bool msm, bool dump, int sm_count, int cap_steps, int cap_subs,
+                                LaunchInfo* info);
 // initial boundary temperatures: min(0, t_point[l] + (dem - elev) * -0.006), model.py:133-143
 template <typename R>
 cudaError_t launch_msm_init(const float* dem, int dem_pitch, int pitch, int band_row0, int band_rows_pad,

@@ -418,6 +418,9 @@ int run_prepass(const PrepassInput& in, PrepassOutput& out, std::string& err) {
   }
 
   // time blocks: as many consecutive steps as fit the smem staging buffers
+  out.cap_steps = std::max(in.cap_steps, 1);
+  out.cap_subs = std::max(in.cap_subs, 1);
+  for (int i = 0; i < T; ++i) out.cap_subs = std::max(out.cap_subs, out.sub_count[i]);
   int t = 0;
   while (t < T) {
     TimeBlock b;
@@ -425,7 +428,7 @@ int run_prepass(const PrepassInput& in, PrepassOutput& out, std::string& err) {
     b.sub_begin = out.sub_first[t];
     int n_sub = 0;
     int e = t;
-    while (e < T && e - t < kMaxStepsPerBlock && n_sub + out.sub_count[e] <= kMaxSubsPerBlock) {
+    while (e < T && e - t < out.cap_steps && n_sub + out.sub_count[e] <= out.cap_subs) {
       n_sub += out.sub_count[e];
       ++e;
     }

@@ -32,6 +32,8 @@ struct PrepassInput {
   const float* dem;        // full host DEM [rows][cols]; only needed (non-null) for the shading ray of the AWS cell
   float nbhd[9];           // DEM at the AWS cell and its 8 neighbours (row-major 3 x 3, NaN outside the grid)
   float zmax;              // max of the valid DEM (top of the device max pyramid)
+  int cap_steps = kStepsPerBlock;   // time-block capacities (smem staging buffers of the kernel)
+  int cap_subs = kSubsPerBlock;     // ... grown to the largest sub-step count of a single step
   int n_steps;
   const double* forcing;   // [n_steps][ENRGY_F_COUNT]
   const double* pot_aws;   // streamed mode: potential insolation at the AWS cell per step [kWh m-2]
@@ -47,6 +49,7 @@ struct PrepassOutput {
   std::vector<SubHost> subs;              // sunlit sub-steps of all steps, in order
   std::vector<int> sub_first, sub_count;  // per step: range into subs
   std::vector<TimeBlock> blocks;
+  int cap_steps = 0, cap_subs = 0;        // capacities the blocks were cut for
   std::vector<double> point;              // [n_steps][ENRGY_P_COUNT]
   float zmax = 0.f;                       // max of the valid DEM (ray termination)
 };

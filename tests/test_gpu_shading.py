@@ -94,3 +94,15 @@ def test_large_raster_spot_check():
             assert 0.005 < 1.0 - lit.mean() < 0.995    # the case really has both shade and light
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("step_s,n_steps", [(900, 40), (6 * 3600, 10), (24 * 3600, 4)])
+@pytest.mark.parametrize("f64", [False, True])
+def test_other_time_bases_with_shading(step_s, n_steps, f64):
+    """15-minute rows (BASELINE config C4's time base: one sun position per row), 6-hourly rows
+    (24 sub-steps per row) and daily rows (96 sub-steps per row, more than the default sub-step
+    capacity of a shading time block, which therefore has to grow) -- whole run vs the oracle."""
+    case = make_case(72, n_steps, w=100, seed=21, step_s=step_s, start="20220620 00:00:00")
+    res = P.compare_run(case, f64, computed=True, shadow=True)
+    worst = max(res.values())
+    assert worst < (1e-9 if f64 else 1e-4), res
