@@ -103,7 +103,8 @@ struct enrgy_ctx {
   DevBuf<ShadeRec> d_shades;
   DevBuf<TimeBlock> d_blocks;
   DevBuf<int2> d_tiles;
-  DevBuf<int> d_counts;
+  DevBuf<int> d_counts, d_demkeys;
+  bool dem_nonneg = false;   // no negative elevation: the shading samples use the integer copy (kInsolShadowKeys)
   DevBuf<double> d_partials, d_stats, d_small;
   DevBuf<unsigned long long> d_counters;
   DevBuf<unsigned> d_masks;
@@ -211,6 +212,7 @@ int fill_args(enrgy_ctx* c, int t0, int t1, KernelArgs<R>& a) {
   a.band_row0 = c->band_row0; a.band_rows = c->band_rows; a.rows_pad_full = c->rows_pad_full;
   a.dem = c->dem0; a.dem_pitch = c->dem_pitch;
   a.blockmax = c->d_blockmax.p; a.pyramid = c->pyramid;
+  a.dem_keys = c->d_demkeys.p ? c->d_demkeys.p + (size_t)kDemApron * c->dem_pitch + kDemApron : nullptr;
   a.nx = (const R*)c->d_nx.p; a.ny = (const R*)c->d_ny.p; a.nz = (const R*)c->d_nz.p;
   a.albedo = c->d_albedo.p;
   a.map_stride = c->band_elems;
@@ -251,7 +253,8 @@ int fill_args(enrgy_ctx* c, int t0, int t1, KernelArgs<R>& a) {
 
 int insol_variant(const enrgy_ctx* c) {
   if (c->p.insol_mode == ENRGY_INSOL_STREAMED) return kInsolStreamed;
-  return c->p.shadow ? kInsolShadow : kInsolComputed;
+  if (!c->p.shadow) return kInsolComputed;
+  return c->dem_nonneg ? kInsolShadowKeys : kInsolShadow;
 }
 
 int check_run_ready(enrgy_ctx* c, int t0, int t1) {
@@ -314,7 +317,7 @@ int dump_typed(enrgy_ctx* c, int t0, int t1, double* out, unsigned* mask_host, i
   const size_t per_step = (size_t)ENRGY_D_COUNT * c->band_elems;
   int n_sub = 0;
   if (mask_host) {
-    if (insol != kInsolShadow) return fail(ENRGY_ERR_ARG, "shade masks need insol_mode = COMPUTED with shadow = 1");
+    if (!insol_shadow(insol)) return fail(ENRGY_ERR_ARG, "shade masks need insol_mode = COMPUTED with shadow = 1");
     n_sub = c->pre.sub_count[t0];
     if (n_sub > max_sub) return fail(ENRGY_ERR_ARG, "step has %d sunlit sub-steps, buffer holds %d", n_sub, max_sub);
     a.mask_words = (c->cols + 31) / 32;
@@ -409,7 +412,7 @@ int enrgy_destroy(enrgy_ctx* c) {
   c->d_ti.release(); c->d_dump.release(); c->d_stage.release(); c->d_steps.release(); c->d_subs.release();
   c->d_steps64.release(); c->d_shades.release(); c->d_blocks.release(); c->d_tiles.release();
   c->d_counts.release(); c->d_partials.release(); c->d_stats.release(); c->d_small.release();
-  c->d_counters.release(); c->d_masks.release(); c->d_snap.release(); c->d_blockmax.release(); c->d_layer_t.release();
+  c->d_counters.release(); c->d_masks.release(); c->d_snap.release(); c->d_blockmax.release(); c->d_layer_t.release(); c->d_demkeys.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -514,6 +517,21 @@ int enrgy_set_dem(enrgy_ctx* c, const float* dem) {
     for (float v : tv) c->zmax = std::max(c->zmax, v);
   }
   c->launches++;
+  // shading: integer copy of the DEM buffer for the samples (march<K, KEYS>), used when no valid
+  // cell is negative
+  c->dem_nonneg = false;
+  if (c->p.insol_mode == ENRGY_INSOL_COMPUTED && c->p.shadow) {
+    CU_TRY(c->d_demkeys.alloc(dem_elems + 1));
+    int* d_min = c->d_demkeys.p + dem_elems;
+    const int int_max = 0x7fffffff;
+    CU_TRY(cudaMemcpyAsync(d_min, &int_max, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(launch_dem_keys(c->d_dem.p, c->d_demkeys.p, dem_elems, d_min, c->stream));
+    c->launches++;
+    int min_key = 0;
+    CU_TRY(cudaMemcpyAsync(&min_key, d_min, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    c->dem_nonneg = min_key >= 0 && c->p.shadow != 2;
+  }
   // active tiles of the band
   c->tiles_r = (c->band_rows + c->tile_h - 1) / c->tile_h;
   c->tiles_c = c->pitch / c->tile_w;
@@ -760,7 +778,7 @@ int enrgy_prepass(enrgy_ctx* c) {
   in.dem = c->h_dem.empty() ? nullptr : c->h_dem.data(); in.n_steps = c->n_steps; in.forcing = c->forcing.data();
   std::memcpy(in.nbhd, c->aws_nbhd, sizeof(in.nbhd)); in.zmax = c->zmax;
   in.pot_aws = c->pot_aws.data();
-  if (insol_variant(c) == kInsolShadow) { in.cap_steps = kShadowStepsPerBlock; in.cap_subs = kShadowSubsPerBlock; }
+  if (insol_shadow(insol_variant(c))) { in.cap_steps = kShadowStepsPerBlock; in.cap_subs = kShadowSubsPerBlock; }
   in.alb_aws = c->alb_aws; in.swe_aws = c->swe_aws; in.layer_t_aws = c->layer_t_aws;
   if (c->p.msm_layers > 0 && !c->have_msm) return fail(ENRGY_ERR_ARG, "enrgy_set_msm must precede prepass when msm_layers > 0");
   if (c->p.msm_layers > 0 && !c->p.albedo_const && (int)c->alb_aws.size() != c->n_maps)

@@ -232,6 +232,27 @@ cudaError_t launch_tile_scan(const float* dem, int pitch, int band_row0, int ban
   return cudaGetLastError();
 }
 
+// Integer copy of the DEM buffer (apron included) for the shading samples: -(bit pattern) of a valid
+// cell, +1 for NaN, so that "sample > ray height" reads "height bits + key < 0" for non-negative
+// floats.  min_key receives the order-preserving key of the lowest valid cell (negative iff the DEM
+// has a negative elevation, in which case the float samples are used instead).
+__global__ void dem_key_kernel(const float* __restrict__ dem, int* __restrict__ keys, size_t n, int* min_key) {
+  int lo = 0x7fffffff;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float z = dem[i];
+    const int b = __float_as_int(z);
+    const bool v = z == z;
+    keys[i] = v ? -b : 1;
+    if (v) lo = min(lo, b ^ ((b >> 31) & 0x7fffffff));
+  }
+  lo = __reduce_min_sync(0xffffffffu, lo);
+  if ((threadIdx.x & 31) == 0 && lo != 0x7fffffff) atomicMin(min_key, lo);
+}
+cudaError_t launch_dem_keys(const float* dem_buf, int* key_buf, size_t n, int* min_key, cudaStream_t stream) {
+  dem_key_kernel<<<1184, 256, 0, stream>>>(dem_buf, key_buf, n, min_key);
+  return cudaGetLastError();
+}
+
 // counters[0] += cells valid in the DEM but NaN in `other`; counters[1] += the opposite
 __global__ void mask_check_kernel(const float* __restrict__ dem, int dem_pitch,
                                   const float* __restrict__ other, int pitch, int band_row0,
@@ -473,7 +494,13 @@ __device__ __forceinline__ float key_float(int k) {
 // (c) samples the chunk: one coalesced 128 B read of the replicated DEM per cell row and step.
 // The NaN apron of kDemApron = kRayChunk cells lets a chunk that starts inside the grid run
 // without per-sample bounds checks.
-template <int K>
+//
+// KEYS: the samples come from the integer copy of the DEM (dem_key_kernel: minus the float's bit
+// pattern, +1 for NaN).  For non-negative floats the bit pattern orders like the value, so
+// "sample > ray height" is "height bits + key < 0" and the running test is ONE integer
+// add-and-minimum per sample (VIADDMNMX) instead of a subtract and a maximum.  The host picks this
+// path when the DEM has no negative elevation (ray heights only grow, so they are non-negative too).
+template <int K, bool KEYS>
 __device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem_pitch, float* win,
                                           int rows_full, int cols,
                                           const float* __restrict__ pyr, const MaxPyramid& py,
@@ -556,15 +583,17 @@ __device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem
     const int shift = x_buf - x_al;
     __syncwarp();                                          // every lane is done with the previous window
     {
+      // lane -> 16-byte column chunk (lane % 13) of the rows (lane / 13) + 2 * it; 26 lanes, 12 copies
+      // each, one 64-bit add per copy
       constexpr int kChunksPerRow = kWinW / 4;             // 13 x 16 B
-      const float* src0 = dem + ((long long)rmin * dem_pitch + (x_al - kDemApron));
+      const int rr = lane >= kChunksPerRow ? 1 : 0, cc = lane - rr * kChunksPerRow;
+      const float* src = dem + ((long long)(rmin + rr) * dem_pitch + (x_al - kDemApron) + cc * 4);
+      const uint32_t dst = smem_u32(win + rr * kWinW + cc * 4);
+      const long long stride = 2LL * dem_pitch;
+      if (lane < 2 * kChunksPerRow) {
 #pragma unroll
-      for (int q0 = 0; q0 < kWinH * kChunksPerRow; q0 += 32) {
-        const int q = q0 + lane;
-        if (q < kWinH * kChunksPerRow) {
-          const int r = q / kChunksPerRow, cc = q - r * kChunksPerRow;
-          const float* src = src0 + ((long long)r * dem_pitch + cc * 4);
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(win + r * kWinW + cc * 4)), "l"(src)
+        for (int it = 0; it < kWinH / 2; ++it) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + it * (2 * kWinW * 4)), "l"(src + it * stride)
                        : "memory");
         }
       }
@@ -577,25 +606,45 @@ __device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem
     const int ab_l = (ro_l - ro_min) * kWinW + (co_l - co_min) + shift;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    float over[K];                                         // max over the chunk of (sample - ray height)
-#pragma unroll
-    for (int i = 0; i < K; ++i) over[i] = -INFINITY;
-#pragma unroll(kRayUnroll)
-    for (int j = 0; j < kRayChunk; ++j) {
-      const int ab = __shfl_sync(full, ab_l, j) + lane;
-      const float kdz = __fmul_rn((float)(k + j), s.dz);
-      const float* p = win + ab;
-#pragma unroll
-      for (int i = 0; i < K; ++i) {
-        const float smp = p[i * kWinW];
-        const float zk = __fadd_rn(z0[i], kdz);
-        // smp > zk  <=>  smp - zk > 0 (IEEE subtraction keeps the sign; NaN samples never count)
-        over[i] = fmaxf(over[i], __fsub_rn(smp, zk));
-      }
-    }
     unsigned hit = 0u;
+    if (KEYS) {
+      int under[K];                                        // min over the chunk of (height bits - sample bits)
 #pragma unroll
-    for (int i = 0; i < K; ++i) hit |= (over[i] > 0.0f) ? (1u << i) : 0u;
+      for (int i = 0; i < K; ++i) under[i] = 0x7fffffff;
+      const int* wkeys = reinterpret_cast<const int*>(win);
+#pragma unroll(kRayUnroll)
+      for (int j = 0; j < kRayChunk; ++j) {
+        const int ab = __shfl_sync(full, ab_l, j) + lane;
+        const float kdz = __fmul_rn((float)(k + j), s.dz);
+        const int* p = wkeys + ab;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          const float zk = __fadd_rn(z0[i], kdz);
+          under[i] = min(under[i], __float_as_int(zk) + p[i * kWinW]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < K; ++i) hit |= (under[i] < 0) ? (1u << i) : 0u;
+    } else {
+      float over[K];                                       // max over the chunk of (sample - ray height)
+#pragma unroll
+      for (int i = 0; i < K; ++i) over[i] = -INFINITY;
+#pragma unroll(kRayUnroll)
+      for (int j = 0; j < kRayChunk; ++j) {
+        const int ab = __shfl_sync(full, ab_l, j) + lane;
+        const float kdz = __fmul_rn((float)(k + j), s.dz);
+        const float* p = win + ab;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          const float smp = p[i * kWinW];
+          const float zk = __fadd_rn(z0[i], kdz);
+          // smp > zk  <=>  smp - zk > 0 (IEEE subtraction keeps the sign; NaN samples never count)
+          over[i] = fmaxf(over[i], __fsub_rn(smp, zk));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < K; ++i) hit |= (over[i] > 0.0f) ? (1u << i) : 0u;
+    }
     // samples of a retired ray do not count: it left the grid or cleared the terrain before
     hit &= active;
     lit &= ~hit;
@@ -619,7 +668,7 @@ __device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem
 #define ENRGY_SHADOW_WARPS 1
 #endif
 template <int INSOL>
-constexpr int kWarpsFor = (INSOL == kInsolShadow) ? ENRGY_SHADOW_WARPS : kWarps;
+constexpr int kWarpsFor = insol_shadow(INSOL) ? ENRGY_SHADOW_WARPS : kWarps;
 __host__ __device__ constexpr int warps_x(int w) { return w >= 4 ? 4 : w; }          // patches side by side in a tile
 
 // Shared-memory carve-up of a CTA.  The capacities of a time block (steps, sunlit sub-steps) are
@@ -665,7 +714,7 @@ __host__ __device__ inline SmemPlan<R> smem_plan(int warps, int cap_steps, int c
 #define ENRGY_MINB_SHADOW 12
 #endif
 template <typename R, int K, int INSOL, bool MSM, bool DUMP>
-__global__ void __launch_bounds__(32 * kWarpsFor<INSOL>, INSOL == kInsolShadow
+__global__ void __launch_bounds__(32 * kWarpsFor<INSOL>, insol_shadow(INSOL)
                                                             ? ENRGY_MINB_SHADOW
                                                             : (sizeof(R) == 4 ? ENRGY_MINB32 : ENRGY_MINB64))
 energy_balance_kernel(const KernelArgs<R> a) {
@@ -674,7 +723,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
   constexpr int NT = 32 * W;                       // threads per CTA
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int cap_steps = a.cap_steps, cap_subs = a.cap_subs;
-  const SmemPlan<R> plan = smem_plan<R>(W, cap_steps, cap_subs, INSOL != kInsolStreamed, INSOL == kInsolShadow, MSM);
+  const SmemPlan<R> plan = smem_plan<R>(W, cap_steps, cap_subs, INSOL != kInsolStreamed, insol_shadow(INSOL), MSM);
   StepRec<R>* const sm_steps = reinterpret_cast<StepRec<R>*>(smem_raw + plan.steps);     // [2][cap_steps]
   SubRec<R>* const sm_subs = reinterpret_cast<SubRec<R>*>(smem_raw + plan.subs);         // [2][cap_subs]
   ShadeRec* const sm_shades = reinterpret_cast<ShadeRec*>(smem_raw + plan.shades);       // [2][cap_subs]
@@ -697,7 +746,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
   unsigned phase[2] = {0u, 0u};
   float* const my_win = win_base + (size_t)(tid >> 5) * (kWinBytes / sizeof(float));
 
-  const bool use_shades = INSOL == kInsolShadow;
+  const bool use_shades = insol_shadow(INSOL);
   auto issue_block = [&](int b, int buf) {
     // one elected thread: stage the per-step records (and sub-step records) of time block b
     const TimeBlock tb = a.blocks[b];
@@ -844,7 +893,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
           for (int j = j0; j < j0 + nj; ++j) {
             const SubRec<R> sb = sm_subs[buf * cap_subs + j];
             unsigned lit = 0xffffffffu;
-            if (INSOL == kInsolShadow) {
+            if (insol_shadow(INSOL)) {
               // production runs skip cells that face away from the sun (direct beam = 0 whatever
               // the mask says); the mask dump marches every glacier cell
               unsigned start_bits = valid_bits;
@@ -855,7 +904,8 @@ energy_balance_kernel(const KernelArgs<R> a) {
                   if (!(c > (R)0)) start_bits &= ~(1u << i);
                 }
               }
-              lit = march<K>(a.dem, a.dem_pitch, my_win, a.rows_full, a.cols, a.blockmax,
+              constexpr bool KEYS = INSOL == kInsolShadowKeys;
+              lit = march<K, KEYS>(KEYS ? reinterpret_cast<const float*>(a.dem_keys) : a.dem, a.dem_pitch, my_win, a.rows_full, a.cols, a.blockmax,
                              a.pyramid, rowf, col, z0, start_bits, sm_shades[buf * cap_subs + j], (float)a.zmax, lane);
               if (DUMP && a.mask_out != nullptr && t == a.t0) {
 #pragma unroll
@@ -872,7 +922,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
               // cos(incidence) / nz; nxv, nyv hold nx/nz, ny/nz (terrain_kernel)
               R c = sb.u + nxv[i] * sb.e + nyv[i] * sb.n;
               c = fmax_(c, (R)0);
-              if (INSOL == kInsolShadow) c = ((lit >> i) & 1u) ? c : (R)0;
+              if (insol_shadow(INSOL)) c = ((lit >> i) & 1u) ? c : (R)0;
               direct[i] += sb.b * c;
             }
           }
@@ -1113,7 +1163,7 @@ struct CellsPerThread {
 template <typename R>
 void energy_balance_tile(bool msm, int insol, int* tile_h, int* tile_w) {
   const int k = msm ? CellsPerThread<R, true>::value : CellsPerThread<R, false>::value;
-  const int w = insol == kInsolShadow ? kWarpsFor<kInsolShadow> : kWarpsFor<kInsolComputed>;
+  const int w = insol_shadow(insol) ? kWarpsFor<kInsolShadow> : kWarpsFor<kInsolComputed>;
   *tile_w = 32 * warps_x(w);
   *tile_h = (w / warps_x(w)) * k;
 }
@@ -1125,7 +1175,7 @@ static cudaError_t configure(int sm_count, int cap_steps, int cap_subs, LaunchIn
   constexpr int K = CellsPerThread<R, MSM>::value;
   auto kern = energy_balance_kernel<R, K, INSOL, MSM, DUMP>;
   const int smem = smem_plan<R>(kWarpsFor<INSOL>, cap_steps, cap_subs, INSOL != kInsolStreamed,
-                                INSOL == kInsolShadow, MSM).total;
+                                insol_shadow(INSOL), MSM).total;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
@@ -1163,10 +1213,10 @@ template <typename R, typename F>
 static cudaError_t dispatch(int insol, bool msm, bool dump, F&& f) {
 #define ENRGY_CASE(I, M, D) \
   if (insol == I && msm == M && dump == D) return f(std::integral_constant<int, I>{}, std::integral_constant<bool, M>{}, std::integral_constant<bool, D>{});
-  ENRGY_CASE(0, false, false) ENRGY_CASE(1, false, false) ENRGY_CASE(2, false, false)
-  ENRGY_CASE(0, true, false) ENRGY_CASE(1, true, false) ENRGY_CASE(2, true, false)
-  ENRGY_CASE(0, false, true) ENRGY_CASE(1, false, true) ENRGY_CASE(2, false, true)
-  ENRGY_CASE(0, true, true) ENRGY_CASE(1, true, true) ENRGY_CASE(2, true, true)
+  ENRGY_CASE(0, false, false) ENRGY_CASE(1, false, false) ENRGY_CASE(2, false, false) ENRGY_CASE(3, false, false)
+  ENRGY_CASE(0, true, false) ENRGY_CASE(1, true, false) ENRGY_CASE(2, true, false) ENRGY_CASE(3, true, false)
+  ENRGY_CASE(0, false, true) ENRGY_CASE(1, false, true) ENRGY_CASE(2, false, true) ENRGY_CASE(3, false, true)
+  ENRGY_CASE(0, true, true) ENRGY_CASE(1, true, true) ENRGY_CASE(2, true, true) ENRGY_CASE(3, true, true)
 #undef ENRGY_CASE
   return cudaErrorInvalidValue;
 }

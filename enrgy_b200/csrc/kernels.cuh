@@ -10,6 +10,8 @@ namespace enrgy {
 constexpr int kInsolStreamed = 0;  // per-step kWh m-2 raster streamed from HBM
 constexpr int kInsolComputed = 1;  // terrain normal . sun vector per sub-step, no shadows
 constexpr int kInsolShadow = 2;    // ... with the ray-marched sunlit mask
+constexpr int kInsolShadowKeys = 3;  // ... the same, sampling the integer copy of the DEM (no negative elevations)
+__host__ __device__ constexpr bool insol_shadow(int insol) { return insol >= kInsolShadow; }
 
 // Max pyramid of the DEM: level l holds the max of the valid cells of every (16 << l)^2 block as
 // [(nbr + 2)][(nbc + 2)] floats with one ring of -inf blocks, at offset off[l] of one buffer.
@@ -28,6 +30,7 @@ struct KernelArgs {
   const float* dem;               // full DEM (replicated for shading), pointing at cell (0, 0) of a
                                   // buffer with a NaN apron of kDemApron cells on every side
   int dem_pitch;                  // row stride of the DEM buffer
+  const int* dem_keys;            // same layout: -(bit pattern) of every valid cell, +1 for NaN (dem_key_kernel)
   const float* blockmax;          // max pyramid of the DEM (shading early exit), see MaxPyramid
   MaxPyramid pyramid;
   const R* nx;                    // [band_rows_pad][pitch] terrain normal (computed insolation)
@@ -95,6 +98,9 @@ cudaError_t launch_terrain(const float* dem, int dem_pitch, int rows_full, int c
                            cudaStream_t stream);
 cudaError_t launch_blockmax(const float* dem, int dem_pitch, int rows_full, int cols, const MaxPyramid& py,
                             float* buffer, cudaStream_t stream);
+// integer copy of the DEM buffer for the shading samples + min of the valid cells (as float bits key)
+cudaError_t launch_dem_keys(const float* dem_buf, int* key_buf, size_t n, int* min_key /*device, preset INT_MAX*/,
+                            cudaStream_t stream);
 cudaError_t launch_tile_scan(const float* dem, int pitch, int band_row0, int band_rows, int cols,
                              int tile_h, int tile_w, int tiles_r, int tiles_c, int* counts,
                              cudaStream_t stream);

@@ -49,7 +49,7 @@ class Engine:
         p.snow_density = nan if snow_density is None else snow_density
         p.ice_density = nan if ice_density is None else ice_density
         p.insol_mode = int(insol_mode)
-        p.shadow = 1 if shadow else 0
+        p.shadow = int(shadow) if shadow in (0, 1, 2) else (1 if shadow else 0)   # 2: float-sample march
         p.lat_deg, p.lon_deg = float(lat), float(lon)
         p.solar_const = nan if solar_const is None else solar_const
         p.transmittance = nan if transmittance is None else transmittance

@@ -129,7 +129,9 @@ typedef struct enrgy_params {
   double ice_density;    /* NaN = 900 */
   /* --- insolation (saga_lighting.py:42-44 options) --- */
   int32_t insol_mode;    /* ENRGY_INSOL_* */
-  int32_t shadow;        /* 1 = topographic shading ray march (SAGA -SHADOW) */
+  int32_t shadow;        /* 1 = topographic shading ray march (SAGA -SHADOW); 2 = the same, forcing the
+                            float-sample variant of the march (the default picks it only for DEMs with
+                            negative elevations; masks are identical either way) */
   double lat_deg;        /* grid reference latitude / longitude for the sun position */
   double lon_deg;
   double solar_const;    /* NaN = 1367 */

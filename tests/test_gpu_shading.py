@@ -106,3 +106,41 @@ def test_other_time_bases_with_shading(step_s, n_steps, f64):
     res = P.compare_run(case, f64, computed=True, shadow=True)
     worst = max(res.values())
     assert worst < (1e-9 if f64 else 1e-4), res
+
+
+def test_float_sample_variant_gives_the_same_masks():
+    """The march samples an integer copy of the DEM when no elevation is negative (one fused
+    integer add-min per sample); shadow=2 forces the float-sample variant.  Same masks, same run."""
+    case = make_case(120, 12, w=136, seed=31)
+    e_int, e_flt = P.make_engine(case, False, computed=True, shadow=1), P.make_engine(case, False, computed=True, shadow=2)
+    try:
+        for step in (1, 6, 10):
+            assert np.array_equal(e_int.shade_masks(step), e_flt.shade_masks(step))
+        assert np.array_equal(e_int.run(0, 12), e_flt.run(0, 12))
+        for a, b in zip(e_int.state(np.float64), e_flt.state(np.float64)):
+            assert np.array_equal(a, b, equal_nan=True)
+    finally:
+        e_int.close()
+        e_flt.close()
+
+
+def test_negative_elevations_fall_back_to_float_samples():
+    """A DEM with negative elevations (bit patterns of negative floats do not order like the values)
+    takes the float-sample march on its own; masks bit-exact vs the oracle."""
+    case = make_case(96, 8, w=110, seed=33)
+    case.dem[...] = case.dem - np.float32(520.0)          # spans about -320 .. +280 m
+    case.elev_aws = float(case.dem[case.aws_rc])
+    assert np.nanmin(case.dem) < 0 < np.nanmax(case.dem)
+    eng = _engine(case)
+    try:
+        valid = ~np.isnan(case.dem)
+        for step in (0, 3, 7):
+            table = I.substep_table(I.to_unix(case.aws_rows[step]["DATE"]), time_step_seconds(case.aws_rows, step),
+                                    case.lat, case.lon, case.cell)
+            masks = eng.shade_masks(step)
+            assert masks.shape[0] == len(table)
+            for j, sub in enumerate(table):
+                lit = I.shadow_mask(case.dem, sub["dc_fix"], sub["dr_fix"], sub["dz"])
+                assert np.array_equal(masks[j][valid], lit[valid]), (step, j)
+    finally:
+        eng.close()
