@@ -710,6 +710,9 @@ __host__ __device__ inline SmemPlan<R> smem_plan(int warps, int cap_steps, int c
 #define ENRGY_MINB64 2
 #endif
 
+#ifndef ENRGY_SUB_PHASES
+#define ENRGY_SUB_PHASES 1
+#endif
 #ifndef ENRGY_MINB_SHADOW
 #define ENRGY_MINB_SHADOW 12
 #endif
@@ -777,7 +780,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
     const int2 tile = a.tiles[ti];
     // ---- prologue: per-cell invariants and state into registers --------------------------------
     int rowb[K], col[K];           // band-local row, column
-    R delta[K], pw[K], a0[K], da[K], nxv[K], nyv[K], nzv[K], swe[K], tsn[K], tic[K], wgt[K];
+    R delta[K], pw[K], a0[K], da[K], nxv[K], nyv[K], nzv[K], swe[K], tic[K];
     float z0[K];
     int rowf[K];
     R tl[K][NB];                   // sub-surface boundary temperatures [deg C] (MSM)
@@ -799,7 +802,6 @@ energy_balance_kernel(const KernelArgs<R> a) {
       float z = inside ? __ldg(a.dem + (size_t)rowf[i] * a.dem_pitch + col[i]) : __int_as_float(0x7fc00000);
       const bool v = z == z;
       valid_bits |= v ? (1u << i) : 0u;
-      wgt[i] = v ? (R)1 : (R)0;
       z0[i] = z;
       if (!v) z = (float)a.elev_aws;           // keep the arithmetic of masked cells finite
       delta[i] = (R)z - a.elev_aws;            // var_classes.py:114
@@ -812,7 +814,6 @@ energy_balance_kernel(const KernelArgs<R> a) {
         nxv[i] = nyv[i] = (R)0; nzv[i] = (R)1;
       }
       swe[i] = v ? a.swe[o] : (R)0;
-      tsn[i] = swe[i];               // SWE at the start of the run, for total_snow in the epilogue
       tic[i] = v ? a.total_ice[o] : (R)0;
       a0[i] = a.albedo_const ? a.albedo_ice : (R)0.5;
       da[i] = (R)0;
@@ -917,6 +918,24 @@ energy_balance_kernel(const KernelArgs<R> a) {
                 }
               }
             }
+#if ENRGY_SUB_PHASES
+            {
+              // cos(incidence) / nz; nxv, nyv hold nx/nz, ny/nz (terrain_kernel).  Written phase by
+              // phase over the K cells so that the K dependency chains interleave.
+              R c[K];
+#pragma unroll
+              for (int i = 0; i < K; ++i) c[i] = sb.u + nxv[i] * sb.e;
+#pragma unroll
+              for (int i = 0; i < K; ++i) c[i] = c[i] + nyv[i] * sb.n;
+#pragma unroll
+              for (int i = 0; i < K; ++i) {
+                c[i] = fmax_(c[i], (R)0);
+                if (insol_shadow(INSOL)) c[i] = ((lit >> i) & 1u) ? c[i] : (R)0;
+              }
+#pragma unroll
+              for (int i = 0; i < K; ++i) direct[i] += sb.b * c[i];
+            }
+#else
 #pragma unroll
             for (int i = 0; i < K; ++i) {
               // cos(incidence) / nz; nxv, nyv hold nx/nz, ny/nz (terrain_kernel)
@@ -925,6 +944,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
               if (insol_shadow(INSOL)) c = ((lit >> i) & 1u) ? c : (R)0;
               direct[i] += sb.b * c;
             }
+#endif
           }
 #pragma unroll
           // direct * nz + dsum * (1 + nz), two instructions
@@ -1060,17 +1080,20 @@ energy_balance_kernel(const KernelArgs<R> a) {
           const R we = mf * s.c_melt;
           const R snow = fmin_(we, swe[i]);
           const R ice = we - snow;
-          const R w = wgt[i];
-          acc[K_RS] += w * rs;
-          acc[K_SENS] += w * sens;
-          acc[K_LAT] += w * lat;
-          acc[K_MELT] += w * mf;
+          // off-glacier cells of a visited tile carry finite dummy values: they are left out by
+          // predicated adds on the validity bit (no per-cell weight register)
+          if ((valid_bits >> i) & 1u) {
+            acc[K_RS] += rs;
+            acc[K_SENS] += sens;
+            acc[K_LAT] += lat;
+            acc[K_MELT] += mf;
+            if (MSM) {
+              acc_m[M_LWU] += lwu;
+              acc_m[M_G] += gfl;
+            }
+          }
           acc[K_SNOW] += snow;          // masked cells: swe = 0 -> snow = 0
           acc[K_SWE] += swe[i];
-          if (MSM) {
-            acc_m[M_LWU] += w * lwu;
-            acc_m[M_G] += w * gfl;
-          }
           n_snow += has_snow ? 1 : 0;
           if (DUMP && a.dump != nullptr) {
             if ((valid_bits >> i) & 1u) {
@@ -1139,8 +1162,10 @@ energy_balance_kernel(const KernelArgs<R> a) {
         if (rowb[i] < a.band_rows && col[i] < a.cols) {
           const size_t o = (size_t)rowb[i] * a.pitch + col[i];
           const bool v = (valid_bits >> i) & 1u;
+          // total_snow grows by swe(start) - swe(end); the start value is still in HBM
+          const R swe_start = v ? a.swe[o] : (R)0;
           a.swe[o] = v ? swe[i] : qnan;
-          a.total_snow[o] = v ? a.total_snow[o] + (tsn[i] - swe[i]) : qnan;
+          a.total_snow[o] = v ? a.total_snow[o] + (swe_start - swe[i]) : qnan;
           a.total_ice[o] = v ? tic[i] : qnan;
           if (MSM) {
 #pragma unroll
