@@ -106,6 +106,11 @@ struct Num<double> {
   static __device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }
 };
 
+// value barrier: the compiler may neither rematerialise x from its inputs nor see through it
+__device__ __forceinline__ void keep_in_register(float& x) { asm volatile("" : "+f"(x)); }
+__device__ __forceinline__ void keep_in_register(double& x) { asm volatile("" : "+d"(x)); }
+__device__ __forceinline__ void keep_in_register(unsigned& x) { asm volatile("" : "+r"(x)); }
+
 // single-instruction min / max (FMNMX / DMNMX); glacier cells never carry NaN here
 __device__ __forceinline__ float fmax_(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ float fmin_(float a, float b) { return fminf(a, b); }
@@ -806,6 +811,9 @@ energy_balance_kernel(const KernelArgs<R> a) {
       if (!v) z = (float)a.elev_aws;           // keep the arithmetic of masked cells finite
       delta[i] = (R)z - a.elev_aws;            // var_classes.py:114
       pw[i] = Num<R>::pow10(-delta[i] / (R)kVapourScale);   // var_classes.py:162
+      // keep delta itself in a register: left alone, the compiler re-derives it (and the validity
+      // test) from the raw elevation in every step, three extra instructions per cell-step
+      if (sizeof(R) == 4) keep_in_register(delta[i]);   // (float64 is short of registers: it may)
       if (INSOL != kInsolStreamed) {
         nxv[i] = v ? a.nx[o] : (R)0;
         nyv[i] = v ? a.ny[o] : (R)0;
@@ -815,7 +823,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
       }
       swe[i] = v ? a.swe[o] : (R)0;
       tic[i] = v ? a.total_ice[o] : (R)0;
-      a0[i] = a.albedo_const ? a.albedo_ice : (R)0.5;
+      a0[i] = a.albedo_const ? (R)1 - a.albedo_ice : (R)0.5;   // a0, da hold 1 - albedo (see the albedo step)
       da[i] = (R)0;
       if (MSM) {
 #pragma unroll
@@ -826,6 +834,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
       }
     }
 
+    keep_in_register(valid_bits);
     int buf = 0;
     if (tid == 0) issue_block(a.block_begin, 0);
 
@@ -862,8 +871,8 @@ energy_balance_kernel(const KernelArgs<R> a) {
               // + ensemble offset, clipped like the loader clips a raster (identity for offset 0)
               const R x0 = v ? fmin_(fmax_((R)__ldg(m0 + o) + a.albedo_offset, (R)0.001f), (R)1) : (R)0.5;
               const R x1 = v ? fmin_(fmax_((R)__ldg(m1 + o) + a.albedo_offset, (R)0.001f), (R)1) : (R)0.5;
-              a0[i] = x0;
-              da[i] = x1 - x0;
+              a0[i] = (R)1 - x0;               // the loop works with 1 - albedo
+              da[i] = x0 - x1;
             }
           }
         }
@@ -959,8 +968,10 @@ energy_balance_kernel(const KernelArgs<R> a) {
         R acc_m[kStatsM] = {(R)0, (R)0};
         // albedo of snow-covered cells: the aged value when ageing is on, else the blended map
         // (uniform per step): alb_snow = alb * keep_map + snow_const
+        // (the loop carries 1 - albedo: a0, da and these constants are complemented)
         const R keep_map = s.snow_alb >= (R)0 ? (R)0 : (R)1;
-        const R snow_const = s.snow_alb >= (R)0 ? s.snow_alb : (R)0;
+        const R snow_const = s.snow_alb >= (R)0 ? (R)1 - s.snow_alb : (R)0;
+        const R ice_floor = (R)1 - a.max_ice_albedo;      // 1 - cap (-inf with constant albedo)
 #pragma unroll
         for (int i = 0; i < K; ++i) {
           // lapse-rate distribution, var_classes.py:113-125
@@ -992,7 +1003,9 @@ energy_balance_kernel(const KernelArgs<R> a) {
             r_rt = Num<R>::rcp((R)kRair * tz);
             r_p = Num<R>::rcp(p_hpa);
           }
-          const R sens = (s.c_sens * p_hpa) * (r_rt * d_t);
+          // every flux is (per-step scalar) x (per-cell factor): the scalar rides the FMA chain of the
+          // balance and scales the area sums afterwards (finalize_stats_kernel), the loop keeps the factor
+          const R x_sens = p_hpa * (r_rt * d_t);            // sens = c_sens * x_sens
           // saturation vapour pressure of the melting surface, turbo.py:368-379 with t = 0:
           // exp(0) = 1 exactly, so es = 611.2 * f(p).  ez = e_max * (e / e_max) = e (one rounding).
           const R f_p = (R)1.0016 + (R)(3.15 * 1e-6) * p_hpa - (R)0.074 * r_p;
@@ -1001,11 +1014,10 @@ energy_balance_kernel(const KernelArgs<R> a) {
             const R t0 = tl[i][0];
             es_t = (R)611.2 * Num<R>::exp_(((R)17.62 * t0) * Num<R>::rcp((R)243.12 + t0));
           }
-          const R lat = (s.c_lat * r_rt) * (e - es_t * f_p);
+          const R x_lat = r_rt * (e - es_t * f_p);          // lat = c_lat * x_lat
           // longwave, model.py:533-545
           const R tz2 = tz * tz;
           const R tz4 = tz2 * tz2;
-          const R lwd = s.c_lwd * tz4;                      // (only the dump needs it separately)
           R lwu = s.c_lwu;
           if (MSM) {
             if (sizeof(R) == 4) {
@@ -1024,16 +1036,15 @@ energy_balance_kernel(const KernelArgs<R> a) {
           // maps: blend of the bracketing maps; snow cells take the aged snow albedo when ageing
           // is on; ice cells are capped.  Constant albedo rides the same formula: a0 = ice,
           // da = 0, snow_alb = snow (so keep_map = 0), cap = +inf (set up by the host).
-          const R blend = a0[i] + s.alb_w * da[i];
-          const R alb = has_snow ? blend * keep_map + snow_const : fmin_(blend, a.max_ice_albedo);
-          // shortwave, model.py:483-497
-          const R sw_in = pot[i] * s.c_sw;
-          const R rs = sw_in - sw_in * alb;                 // incoming * (1 - albedo)
+          const R blend = a0[i] + s.alb_w * da[i];          // 1 - blended albedo
+          const R oma = has_snow ? blend * keep_map + snow_const : fmax_(blend, ice_floor);
+          // shortwave, model.py:483-497: rs = potential * c_sw * (1 - albedo)
+          const R x_rs = pot[i] * oma;
           // balance, clamp, melt partition: model.py:411, :434-438, msm.py:193-203
           // rs + lwd - lwu + sens + lat with lwd = c_lwd * Tz^4 folded into one FMA; the area sum
           // of lwd is not reduced here: Tz is linear in the elevation, so it follows from the first
           // four moments of (dem - elev_aws), see finalize_stats_kernel
-          const R atmo = DUMP ? (rs + lwd - lwu + sens + lat) : (s.c_lwd * tz4 + (rs - lwu + sens + lat));
+          const R atmo = s.c_lat * x_lat + (s.c_sens * x_sens + (s.c_sw * x_rs + (s.c_lwd * tz4 - lwu)));
           R mf, gfl = (R)0;
           if (MSM) {
             // explicit conduction through the layer stack and the surface-layer melt gate,
@@ -1083,9 +1094,9 @@ energy_balance_kernel(const KernelArgs<R> a) {
           // off-glacier cells of a visited tile carry finite dummy values: they are left out by
           // predicated adds on the validity bit (no per-cell weight register)
           if ((valid_bits >> i) & 1u) {
-            acc[K_RS] += rs;
-            acc[K_SENS] += sens;
-            acc[K_LAT] += lat;
+            acc[K_RS] += x_rs;
+            acc[K_SENS] += x_sens;
+            acc[K_LAT] += x_lat;
             acc[K_MELT] += mf;
             if (MSM) {
               acc_m[M_LWU] += lwu;
@@ -1099,16 +1110,16 @@ energy_balance_kernel(const KernelArgs<R> a) {
             if ((valid_bits >> i) & 1u) {
               R* d = a.dump + (size_t)(t - a.t0) * ENRGY_D_COUNT * a.dump_field_stride +
                      (size_t)rowb[i] * a.pitch + col[i];
-              d[ENRGY_D_RS * a.dump_field_stride] = rs;
-              d[ENRGY_D_LWD * a.dump_field_stride] = lwd;
+              d[ENRGY_D_RS * a.dump_field_stride] = s.c_sw * x_rs;
+              d[ENRGY_D_LWD * a.dump_field_stride] = s.c_lwd * tz4;
               d[ENRGY_D_LWU * a.dump_field_stride] = lwu;
-              d[ENRGY_D_SENS * a.dump_field_stride] = sens;
-              d[ENRGY_D_LAT * a.dump_field_stride] = lat;
+              d[ENRGY_D_SENS * a.dump_field_stride] = s.c_sens * x_sens;
+              d[ENRGY_D_LAT * a.dump_field_stride] = s.c_lat * x_lat;
               d[ENRGY_D_ATMO * a.dump_field_stride] = atmo;
               d[ENRGY_D_MELT * a.dump_field_stride] = mf;
               d[ENRGY_D_SNOW * a.dump_field_stride] = snow;
               d[ENRGY_D_ICE * a.dump_field_stride] = ice;
-              d[ENRGY_D_ALBEDO * a.dump_field_stride] = alb;
+              d[ENRGY_D_ALBEDO * a.dump_field_stride] = (R)1 - oma;
               d[ENRGY_D_POT * a.dump_field_stride] = pot[i];
               d[ENRGY_D_G * a.dump_field_stride] = gfl;
             }
@@ -1411,6 +1422,10 @@ __global__ void finalize_stats_kernel(const FinalizeArgs f) {
   const StepRec<double> s = f.steps64[f.t0 + t];
   const double lwu_cell = f32_mode ? (double)(float)s.c_lwu : s.c_lwu;
   const double c_melt = f32_mode ? (double)(float)s.c_melt : s.c_melt;
+  // the kernel sums the per-cell factors of the fluxes; their per-step scalars come in here
+  k[K_RS] *= f32_mode ? (double)(float)s.c_sw : s.c_sw;
+  k[K_SENS] *= f32_mode ? (double)(float)s.c_sens : s.c_sens;
+  k[K_LAT] *= f32_mode ? (double)(float)s.c_lat : s.c_lat;
   double* o = f.stats + (size_t)t * ENRGY_S_COUNT;
   const double lwu = f.msm ? k[kStatsK + M_LWU] : f.n_valid * lwu_cell;
   // sum over glacier cells of c_lwd * Tz^4 with Tz = a + g * delta: quartic in the moments of delta
