@@ -110,6 +110,70 @@ struct Num<double> {
 __device__ __forceinline__ void keep_in_register(float& x) { asm volatile("" : "+f"(x)); }
 __device__ __forceinline__ void keep_in_register(double& x) { asm volatile("" : "+d"(x)); }
 __device__ __forceinline__ void keep_in_register(unsigned& x) { asm volatile("" : "+r"(x)); }
+template <typename R>
+struct V2;
+
+// ---- packed pairs of cells --------------------------------------------------------------------
+// sm_100 executes fma/add/mul.f32x2 (SASS FFMA2 / FADD2 / FMUL2) on an aligned register pair: two
+// cells per issue slot.  The FP32 pipe takes two cycles for a packed instruction, so the FLOP peak is
+// unchanged, but the freed issue slots carry the min/max/select/MUFU work of the other pipes
+// (measured on B200, scratch/ffma2_bench.cu: 16 FMA + 8 FMNMX per round take 24.7 clk scalar, 19 clk
+// packed).  V2<double> is the same interface over two plain doubles.
+template <typename R>
+struct V2;
+template <>
+struct V2<float> {
+  unsigned long long v;
+  static __device__ __forceinline__ V2 make(float lo, float hi) {
+    V2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+  }
+  static __device__ __forceinline__ V2 splat(float x) { return make(x, x); }
+  __device__ __forceinline__ float lo() const { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
+  __device__ __forceinline__ float hi() const { return __uint_as_float((unsigned)(v >> 32)); }
+};
+template <>
+struct V2<double> {
+  double a, b;
+  static __device__ __forceinline__ V2 make(double lo, double hi) { return V2{lo, hi}; }
+  static __device__ __forceinline__ V2 splat(double x) { return V2{x, x}; }
+  __device__ __forceinline__ double lo() const { return a; }
+  __device__ __forceinline__ double hi() const { return b; }
+};
+__device__ __forceinline__ V2<float> fma2(V2<float> a, V2<float> b, V2<float> c) {
+  V2<float> d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return d;
+}
+__device__ __forceinline__ V2<float> add2(V2<float> a, V2<float> b) {
+  V2<float> d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+  return d;
+}
+__device__ __forceinline__ V2<float> sub2(V2<float> a, V2<float> b) {
+  V2<float> d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+  return d;
+}
+__device__ __forceinline__ V2<float> mul2(V2<float> a, V2<float> b) {
+  V2<float> d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+  return d;
+}
+__device__ __forceinline__ V2<double> fma2(V2<double> a, V2<double> b, V2<double> c) {
+  return V2<double>{a.a * b.a + c.a, a.b * b.b + c.b};
+}
+__device__ __forceinline__ V2<double> add2(V2<double> a, V2<double> b) { return V2<double>{a.a + b.a, a.b + b.b}; }
+__device__ __forceinline__ V2<double> sub2(V2<double> a, V2<double> b) { return V2<double>{a.a - b.a, a.b - b.b}; }
+__device__ __forceinline__ V2<double> mul2(V2<double> a, V2<double> b) { return V2<double>{a.a * b.a, a.b * b.b}; }
+// delta * lapse rounded to float32 before it is added (NumPy float32 semantics), never contracted
+__device__ __forceinline__ V2<float> lapse_product(V2<float> d, float g) {
+  return V2<float>::make(__fmul_rn(d.lo(), g), __fmul_rn(d.hi(), g));
+}
+__device__ __forceinline__ V2<double> lapse_product(V2<double> d, double g) { return V2<double>{d.a * g, d.b * g}; }
+__device__ __forceinline__ void keep_in_register(V2<float>& x) { asm volatile("" : "+l"(x.v)); }
+__device__ __forceinline__ void keep_in_register(V2<double>&) {}   // (float64 is short of registers: it may rematerialise)
 
 // single-instruction min / max (FMNMX / DMNMX); glacier cells never carry NaN here
 __device__ __forceinline__ float fmax_(float a, float b) { return fmaxf(a, b); }
@@ -672,8 +736,14 @@ __device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem
 #ifndef ENRGY_SHADOW_WARPS
 #define ENRGY_SHADOW_WARPS 1
 #endif
-template <int INSOL>
-constexpr int kWarpsFor = insol_shadow(INSOL) ? ENRGY_SHADOW_WARPS : kWarps;
+#ifndef ENRGY_WARPS32
+#define ENRGY_WARPS32 8
+#endif
+#ifndef ENRGY_WARPS64
+#define ENRGY_WARPS64 4      // float64: 3 CTAs x 4 warps at 156 registers, no spills (profiles/r01_summary.md)
+#endif
+template <typename R, int INSOL>
+constexpr int kWarpsFor = insol_shadow(INSOL) ? ENRGY_SHADOW_WARPS : (sizeof(R) == 4 ? ENRGY_WARPS32 : ENRGY_WARPS64);
 __host__ __device__ constexpr int warps_x(int w) { return w >= 4 ? 4 : w; }          // patches side by side in a tile
 
 // Shared-memory carve-up of a CTA.  The capacities of a time block (steps, sunlit sub-steps) are
@@ -712,21 +782,18 @@ __host__ __device__ inline SmemPlan<R> smem_plan(int warps, int cap_steps, int c
 #define ENRGY_MINB32 2
 #endif
 #ifndef ENRGY_MINB64
-#define ENRGY_MINB64 2
+#define ENRGY_MINB64 3
 #endif
 
-#ifndef ENRGY_SUB_PHASES
-#define ENRGY_SUB_PHASES 1
-#endif
 #ifndef ENRGY_MINB_SHADOW
 #define ENRGY_MINB_SHADOW 12
 #endif
 template <typename R, int K, int INSOL, bool MSM, bool DUMP>
-__global__ void __launch_bounds__(32 * kWarpsFor<INSOL>, insol_shadow(INSOL)
+__global__ void __launch_bounds__(32 * kWarpsFor<R, INSOL>, insol_shadow(INSOL)
                                                             ? ENRGY_MINB_SHADOW
                                                             : (sizeof(R) == 4 ? ENRGY_MINB32 : ENRGY_MINB64))
 energy_balance_kernel(const KernelArgs<R> a) {
-  constexpr int W = kWarpsFor<INSOL>;              // warps per CTA
+  constexpr int W = kWarpsFor<R, INSOL>;           // warps per CTA
   constexpr int WX = warps_x(W), WY = W / WX;      // patches of a tile: WX across, WY down
   constexpr int NT = 32 * W;                       // threads per CTA
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -784,10 +851,18 @@ energy_balance_kernel(const KernelArgs<R> a) {
   for (int ti = blockIdx.x; ti < a.n_tiles; ti += gridDim.x) {
     const int2 tile = a.tiles[ti];
     // ---- prologue: per-cell invariants and state into registers --------------------------------
-    int rowb[K], col[K];           // band-local row, column
-    R delta[K], pw[K], a0[K], da[K], nxv[K], nyv[K], nzv[K], swe[K], tic[K];
-    float z0[K];
-    int rowf[K];
+    // A warp owns a compact 32-column x K-row patch (lane = column): every raster access is one
+    // coalesced 128 B line per row, and the patch keeps the shading bounding box tight.  The K cells
+    // of a thread are kept as K/2 PAIRS (rows 2q, 2q+1): all multiply/add arithmetic of the time
+    // loop runs on both cells of a pair with one packed instruction (V2, FFMA2/FADD2/FMUL2).
+    constexpr int KP = K / 2;
+    static_assert(K % 2 == 0, "cells per thread come in pairs");
+    using V = V2<R>;
+    const int row0 = tile.x * TILE_H + (warp / WX) * K;           // band-local row of cell 0
+    const int colx = tile.y * TILE_W + (warp % WX) * 32 + lane;   // this lane's column
+    V delta2[KP], pw2[KP], om2[KP], nx2[KP], ny2[KP], nz2[KP], swe2[KP], tic2[KP];
+    float z0[K];                   // shading: ray start heights
+    int rowf[K], col[K];           // shading: full-raster row, column
     R tl[K][NB];                   // sub-surface boundary temperatures [deg C] (MSM)
     // The reference's top boundary turns float64 after its first tick (NEP 50: float32 array +
     // float64 increment), so its round-off does not random-walk at float32 spacing; the float32
@@ -795,46 +870,58 @@ energy_balance_kernel(const KernelArgs<R> a) {
     double t0_acc[MSM ? K : 1];
     unsigned valid_bits = 0;
     int cur_pair = -1;
+    R cur_w = (R)-1;
 #pragma unroll
-    for (int i = 0; i < K; ++i) {
-      // a warp owns a compact 32-column x K-row patch (lane = column): every raster access is one
-      // coalesced 128 B line per row, and the patch keeps the shading bounding box tight
-      rowb[i] = tile.x * TILE_H + (warp / WX) * K + i;
-      col[i] = tile.y * TILE_W + (warp % WX) * 32 + lane;
-      rowf[i] = rowb[i] + a.band_row0;
-      const size_t o = (size_t)rowb[i] * a.pitch + col[i];
-      const bool inside = rowb[i] < a.band_rows && col[i] < a.cols;
-      float z = inside ? __ldg(a.dem + (size_t)rowf[i] * a.dem_pitch + col[i]) : __int_as_float(0x7fc00000);
-      const bool v = z == z;
-      valid_bits |= v ? (1u << i) : 0u;
-      z0[i] = z;
-      if (!v) z = (float)a.elev_aws;           // keep the arithmetic of masked cells finite
-      delta[i] = (R)z - a.elev_aws;            // var_classes.py:114
-      pw[i] = Num<R>::pow10(-delta[i] / (R)kVapourScale);   // var_classes.py:162
-      // keep delta itself in a register: left alone, the compiler re-derives it (and the validity
-      // test) from the raw elevation in every step, three extra instructions per cell-step
-      if (sizeof(R) == 4) keep_in_register(delta[i]);   // (float64 is short of registers: it may)
-      if (INSOL != kInsolStreamed) {
-        nxv[i] = v ? a.nx[o] : (R)0;
-        nyv[i] = v ? a.ny[o] : (R)0;
-        nzv[i] = v ? a.nz[o] : (R)1;
-      } else {
-        nxv[i] = nyv[i] = (R)0; nzv[i] = (R)1;
-      }
-      swe[i] = v ? a.swe[o] : (R)0;
-      tic[i] = v ? a.total_ice[o] : (R)0;
-      a0[i] = a.albedo_const ? (R)1 - a.albedo_ice : (R)0.5;   // a0, da hold 1 - albedo (see the albedo step)
-      da[i] = (R)0;
-      if (MSM) {
+    for (int q = 0; q < KP; ++q) {
+      R d_[2], p_[2], x_[2], y_[2], n_[2], s_[2], t_[2];
 #pragma unroll
-        for (int l = 0; l < NB; ++l) {
-          tl[i][l] = (v && l <= a.msm.layers) ? a.layer_t[(size_t)l * a.layer_stride + o] : (R)0;
+      for (int h = 0; h < 2; ++h) {
+        const int i = 2 * q + h;
+        const int rowb = row0 + i;
+        col[i] = colx;
+        rowf[i] = rowb + a.band_row0;
+        const size_t o = (size_t)rowb * a.pitch + colx;
+        const bool inside = rowb < a.band_rows && colx < a.cols;
+        float z = inside ? __ldg(a.dem + (size_t)rowf[i] * a.dem_pitch + colx) : __int_as_float(0x7fc00000);
+        const bool v = z == z;
+        valid_bits |= v ? (1u << i) : 0u;
+        z0[i] = z;
+        if (!v) z = (float)a.elev_aws;           // keep the arithmetic of masked cells finite
+        d_[h] = (R)z - a.elev_aws;               // var_classes.py:114
+        p_[h] = Num<R>::pow10(-d_[h] / (R)kVapourScale);   // var_classes.py:162
+        if (INSOL != kInsolStreamed) {
+          x_[h] = v ? a.nx[o] : (R)0;
+          y_[h] = v ? a.ny[o] : (R)0;
+          n_[h] = v ? a.nz[o] : (R)1;
+        } else {
+          x_[h] = y_[h] = (R)0; n_[h] = (R)1;
         }
-        t0_acc[i] = (double)tl[i][0];
+        s_[h] = v ? a.swe[o] : (R)0;
+        t_[h] = v ? a.total_ice[o] : (R)0;
+        if (MSM) {
+#pragma unroll
+          for (int l = 0; l < NB; ++l) {
+            tl[i][l] = (v && l <= a.msm.layers) ? a.layer_t[(size_t)l * a.layer_stride + o] : (R)0;
+          }
+          t0_acc[i] = (double)tl[i][0];
+        }
       }
+      delta2[q] = V::make(d_[0], d_[1]);
+      // keep the elevation difference itself in registers: left alone, the compiler re-derives it (and
+      // the validity test) from the raw elevation in every step, three extra instructions per cell-step
+      keep_in_register(delta2[q]);
+      pw2[q] = V::make(p_[0], p_[1]);
+      nx2[q] = V::make(x_[0], x_[1]);
+      ny2[q] = V::make(y_[0], y_[1]);
+      nz2[q] = V::make(n_[0], n_[1]);
+      swe2[q] = V::make(s_[0], s_[1]);
+      tic2[q] = V::make(t_[0], t_[1]);
+      // 1 - albedo of the ice surface: the constant, or the blend of the bracketing maps (set below)
+      om2[q] = V::splat(a.albedo_const ? (R)1 - a.albedo_ice : (R)0.5);
     }
-
     keep_in_register(valid_bits);
+    const bool patch_full = __all_sync(0xffffffffu, valid_bits == ((1u << K) - 1u));
+
     int buf = 0;
     if (tid == 0) issue_block(a.block_begin, 0);
 
@@ -850,29 +937,37 @@ energy_balance_kernel(const KernelArgs<R> a) {
       if (INSOL == kInsolStreamed) {
 #pragma unroll
         for (int i = 0; i < K; ++i) {
-          const size_t o = (size_t)(ts - a.pot_t0) * a.pot_stride + (size_t)rowb[i] * a.pitch + col[i];
+          const size_t o = (size_t)(ts - a.pot_t0) * a.pot_stride + (size_t)(row0 + i) * a.pitch + colx;
           pot_next[i] = (valid_bits >> i) & 1u ? __ldg(a.pot + o) : 0.f;
         }
       }
 
       for (int t = ts; t < te; ++t) {
         const StepRec<R> s = sm_steps[buf * cap_steps + (t - tb.t_begin)];
-        // ---- albedo maps of this step's bracket (interpolator.py:12-18) -------------------------
+        // ---- 1 - albedo of the ice surface from this step's bracket of maps (interpolator.py:12-18):
+        // the blend weight counts whole days, so the blend is refreshed once a day from the two
+        // maps (L2) instead of carrying both in registers and blending every step
         if (!a.albedo_const) {
           const int pair = (int)s.alb_pair;
-          if (pair != cur_pair) {      // uniform across the CTA: a few times per season
+          if (pair != cur_pair || s.alb_w != cur_w) {      // uniform across the CTA
             cur_pair = pair;
+            cur_w = s.alb_w;
             const float* m0 = a.albedo + (size_t)(pair >> 8) * a.map_stride;
             const float* m1 = a.albedo + (size_t)(pair & 255) * a.map_stride;
 #pragma unroll
-            for (int i = 0; i < K; ++i) {
-              const size_t o = (size_t)rowb[i] * a.pitch + col[i];
-              const bool v = (valid_bits >> i) & 1u;
-              // + ensemble offset, clipped like the loader clips a raster (identity for offset 0)
-              const R x0 = v ? fmin_(fmax_((R)__ldg(m0 + o) + a.albedo_offset, (R)0.001f), (R)1) : (R)0.5;
-              const R x1 = v ? fmin_(fmax_((R)__ldg(m1 + o) + a.albedo_offset, (R)0.001f), (R)1) : (R)0.5;
-              a0[i] = (R)1 - x0;               // the loop works with 1 - albedo
-              da[i] = x0 - x1;
+            for (int q = 0; q < KP; ++q) {
+              R om[2];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int i = 2 * q + h;
+                const size_t o = (size_t)(row0 + i) * a.pitch + colx;
+                const bool v = (valid_bits >> i) & 1u;
+                // + ensemble offset, clipped like the loader clips a raster (identity for offset 0)
+                const R x0 = v ? fmin_(fmax_((R)__ldg(m0 + o) + a.albedo_offset, (R)0.001f), (R)1) : (R)0.5;
+                const R x1 = v ? fmin_(fmax_((R)__ldg(m1 + o) + a.albedo_offset, (R)0.001f), (R)1) : (R)0.5;
+                om[h] = ((R)1 - x0) + s.alb_w * (x0 - x1);
+              }
+              om2[q] = V::make(om[0], om[1]);
             }
           }
         }
@@ -883,25 +978,30 @@ energy_balance_kernel(const KernelArgs<R> a) {
           if (t + 1 < te) {
 #pragma unroll
             for (int i = 0; i < K; ++i) {
-              const size_t o = (size_t)(t + 1 - a.pot_t0) * a.pot_stride + (size_t)rowb[i] * a.pitch + col[i];
+              const size_t o = (size_t)(t + 1 - a.pot_t0) * a.pot_stride + (size_t)(row0 + i) * a.pitch + colx;
               pot_next[i] = (valid_bits >> i) & 1u ? __ldg(a.pot + o) : 0.f;
             }
           }
         }
 
         // ---- potential insolation of the step [kWh m-2] -----------------------------------------
-        R pot[K];
+        V pot2[KP];
         if (INSOL == kInsolStreamed) {
 #pragma unroll
-          for (int i = 0; i < K; ++i) pot[i] = (R)pot_cur[i];
+          for (int q = 0; q < KP; ++q) pot2[q] = V::make((R)pot_cur[2 * q], (R)pot_cur[2 * q + 1]);
         } else {
-          R direct[K];
+          V direct2[KP];
 #pragma unroll
-          for (int i = 0; i < K; ++i) direct[i] = (R)0;
+          for (int q = 0; q < KP; ++q) direct2[q] = V::splat((R)0);
           const int sub_code = (int)s.sub;
           const int j0 = sub_code >> 8, nj = sub_code & 255;
           for (int j = j0; j < j0 + nj; ++j) {
             const SubRec<R> sb = sm_subs[buf * cap_subs + j];
+            const V e2 = V::splat(sb.e), n2 = V::splat(sb.n), u2 = V::splat(sb.u), b2 = V::splat(sb.b);
+            // cos(incidence) / nz; nx2, ny2 hold nx/nz, ny/nz (terrain_kernel)
+            V c2[KP];
+#pragma unroll
+            for (int q = 0; q < KP; ++q) c2[q] = fma2(ny2[q], n2, fma2(nx2[q], e2, u2));
             unsigned lit = 0xffffffffu;
             if (insol_shadow(INSOL)) {
               // production runs skip cells that face away from the sun (direct beam = 0 whatever
@@ -909,232 +1009,280 @@ energy_balance_kernel(const KernelArgs<R> a) {
               unsigned start_bits = valid_bits;
               if (!(DUMP && a.mask_out != nullptr)) {
 #pragma unroll
-                for (int i = 0; i < K; ++i) {
-                  const R c = sb.u + nxv[i] * sb.e + nyv[i] * sb.n;
-                  if (!(c > (R)0)) start_bits &= ~(1u << i);
+                for (int q = 0; q < KP; ++q) {
+                  if (!(c2[q].lo() > (R)0)) start_bits &= ~(1u << (2 * q));
+                  if (!(c2[q].hi() > (R)0)) start_bits &= ~(1u << (2 * q + 1));
                 }
               }
               constexpr bool KEYS = INSOL == kInsolShadowKeys;
-              lit = march<K, KEYS>(KEYS ? reinterpret_cast<const float*>(a.dem_keys) : a.dem, a.dem_pitch, my_win, a.rows_full, a.cols, a.blockmax,
-                             a.pyramid, rowf, col, z0, start_bits, sm_shades[buf * cap_subs + j], (float)a.zmax, lane);
+              lit = march<K, KEYS>(KEYS ? reinterpret_cast<const float*>(a.dem_keys) : a.dem, a.dem_pitch, my_win,
+                                   a.rows_full, a.cols, a.blockmax, a.pyramid, rowf, col, z0, start_bits,
+                                   sm_shades[buf * cap_subs + j], (float)a.zmax, lane);
               if (DUMP && a.mask_out != nullptr && t == a.t0) {
 #pragma unroll
                 for (int i = 0; i < K; ++i) {
                   const unsigned word = __ballot_sync(0xffffffffu, (lit >> i) & 1u);
-                  if (lane == 0 && rowb[i] < a.band_rows && col[i] < a.cols) {
-                    a.mask_out[((size_t)(j - j0) * a.band_rows + rowb[i]) * a.mask_words + (col[i] >> 5)] = word;
+                  if (lane == 0 && row0 + i < a.band_rows && colx < a.cols) {
+                    a.mask_out[((size_t)(j - j0) * a.band_rows + (row0 + i)) * a.mask_words + (colx >> 5)] = word;
                   }
                 }
               }
             }
-#if ENRGY_SUB_PHASES
-            {
-              // cos(incidence) / nz; nxv, nyv hold nx/nz, ny/nz (terrain_kernel).  Written phase by
-              // phase over the K cells so that the K dependency chains interleave.
-              R c[K];
 #pragma unroll
-              for (int i = 0; i < K; ++i) c[i] = sb.u + nxv[i] * sb.e;
-#pragma unroll
-              for (int i = 0; i < K; ++i) c[i] = c[i] + nyv[i] * sb.n;
-#pragma unroll
-              for (int i = 0; i < K; ++i) {
-                c[i] = fmax_(c[i], (R)0);
-                if (insol_shadow(INSOL)) c[i] = ((lit >> i) & 1u) ? c[i] : (R)0;
+            for (int q = 0; q < KP; ++q) {
+              R c_lo = fmax_(c2[q].lo(), (R)0), c_hi = fmax_(c2[q].hi(), (R)0);
+              if (insol_shadow(INSOL)) {
+                c_lo = ((lit >> (2 * q)) & 1u) ? c_lo : (R)0;
+                c_hi = ((lit >> (2 * q + 1)) & 1u) ? c_hi : (R)0;
               }
-#pragma unroll
-              for (int i = 0; i < K; ++i) direct[i] += sb.b * c[i];
+              direct2[q] = fma2(b2, V::make(c_lo, c_hi), direct2[q]);
             }
-#else
-#pragma unroll
-            for (int i = 0; i < K; ++i) {
-              // cos(incidence) / nz; nxv, nyv hold nx/nz, ny/nz (terrain_kernel)
-              R c = sb.u + nxv[i] * sb.e + nyv[i] * sb.n;
-              c = fmax_(c, (R)0);
-              if (insol_shadow(INSOL)) c = ((lit >> i) & 1u) ? c : (R)0;
-              direct[i] += sb.b * c;
-            }
-#endif
           }
-#pragma unroll
           // direct * nz + dsum * (1 + nz), two instructions
-          for (int i = 0; i < K; ++i) pot[i] = nzv[i] * (direct[i] + s.dsum) + s.dsum;
+          const V dsum2 = V::splat(s.dsum);
+#pragma unroll
+          for (int q = 0; q < KP; ++q) pot2[q] = fma2(nz2[q], add2(direct2[q], dsum2), dsum2);
         }
 
         // ---- per-cell energy balance -------------------------------------------------------------
-        R acc[kStatsK];
-#pragma unroll
-        for (int q = 0; q < kStatsK; ++q) acc[q] = (R)0;
+        V acc_rs = V::splat((R)0), acc_sens = acc_rs, acc_lat = acc_rs, acc_mf = acc_rs, acc_snow = acc_rs,
+          acc_swe = acc_rs, acc_lwu = acc_rs, acc_g = acc_rs;
         int n_snow = 0;
-        R acc_m[kStatsM] = {(R)0, (R)0};
         // albedo of snow-covered cells: the aged value when ageing is on, else the blended map
-        // (uniform per step): alb_snow = alb * keep_map + snow_const
-        // (the loop carries 1 - albedo: a0, da and these constants are complemented)
-        const R keep_map = s.snow_alb >= (R)0 ? (R)0 : (R)1;
-        const R snow_const = s.snow_alb >= (R)0 ? (R)1 - s.snow_alb : (R)0;
+        // (uniform per step): (1 - alb_snow) = (1 - alb) * keep_map + snow_const
+        const V keep_map = V::splat(s.snow_alb >= (R)0 ? (R)0 : (R)1);
+        const V snow_const = V::splat(s.snow_alb >= (R)0 ? (R)1 - s.snow_alb : (R)0);
         const R ice_floor = (R)1 - a.max_ice_albedo;      // 1 - cap (-inf with constant albedo)
+        const V t_aws = V::splat(s.t_air), lapse2 = V::splat(s.lapse), p_aws = V::splat(s.p_hpa), e_aws = V::splat(s.e_aws);
+        const V c_sens = V::splat(s.c_sens), c_lat = V::splat(s.c_lat), c_lwd = V::splat(s.c_lwd), c_sw = V::splat(s.c_sw),
+                c_melt = V::splat(s.c_melt);
+        const V k273 = V::splat((R)273.15), k_plapse = V::splat((R)kPressureLapse), k_rair = V::splat((R)kRair),
+                k_fp0 = V::splat((R)1.0016), k_fp1 = V::splat((R)(3.15 * 1e-6)), k_fp2 = V::splat((R)-0.074);
 #pragma unroll
-        for (int i = 0; i < K; ++i) {
-          // lapse-rate distribution, var_classes.py:113-125
-          const R t_air = Num<R>::lapse(s.t_air, delta[i], s.lapse);
-          const R tz = t_air + (R)273.15;
+        for (int q = 0; q < KP; ++q) {
+          // lapse-rate distribution, var_classes.py:113-125.  float32 evaluates T + delta * lapse the
+          // way NumPy float32 does (rounded product, rounded sum)
+          // (the product is formed per cell with __fmul_rn: ptxas contracts a packed mul + add into FFMA2)
+          const V t_air = sizeof(R) == 4 ? add2(t_aws, lapse_product(delta2[q], s.lapse)) : fma2(delta2[q], lapse2, t_aws);
+          const V tz = add2(t_air, k273);
           // surface temperature: 0 degC without the sub-surface model, else the top
           // boundary of the layer stack (model.py:207-210)
-          const R ts_k = MSM ? tl[i][0] + (R)273.15 : (R)273.15;
-          R d_t = tz - ts_k;                                // Tz - Ts
-          if (MSM && sizeof(R) == 4) {
-            // float32 + sub-surface model: the reference's surface temperature raster turns
-            // float64 after the first tick, so its Tz - Ts is float32(Tz) - (t0 + 273.15) without
-            // a Kelvin rounding of Ts.  tz - 273.15f is exact (same binade); the second constant
-            // is float(273.15) - 273.15.
-            d_t = ((tz - (R)273.15) + (R)-6.103515625e-06) - tl[i][0];
+          V d_t = sub2(tz, k273);                            // Tz - Ts
+          if (MSM) {
+            R d[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int i = 2 * q + h;
+              const R tzh = h ? tz.hi() : tz.lo();
+              d[h] = tzh - (tl[i][0] + (R)273.15);
+              if (sizeof(R) == 4) {
+                // float32 + sub-surface model: the reference's surface temperature raster turns
+                // float64 after the first tick, so its Tz - Ts is float32(Tz) - (t0 + 273.15) without
+                // a Kelvin rounding of Ts.  tz - 273.15f is exact (same binade); the second constant
+                // is float(273.15) - 273.15.
+                d[h] = ((tzh - (R)273.15) + (R)-6.103515625e-06) - tl[i][0];
+              }
+            }
+            d_t = V::make(d[0], d[1]);
           }
-          const R p_hpa = s.p_hpa + delta[i] * (R)kPressureLapse;
-          const R e = s.e_aws * pw[i];
+          const V p_hpa = fma2(delta2[q], k_plapse, p_aws);
+          const V e = mul2(pw2[q], e_aws);
           // bulk fluxes, turbo.py:140-196 with rho = P / (R Tz) and rho / P = 1 / (R Tz);
           // c_sens carries CH * Cp * uz * 100 (Pa per hPa), c_lat carries CE * uz * 0.622 * Lv
-          R r_rt, r_p;                                      // 1 / (R Tz) and 1 / p_hpa
-          if (sizeof(R) == 8) {
-            // float64: one division serves both reciprocals (a DP division is ~20 instructions)
-            const R rt = (R)kRair * tz;
-            const R inv = (R)1 / (rt * p_hpa);
-            r_rt = inv * p_hpa;
-            r_p = inv * rt;
-          } else {
-            r_rt = Num<R>::rcp((R)kRair * tz);
-            r_p = Num<R>::rcp(p_hpa);
+          V r_rt, r_p;                                      // 1 / (R Tz) and 1 / p_hpa
+          {
+            const V rt = mul2(tz, k_rair);
+            if (sizeof(R) == 8) {
+              // float64: one division serves both reciprocals (a DP division is ~20 instructions)
+              const V den = mul2(rt, p_hpa);
+              const V inv = V::make((R)1 / den.lo(), (R)1 / den.hi());
+              r_rt = mul2(inv, p_hpa);
+              r_p = mul2(inv, rt);
+            } else {
+              r_rt = V::make(Num<R>::rcp(rt.lo()), Num<R>::rcp(rt.hi()));
+              r_p = V::make(Num<R>::rcp(p_hpa.lo()), Num<R>::rcp(p_hpa.hi()));
+            }
           }
           // every flux is (per-step scalar) x (per-cell factor): the scalar rides the FMA chain of the
           // balance and scales the area sums afterwards (finalize_stats_kernel), the loop keeps the factor
-          const R x_sens = p_hpa * (r_rt * d_t);            // sens = c_sens * x_sens
+          const V x_sens = mul2(p_hpa, mul2(r_rt, d_t));    // sens = c_sens * x_sens
           // saturation vapour pressure of the melting surface, turbo.py:368-379 with t = 0:
           // exp(0) = 1 exactly, so es = 611.2 * f(p).  ez = e_max * (e / e_max) = e (one rounding).
-          const R f_p = (R)1.0016 + (R)(3.15 * 1e-6) * p_hpa - (R)0.074 * r_p;
-          R es_t = (R)611.2;
+          const V f_p = fma2(r_p, k_fp2, fma2(p_hpa, k_fp1, k_fp0));
+          V es_neg = V::splat((R)-611.2);
           if (MSM) {                                        // Magnus term of the surface, turbo.py:377
-            const R t0 = tl[i][0];
-            es_t = (R)611.2 * Num<R>::exp_(((R)17.62 * t0) * Num<R>::rcp((R)243.12 + t0));
-          }
-          const R x_lat = r_rt * (e - es_t * f_p);          // lat = c_lat * x_lat
-          // longwave, model.py:533-545
-          const R tz2 = tz * tz;
-          const R tz4 = tz2 * tz2;
-          R lwu = s.c_lwu;
-          if (MSM) {
-            if (sizeof(R) == 4) {
-              // (273.15 + t0)^4 = 273.15^4 (1 + x)^4, x = t0 / 273.15: keeps the low bits of t0 that
-              // a float32 Kelvin temperature would drop
-              const R x = tl[i][0] * (R)(1.0 / 273.15);
-              const R poly = (R)1 + x * ((R)4 + x * ((R)6 + x * ((R)4 + x)));
-              lwu = (s.c_lwu * (R)(273.15 * 273.15 * 273.15 * 273.15)) * poly;
-            } else {
-              const R ts2 = ts_k * ts_k;
-              lwu = s.c_lwu * (ts2 * ts2);
-            }
-          }
-          // albedo, model.py:298-337
-          const bool has_snow = swe[i] > (R)0;
-          // maps: blend of the bracketing maps; snow cells take the aged snow albedo when ageing
-          // is on; ice cells are capped.  Constant albedo rides the same formula: a0 = ice,
-          // da = 0, snow_alb = snow (so keep_map = 0), cap = +inf (set up by the host).
-          const R blend = a0[i] + s.alb_w * da[i];          // 1 - blended albedo
-          const R oma = has_snow ? blend * keep_map + snow_const : fmax_(blend, ice_floor);
-          // shortwave, model.py:483-497: rs = potential * c_sw * (1 - albedo)
-          const R x_rs = pot[i] * oma;
-          // balance, clamp, melt partition: model.py:411, :434-438, msm.py:193-203
-          // rs + lwd - lwu + sens + lat with lwd = c_lwd * Tz^4 folded into one FMA; the area sum
-          // of lwd is not reduced here: Tz is linear in the elevation, so it follows from the first
-          // four moments of (dem - elev_aws), see finalize_stats_kernel
-          const R atmo = s.c_lat * x_lat + (s.c_sens * x_sens + (s.c_sw * x_rs + (s.c_lwd * tz4 - lwu)));
-          R mf, gfl = (R)0;
-          if (MSM) {
-            // explicit conduction through the layer stack and the surface-layer melt gate,
-            // msm.py:31-107 (snow depth = swe / snow_density, model.py:428)
-            const MsmParams<R>& m = a.msm;
-            R sd = swe[i] * m.inv_snow_density;
-            R grad_prev = (R)0, t_next = tl[i][0];
-            const R dt = s.dt;
-            const R inv_dt = (R)1 / dt;
-            mf = (R)0;
+            R x[2];
 #pragma unroll
-            for (int l = 0; l < kMaxLayers; ++l) {
-              if (l < m.layers) {
-                const R t_here = t_next;
-                t_next = tl[i][l + 1];
-                const R grad = (t_next - t_here) * m.inv_d[l];            // msm.py:18-28
-                const R ratio = sd > m.d[l] ? (R)1 : sd * m.inv_d[l];     // msm.py:63
-                const R kap = ratio * m.k_snow + ((R)1 - ratio) * m.k_ice;
-                const R rho = ratio * m.rho_snow + ((R)1 - ratio) * m.rho_ice;
-                sd = fmax_(sd - m.d[l], (R)0);
-                R delta;
-                if (l == 0) {                                             // surface layer, msm.py:80-101
-                  gfl = kap * grad * m.c_ice * rho;
-                  const R full = atmo + gfl;
-                  const R crd = m.c_ice * rho * m.d[0];
-                  const R q0 = -t_here * crd * inv_dt;
-                  mf = fmax_(full - q0, (R)0);
-                  delta = (full - mf) * Num<R>::rcp(crd);
-                } else {
-                  delta = kap * (grad - grad_prev) * m.inv_d[l];          // msm.py:103
-                }
-                grad_prev = grad;
-                if (l == 0 && sizeof(R) == 4) {
-                  t0_acc[i] += (double)(delta * dt);
-                  tl[i][0] = (R)t0_acc[i];
-                } else {
-                  tl[i][l] = t_here + delta * dt;
-                }
+            for (int h = 0; h < 2; ++h) {
+              const R t0 = tl[2 * q + h][0];
+              x[h] = (R)-611.2 * Num<R>::exp_(((R)17.62 * t0) * Num<R>::rcp((R)243.12 + t0));
+            }
+            es_neg = V::make(x[0], x[1]);
+          }
+          const V x_lat = mul2(r_rt, fma2(es_neg, f_p, e)); // lat = c_lat * x_lat
+          // longwave, model.py:533-545
+          const V tzsq = mul2(tz, tz);
+          const V tz4 = mul2(tzsq, tzsq);
+          V lwu = V::splat(s.c_lwu);
+          if (MSM) {
+            R x[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const R t0 = tl[2 * q + h][0];
+              if (sizeof(R) == 4) {
+                // (273.15 + t0)^4 = 273.15^4 (1 + x)^4, x = t0 / 273.15: keeps the low bits of t0 that
+                // a float32 Kelvin temperature would drop
+                const R y = t0 * (R)(1.0 / 273.15);
+                const R poly = (R)1 + y * ((R)4 + y * ((R)6 + y * ((R)4 + y)));
+                x[h] = (s.c_lwu * (R)(273.15 * 273.15 * 273.15 * 273.15)) * poly;
+              } else {
+                const R ts_k = t0 + (R)273.15;
+                const R ts2 = ts_k * ts_k;
+                x[h] = s.c_lwu * (ts2 * ts2);
               }
             }
-          } else {
-            mf = fmax_(atmo, (R)0);
+            lwu = V::make(x[0], x[1]);
           }
-          const R we = mf * s.c_melt;
-          const R snow = fmin_(we, swe[i]);
-          const R ice = we - snow;
-          // off-glacier cells of a visited tile carry finite dummy values: they are left out by
-          // predicated adds on the validity bit (no per-cell weight register)
-          if ((valid_bits >> i) & 1u) {
-            acc[K_RS] += x_rs;
-            acc[K_SENS] += x_sens;
-            acc[K_LAT] += x_lat;
-            acc[K_MELT] += mf;
+          // albedo, model.py:298-337, as 1 - albedo.  Maps: blend of the bracketing maps; snow cells
+          // take the aged snow albedo when ageing is on; ice cells are capped.  Constant albedo rides
+          // the same formula: om = 1 - ice, snow_alb = snow (so keep_map = 0), cap = +inf.
+          const bool snow_lo = swe2[q].lo() > (R)0, snow_hi = swe2[q].hi() > (R)0;
+          const V om_snow = fma2(om2[q], keep_map, snow_const);
+          const V oma = V::make(snow_lo ? om_snow.lo() : fmax_(om2[q].lo(), ice_floor),
+                                snow_hi ? om_snow.hi() : fmax_(om2[q].hi(), ice_floor));
+          // shortwave, model.py:483-497: rs = potential * c_sw * (1 - albedo)
+          const V x_rs = mul2(pot2[q], oma);
+          // balance, clamp, melt partition: model.py:411, :434-438, msm.py:193-203
+          // rs + lwd - lwu + sens + lat as one FMA chain; the area sum of lwd is not reduced here: Tz
+          // is linear in the elevation, so it follows from the first four moments of
+          // (dem - elev_aws), see finalize_stats_kernel
+          const V atmo = fma2(c_lat, x_lat, fma2(c_sens, x_sens, fma2(c_sw, x_rs, sub2(mul2(c_lwd, tz4), lwu))));
+          V mf, gfl = V::splat((R)0);
+          if (MSM) {
+            R mfh[2], gh[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int i = 2 * q + h;
+              // explicit conduction through the layer stack and the surface-layer melt gate,
+              // msm.py:31-107 (snow depth = swe / snow_density, model.py:428)
+              const MsmParams<R>& m = a.msm;
+              const R atmo_h = h ? atmo.hi() : atmo.lo();
+              R sd = (h ? swe2[q].hi() : swe2[q].lo()) * m.inv_snow_density;
+              R grad_prev = (R)0, t_next = tl[i][0];
+              const R dt = s.dt;
+              const R inv_dt = (R)1 / dt;
+              R mfv = (R)0, gv = (R)0;
+#pragma unroll
+              for (int l = 0; l < kMaxLayers; ++l) {
+                if (l < m.layers) {
+                  const R t_here = t_next;
+                  t_next = tl[i][l + 1];
+                  const R grad = (t_next - t_here) * m.inv_d[l];            // msm.py:18-28
+                  const R ratio = sd > m.d[l] ? (R)1 : sd * m.inv_d[l];     // msm.py:63
+                  const R kap = ratio * m.k_snow + ((R)1 - ratio) * m.k_ice;
+                  const R rho = ratio * m.rho_snow + ((R)1 - ratio) * m.rho_ice;
+                  sd = fmax_(sd - m.d[l], (R)0);
+                  R dlt;
+                  if (l == 0) {                                             // surface layer, msm.py:80-101
+                    gv = kap * grad * m.c_ice * rho;
+                    const R full = atmo_h + gv;
+                    const R crd = m.c_ice * rho * m.d[0];
+                    const R q0 = -t_here * crd * inv_dt;
+                    mfv = fmax_(full - q0, (R)0);
+                    dlt = (full - mfv) * Num<R>::rcp(crd);
+                  } else {
+                    dlt = kap * (grad - grad_prev) * m.inv_d[l];            // msm.py:103
+                  }
+                  grad_prev = grad;
+                  if (l == 0 && sizeof(R) == 4) {
+                    t0_acc[i] += (double)(dlt * dt);
+                    tl[i][0] = (R)t0_acc[i];
+                  } else {
+                    tl[i][l] = t_here + dlt * dt;
+                  }
+                }
+              }
+              mfh[h] = mfv;
+              gh[h] = gv;
+            }
+            mf = V::make(mfh[0], mfh[1]);
+            gfl = V::make(gh[0], gh[1]);
+          } else {
+            mf = V::make(fmax_(atmo.lo(), (R)0), fmax_(atmo.hi(), (R)0));
+          }
+          const V we = mul2(mf, c_melt);
+          const V snow = V::make(fmin_(we.lo(), swe2[q].lo()), fmin_(we.hi(), swe2[q].hi()));
+          const V ice = sub2(we, snow);
+          // statistics.  Off-glacier cells of a visited patch carry finite dummy values: they are
+          // zeroed before the packed adds, on patches that have any (warp-uniform test)
+          V m_rs = x_rs, m_sens = x_sens, m_lat = x_lat, m_mf = mf, m_lwu = lwu, m_g = gfl;
+          if (!patch_full) {
+            const bool v_lo = (valid_bits >> (2 * q)) & 1u, v_hi = (valid_bits >> (2 * q + 1)) & 1u;
+            m_rs = V::make(v_lo ? x_rs.lo() : (R)0, v_hi ? x_rs.hi() : (R)0);
+            m_sens = V::make(v_lo ? x_sens.lo() : (R)0, v_hi ? x_sens.hi() : (R)0);
+            m_lat = V::make(v_lo ? x_lat.lo() : (R)0, v_hi ? x_lat.hi() : (R)0);
+            m_mf = V::make(v_lo ? mf.lo() : (R)0, v_hi ? mf.hi() : (R)0);
             if (MSM) {
-              acc_m[M_LWU] += lwu;
-              acc_m[M_G] += gfl;
+              m_lwu = V::make(v_lo ? lwu.lo() : (R)0, v_hi ? lwu.hi() : (R)0);
+              m_g = V::make(v_lo ? gfl.lo() : (R)0, v_hi ? gfl.hi() : (R)0);
             }
           }
-          acc[K_SNOW] += snow;          // masked cells: swe = 0 -> snow = 0
-          acc[K_SWE] += swe[i];
-          n_snow += has_snow ? 1 : 0;
+          acc_rs = add2(acc_rs, m_rs);
+          acc_sens = add2(acc_sens, m_sens);
+          acc_lat = add2(acc_lat, m_lat);
+          acc_mf = add2(acc_mf, m_mf);
+          acc_snow = add2(acc_snow, snow);        // masked cells: swe = 0 -> snow = 0
+          acc_swe = add2(acc_swe, swe2[q]);
+          if (MSM) {
+            acc_lwu = add2(acc_lwu, m_lwu);
+            acc_g = add2(acc_g, m_g);
+          }
+          n_snow += (snow_lo ? 1 : 0) + (snow_hi ? 1 : 0);
           if (DUMP && a.dump != nullptr) {
-            if ((valid_bits >> i) & 1u) {
-              R* d = a.dump + (size_t)(t - a.t0) * ENRGY_D_COUNT * a.dump_field_stride +
-                     (size_t)rowb[i] * a.pitch + col[i];
-              d[ENRGY_D_RS * a.dump_field_stride] = s.c_sw * x_rs;
-              d[ENRGY_D_LWD * a.dump_field_stride] = s.c_lwd * tz4;
-              d[ENRGY_D_LWU * a.dump_field_stride] = lwu;
-              d[ENRGY_D_SENS * a.dump_field_stride] = s.c_sens * x_sens;
-              d[ENRGY_D_LAT * a.dump_field_stride] = s.c_lat * x_lat;
-              d[ENRGY_D_ATMO * a.dump_field_stride] = atmo;
-              d[ENRGY_D_MELT * a.dump_field_stride] = mf;
-              d[ENRGY_D_SNOW * a.dump_field_stride] = snow;
-              d[ENRGY_D_ICE * a.dump_field_stride] = ice;
-              d[ENRGY_D_ALBEDO * a.dump_field_stride] = (R)1 - oma;
-              d[ENRGY_D_POT * a.dump_field_stride] = pot[i];
-              d[ENRGY_D_G * a.dump_field_stride] = gfl;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int i = 2 * q + h;
+              if ((valid_bits >> i) & 1u) {
+                R* d = a.dump + (size_t)(t - a.t0) * ENRGY_D_COUNT * a.dump_field_stride +
+                       (size_t)(row0 + i) * a.pitch + colx;
+                auto half = [&](const V& x) { return h ? x.hi() : x.lo(); };
+                d[ENRGY_D_RS * a.dump_field_stride] = s.c_sw * half(x_rs);
+                d[ENRGY_D_LWD * a.dump_field_stride] = s.c_lwd * half(tz4);
+                d[ENRGY_D_LWU * a.dump_field_stride] = half(lwu);
+                d[ENRGY_D_SENS * a.dump_field_stride] = s.c_sens * half(x_sens);
+                d[ENRGY_D_LAT * a.dump_field_stride] = s.c_lat * half(x_lat);
+                d[ENRGY_D_ATMO * a.dump_field_stride] = half(atmo);
+                d[ENRGY_D_MELT * a.dump_field_stride] = half(mf);
+                d[ENRGY_D_SNOW * a.dump_field_stride] = half(snow);
+                d[ENRGY_D_ICE * a.dump_field_stride] = half(ice);
+                d[ENRGY_D_ALBEDO * a.dump_field_stride] = (R)1 - half(oma);
+                d[ENRGY_D_POT * a.dump_field_stride] = half(pot2[q]);
+                d[ENRGY_D_G * a.dump_field_stride] = half(gfl);
+              }
             }
           }
           // state update, model.py:258-261.  total_snow is not accumulated here: it equals
           // swe(start) - swe(end) and is added once in the epilogue.
-          swe[i] -= snow;
-          tic[i] += ice;
+          swe2[q] = sub2(swe2[q], snow);
+          tic2[q] = add2(tic2[q], ice);
         }
-        acc[K_NSNOW] = (R)n_snow;
         // ---- per-step statistics: warp butterfly, one slot per warp --------------------------------
         if (!DUMP) {
+          R acc[kStatsK];
+          acc[K_RS] = acc_rs.lo() + acc_rs.hi();
+          acc[K_LWD] = (R)0;
+          acc[K_SENS] = acc_sens.lo() + acc_sens.hi();
+          acc[K_LAT] = acc_lat.lo() + acc_lat.hi();
+          acc[K_MELT] = acc_mf.lo() + acc_mf.hi();
+          acc[K_SNOW] = acc_snow.lo() + acc_snow.hi();
+          acc[K_SWE] = acc_swe.lo() + acc_swe.hi();
+          acc[K_NSNOW] = (R)n_snow;
           const R tot = warp_reduce8<R>(acc, lane);
           if ((lane & 3) == 0) sm_slots[(warp * cap_steps + (t - tb.t_begin)) * kStatsK + stat_of_lane(lane)] = tot;
           if (MSM) {
+            R acc_m[kStatsM];
+            acc_m[M_LWU] = acc_lwu.lo() + acc_lwu.hi();
+            acc_m[M_G] = acc_g.lo() + acc_g.hi();
 #pragma unroll
             for (int q = 0; q < kStatsM; ++q) {
               R v = acc_m[q];
@@ -1158,7 +1306,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
 #pragma unroll
           for (int w = 0; w < W; ++w) {
             sum += q < kStatsK ? (double)sm_slots[(w * cap_steps + sl) * kStatsK + q]
-                           : (double)sm_slots_m[(w * cap_steps + sl) * kStatsM + (q - kStatsK)];
+                               : (double)sm_slots_m[(w * cap_steps + sl) * kStatsM + (q - kStatsK)];
           }
           my_partials[(size_t)(ts - a.t0 + step) * kStatsP + q] += sum;
         }
@@ -1170,14 +1318,17 @@ energy_balance_kernel(const KernelArgs<R> a) {
     if (!DUMP) {
 #pragma unroll
       for (int i = 0; i < K; ++i) {
-        if (rowb[i] < a.band_rows && col[i] < a.cols) {
-          const size_t o = (size_t)rowb[i] * a.pitch + col[i];
+        const int rowb = row0 + i;
+        if (rowb < a.band_rows && colx < a.cols) {
+          const size_t o = (size_t)rowb * a.pitch + colx;
           const bool v = (valid_bits >> i) & 1u;
+          const R swe_i = (i & 1) ? swe2[i / 2].hi() : swe2[i / 2].lo();
+          const R tic_i = (i & 1) ? tic2[i / 2].hi() : tic2[i / 2].lo();
           // total_snow grows by swe(start) - swe(end); the start value is still in HBM
           const R swe_start = v ? a.swe[o] : (R)0;
-          a.swe[o] = v ? swe[i] : qnan;
-          a.total_snow[o] = v ? a.total_snow[o] + (swe_start - swe[i]) : qnan;
-          a.total_ice[o] = v ? tic[i] : qnan;
+          a.swe[o] = v ? swe_i : qnan;
+          a.total_snow[o] = v ? a.total_snow[o] + (swe_start - swe_i) : qnan;
+          a.total_ice[o] = v ? tic_i : qnan;
           if (MSM) {
 #pragma unroll
             for (int l = 0; l < NB; ++l) {
@@ -1199,7 +1350,7 @@ struct CellsPerThread {
 template <typename R>
 void energy_balance_tile(bool msm, int insol, int* tile_h, int* tile_w) {
   const int k = msm ? CellsPerThread<R, true>::value : CellsPerThread<R, false>::value;
-  const int w = insol_shadow(insol) ? kWarpsFor<kInsolShadow> : kWarpsFor<kInsolComputed>;
+  const int w = insol_shadow(insol) ? kWarpsFor<R, kInsolShadow> : kWarpsFor<R, kInsolComputed>;
   *tile_w = 32 * warps_x(w);
   *tile_h = (w / warps_x(w)) * k;
 }
@@ -1210,12 +1361,12 @@ template <typename R, int INSOL, bool MSM, bool DUMP>
 static cudaError_t configure(int sm_count, int cap_steps, int cap_subs, LaunchInfo* info) {
   constexpr int K = CellsPerThread<R, MSM>::value;
   auto kern = energy_balance_kernel<R, K, INSOL, MSM, DUMP>;
-  const int smem = smem_plan<R>(kWarpsFor<INSOL>, cap_steps, cap_subs, INSOL != kInsolStreamed,
+  const int smem = smem_plan<R>(kWarpsFor<R, INSOL>, cap_steps, cap_subs, INSOL != kInsolStreamed,
                                 insol_shadow(INSOL), MSM).total;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * kWarpsFor<INSOL>, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * kWarpsFor<R, INSOL>, smem);
   if (e != cudaSuccess) return e;
   cudaFuncAttributes fa;
   e = cudaFuncGetAttributes(&fa, kern);
@@ -1240,7 +1391,7 @@ static cudaError_t launch_one(const KernelArgs<R>& a, int sm_count, int forced_g
   li.grid = grid;
   if (info) *info = li;
   if (a.n_tiles == 0 || a.t1 <= a.t0) return cudaSuccess;
-  energy_balance_kernel<R, K, INSOL, MSM, DUMP><<<grid, 32 * kWarpsFor<INSOL>, li.smem_bytes, stream>>>(a);
+  energy_balance_kernel<R, K, INSOL, MSM, DUMP><<<grid, 32 * kWarpsFor<R, INSOL>, li.smem_bytes, stream>>>(a);
   return cudaGetLastError();
 }
 
