@@ -143,9 +143,9 @@ def upload(eng, case, dem_full, table, pinned=None):
     src = pinned if pinned is not None else {
         "dem": dem_full, "swe": case.swe, "alb": [case.albedo_maps[k] for k in case.albedo_maps]}
     eng.set_dem(src["dem"])
+    eng.set_forcing(table)            # the host pre-pass starts here and overlaps the raster uploads
     eng.set_albedo_maps(src["alb"])
     eng.set_swe(src["swe"])
-    eng.set_forcing(table)
     eng.prepass()
 
 

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/enrgy_b200.h"
@@ -104,6 +105,11 @@ struct enrgy_ctx {
   DevBuf<TimeBlock> d_blocks;
   DevBuf<int2> d_tiles;
   DevBuf<int> d_counts, d_demkeys;
+  // host pre-pass started ahead of enrgy_prepass (see start_early_prepass)
+  std::thread pre_thread;
+  PrepassOutput pre_early;
+  int pre_early_rc = 0;
+  std::string pre_early_err;
   bool dem_nonneg = false;   // no negative elevation: the shading samples use the integer copy (kInsolShadowKeys)
   DevBuf<double> d_partials, d_stats, d_small;
   DevBuf<unsigned long long> d_counters;
@@ -203,6 +209,35 @@ int upload_tables(enrgy_ctx* c) {
   }
   CU_TRY(cudaStreamSynchronize(c->stream));   // host vectors go out of scope
   return ENRGY_OK;
+}
+
+// ---- early host pre-pass ----------------------------------------------------------------------
+// The per-step scalars depend on the forcing table, the parameters and the DEM around the AWS cell
+// only (not on the albedo / SWE rasters, unless the sub-surface model integrates the AWS cell).  So
+// when the forcing arrives after the DEM, the pre-pass starts on a host thread right away and runs
+// while the caller is still uploading rasters; enrgy_prepass() joins it.  Any call that changes an
+// input of the pre-pass drops the early result first.
+void fill_prepass_input(enrgy_ctx* c, PrepassInput& in) {
+  in.p = c->p; in.precision = c->precision; in.rows = c->rows; in.cols = c->cols;
+  in.albedo_offset = c->albedo_offset;
+  in.dem = c->h_dem.empty() ? nullptr : c->h_dem.data(); in.n_steps = c->n_steps; in.forcing = c->forcing.data();
+  std::memcpy(in.nbhd, c->aws_nbhd, sizeof(in.nbhd)); in.zmax = c->zmax;
+  in.pot_aws = c->pot_aws.data();
+  if (c->p.insol_mode == ENRGY_INSOL_COMPUTED && c->p.shadow) { in.cap_steps = kShadowStepsPerBlock; in.cap_subs = kShadowSubsPerBlock; }
+  in.alb_aws = c->alb_aws; in.swe_aws = c->swe_aws; in.layer_t_aws = c->layer_t_aws;
+}
+void drop_early_prepass(enrgy_ctx* c) {
+  if (c->pre_thread.joinable()) c->pre_thread.join();
+  c->pre_early = PrepassOutput{};
+  c->pre_early_rc = -1000;   // "no early result"
+}
+void start_early_prepass(enrgy_ctx* c) {
+  drop_early_prepass(c);
+  if (!c->have_dem || !c->have_forcing || c->p.msm_layers > 0 || c->p.insol_mode != ENRGY_INSOL_COMPUTED) return;
+  c->pre_early_rc = 0;
+  PrepassInput in;                 // snapshot taken on the calling thread
+  fill_prepass_input(c, in);
+  c->pre_thread = std::thread([c, in]() { c->pre_early_rc = run_prepass(in, c->pre_early, c->pre_early_err); });
 }
 
 template <typename R>
@@ -405,6 +440,7 @@ int enrgy_create(int device, int rows, int cols, int precision, enrgy_ctx** out)
 
 int enrgy_destroy(enrgy_ctx* c) {
   if (!c) return ENRGY_OK;
+  drop_early_prepass(c);
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->d_dem.release(); c->d_albedo.release(); c->d_pot.release(); c->d_tmp32.release();
@@ -424,6 +460,7 @@ int enrgy_set_params(enrgy_ctx* c, const enrgy_params* pin) {
   if (int e = use_device(c)) return e;
   if (!pin) return fail(ENRGY_ERR_ARG, "params is null");
   if (c->have_dem) return fail(ENRGY_ERR_ARG, "set_params must precede set_dem");
+  drop_early_prepass(c);
   enrgy_params p = *pin;
   auto dflt = [](double& v, double d) { if (std::isnan(v)) v = d; };
   dflt(p.zm, 0.001);                 // turbo.py:273-274
@@ -471,6 +508,7 @@ int enrgy_set_dem(enrgy_ctx* c, const float* dem) {
   if (int e = use_device(c)) return e;
   if (!c->have_params) return fail(ENRGY_ERR_ARG, "set_params must precede set_dem");
   if (!dem) return fail(ENRGY_ERR_ARG, "dem is null");
+  drop_early_prepass(c);
   if (c->p.aws_row < 0 || c->p.aws_row >= c->rows || c->p.aws_col < 0 || c->p.aws_col >= c->cols)
     return fail(ENRGY_ERR_ARG, "AWS cell (%d, %d) outside the %d x %d raster", c->p.aws_row, c->p.aws_col, c->rows, c->cols);
   for (int dr = -1; dr <= 1; ++dr)
@@ -710,6 +748,7 @@ int enrgy_set_msm(enrgy_ctx* c, const double* temps, double elev) {
 int enrgy_set_member(enrgy_ctx* c, double albedo_offset, double zm, double z_h_or_e) {
   if (int e = use_device(c)) return e;
   if (!c->have_params) return fail(ENRGY_ERR_ARG, "set_params must precede set_member");
+  drop_early_prepass(c);
   if (std::isnan(albedo_offset)) albedo_offset = 0.0;
   if (!std::isnan(zm)) {
     if (!(zm > 0)) return fail(ENRGY_ERR_ARG, "zm must be > 0");
@@ -737,11 +776,13 @@ int enrgy_set_forcing(enrgy_ctx* c, int n_steps, const double* forcing) {
     if (!(f[ENRGY_F_RH] <= 1.0)) return fail(ENRGY_ERR_RANGE, "row %d: HUMID must be a 0..1 fraction here (helpers.py:74-87)", i);
     if (!(f[ENRGY_F_DT] > 0)) return fail(ENRGY_ERR_RANGE, "row %d: time step must be > 0", i);
   }
+  drop_early_prepass(c);
   c->forcing.assign(forcing, forcing + (size_t)n_steps * ENRGY_F_COUNT);
   c->n_steps = n_steps;
   c->pot_aws.assign(n_steps, std::numeric_limits<double>::quiet_NaN());
   c->have_forcing = true;
   c->prepass_done = false;
+  start_early_prepass(c);      // runs while the caller uploads the remaining rasters
   return ENRGY_OK;
 }
 
@@ -772,19 +813,23 @@ int enrgy_set_insolation(enrgy_ctx* c, int t0, int n, const float* pot) {
 int enrgy_prepass(enrgy_ctx* c) {
   if (int e = use_device(c)) return e;
   if (!c->have_dem || !c->have_forcing) return fail(ENRGY_ERR_ARG, "set_dem and set_forcing must precede prepass");
-  PrepassInput in;
-  in.p = c->p; in.precision = c->precision; in.rows = c->rows; in.cols = c->cols;
-  in.albedo_offset = c->albedo_offset;
-  in.dem = c->h_dem.empty() ? nullptr : c->h_dem.data(); in.n_steps = c->n_steps; in.forcing = c->forcing.data();
-  std::memcpy(in.nbhd, c->aws_nbhd, sizeof(in.nbhd)); in.zmax = c->zmax;
-  in.pot_aws = c->pot_aws.data();
-  if (insol_shadow(insol_variant(c))) { in.cap_steps = kShadowStepsPerBlock; in.cap_subs = kShadowSubsPerBlock; }
-  in.alb_aws = c->alb_aws; in.swe_aws = c->swe_aws; in.layer_t_aws = c->layer_t_aws;
   if (c->p.msm_layers > 0 && !c->have_msm) return fail(ENRGY_ERR_ARG, "enrgy_set_msm must precede prepass when msm_layers > 0");
   if (c->p.msm_layers > 0 && !c->p.albedo_const && (int)c->alb_aws.size() != c->n_maps)
     return fail(ENRGY_ERR_ARG, "the AWS cell lies outside this handle's row band: its albedo/SWE are needed for the sub-surface pre-pass");
+  int rc;
   std::string err;
-  const int rc = run_prepass(in, c->pre, err);
+  if (c->pre_thread.joinable()) {          // started by enrgy_set_forcing, inputs unchanged since
+    c->pre_thread.join();
+    rc = c->pre_early_rc;
+    err = c->pre_early_err;
+    c->pre = std::move(c->pre_early);
+    c->pre_early = PrepassOutput{};
+    c->pre_early_rc = -1000;
+  } else {
+    PrepassInput in;
+    fill_prepass_input(c, in);
+    rc = run_prepass(in, c->pre, err);
+  }
   if (rc != ENRGY_OK) return fail(rc, "%s", err.c_str());
   const int urc = c->precision == ENRGY_F32 ? upload_tables<float>(c) : upload_tables<double>(c);
   if (urc != ENRGY_OK) return urc;

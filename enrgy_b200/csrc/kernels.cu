@@ -737,7 +737,7 @@ __device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem
 #define ENRGY_SHADOW_WARPS 1
 #endif
 #ifndef ENRGY_WARPS32
-#define ENRGY_WARPS32 8
+#define ENRGY_WARPS32 4      // float32: 4 CTAs x 4 warps at 128 registers (profiles/r01_summary.md)
 #endif
 #ifndef ENRGY_WARPS64
 #define ENRGY_WARPS64 4      // float64: 3 CTAs x 4 warps at 156 registers, no spills (profiles/r01_summary.md)
@@ -779,7 +779,7 @@ __host__ __device__ inline SmemPlan<R> smem_plan(int warps, int cap_steps, int c
 #define ENRGY_K64 4
 #endif
 #ifndef ENRGY_MINB32
-#define ENRGY_MINB32 2
+#define ENRGY_MINB32 4
 #endif
 #ifndef ENRGY_MINB64
 #define ENRGY_MINB64 3

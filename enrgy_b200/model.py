@@ -228,11 +228,11 @@ class Energy:
             eng.set_dem(self.base_dem_array)
             if self.use_msm:
                 eng.set_msm(self._msm_point_temps, self._msm_elev)
+            eng.set_forcing(table)    # the library starts its host pre-pass here, under the raster uploads
             if keys is not None:
                 eng.set_albedo_maps([self.albedo_arrays[k] for k in keys])
             if self._swe_given:
                 eng.set_swe(self.swe_array)
-            eng.set_forcing(table)
 
             # step ranges: cut at the checkpoint rows (model.py:279-283) and, for streamed
             # insolation, at the residency limit

@@ -37,12 +37,12 @@ table = build_forcing(case.aws_rows, keys)
 for it in range(4):
     t = [time.perf_counter()]
     eng.set_dem(pd.numpy()); t.append(time.perf_counter())
+    eng.set_forcing(table); t.append(time.perf_counter())
     eng.set_albedo_maps([a.numpy() for a in pa]); t.append(time.perf_counter())
     eng.set_swe(ps.numpy()); t.append(time.perf_counter())
-    eng.set_forcing(table); t.append(time.perf_counter())
     eng.prepass(); t.append(time.perf_counter())
     check(eng.lib.enrgy_run(eng.h, 0, T, stats.numpy().ctypes.data)); t.append(time.perf_counter())
     check(eng.lib.enrgy_get_state(eng.h, 32, *[o.numpy().ctypes.data for o in out])); t.append(time.perf_counter())
-    names = ["set_dem", "set_albedo_maps", "set_swe", "set_forcing", "prepass", "run", "get_state"]
+    names = ["set_dem", "set_forcing", "set_albedo_maps", "set_swe", "prepass", "run", "get_state"]
     print("  ".join("%s %.2f" % (nm, (b - a) * 1e3) for nm, a, b in zip(names, t, t[1:])), " total %.2f ms  kernel %.2f" % ((t[-1] - t[0]) * 1e3, eng.last_kernel_ms()))
 eng.close()
