@@ -34,11 +34,14 @@ N_STEPS = 2200
 # Algorithmic work per glacier cell-step.  SURVEY.md 8(d): energy-balance core 93 FLOP (+ 2 exp, not
 # counted) + 12 FLOP per insolation sub-step; C2 has 4 sub-steps per step -> 141 FLOP.  That is the
 # REFERENCE's arithmetic after hoisting per-cell invariants; the kernel executes less (DESIGN.md 4.1:
-# ez = e, exp(0) = 1, one reciprocal, analytic longwave sum ...): 85 FLOP = 63 issue slots when an
-# FMA counts once.  Both are reported; `roofline.frac` uses the SURVEY figure as the contract asks.
+# ez = e, exp(0) = 1, one reciprocal per quantity, analytic longwave sum, daily albedo blend, flux
+# scalars folded into the balance FMA chain): 79 FLOP = 48 FP32-pipe operations (FMA/ADD/MUL, two
+# cells per packed instruction) + 12 min/max/select/MUFU operations on the other pipes.  Both are
+# reported; `roofline.frac` uses the SURVEY figure as the contract asks.
 FLOP_PER_CELL_STEP = 141.0
-FLOP_EXECUTED_PER_CELL_STEP = 85.0
-OPS_PER_CELL_STEP = 63.0
+FLOP_EXECUTED_PER_CELL_STEP = 79.0
+FP32_PIPE_OPS_PER_CELL_STEP = 48.0       # lane-operations on the FMA pipe (a packed FFMA2 is two)
+ISSUE_SLOTS_PER_CELL_STEP = 36.5         # 47 packed / 2 + 1 scalar FMUL + 12 ALU/XU instructions
 METRIC = "cell-timesteps/s"
 SHADOW = False                   # --shadow: C3-style run with the per-sub-step shading ray march
 
@@ -273,7 +276,8 @@ def run_ours(args):
                        "band_rows": [b[1] for b in case.meta["bands"]],
                        "l2": "per-pass inputs ~%.0f MB > 126 MB L2, no flush" % (bytes_per_launch / 1e6)},
             "roofline": {"bound": "fp32" if args.dtype == "f32" else "fp64", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                         "traffic": measured_traffic(args.dtype, SHADOW),
                          "peak_source": "enrgy_microbench FMA loop on this GPU (MEASURED_PEAKS.json has no FP32/FP64 pipe peak)",
                          "flop_per_cell_step": FLOP_PER_CELL_STEP, "kernel_ms": kernel_ms,
                          "flop_source": "SURVEY.md 8(d): 93 (core) + 4 x 12 (insolation sub-steps), glacier cells only",
@@ -283,10 +287,8 @@ def run_ours(args):
                          "glacier_cell_fraction": n_valid / (float(n) * n),
                          "hbm": {"achieved": bytes_per_launch / (kernel_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                                  "frac": bytes_per_launch / (kernel_ms * 1e-3) / 1e9 / hbm},
-                         # the binding resource is instruction issue (ncu: DRAM < 1 %, issue slots ~80 % busy):
-                         # algorithmic operations (FMA = one) per second against 4 schedulers x 32 lanes x
-                         # SMs x the SM clock sampled during the run
-                         "issue": issue_roofline(n_valid * T, kernel_ms, clocks, args.dtype)},
+                         # the binding resources (ncu: DRAM < 1 %): FP32-pipe operations and issue slots
+                         "pipes": issue_roofline(n_valid * T, kernel_ms, clocks, args.dtype)},
             "e2e": {"value": e2e_value, "unit": "cell-timesteps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t_e.item()) * 1e3, "steps": e2e_steps},
             "gpu_launches": int(launches),
@@ -305,12 +307,32 @@ def run_ours(args):
 
 
 def issue_roofline(cell_steps, kernel_ms, clocks, dtype):
+    """The binding resources of the fused kernel (ncu: DRAM < 1 %): FP32-pipe lane-operations per
+    second against 128 lanes x SMs x clock, and instruction issue slots against 4 schedulers x 32
+    lanes x SMs x clock, both at the SM clock sampled during the run.  float32 figures (the packed
+    path); float64 runs the same algorithm on the FP64 pipe (64 lanes per SM)."""
     mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
-    lanes = 32 if dtype == "f32" else 16            # FP64 pipe: 64 lanes per SM = 16 per scheduler
-    peak = 148 * 4 * lanes * mhz * 1e6 / 1e12       # Tera-operations per second
-    achieved = OPS_PER_CELL_STEP * cell_steps / (kernel_ms * 1e-3) / 1e12
-    return {"achieved": achieved, "peak": peak, "unit": "Tops/s", "frac": achieved / peak,
-            "ops_per_cell_step": OPS_PER_CELL_STEP, "sm_mhz": mhz}
+    lanes = 128 if dtype == "f32" else 64
+    peak = 148 * lanes * mhz * 1e6 / 1e12
+    pipe = FP32_PIPE_OPS_PER_CELL_STEP * cell_steps / (kernel_ms * 1e-3) / 1e12
+    slots = ISSUE_SLOTS_PER_CELL_STEP * cell_steps / (kernel_ms * 1e-3) / 1e12
+    issue_peak = 148 * 128 * mhz * 1e6 / 1e12
+    return {"fp_pipe": {"achieved": pipe, "peak": peak, "unit": "Tera lane-ops/s", "frac": pipe / peak,
+                        "ops_per_cell_step": FP32_PIPE_OPS_PER_CELL_STEP},
+            "issue_slots": {"achieved": slots, "peak": issue_peak, "unit": "Tera thread-instr/s", "frac": slots / issue_peak,
+                            "slots_per_cell_step": ISSUE_SLOTS_PER_CELL_STEP,
+                            "note": "float32: two cells per packed instruction (FFMA2/FADD2/FMUL2)"},
+            "sm_mhz": mhz}
+
+
+def measured_traffic(dtype, shadow):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel for this workload, from the
+    committed ncu --set full capture (profiles/r01_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.isfile(path):
+        return None
+    key = ("shadow_" if shadow else "") + dtype
+    return json.load(open(path)).get(key)
 
 
 def algorithmic_bytes(case, precision):

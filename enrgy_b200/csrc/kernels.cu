@@ -673,6 +673,7 @@ __device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem
     const int ro_l = (kl * s.dr_fix + 32768) >> 16;
     const int co_l = (kl * s.dc_fix + 32768) >> 16;
     const int ab_l = (ro_l - ro_min) * kWinW + (co_l - co_min) + shift;
+    const float kdz_l = __fmul_rn((float)kl, s.dz);        // rise of the ray at this lane's step
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     unsigned hit = 0u;
@@ -680,12 +681,12 @@ __device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem
       int under[K];                                        // min over the chunk of (height bits - sample bits)
 #pragma unroll
       for (int i = 0; i < K; ++i) under[i] = 0x7fffffff;
-      const int* wkeys = reinterpret_cast<const int*>(win);
+      const int* wkeys = reinterpret_cast<const int*>(win) + lane;
 #pragma unroll(kRayUnroll)
       for (int j = 0; j < kRayChunk; ++j) {
-        const int ab = __shfl_sync(full, ab_l, j) + lane;
-        const float kdz = __fmul_rn((float)(k + j), s.dz);
-        const int* p = wkeys + ab;
+        // step j of the chunk: window offset and rise come from lane j (two shuffles, one LEA)
+        const int* p = wkeys + __shfl_sync(full, ab_l, j);
+        const float kdz = __shfl_sync(full, kdz_l, j);
 #pragma unroll
         for (int i = 0; i < K; ++i) {
           const float zk = __fadd_rn(z0[i], kdz);
@@ -698,11 +699,11 @@ __device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem
       float over[K];                                       // max over the chunk of (sample - ray height)
 #pragma unroll
       for (int i = 0; i < K; ++i) over[i] = -INFINITY;
+      const float* wlane = win + lane;
 #pragma unroll(kRayUnroll)
       for (int j = 0; j < kRayChunk; ++j) {
-        const int ab = __shfl_sync(full, ab_l, j) + lane;
-        const float kdz = __fmul_rn((float)(k + j), s.dz);
-        const float* p = win + ab;
+        const float* p = wlane + __shfl_sync(full, ab_l, j);
+        const float kdz = __shfl_sync(full, kdz_l, j);
 #pragma unroll
         for (int i = 0; i < K; ++i) {
           const float smp = p[i * kWinW];
