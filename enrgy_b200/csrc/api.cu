@@ -111,7 +111,8 @@ struct enrgy_ctx {
   int pre_early_rc = 0;
   std::string pre_early_err;
   bool dem_nonneg = false;   // no negative elevation: the shading samples use the integer copy (kInsolShadowKeys)
-  DevBuf<double> d_partials, d_stats, d_small;
+  DevBuf<double> d_stats, d_small;
+  DevBuf<unsigned char> d_partials;
   DevBuf<unsigned long long> d_counters;
   DevBuf<unsigned> d_masks;
   // SWE statistics of the initial raster (first CSV row)
@@ -315,9 +316,10 @@ int run_typed(enrgy_ctx* c, int t0, int t1, double* d_stats, cudaStream_t stream
   CU_TRY(energy_balance_grid<R>(insol, msm, false, c->sm_count, a.cap_steps, a.cap_subs, &li));
   int grid = std::min(li.grid, std::max(c->n_tiles, 1));
   const int n = t1 - t0;
-  CU_TRY(c->d_partials.alloc((size_t)grid * std::max(n, 1) * kStatsP));
-  CU_TRY(cudaMemsetAsync(c->d_partials.p, 0, (size_t)grid * std::max(n, 1) * kStatsP * sizeof(double), stream));
-  a.partials = c->d_partials.p;
+  const size_t partial_bytes = (size_t)grid * std::max(n, 1) * (msm ? kStatsP : kStatsK) * sizeof(R);
+  CU_TRY(c->d_partials.alloc(partial_bytes));
+  CU_TRY(cudaMemsetAsync(c->d_partials.p, 0, partial_bytes, stream));
+  a.partials = (R*)c->d_partials.p;
   if (n > 0 && !c->state_advanced) {
     CU_TRY(launch_nan_offglacier<R>(c->dem0, c->dem_pitch, c->pitch, c->band_row0, c->band_rows, c->cols, a.swe,
                                     a.total_snow, a.total_ice, stream));

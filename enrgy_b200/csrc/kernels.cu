@@ -846,7 +846,9 @@ energy_balance_kernel(const KernelArgs<R> a) {
   };
 
   const int n_steps_run = a.t1 - a.t0;
-  double* my_partials = a.partials ? a.partials + (size_t)blockIdx.x * n_steps_run * kStatsP : nullptr;
+  // this CTA's rows of per-step sums (in R: in float32 mode the 40 MB of rows stay L2-resident)
+  constexpr int kRow = MSM ? kStatsP : kStatsK;
+  R* my_partials = a.partials ? a.partials + (size_t)blockIdx.x * n_steps_run * kRow : nullptr;
   constexpr int NB = MSM ? kMaxLayers + 1 : 1;       // boundary temperatures kept per cell
 
   for (int ti = blockIdx.x; ti < a.n_tiles; ti += gridDim.x) {
@@ -1309,7 +1311,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
             sum += q < kStatsK ? (double)sm_slots[(w * cap_steps + sl) * kStatsK + q]
                                : (double)sm_slots_m[(w * cap_steps + sl) * kStatsM + (q - kStatsK)];
           }
-          my_partials[(size_t)(ts - a.t0 + step) * kStatsP + q] += sum;
+          my_partials[(size_t)(ts - a.t0 + step) * kRow + q] += (R)sum;
         }
       }
       __syncthreads();
@@ -1567,9 +1569,16 @@ __global__ void finalize_stats_kernel(const FinalizeArgs f) {
   if (t >= f.n_steps) return;
   double k[kStatsP];
   for (int q = 0; q < kStatsP; ++q) k[q] = 0.0;
+  const int row = f.msm ? kStatsP : kStatsK;
   for (int c = 0; c < f.n_ctas; ++c) {
-    const double* p = f.partials + ((size_t)c * f.n_steps + t) * kStatsP;
-    for (int q = 0; q < kStatsP; ++q) k[q] += p[q];
+    const size_t o = ((size_t)c * f.n_steps + t) * row;
+    if (f32_mode) {
+      const float* p = static_cast<const float*>(f.partials) + o;
+      for (int q = 0; q < row; ++q) k[q] += (double)p[q];
+    } else {
+      const double* p = static_cast<const double*>(f.partials) + o;
+      for (int q = 0; q < row; ++q) k[q] += p[q];
+    }
   }
   const StepRec<double> s = f.steps64[f.t0 + t];
   const double lwu_cell = f32_mode ? (double)(float)s.c_lwu : s.c_lwu;

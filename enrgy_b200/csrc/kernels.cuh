@@ -67,7 +67,7 @@ struct KernelArgs {
   const int2* tiles;              // active tiles (tile row, tile col) of the band
   int n_tiles;
   // statistics: per-CTA partial sums [gridDim.x][t1 - t0][kStatsP] float64
-  double* partials;
+  R* partials;                    // [gridDim.x][t1 - t0][kStatsK (+ kStatsM with the sub-surface model)] in R
   // dump mode: [t1 - t0][ENRGY_D_COUNT][band_rows_pad][pitch] R (may be null)
   R* dump;
   size_t dump_field_stride;
@@ -77,7 +77,7 @@ struct KernelArgs {
 };
 
 struct FinalizeArgs {
-  const double* partials;   // [n_ctas][n_steps][kStatsP]
+  const void* partials;     // [n_ctas][n_steps][row], row = kStatsK (+ kStatsM with msm); float if f32_mode else double
   int msm;                  // sub-surface model on: lwu and g are summed per cell
   int n_ctas, n_steps, t0;
   double n_valid;           // valid cells of the band
