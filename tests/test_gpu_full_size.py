@@ -1,0 +1,145 @@
+"""BASELINE.json's full sizes.  The NumPy oracle is far too slow for 2048 x 2048 x 2200 (20 minutes),
+so the full-size runs are checked (a) against the oracle on a WINDOW of the raster around the AWS
+cell for the whole season -- cells are independent given the AWS-cell scalars, so the window's cells
+must come out the same as in the full run -- and (b) through size-independent properties: closure of
+the melt totals against the per-step area sums, SWE bookkeeping, split runs, row bands."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+from enrgy_b200 import _lib
+from enrgy_b200.engine import Engine
+from enrgy_b200.forcing import build_forcing
+from enrgy_b200.synthetic import make_case
+from oracle import insolation_oracle as I
+from tests import parity as P
+
+pytestmark = pytest.mark.gpu
+
+N, T = 2048, 2200            # config C2 of BASELINE.json
+
+
+@pytest.fixture(scope="module")
+def c2_case():
+    return make_case(N, T, seed=0)
+
+
+def _engine(case, f64, shadow=False, band=None):
+    h, w = case.shape
+    eng = Engine(h, w, precision=_lib.F64 if f64 else _lib.F32)
+    r0, rows = band if band else (0, h)
+    eng.set_params(cell_size=case.cell, elev_aws=case.elev_aws, aws_row=case.aws_rc[0], aws_col=case.aws_rc[1],
+                   sensor_z=1.6, zm=1e-3, z_h_or_e=1e-4, emissivity=0.98, insol_mode=_lib.INSOL_COMPUTED,
+                   shadow=shadow, lat=case.lat, lon=case.lon, band_row0=r0, band_rows=rows)
+    eng.set_dem(case.dem)
+    alb = P.clipped_albedo(case, np.float32)
+    keys = list(alb)
+    eng.set_forcing(build_forcing(case.aws_rows, keys))
+    eng.set_albedo_maps([alb[k][r0:r0 + rows] for k in keys])
+    eng.set_swe(case.swe[r0:r0 + rows])
+    eng.prepass()
+    return eng
+
+
+def _window(case, half):
+    """The case cut to (2 half + 1)^2 cells around the AWS cell, plus a one-cell halo for the terrain
+    normals; same forcing, same AWS cell (geotransform shifted)."""
+    r, c = case.aws_rc
+    r0, r1, c0, c1 = r - half - 1, r + half + 2, c - half - 1, c + half + 2
+    gt = list(case.geotransform)
+    gt[0] += c0 * case.cell
+    gt[3] -= r0 * case.cell
+    sl = (slice(r0, r1), slice(c0, c1))
+    return dataclasses.replace(case, dem=case.dem[sl].copy(), geotransform=tuple(gt), swe=case.swe[sl].copy(),
+                               albedo_maps={k: a[sl].copy() for k, a in case.albedo_maps.items()},
+                               aws_rc=(r - r0, c - c0)), sl
+
+
+@pytest.mark.parametrize("f64", [True, False])
+def test_c2_full_season_window_vs_oracle(c2_case, f64):
+    case = c2_case
+    eng = _engine(case, f64)
+    try:
+        stats = eng.run(0, T)
+        swe, tsn, tic = eng.state(np.float64)
+    finally:
+        eng.close()
+    win, sl = _window(case, 24)
+    pot = I.insolation_series(win, shadow=False, dtype=np.float64)
+    ora = P.run_oracle(win, pot if f64 else pot.astype(np.float32), f64)
+    inner = (slice(1, -1), slice(1, -1))           # the halo cells see other neighbours than in the full raster
+    tol, floor = (1e-9, 1e-6) if f64 else (1e-4, 1e-3)
+    for got, name in ((swe, "swe"), (tsn, "total_snow"), (tic, "total_ice")):
+        err = P.max_rel_err(got[sl][inner], np.asarray(ora[name], dtype=np.float64)[inner], floor)
+        assert err < tol, (name, err)
+    assert np.nanmax(tic[sl][inner]) > 0.5         # the season really melts ice there (metres w.e.)
+
+    # closure: melt totals of the rasters == per-step area sums added up over the season
+    valid = ~np.isnan(case.dem)
+    total_rasters = float(np.sum(tsn[valid]) + np.sum(tic[valid]))
+    total_steps = float(np.sum(stats[:, _lib.S_SNOW]) + np.sum(stats[:, _lib.S_ICE]))
+    assert abs(total_rasters - total_steps) < (1e-9 if f64 else 2e-5) * total_rasters
+    # SWE bookkeeping: what left the snow pack is the snow melt
+    assert np.allclose(case.swe[valid].astype(np.float64) - swe[valid], tsn[valid], rtol=0, atol=1e-12 if f64 else 1e-6)
+    # off-glacier cells are NaN in all three rasters (model.py:258)
+    assert np.isnan(swe[~valid]).all() and np.isnan(tsn[~valid]).all() and np.isnan(tic[~valid]).all()
+    assert stats[-1, _lib.S_NVALID] == valid.sum()
+
+
+def test_c2_split_runs_and_row_bands_bit_identical(c2_case):
+    """Season in one launch == season in three launches == two row bands side by side (float32)."""
+    case = c2_case
+    one = _engine(case, False)
+    s_one = one.run(0, T)
+    st_one = one.state(np.float32)
+    one.close()
+    three = _engine(case, False)
+    s_three = np.concatenate([three.run(0, 700), three.run(700, 1501), three.run(1501, T)])
+    st_three = three.state(np.float32)
+    three.close()
+    assert np.array_equal(s_one, s_three)
+    for a, b in zip(st_one, st_three):
+        assert np.array_equal(a, b, equal_nan=True)
+    total = np.zeros_like(s_one)
+    for band in ((0, 1040), (1040, N - 1040)):
+        eng = _engine(case, False, band=band)
+        total += eng.run(0, T)
+        part = eng.state(np.float32)
+        eng.close()
+        for a, b in zip(part, st_one):
+            assert np.array_equal(a, b[band[0]:band[0] + band[1]], equal_nan=True)
+    cols = [_lib.S_RS, _lib.S_SENS, _lib.S_LAT, _lib.S_MELT, _lib.S_SNOW, _lib.S_ICE]
+    assert np.allclose(total[1:, cols], s_one[1:, cols], rtol=2e-6, atol=1e-6)
+
+
+def test_c3_size_shading_bands_and_rays():
+    """8192-row raster with the shading ray march (config C3's size along the band axis): two row
+    bands give bit-identical rasters to the whole raster -- rays cross the cut -- and 12000 rays
+    traced one by one with the specification agree with the masks."""
+    from oracle.enrgy_oracle import time_step_seconds
+    case = make_case(8192, 6, w=1024, seed=11, start="20220615 18:00:00")
+    whole = _engine(case, False, shadow=True)
+    try:
+        whole.run(0, 6)
+        st = whole.state(np.float32)
+        step = 3
+        table = I.substep_table(I.to_unix(case.aws_rows[step]["DATE"]), time_step_seconds(case.aws_rows, step),
+                                case.lat, case.lon, case.cell)
+        masks = whole.shade_masks(step)
+    finally:
+        whole.close()
+    for band in ((0, 4000), (4000, 4192)):
+        eng = _engine(case, False, shadow=True, band=band)
+        eng.run(0, 6)
+        part = eng.state(np.float32)
+        eng.close()
+        for a, b in zip(part, st):
+            assert np.array_equal(a, b[band[0]:band[0] + band[1]], equal_nan=True)
+    rng = np.random.default_rng(1)
+    rr, cc = rng.integers(0, 8192, 12000), rng.integers(0, 1024, 12000)
+    ok = ~np.isnan(case.dem[rr, cc])
+    rr, cc = rr[ok], cc[ok]
+    for j, sub in enumerate(table):
+        lit = I.trace_cells(case.dem, rr, cc, sub["dc_fix"], sub["dr_fix"], sub["dz"])
+        assert np.array_equal(masks[j][rr, cc], lit), j
