@@ -260,7 +260,8 @@ def run_ours(args):
         peak = peak32 if args.dtype == "f32" else peak64
         # algorithmic FLOPs are counted on GLACIER cells only (off-glacier cells are skipped, they
         # count toward the metric's H*W*T but do no arithmetic)
-        n_valid = float(stats_host[0, _lib.S_NVALID])
+        # (this rank's band: the kernel time below is this rank's too; the statistics are global)
+        n_valid = float(np.count_nonzero(~np.isnan(case.dem)))
         achieved = FLOP_PER_CELL_STEP * n_valid * T / (kernel_ms * 1e-3) / 1e12
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm = json.load(open(peaks_file))["hbm_gbs"] if os.path.isfile(peaks_file) else 6650.0
@@ -275,7 +276,8 @@ def run_ours(args):
                        "raster": [n * world, n], "steps_per_pass": T, "parallelism": "row bands x%d, balanced by glacier cells" % world,
                        "band_rows": [b[1] for b in case.meta["bands"]],
                        "l2": "per-pass inputs ~%.0f MB > 126 MB L2, no flush" % (bytes_per_launch / 1e6)},
-            "roofline": {"bound": "fp32" if args.dtype == "f32" else "fp64", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "fp32" if args.dtype == "f32" else "fp64",
+                         "bound_note": "no dense contraction and 0.03 B of HBM traffic per cell-step: neither 'tensor' nor 'hbm' binds; the FP32 (FP64) pipe does" + ("; with --shadow the ray march dominates (integer/LDS work, see profiles/r01_summary.md) and this FLOP roofline covers the energy balance only" if SHADOW else ""), "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                          "traffic": measured_traffic(args.dtype, SHADOW),
                          "peak_source": "enrgy_microbench FMA loop on this GPU (MEASURED_PEAKS.json has no FP32/FP64 pipe peak)",
@@ -284,7 +286,7 @@ def run_ours(args):
                          "as_executed": {"flop_per_cell_step": FLOP_EXECUTED_PER_CELL_STEP,
                                          "achieved": FLOP_EXECUTED_PER_CELL_STEP * n_valid * T / (kernel_ms * 1e-3) / 1e12,
                                          "frac": (FLOP_EXECUTED_PER_CELL_STEP * n_valid * T / (kernel_ms * 1e-3) / 1e12 / peak) if peak else None},
-                         "glacier_cell_fraction": n_valid / (float(n) * n),
+                         "glacier_cell_fraction": n_valid / float(case.dem.size),
                          "hbm": {"achieved": bytes_per_launch / (kernel_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                                  "frac": bytes_per_launch / (kernel_ms * 1e-3) / 1e9 / hbm},
                          # the binding resources (ncu: DRAM < 1 %): FP32-pipe operations and issue slots

@@ -1159,7 +1159,8 @@ energy_balance_kernel(const KernelArgs<R> a) {
           // rs + lwd - lwu + sens + lat as one FMA chain; the area sum of lwd is not reduced here: Tz
           // is linear in the elevation, so it follows from the first four moments of
           // (dem - elev_aws), see finalize_stats_kernel
-          const V atmo = fma2(c_lat, x_lat, fma2(c_sens, x_sens, fma2(c_sw, x_rs, sub2(mul2(c_lwd, tz4), lwu))));
+          const V lwu_neg = V::make(-lwu.lo(), -lwu.hi());
+          const V atmo = fma2(c_lat, x_lat, fma2(c_sens, x_sens, fma2(c_sw, x_rs, fma2(c_lwd, tz4, lwu_neg))));
           V mf, gfl = V::splat((R)0);
           if (MSM) {
             R mfh[2], gh[2];
@@ -1347,7 +1348,8 @@ energy_balance_kernel(const KernelArgs<R> a) {
 // cells per thread: the sub-surface model carries 8 more registers per cell
 template <typename R, bool MSM>
 struct CellsPerThread {
-  static constexpr int value = (sizeof(R) == 4 ? ENRGY_K32 : ENRGY_K64) / (MSM ? 2 : 1);
+  static constexpr int kBase = sizeof(R) == 4 ? ENRGY_K32 : ENRGY_K64;
+  static constexpr int value = MSM ? ((kBase / 2 + 1) & ~1) : kBase;   // an even number: cells come in pairs
 };
 
 template <typename R>
