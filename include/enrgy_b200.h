@@ -179,7 +179,11 @@ int enrgy_set_msm(enrgy_ctx* ctx, const double* temps, double elev);
  * restore), enrgy_prepass and enrgy_run afterwards. */
 int enrgy_set_member(enrgy_ctx* ctx, double albedo_offset, double zm, double z_h_or_e);
 
-/* forcing table [n_steps][ENRGY_F_COUNT] (model.py:182-230) */
+/* forcing table [n_steps][ENRGY_F_COUNT] (model.py:182-230).  With in-kernel insolation and no
+ * sub-surface model the host pre-pass needs nothing else besides the DEM, so it is started here on a
+ * worker thread: call this right after enrgy_set_dem and the pre-pass runs while the albedo / SWE
+ * rasters upload; enrgy_prepass() then only joins it (any other call order works, just without the
+ * overlap). */
 int enrgy_set_forcing(enrgy_ctx* ctx, int n_steps, const double* forcing);
 
 /* streamed insolation (model.py:471-481): kWh m-2 rasters of steps [t0, t0 + n) */
