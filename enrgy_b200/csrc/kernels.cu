@@ -539,6 +539,9 @@ cudaError_t launch_blockmax(const float* dem, int dem_pitch, int rows_full, int 
   return cudaGetLastError();
 }
 
+#ifdef ENRGY_MARCH_STATS
+__device__ unsigned long long g_march_stats[32];
+#endif
 constexpr int kWinW = 52;                       // DEM window of a ray chunk: 32 columns + 16 steps + 3 (alignment)
 constexpr int kWinH = 24;                       //                            K <= 8 rows + 16 steps
 constexpr int kWinBytes = kWinW * kWinH * 4;    // 4992 B = 39 x 128 B
@@ -640,6 +643,21 @@ __device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem
       }
       if (!__any_sync(full, active != 0u)) break;
     }
+#ifdef ENRGY_MARCH_STATS
+    {
+      const unsigned n_act = __reduce_add_sync(full, __popc(active));
+      unsigned any_rows = 0;
+#pragma unroll
+      for (int i = 0; i < K; ++i) any_rows |= __any_sync(full, (active >> i) & 1u) ? (1u << i) : 0u;
+      if (lane == 0) {
+        atomicAdd(&g_march_stats[0], 1ull);
+        atomicAdd(&g_march_stats[1], (unsigned long long)n_act);
+        atomicAdd(&g_march_stats[2], (unsigned long long)(K - __popc(any_rows)));
+        atomicAdd(&g_march_stats[4 + min((k - 1) / kRayChunk, 11)], 1ull);
+        atomicAdd(&g_march_stats[16 + min((int)n_act / 32, 8)], 1ull);
+      }
+    }
+#endif
     // (c) stage the chunk's DEM window (kWinH rows x kWinW columns, 16-byte aligned origin) in this
     // warp's shared-memory buffer with asynchronous 16 B copies (cp.async / LDGSTS: 10 per lane, no
     // registers, all in flight together), then sample it: a sample is LDS [idx + i * row pitch].
@@ -1625,6 +1643,11 @@ __global__ void finalize_stats_kernel(const FinalizeArgs f) {
   }
 }
 
+#ifdef ENRGY_MARCH_STATS
+extern "C" int enrgy_debug_march_stats(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_march_stats, sizeof(g_march_stats));
+}
+#endif
 cudaError_t launch_finalize(const FinalizeArgs& f, cudaStream_t stream) {
   if (f.n_steps <= 0) return cudaSuccess;
   finalize_stats_kernel<<<(f.n_steps + 127) / 128, 128, 0, stream>>>(f);

@@ -41,9 +41,14 @@ def run_members(engine, members, indices=None, n_steps=None, keep_rasters=False)
         engine.set_member(m.get("albedo_offset", 0.0), m.get("zm"), m.get("z_h_or_e"))
         engine.prepass()
         stats = engine.run(0, n_steps)
-        swe, tsn, tic = engine.state(np.float32)
-        res = dict(stats=stats, mean_ice=float(np.nanmean(tic)), mean_snow=float(np.nanmean(tsn)))
+        # glacier-wide melt totals from the per-step area sums (the melt rasters add up to exactly
+        # these, tests/test_gpu_full_size.py): no raster leaves the device unless it is asked for
+        n_valid = float(stats[-1, _lib.S_NVALID]) if n_steps else 0.0
+        res = dict(stats=stats,
+                   mean_ice=float(stats[:, _lib.S_ICE].sum() / n_valid) if n_valid else float("nan"),
+                   mean_snow=float(stats[:, _lib.S_SNOW].sum() / n_valid) if n_valid else float("nan"))
         if keep_rasters:
+            swe, tsn, tic = engine.state(np.float32)
             res.update(swe=swe, total_snow=tsn, total_ice=tic)
         out[i] = res
     return out

@@ -38,5 +38,7 @@ def test_members_match_reference_on_perturbed_inputs(const):
         ora = P.run_oracle_arrays(c2, pot, True, **okw)
         assert P.max_rel_err(got[i]["total_ice"], ora["total_ice"], 1e-3) < 2e-7, i
         assert P.max_rel_err(got[i]["swe"], ora["swe"], 1e-3) < 2e-7, i
+        # the per-member totals come from the per-step area sums: same number as the raster mean
+        assert abs(got[i]["mean_ice"] - np.nanmean(got[i]["total_ice"])) < 1e-6 * max(np.nanmean(got[i]["total_ice"]), 1e-3), i
     assert abs(got[0]["mean_ice"] - got[3]["mean_ice"]) > 1e-6    # the perturbation really acts
     assert shard(members, 3, 1) == [1]
