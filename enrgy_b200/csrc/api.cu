@@ -87,7 +87,8 @@ struct enrgy_ctx {
   std::vector<double> pot_aws;
   PrepassOutput pre;
   // device rasters
-  DevBuf<float> d_dem, d_albedo, d_pot, d_tmp32, d_blockmax;
+  DevBuf<float> d_dem, d_albedo, d_pot, d_tmp32, d_blockmax, d_gstep;
+  int pyr_stride = 0;
   int dem_pitch = 0;
   MaxPyramid pyramid{};
   float* dem0 = nullptr;          // cell (0, 0) inside the apron buffer
@@ -110,6 +111,7 @@ struct enrgy_ctx {
   PrepassOutput pre_early;
   int pre_early_rc = 0;
   std::string pre_early_err;
+  float dem_min = 0.f;       // lowest valid elevation (shading only)
   bool dem_nonneg = false;   // no negative elevation: the shading samples use the integer copy (kInsolShadowKeys)
   DevBuf<double> d_stats, d_small;
   DevBuf<unsigned char> d_partials;
@@ -248,6 +250,9 @@ int fill_args(enrgy_ctx* c, int t0, int t1, KernelArgs<R>& a) {
   a.band_row0 = c->band_row0; a.band_rows = c->band_rows; a.rows_pad_full = c->rows_pad_full;
   a.dem = c->dem0; a.dem_pitch = c->dem_pitch;
   a.blockmax = c->d_blockmax.p; a.pyramid = c->pyramid;
+  // the step-rise test's margin (1 cm) assumes float32 ray heights below 16 km
+  a.gstep = (std::fabs(c->zmax) < 16000.f && c->dem_min > -16000.f) ? c->d_gstep.p : nullptr;
+  a.pyr_stride = c->pyr_stride;
   a.dem_keys = c->d_demkeys.p ? c->d_demkeys.p + (size_t)kDemApron * c->dem_pitch + kDemApron : nullptr;
   a.nx = (const R*)c->d_nx.p; a.ny = (const R*)c->d_ny.p; a.nz = (const R*)c->d_nz.p;
   a.albedo = c->d_albedo.p;
@@ -450,7 +455,7 @@ int enrgy_destroy(enrgy_ctx* c) {
   c->d_ti.release(); c->d_dump.release(); c->d_stage.release(); c->d_steps.release(); c->d_subs.release();
   c->d_steps64.release(); c->d_shades.release(); c->d_blocks.release(); c->d_tiles.release();
   c->d_counts.release(); c->d_partials.release(); c->d_stats.release(); c->d_small.release();
-  c->d_counters.release(); c->d_masks.release(); c->d_snap.release(); c->d_blockmax.release(); c->d_layer_t.release(); c->d_demkeys.release();
+  c->d_counters.release(); c->d_masks.release(); c->d_snap.release(); c->d_blockmax.release(); c->d_layer_t.release(); c->d_demkeys.release(); c->d_gstep.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -561,6 +566,12 @@ int enrgy_set_dem(enrgy_ctx* c, const float* dem) {
   // cell is negative
   c->dem_nonneg = false;
   if (c->p.insol_mode == ENRGY_INSOL_COMPUTED && c->p.shadow) {
+    // step-rise pyramids of the 8 ray octants (second skip test of the march)
+    c->pyr_stride = c->pyramid.off[c->pyramid.levels - 1] +
+                    (c->pyramid.nbr[c->pyramid.levels - 1] + 2) * (c->pyramid.nbc[c->pyramid.levels - 1] + 2);
+    CU_TRY(c->d_gstep.alloc((size_t)8 * c->pyr_stride));
+    CU_TRY(launch_gstep(c->dem0, c->dem_pitch, c->rows, c->cols, c->pyramid, c->pyr_stride, c->d_gstep.p, c->stream));
+    c->launches++;
     CU_TRY(c->d_demkeys.alloc(dem_elems + 1));
     int* d_min = c->d_demkeys.p + dem_elems;
     const int int_max = 0x7fffffff;
@@ -571,6 +582,11 @@ int enrgy_set_dem(enrgy_ctx* c, const float* dem) {
     CU_TRY(cudaMemcpyAsync(&min_key, d_min, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     c->dem_nonneg = min_key >= 0 && c->p.shadow != 2;
+    {
+      const int bits = min_key ^ ((min_key >> 31) & 0x7fffffff);     // key -> float bits
+      std::memcpy(&c->dem_min, &bits, sizeof(float));
+      if (min_key == 0x7fffffff) c->dem_min = 0.f;                    // no valid cell
+    }
   }
   // active tiles of the band
   c->tiles_r = (c->band_rows + c->tile_h - 1) / c->tile_h;

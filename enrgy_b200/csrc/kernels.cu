@@ -539,6 +539,80 @@ cudaError_t launch_blockmax(const float* dem, int dem_pitch, int rows_full, int 
   return cudaGetLastError();
 }
 
+// Step-rise pyramids.  A ray advances one cell along its dominant axis per step and zero or one cell
+// along the other, so between consecutive steps the terrain under it rises by at most
+//   G(Q) = max(dem(Q + major) - dem(Q), dem(Q + major + minor) - dem(Q))
+// of the cell Q it leaves.  If G <= dz - eps for every cell a bundle of rays can leave during the
+// next n steps, and no ray has been hit so far, none can be hit in those n steps: the terrain
+// cannot catch up with a ray that rises dz per step (induction over the steps).
+// One max pyramid of G per octant (dominant axis, its sign, sign of the other axis), level 0 = max
+// over the cells of a 16 x 16 block, +inf if the block holds a NaN cell inside the grid (the chain
+// of differences breaks there), -inf for the ring of blocks outside the grid.
+__global__ void gstep_kernel(const float* __restrict__ dem, int dem_pitch, int rows_full, int cols, int nbr, int nbc,
+                             int stride, float* __restrict__ out) {
+  const int bc = (int)blockIdx.x - 1, br = (int)blockIdx.y - 1;
+  float g[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) g[o] = -INFINITY;
+  bool has_nan = false;
+  if (br >= 0 && br < nbr && bc >= 0 && bc < nbc) {
+    auto at = [&](int r, int c) -> float {   // NaN outside the grid
+      return (r >= 0 && r < rows_full && c >= 0 && c < cols) ? dem[(long long)r * dem_pitch + c] : __int_as_float(0x7fc00000);
+    };
+    for (int i = threadIdx.x; i < kMaxBlock * kMaxBlock; i += blockDim.x) {
+      const int r = br * kMaxBlock + i / kMaxBlock, c = bc * kMaxBlock + i % kMaxBlock;
+      if (r >= rows_full || c >= cols) continue;
+      const float z = dem[(long long)r * dem_pitch + c];
+      if (!(z == z)) { has_nan = true; continue; }
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        const bool col_major = o & 4;
+        const int s_major = (o & 2) ? -1 : 1, s_minor = (o & 1) ? -1 : 1;
+        const int r1 = col_major ? r : r + s_major, c1 = col_major ? c + s_major : c;          // + major
+        const int r2 = col_major ? r + s_minor : r + s_major, c2 = col_major ? c + s_major : c + s_minor;   // + major + minor
+        // fmaxf ignores NaN: a ray cannot be hit by a cell outside the grid, and a NaN cell inside
+        // the grid marks its own block
+        g[o] = fmaxf(g[o], fmaxf(__fsub_ru(at(r1, c1), z), __fsub_ru(at(r2, c2), z)));
+      }
+    }
+  }
+  __shared__ float sh[8][8];
+  __shared__ int sh_nan;
+  if (threadIdx.x == 0) sh_nan = 0;
+  __syncthreads();
+  if (has_nan) sh_nan = 1;
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    float m = g[o];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0) sh[o][threadIdx.x >> 5] = m;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    const int o = threadIdx.x;
+    float m = -INFINITY;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, sh[o][w]);
+    if (sh_nan) m = INFINITY;
+    out[(size_t)o * stride + (size_t)blockIdx.y * (nbc + 2) + blockIdx.x] = m;
+  }
+}
+cudaError_t launch_gstep(const float* dem, int dem_pitch, int rows_full, int cols, const MaxPyramid& py, int stride,
+                         float* buffer, cudaStream_t stream) {
+  gstep_kernel<<<dim3(py.nbc[0] + 2, py.nbr[0] + 2), 256, 0, stream>>>(dem, dem_pitch, rows_full, cols, py.nbr[0],
+                                                                       py.nbc[0], stride, buffer + py.off[0]);
+  for (int o = 0; o < 8; ++o) {
+    float* b = buffer + (size_t)o * stride;
+    for (int l = 1; l < py.levels; ++l) {
+      blockmax_coarsen_kernel<<<dim3((py.nbc[l] + 2 + 127) / 128, py.nbr[l] + 2), 128, 0, stream>>>(
+          b + py.off[l - 1], py.nbr[l - 1], py.nbc[l - 1], b + py.off[l], py.nbr[l], py.nbc[l]);
+    }
+  }
+  return cudaGetLastError();
+}
+constexpr float kGstepEps = 0.01f;   // margin of the step-rise test [m]: above the float32 rounding of ray heights
+                                     // below 16 km (2 ulp = 2e-3 m) and of the stored rises (rounded up)
+
 #ifdef ENRGY_MARCH_STATS
 __device__ unsigned long long g_march_stats[32];
 #endif
@@ -575,7 +649,8 @@ __device__ __forceinline__ float key_float(int k) {
 template <int K, bool KEYS>
 __device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem_pitch, float* win,
                                           int rows_full, int cols,
-                                          const float* __restrict__ pyr, const MaxPyramid& py,
+                                          const float* __restrict__ pyr, const float* __restrict__ gstep,
+                                          int pyr_stride, const MaxPyramid& py,
                                           const int (&row)[K], const int (&col)[K], const float (&z0)[K],
                                           unsigned start_bits, const ShadeRec s, float zmax, int lane) {
   const unsigned full = 0xffffffffu;
@@ -595,6 +670,14 @@ __device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem
   };
   if (!__any_sync(full, active != 0u)) return lit;
   float z0min = lowest(active);
+  // step-rise pyramid of this direction's octant (gstep_kernel)
+  const int adr = abs(s.dr_fix), adc = abs(s.dc_fix);
+  const bool col_major = adc > adr;
+  const int octant = (col_major ? 4 : 0) | ((col_major ? s.dc_fix : s.dr_fix) < 0 ? 2 : 0) |
+                     ((col_major ? s.dr_fix : s.dc_fix) < 0 ? 1 : 0);
+  const bool rise_test = gstep != nullptr;                 // (off for rasters beyond +-16 km, where its margin is too small)
+  const float* __restrict__ gpyr = gstep + (size_t)octant * pyr_stride;
+  const float g_limit = s.dz - kGstepEps;                  // terrain rising less than this per step cannot catch a ray
   int level = 0;
   int k = 1;
   while (k < 32768) {                                      // rasters are at most 32767 cells wide
@@ -609,20 +692,32 @@ __device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem
     const int cmin = c_lo + co_min, cmax = c_hi + max(co_a, co_b);
     // the patch left the grid for good (offsets are monotone in k)
     if (r_hi + ro_a < 0 || r_lo + ro_a >= rows_full || c_hi + co_a < 0 || c_lo + co_a >= cols) break;
-    // (b) can these n steps hit anything?  max of the pyramid blocks (edge 16 << level) under the
-    // swept bounding box: at most 3 x 4 blocks, one per lane, one REDUX
+    // (b) can these n steps hit anything?  Two conservative tests on the blocks (edge 16 << level)
+    // under the bounding box swept from step k - 1 to step k + n - 1 (at most 4 x 4 blocks):
+    //   lanes 0-15  the max pyramid: nothing in reach is as high as the LOWEST ray, or
+    //   lanes 16-31 the step-rise pyramid: nowhere in reach does the terrain rise as fast as the rays
+    //               (none of which has been hit so far), so it cannot catch up with any of them.
+    // One block per lane, one REDUX each.
     {
+      const int kp = k - 1;
+      const int ro_p = (kp * s.dr_fix + 32768) >> 16, co_p = (kp * s.dc_fix + 32768) >> 16;
       const int sh = 4 + level;
-      const int br0 = rmin >> sh, br1 = rmax >> sh, bc0 = cmin >> sh, bc1 = cmax >> sh;
+      const int br0 = min(rmin, r_lo + ro_p) >> sh, br1 = max(rmax, r_hi + ro_p) >> sh;
+      const int bc0 = min(cmin, c_lo + co_p) >> sh, bc1 = max(cmax, c_hi + co_p) >> sh;
       const int nbr = py.nbr[level], nbc = py.nbc[level];
       float m = -INFINITY;
-      const int br = br0 + (lane >> 2), bc = bc0 + (lane & 3);
+      const int l16 = lane & 15;
+      const int br = br0 + (l16 >> 2), bc = bc0 + (l16 & 3);
       if (br <= br1 && bc <= bc1) {
         const int cr = min(max(br, -1), nbr), cc = min(max(bc, -1), nbc);
-        m = __ldg(pyr + py.off[level] + (size_t)(cr + 1) * (nbc + 2) + (cc + 1));
+        const float* __restrict__ src = lane < 16 ? pyr : gpyr;
+        if (lane < 16 || rise_test) m = __ldg(src + py.off[level] + (size_t)(cr + 1) * (nbc + 2) + (cc + 1));
       }
-      const int region_key = __reduce_max_sync(full, float_key(m));
-      if (float_key(zlow) > region_key) {                  // nothing in reach is as high as the lowest ray
+      const int key = float_key(m);
+      const int region_key = __reduce_max_sync(full, lane < 16 ? key : (int)0x80000000);
+      const int rise_key = __reduce_max_sync(full, lane < 16 ? (int)0x80000000 : key);
+      const bool fits = br1 - br0 <= 3 && bc1 - bc0 <= 3;
+      if (fits && (float_key(zlow) > region_key || (rise_test && rise_key <= float_key(g_limit)))) {
         k += n;
         level = min(level + 1, py.levels - 1);
         continue;
@@ -1037,7 +1132,8 @@ energy_balance_kernel(const KernelArgs<R> a) {
               }
               constexpr bool KEYS = INSOL == kInsolShadowKeys;
               lit = march<K, KEYS>(KEYS ? reinterpret_cast<const float*>(a.dem_keys) : a.dem, a.dem_pitch, my_win,
-                                   a.rows_full, a.cols, a.blockmax, a.pyramid, rowf, col, z0, start_bits,
+                                   a.rows_full, a.cols, a.blockmax, a.gstep, a.pyr_stride, a.pyramid, rowf, col, z0,
+                                   start_bits,
                                    sm_shades[buf * cap_subs + j], (float)a.zmax, lane);
               if (DUMP && a.mask_out != nullptr && t == a.t0) {
 #pragma unroll

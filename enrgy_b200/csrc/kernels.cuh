@@ -33,6 +33,8 @@ struct KernelArgs {
   const int* dem_keys;            // same layout: -(bit pattern) of every valid cell, +1 for NaN (dem_key_kernel)
   const float* blockmax;          // max pyramid of the DEM (shading early exit), see MaxPyramid
   MaxPyramid pyramid;
+  const float* gstep;             // 8 step-rise pyramids (one per ray octant, same layout), see gstep_kernel
+  int pyr_stride;                 // floats per pyramid
   const R* nx;                    // [band_rows_pad][pitch] terrain normal (computed insolation)
   const R* ny;
   const R* nz;
@@ -101,6 +103,9 @@ cudaError_t launch_blockmax(const float* dem, int dem_pitch, int rows_full, int 
 // integer copy of the DEM buffer for the shading samples + min of the valid cells (as float bits key)
 cudaError_t launch_dem_keys(const float* dem_buf, int* key_buf, size_t n, int* min_key /*device, preset INT_MAX*/,
                             cudaStream_t stream);
+// step-rise pyramids of the 8 ray octants: buffer[oct * stride + pyramid layout], stride = floats per pyramid
+cudaError_t launch_gstep(const float* dem, int dem_pitch, int rows_full, int cols, const MaxPyramid& py, int stride,
+                         float* buffer, cudaStream_t stream);
 cudaError_t launch_tile_scan(const float* dem, int pitch, int band_row0, int band_rows, int cols,
                              int tile_h, int tile_w, int tiles_r, int tiles_c, int* counts,
                              cudaStream_t stream);

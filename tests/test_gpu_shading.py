@@ -144,3 +144,40 @@ def test_negative_elevations_fall_back_to_float_samples():
                 assert np.array_equal(masks[j][valid], lit[valid]), (step, j)
     finally:
         eng.close()
+
+
+def test_step_rise_skip_on_smooth_terrain():
+    """Smooth slopes under a high sun (46 N) with an isolated sharp ridge and a NaN hole: here the
+    march skips most chunks through the step-rise pyramids (terrain that rises less per step than
+    the rays cannot catch them), so this is where a non-conservative skip would show.  Masks
+    bit-exact vs the oracle, both sample variants."""
+    case = make_case(160, 16, w=192, seed=41, start="20220621 04:00:00", glacier_mask=False)
+    r, c = np.mgrid[0:160, 0:192].astype(np.float64)
+    dem = 1000.0 + 0.6 * r + 25.0 * np.sin(c / 40.0) + 4.0 * np.cos(r / 9.0)
+    dem += 160.0 * np.exp(-(((r - 70) / 3.0) ** 2 + ((c - 110) / 18.0) ** 2))      # a sharp east-west ridge
+    dem += 90.0 * np.exp(-(((r - 120) / 10.0) ** 2 + ((c - 40) / 2.5) ** 2))       # and a north-south one
+    dem[30:44, 150:170] = np.nan                                                    # a hole rays cross
+    case.dem[...] = dem.astype(np.float32)
+    for a in case.albedo_maps.values():
+        a[np.isnan(case.dem)] = np.nan
+    case.swe[np.isnan(case.dem)] = np.nan
+    case.elev_aws = float(case.dem[case.aws_rc])
+    case.lat, case.lon = 46.0, 8.0
+    valid = ~np.isnan(case.dem)
+    shaded_any = 0
+    for shadow in (1, 2):
+        eng = P.make_engine(case, False, computed=True, shadow=shadow)
+        try:
+            for step in range(0, 16, 2):
+                table = I.substep_table(I.to_unix(case.aws_rows[step]["DATE"]), time_step_seconds(case.aws_rows, step),
+                                        case.lat, case.lon, case.cell)
+                if not table:
+                    continue
+                masks = eng.shade_masks(step)
+                for j, sub in enumerate(table):
+                    lit = I.shadow_mask(case.dem, sub["dc_fix"], sub["dr_fix"], sub["dz"])
+                    assert np.array_equal(masks[j][valid], lit[valid]), (shadow, step, j)
+                    shaded_any += int((~lit[valid]).sum())
+        finally:
+            eng.close()
+    assert shaded_any > 1000
