@@ -899,6 +899,10 @@ __host__ __device__ inline SmemPlan<R> smem_plan(int warps, int cap_steps, int c
 #define ENRGY_MINB64 3
 #endif
 
+#ifndef ENRGY_SUB_UNROLL
+#define ENRGY_SUB_UNROLL 4
+#endif
+constexpr int kSubUnroll = ENRGY_SUB_UNROLL;   // unroll factor of the insolation sub-step loop (not with the inlined march)
 #ifndef ENRGY_MINB_SHADOW
 #define ENRGY_MINB_SHADOW 12
 #endif
@@ -1111,6 +1115,9 @@ energy_balance_kernel(const KernelArgs<R> a) {
           for (int q = 0; q < KP; ++q) direct2[q] = V::splat((R)0);
           const int sub_code = (int)s.sub;
           const int j0 = sub_code >> 8, nj = sub_code & 255;
+          // hourly rows carry four sunlit sub-steps by day: unrolled by four the loads of the records run
+          // ahead and the chains of consecutive sub-steps interleave (the inlined ray march stays rolled)
+#pragma unroll(insol_shadow(INSOL) ? 1 : kSubUnroll)
           for (int j = j0; j < j0 + nj; ++j) {
             const SubRec<R> sb = sm_subs[buf * cap_subs + j];
             const V e2 = V::splat(sb.e), n2 = V::splat(sb.n), u2 = V::splat(sb.u), b2 = V::splat(sb.b);
