@@ -1062,6 +1062,12 @@ energy_balance_kernel(const KernelArgs<R> a) {
         }
       }
 
+      // The step loop exists twice: for patches without off-glacier cells (no masking of the
+      // statistics, so the whole balance of a step is one basic block the scheduler can interleave
+      // freely: +3 %) and for patches with some.  (Reducing the statistics one step late, so that the
+      // shuffle butterfly of step t - 1 overlaps the balance of step t, measured 1 % slower.)
+      auto run_steps = [&](auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;
       for (int t = ts; t < te; ++t) {
         const StepRec<R> s = sm_steps[buf * cap_steps + (t - tb.t_begin)];
         // ---- 1 - albedo of the ice surface from this step's bracket of maps (interpolator.py:12-18):
@@ -1104,70 +1110,8 @@ energy_balance_kernel(const KernelArgs<R> a) {
           }
         }
 
-        // ---- potential insolation of the step [kWh m-2] -----------------------------------------
         V pot2[KP];
-        if (INSOL == kInsolStreamed) {
-#pragma unroll
-          for (int q = 0; q < KP; ++q) pot2[q] = V::make((R)pot_cur[2 * q], (R)pot_cur[2 * q + 1]);
-        } else {
-          V direct2[KP];
-#pragma unroll
-          for (int q = 0; q < KP; ++q) direct2[q] = V::splat((R)0);
-          const int sub_code = (int)s.sub;
-          const int j0 = sub_code >> 8, nj = sub_code & 255;
-          // hourly rows carry four sunlit sub-steps by day: unrolled by four the loads of the records run
-          // ahead and the chains of consecutive sub-steps interleave (the inlined ray march stays rolled)
-#pragma unroll(insol_shadow(INSOL) ? 1 : kSubUnroll)
-          for (int j = j0; j < j0 + nj; ++j) {
-            const SubRec<R> sb = sm_subs[buf * cap_subs + j];
-            const V e2 = V::splat(sb.e), n2 = V::splat(sb.n), u2 = V::splat(sb.u), b2 = V::splat(sb.b);
-            // cos(incidence) / nz; nx2, ny2 hold nx/nz, ny/nz (terrain_kernel)
-            V c2[KP];
-#pragma unroll
-            for (int q = 0; q < KP; ++q) c2[q] = fma2(ny2[q], n2, fma2(nx2[q], e2, u2));
-            unsigned lit = 0xffffffffu;
-            if (insol_shadow(INSOL)) {
-              // production runs skip cells that face away from the sun (direct beam = 0 whatever
-              // the mask says); the mask dump marches every glacier cell
-              unsigned start_bits = valid_bits;
-              if (!(DUMP && a.mask_out != nullptr)) {
-#pragma unroll
-                for (int q = 0; q < KP; ++q) {
-                  if (!(c2[q].lo() > (R)0)) start_bits &= ~(1u << (2 * q));
-                  if (!(c2[q].hi() > (R)0)) start_bits &= ~(1u << (2 * q + 1));
-                }
-              }
-              constexpr bool KEYS = INSOL == kInsolShadowKeys;
-              lit = march<K, KEYS>(KEYS ? reinterpret_cast<const float*>(a.dem_keys) : a.dem, a.dem_pitch, my_win,
-                                   a.rows_full, a.cols, a.blockmax, a.gstep, a.pyr_stride, a.pyramid, rowf, col, z0,
-                                   start_bits,
-                                   sm_shades[buf * cap_subs + j], (float)a.zmax, lane);
-              if (DUMP && a.mask_out != nullptr && t == a.t0) {
-#pragma unroll
-                for (int i = 0; i < K; ++i) {
-                  const unsigned word = __ballot_sync(0xffffffffu, (lit >> i) & 1u);
-                  if (lane == 0 && row0 + i < a.band_rows && colx < a.cols) {
-                    a.mask_out[((size_t)(j - j0) * a.band_rows + (row0 + i)) * a.mask_words + (colx >> 5)] = word;
-                  }
-                }
-              }
-            }
-#pragma unroll
-            for (int q = 0; q < KP; ++q) {
-              R c_lo = fmax_(c2[q].lo(), (R)0), c_hi = fmax_(c2[q].hi(), (R)0);
-              if (insol_shadow(INSOL)) {
-                c_lo = ((lit >> (2 * q)) & 1u) ? c_lo : (R)0;
-                c_hi = ((lit >> (2 * q + 1)) & 1u) ? c_hi : (R)0;
-              }
-              direct2[q] = fma2(b2, V::make(c_lo, c_hi), direct2[q]);
-            }
-          }
-          // direct * nz + dsum * (1 + nz), two instructions
-          const V dsum2 = V::splat(s.dsum);
-#pragma unroll
-          for (int q = 0; q < KP; ++q) pot2[q] = fma2(nz2[q], add2(direct2[q], dsum2), dsum2);
-        }
-
+        auto balance = [&]() {
         // ---- per-cell energy balance -------------------------------------------------------------
         V acc_rs = V::splat((R)0), acc_sens = acc_rs, acc_lat = acc_rs, acc_mf = acc_rs, acc_snow = acc_rs,
           acc_swe = acc_rs, acc_lwu = acc_rs, acc_g = acc_rs;
@@ -1341,7 +1285,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
           // statistics.  Off-glacier cells of a visited patch carry finite dummy values: they are
           // zeroed before the packed adds, on patches that have any (warp-uniform test)
           V m_rs = x_rs, m_sens = x_sens, m_lat = x_lat, m_mf = mf, m_lwu = lwu, m_g = gfl;
-          if (!patch_full) {
+          if (!FULL) {
             const bool v_lo = (valid_bits >> (2 * q)) & 1u, v_hi = (valid_bits >> (2 * q + 1)) & 1u;
             m_rs = V::make(v_lo ? x_rs.lo() : (R)0, v_hi ? x_rs.hi() : (R)0);
             m_sens = V::make(v_lo ? x_sens.lo() : (R)0, v_hi ? x_sens.hi() : (R)0);
@@ -1417,7 +1361,85 @@ energy_balance_kernel(const KernelArgs<R> a) {
             }
           }
         }
+        };
+        // ---- potential insolation of the step [kWh m-2] -----------------------------------------
+        if (INSOL == kInsolStreamed) {
+#pragma unroll
+          for (int q = 0; q < KP; ++q) pot2[q] = V::make((R)pot_cur[2 * q], (R)pot_cur[2 * q + 1]);
+          balance();
+        } else {
+          V direct2[KP];
+#pragma unroll
+          for (int q = 0; q < KP; ++q) direct2[q] = V::splat((R)0);
+          auto finish_step = [&]() {
+            // direct * nz + dsum * (1 + nz), two instructions
+            const V dsum2 = V::splat(s.dsum);
+#pragma unroll
+            for (int q = 0; q < KP; ++q) pot2[q] = fma2(nz2[q], add2(direct2[q], dsum2), dsum2);
+            balance();
+          };
+          const int sub_code = (int)s.sub;
+          const int j0 = sub_code >> 8, nj = sub_code & 255;
+          auto sub_step = [&](int j) {
+            const SubRec<R> sb = sm_subs[buf * cap_subs + j];
+            const V e2 = V::splat(sb.e), n2 = V::splat(sb.n), u2 = V::splat(sb.u), b2 = V::splat(sb.b);
+            // cos(incidence) / nz; nx2, ny2 hold nx/nz, ny/nz (terrain_kernel)
+            V c2[KP];
+#pragma unroll
+            for (int q = 0; q < KP; ++q) c2[q] = fma2(ny2[q], n2, fma2(nx2[q], e2, u2));
+            unsigned lit = 0xffffffffu;
+            if (insol_shadow(INSOL)) {
+              // production runs skip cells that face away from the sun (direct beam = 0 whatever
+              // the mask says); the mask dump marches every glacier cell
+              unsigned start_bits = valid_bits;
+              if (!(DUMP && a.mask_out != nullptr)) {
+#pragma unroll
+                for (int q = 0; q < KP; ++q) {
+                  if (!(c2[q].lo() > (R)0)) start_bits &= ~(1u << (2 * q));
+                  if (!(c2[q].hi() > (R)0)) start_bits &= ~(1u << (2 * q + 1));
+                }
+              }
+              constexpr bool KEYS = INSOL == kInsolShadowKeys;
+              lit = march<K, KEYS>(KEYS ? reinterpret_cast<const float*>(a.dem_keys) : a.dem, a.dem_pitch, my_win,
+                                   a.rows_full, a.cols, a.blockmax, a.gstep, a.pyr_stride, a.pyramid, rowf, col, z0,
+                                   start_bits,
+                                   sm_shades[buf * cap_subs + j], (float)a.zmax, lane);
+              if (DUMP && a.mask_out != nullptr && t == a.t0) {
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                  const unsigned word = __ballot_sync(0xffffffffu, (lit >> i) & 1u);
+                  if (lane == 0 && row0 + i < a.band_rows && colx < a.cols) {
+                    a.mask_out[((size_t)(j - j0) * a.band_rows + (row0 + i)) * a.mask_words + (colx >> 5)] = word;
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < KP; ++q) {
+              R c_lo = fmax_(c2[q].lo(), (R)0), c_hi = fmax_(c2[q].hi(), (R)0);
+              if (insol_shadow(INSOL)) {
+                c_lo = ((lit >> (2 * q)) & 1u) ? c_lo : (R)0;
+                c_hi = ((lit >> (2 * q + 1)) & 1u) ? c_hi : (R)0;
+              }
+              direct2[q] = fma2(b2, V::make(c_lo, c_hi), direct2[q]);
+            }
+          };
+          // hourly rows carry four sunlit sub-steps by day.  That case is straight-line code followed by
+          // its own copy of the balance, so that insolation and balance of a step form one basic block
+          // (the records load ahead, the chains of consecutive sub-steps and the first reciprocals of
+          // the balance interleave); every other count takes the loop.  With the ray march inlined in
+          // the sub-step only the loop exists.
+          if (!insol_shadow(INSOL) && nj == 4) {
+            sub_step(j0); sub_step(j0 + 1); sub_step(j0 + 2); sub_step(j0 + 3);
+            finish_step();
+          } else {
+            for (int j = j0; j < j0 + nj; ++j) sub_step(j);
+            finish_step();
+          }
+        }
       }  // steps of the time block
+      };
+      if (patch_full) run_steps(std::true_type{}); else run_steps(std::false_type{});
 
       // ---- flush the block's statistics into this CTA's partial rows (fixed order) ---------------
       __syncthreads();
