@@ -1296,15 +1296,16 @@ energy_balance_kernel(const KernelArgs<R> a) {
               m_g = V::make(v_lo ? gfl.lo() : (R)0, v_hi ? gfl.hi() : (R)0);
             }
           }
-          acc_rs = add2(acc_rs, m_rs);
-          acc_sens = add2(acc_sens, m_sens);
-          acc_lat = add2(acc_lat, m_lat);
-          acc_mf = add2(acc_mf, m_mf);
-          acc_snow = add2(acc_snow, snow);        // masked cells: swe = 0 -> snow = 0
-          acc_swe = add2(acc_swe, swe2[q]);
+          // (the first pair starts the sums: q is a compile-time constant of the unrolled loop)
+          acc_rs = q == 0 ? m_rs : add2(acc_rs, m_rs);
+          acc_sens = q == 0 ? m_sens : add2(acc_sens, m_sens);
+          acc_lat = q == 0 ? m_lat : add2(acc_lat, m_lat);
+          acc_mf = q == 0 ? m_mf : add2(acc_mf, m_mf);
+          acc_snow = q == 0 ? snow : add2(acc_snow, snow);        // masked cells: swe = 0 -> snow = 0
+          acc_swe = q == 0 ? swe2[q] : add2(acc_swe, swe2[q]);
           if (MSM) {
-            acc_lwu = add2(acc_lwu, m_lwu);
-            acc_g = add2(acc_g, m_g);
+            acc_lwu = q == 0 ? m_lwu : add2(acc_lwu, m_lwu);
+            acc_g = q == 0 ? m_g : add2(acc_g, m_g);
           }
           n_snow += (snow_lo ? 1 : 0) + (snow_hi ? 1 : 0);
           if (DUMP && a.dump != nullptr) {
