@@ -187,7 +187,13 @@ int upload_tables(enrgy_ctx* c) {
     d.t_air = (R)s.t_air; d.lapse = (R)s.lapse; d.p_hpa = (R)s.p_hpa; d.e_aws = (R)s.e_aws;
     d.c_sens = (R)s.c_sens; d.c_lat = (R)s.c_lat; d.c_lwd = (R)s.c_lwd; d.c_lwu = (R)s.c_lwu;
     d.c_sw = (R)s.c_sw; d.c_melt = (R)s.c_melt; d.alb_w = (R)s.alb_w; d.snow_alb = (R)s.snow_alb;
-    d.dsum = (R)s.dsum; d.dt = (R)s.dt; d.alb_pair = (R)s.alb_pair; d.sub = (R)s.sub;
+    d.dsum = (R)s.dsum; d.dt = (R)s.dt;
+    // the two integer codes travel as int32 bit patterns in the low word of their slots (no float -> int
+    // conversion at the head of every step)
+    const int32_t pair_code = (int32_t)s.alb_pair, sub_code = (int32_t)s.sub;
+    d.alb_pair = (R)0; d.sub = (R)0;
+    std::memcpy(&d.alb_pair, &pair_code, sizeof(int32_t));
+    std::memcpy(&d.sub, &sub_code, sizeof(int32_t));
   }
   const size_t ns = o.subs.size();
   std::vector<SubRec<R>> sb(std::max<size_t>(ns, 1));

@@ -87,8 +87,8 @@ struct alignas(16) StepRec {
   R snow_alb;  // aged snow albedo, < 0 = off                    model.py:318-320
   R dsum;      // sum of the diffuse coefficients of the step's sub-steps (computed insolation)
   R dt;        // time step [s]
-  R alb_pair;  // i0 * 256 + i1 (exact small integer)
-  R sub;       // (first sub-step index relative to the time block) * 256 + number of sub-steps
+  R alb_pair;  // i0 * 256 + i1; on the device an int32 bit pattern in the low word (step_code())
+  R sub;       // (first sub-step index relative to the time block) * 256 + number of sub-steps; int32 bits on the device
 };
 
 // ---- per-sub-step record (sun above the horizon only) ------------------------------------------

@@ -106,6 +106,10 @@ struct Num<double> {
   static __device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }
 };
 
+// integer code carried in the low word of a step-record slot (upload_tables)
+__device__ __forceinline__ int step_code(const float& x) { return __float_as_int(x); }
+__device__ __forceinline__ int step_code(const double& x) { return __double2loint(x); }
+
 // value barrier: the compiler may neither rematerialise x from its inputs nor see through it
 __device__ __forceinline__ void keep_in_register(float& x) { asm volatile("" : "+f"(x)); }
 __device__ __forceinline__ void keep_in_register(double& x) { asm volatile("" : "+d"(x)); }
@@ -1068,16 +1072,27 @@ energy_balance_kernel(const KernelArgs<R> a) {
       // shuffle butterfly of step t - 1 overlaps the balance of step t, measured 1 % slower.)
       auto run_steps = [&](auto full_tag) {
       constexpr bool FULL = decltype(full_tag)::value;
+      // the codes that steer a step (sub-step range, albedo bracket and weight) are read one step
+      // ahead, so that their shared-memory latency is off the path to the step's first branch
+      const StepRec<R>* const steps_b = sm_steps + buf * cap_steps - tb.t_begin;
+      int sub_next = step_code(steps_b[ts].sub), pair_next = step_code(steps_b[ts].alb_pair);
+      R w_next = steps_b[ts].alb_w;
       for (int t = ts; t < te; ++t) {
-        const StepRec<R> s = sm_steps[buf * cap_steps + (t - tb.t_begin)];
+        const StepRec<R> s = steps_b[t];
+        const int sub_code = sub_next, pair = pair_next;
+        const R alb_w = w_next;
+        if (t + 1 < te) {
+          sub_next = step_code(steps_b[t + 1].sub);
+          pair_next = step_code(steps_b[t + 1].alb_pair);
+          w_next = steps_b[t + 1].alb_w;
+        }
         // ---- 1 - albedo of the ice surface from this step's bracket of maps (interpolator.py:12-18):
         // the blend weight counts whole days, so the blend is refreshed once a day from the two
         // maps (L2) instead of carrying both in registers and blending every step
         if (!a.albedo_const) {
-          const int pair = (int)s.alb_pair;
-          if (pair != cur_pair || s.alb_w != cur_w) {      // uniform across the CTA
+          if (pair != cur_pair || alb_w != cur_w) {        // uniform across the CTA
             cur_pair = pair;
-            cur_w = s.alb_w;
+            cur_w = alb_w;
             const float* m0 = a.albedo + (size_t)(pair >> 8) * a.map_stride;
             const float* m1 = a.albedo + (size_t)(pair & 255) * a.map_stride;
 #pragma unroll
@@ -1091,7 +1106,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
                 // + ensemble offset, clipped like the loader clips a raster (identity for offset 0)
                 const R x0 = v ? fmin_(fmax_((R)__ldg(m0 + o) + a.albedo_offset, (R)0.001f), (R)1) : (R)0.5;
                 const R x1 = v ? fmin_(fmax_((R)__ldg(m1 + o) + a.albedo_offset, (R)0.001f), (R)1) : (R)0.5;
-                om[h] = ((R)1 - x0) + s.alb_w * (x0 - x1);
+                om[h] = ((R)1 - x0) + alb_w * (x0 - x1);
               }
               om2[q] = V::make(om[0], om[1]);
             }
@@ -1379,7 +1394,6 @@ energy_balance_kernel(const KernelArgs<R> a) {
             for (int q = 0; q < KP; ++q) pot2[q] = fma2(nz2[q], add2(direct2[q], dsum2), dsum2);
             balance();
           };
-          const int sub_code = (int)s.sub;
           const int j0 = sub_code >> 8, nj = sub_code & 255;
           auto sub_step = [&](int j) {
             const SubRec<R> sb = sm_subs[buf * cap_subs + j];
