@@ -1448,6 +1448,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
             sub_step(j0); sub_step(j0 + 1); sub_step(j0 + 2); sub_step(j0 + 3);
             finish_step();
           } else {
+#pragma unroll(insol_shadow(INSOL) ? 1 : kSubUnroll)
             for (int j = j0; j < j0 + nj; ++j) sub_step(j);
             finish_step();
           }
