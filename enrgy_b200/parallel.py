@@ -38,6 +38,24 @@ def row_bands(rows, world, align=16, valid_per_row=None):
     return [(edges[i], edges[i + 1] - edges[i]) for i in range(world)]
 
 
+def rebalance_bands(bands, seconds, valid_per_row, align=16):
+    """New band edges from MEASURED per-band times: with the shading ray march the cost of a glacier
+    cell depends on the terrain around it, so equal glacier-cell counts are not equal times.  The
+    measured time of every band is spread over its rows in proportion to their glacier cells
+    (piecewise-constant cost per glacier cell), and the cuts are placed at equal shares of that
+    estimate.  One or two rounds settle (scripts/measure_modes.py strong)."""
+    w = np.asarray(valid_per_row, dtype=np.float64)
+    rows = w.shape[0]
+    if len(bands) != len(seconds):
+        raise ValueError("one measured time per band")
+    cost = np.zeros(rows, dtype=np.float64)
+    for (r0, n), t in zip(bands, seconds):
+        tot = w[r0:r0 + n].sum()
+        if n > 0:
+            cost[r0:r0 + n] = (w[r0:r0 + n] * (float(t) / tot)) if tot > 0 else 0.0
+    return row_bands(rows, len(bands), align=align, valid_per_row=cost)
+
+
 def allreduce_stats(stats):
     """In-place SUM of a [T, S_COUNT] statistics tensor over all ranks (torch.distributed)."""
     import torch.distributed as dist

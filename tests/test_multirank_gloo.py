@@ -13,7 +13,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from enrgy_b200 import _lib
-from enrgy_b200.parallel import allreduce_stats, means_from_sums, row_bands
+from enrgy_b200.parallel import allreduce_stats, means_from_sums, rebalance_bands, row_bands
 from enrgy_b200.synthetic import make_case
 from oracle import enrgy_oracle as O
 from tests import parity as P
@@ -115,3 +115,19 @@ def test_row_bands_properties():
     w[64:96] = 5.0
     b = row_bands(256, 2, align=16, valid_per_row=w)
     assert b[1][0] < 128                             # the heavy rows pull the cut north
+
+
+def test_rebalance_bands_moves_rows_to_the_fast_ranks():
+    """Bands rebalanced from measured times: a band that took twice as long as the others gives rows
+    away; total rows and alignment are kept; equal times leave the cuts where they are."""
+    rows, world = 1024, 4
+    w = np.full(rows, 100.0)
+    bands = row_bands(rows, world, align=16, valid_per_row=w)
+    assert rebalance_bands(bands, [1.0, 1.0, 1.0, 1.0], w) == bands
+    nb = rebalance_bands(bands, [1.0, 2.0, 1.0, 1.0], w)
+    assert sum(n for _, n in nb) == rows and all(r0 % 16 == 0 for r0, _ in nb)
+    assert nb[1][1] < bands[1][1] and nb[0][1] > bands[0][1] and nb[3][1] > bands[3][1]
+    # estimated cost of the new bands is equal to within the alignment
+    cost = np.concatenate([np.full(n, t / n) for (_, n), t in zip(bands, [1.0, 2.0, 1.0, 1.0])])
+    shares = [cost[r0:r0 + n].sum() for r0, n in nb]
+    assert max(shares) - min(shares) < 0.1
