@@ -1725,13 +1725,15 @@ cudaError_t launch_microbench(int kind, int sm_count, int iters, void* scratch, 
 // statistics: cross-CTA sum in fixed order + the derived columns
 // =================================================================================================
 __global__ void finalize_stats_kernel(const FinalizeArgs f) {
+  // one warp per step: lane l adds the rows of CTAs l, l + 32, ... in that order, then the lanes are
+  // added by a butterfly -- a fixed order, so the sums are reproducible run to run
   const int f32_mode = f.f32_mode;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (t >= f.n_steps) return;
   double k[kStatsP];
   for (int q = 0; q < kStatsP; ++q) k[q] = 0.0;
   const int row = f.msm ? kStatsP : kStatsK;
-  for (int c = 0; c < f.n_ctas; ++c) {
+  for (int c = lane; c < f.n_ctas; c += 32) {
     const size_t o = ((size_t)c * f.n_steps + t) * row;
     if (f32_mode) {
       const float* p = static_cast<const float*>(f.partials) + o;
@@ -1741,6 +1743,12 @@ __global__ void finalize_stats_kernel(const FinalizeArgs f) {
       for (int q = 0; q < row; ++q) k[q] += p[q];
     }
   }
+#pragma unroll
+  for (int q = 0; q < kStatsP; ++q) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) k[q] += __shfl_xor_sync(0xffffffffu, k[q], d);
+  }
+  if (lane != 0) return;
   const StepRec<double> s = f.steps64[f.t0 + t];
   const double lwu_cell = f32_mode ? (double)(float)s.c_lwu : s.c_lwu;
   const double c_melt = f32_mode ? (double)(float)s.c_melt : s.c_melt;
@@ -1791,7 +1799,7 @@ extern "C" int enrgy_debug_march_stats(unsigned long long* out) {
 #endif
 cudaError_t launch_finalize(const FinalizeArgs& f, cudaStream_t stream) {
   if (f.n_steps <= 0) return cudaSuccess;
-  finalize_stats_kernel<<<(f.n_steps + 127) / 128, 128, 0, stream>>>(f);
+  finalize_stats_kernel<<<(f.n_steps + 3) / 4, 128, 0, stream>>>(f);      // four steps (warps) per block
   return cudaGetLastError();
 }
 
