@@ -30,9 +30,9 @@ constexpr double kVapourScale = 6300.0;       // e = e0 * 10**(-dz/6300), var_cl
 constexpr double kMsmInitLapse = -0.006;      // model.py:137
 
 // ---- tiling -----------------------------------------------------------------------------------
-constexpr int kThreads = 256;                 // 8 warps per CTA
+constexpr int kThreads = 256;                 // block size of the set-up reductions (moments, SWE statistics)
 constexpr int kWarps = kThreads / 32;
-constexpr int kTileW = 128;                   // one warp row = 32 lanes x float4
+constexpr int kTileW = 128;                   // raster pitch granularity = widest tile of the fused kernel (4 warp patches of 32 columns)
 constexpr int kStatsK = 8;                    // statistics reduced in the kernel (see StatK)
 constexpr int kStatsM = 2;                    // + upward longwave and in-glacier flux with the sub-surface model
 constexpr int kStatsP = kStatsK + kStatsM;    // columns of a per-CTA partial row

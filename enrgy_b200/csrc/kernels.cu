@@ -1,23 +1,25 @@
 // Fused surface-energy-balance kernels for sm_100a (B200).
 //
 // One persistent CTA per resident slot walks a static list of raster tiles.  For each tile every
-// thread owns K cells for the WHOLE time range: SWE and the two melt totals live in registers, the
-// per-step AWS scalars are staged per time block in shared memory by TMA bulk copies
-// (cp.async.bulk + mbarrier, double buffered), and the only global traffic inside the time loop is
-// the optional streamed insolation raster (4 B per cell-step) and the shading ray samples.
+// thread owns K cells, as K/2 packed pairs (sm_100 f32x2: FFMA2/FADD2/FMUL2), for the WHOLE time
+// range: SWE and the ice-melt total live in registers, the per-step AWS scalars are staged per time
+// block in shared memory by TMA bulk copies (cp.async.bulk + mbarrier, double buffered), and the only
+// global traffic inside the time loop is the daily refresh of the albedo blend, the optional
+// streamed insolation raster (4 B per cell-step) and the shading ray samples.
 //
-// Reference arithmetic being replaced (tepextepex/ENRGY, file:line):
-//   var_classes.py:113-125  lapse-rate distribution of T, p, e            -> cell_step()
-//   turbo.py:140-196        distributed sensible / latent flux            -> cell_step()
-//   turbo.py:368-379        Magnus saturation vapour pressure             -> surface vapour term
-//   model.py:533-545        longwave                                      -> cell_step()
-//   model.py:298-337        albedo                                        -> cell_step()
-//   model.py:464-497        shortwave from potential insolation           -> cell_step()
-//   saga_lighting.py:42-44  potential insolation incl. shadows (SAGA)     -> insolation()/march()
-//   model.py:411, :434-438  flux sum and clamp                            -> cell_step()
-//   msm.py:193-203          melt partition                                -> cell_step()
-//   model.py:258-261        state update                                  -> cell_step()
-//   var_classes.py:45-56, model.py:246-252  per-step area statistics      -> warp_reduce8 + slots
+// Reference arithmetic being replaced (tepextepex/ENRGY, file:line) -> where it lives here:
+//   var_classes.py:113-125  lapse-rate distribution of T, p, e            -> balance() in the step loop
+//   turbo.py:140-196        distributed sensible / latent flux            -> balance()
+//   turbo.py:368-379        Magnus saturation vapour pressure             -> balance(): surface vapour term
+//   model.py:533-545        longwave                                      -> balance(), finalize_stats_kernel
+//   model.py:298-337        albedo                                        -> daily blend + balance()
+//   model.py:464-497        shortwave from potential insolation           -> balance()
+//   saga_lighting.py:42-44  potential insolation incl. shadows (SAGA)     -> sub_step() / march()
+//   model.py:411, :434-438  flux sum and clamp                            -> balance()
+//   msm.py:193-203          melt partition                                -> balance()
+//   msm.py:31-107           sub-surface conduction (MSM variants)         -> balance()
+//   model.py:258-261        state update                                  -> balance(), epilogue
+//   var_classes.py:45-56, model.py:246-252  per-step area statistics      -> warp_reduce8 + slots + finalize
 #include "kernels.cuh"
 
 #include <cstdio>
