@@ -42,11 +42,21 @@ def main():
     a = ap.parse_args()
     prec = _lib.F32 if a.dtype == "f32" else _lib.F64
     if a.mode == "ensemble":
-        # config C5: members share DEM / terrain / maps / forcing on the device
-        from enrgy_b200.ensemble import make_members, run_members
+        # config C5: members share DEM / terrain / maps / forcing on the device; under torchrun the
+        # member axis is sharded over the ranks (members are independent: no collective except the
+        # gather of the per-member totals)
+        from enrgy_b200.ensemble import make_members, run_members, shard
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        rank = int(os.environ.get("RANK", "0"))
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         case, dem = make_band_case(a.n, a.t)
         keys = list(case.albedo_maps)
-        eng = Engine(a.n, a.n, precision=prec)
+        eng = Engine(a.n, a.n, precision=prec, device=local)
         eng.set_params(cell_size=10.0, elev_aws=case.elev_aws, aws_row=case.aws_rc[0], aws_col=case.aws_rc[1],
                        sensor_z=1.6, zm=1e-3, z_h_or_e=1e-4, emissivity=0.98, lat=case.lat, lon=case.lon,
                        insol_mode=_lib.INSOL_COMPUTED)
@@ -55,15 +65,30 @@ def main():
         eng.set_swe(case.swe)
         eng.set_forcing(build_forcing(case.aws_rows, keys))
         members = make_members(a.members)
-        run_members(eng, members, indices=[0])                       # warm-up
+        mine = shard(members, world, rank)
+        run_members(eng, members, indices=mine[:1])                  # warm-up
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
         t0 = time.perf_counter()
-        out = run_members(eng, members)
+        out = run_members(eng, members, indices=mine)
+        totals = np.zeros(a.members, dtype=np.float64)
+        for i, o in out.items():
+            totals[i] = o["mean_ice"]
+        if world > 1:
+            tt = torch.from_numpy(totals).cuda()
+            dist.all_reduce(tt)                                      # gather of the per-member totals
+            totals = tt.cpu().numpy()
+            dist.barrier()
         wall = time.perf_counter() - t0
         cells = float(a.n) * a.n * a.t * a.members
-        print(json.dumps({"mode": "ensemble", "members": a.members, "n": a.n, "t": a.t, "wall_s": wall,
-                          "member_cell_steps_per_s": cells / wall,
-                          "mean_ice_spread": float(np.std([o["mean_ice"] for o in out.values()]))}))
+        if rank == 0:
+            print(json.dumps({"mode": "ensemble", "members": a.members, "gpus": world, "n": a.n, "t": a.t, "wall_s": wall,
+                              "member_cell_steps_per_s": cells / wall,
+                              "mean_ice_spread": float(np.std(totals))}))
         eng.close()
+        if world > 1:
+            dist.destroy_process_group()
         return
     if a.mode in ("streamed", "msm"):
         case, dem = make_band_case(a.n, a.t)

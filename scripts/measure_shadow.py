@@ -17,8 +17,9 @@ ap.add_argument("--size", type=int, default=2048)
 ap.add_argument("--nsteps", type=int, default=256)
 ap.add_argument("--dtype", default="f32")
 ap.add_argument("--noshadow", action="store_true")
+ap.add_argument("--step-s", type=int, default=3600, help="seconds between AWS rows (900 = config C4's time base)")
 a = ap.parse_args()
-case, dem = make_band_case(a.size, a.nsteps)
+case, dem = make_band_case(a.size, a.nsteps, step_s=a.step_s)
 keys = list(case.albedo_maps)
 eng = Engine(a.size, a.size, precision=_lib.F32 if a.dtype == "f32" else _lib.F64)
 eng.set_params(cell_size=10.0, elev_aws=case.elev_aws, aws_row=case.aws_rc[0], aws_col=case.aws_rc[1],
