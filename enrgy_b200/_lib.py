@@ -72,6 +72,7 @@ _PROTOTYPES = {
     "enrgy_set_insolation": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "enrgy_prepass": (C.c_int, [_P]),
     "enrgy_get_point_scalars": (C.c_int, [_P, _P]),
+    "enrgy_host_prepass": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P]),
     "enrgy_run": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "enrgy_run_async": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "enrgy_synchronize": (C.c_int, [_P]),

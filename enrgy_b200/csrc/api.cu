@@ -220,6 +220,22 @@ int upload_tables(enrgy_ctx* c) {
   return ENRGY_OK;
 }
 
+// NaN fields of enrgy_params -> the reference's defaults
+void resolve_defaults(enrgy_params& p) {
+  auto dflt = [](double& v, double d) { if (std::isnan(v)) v = d; };
+  dflt(p.zm, 0.001);                 // turbo.py:273-274
+  dflt(p.z_h_or_e, p.zm / 10);       // turbo.py:275-277
+  dflt(p.emissivity, 0.98);          // model.py:541-542
+  dflt(p.max_ice_albedo, 0.45);      // model.py:325-326
+  dflt(p.snow_density, 387.0);       // var_classes.py:9
+  dflt(p.ice_density, 900.0);
+  dflt(p.solar_const, 1367.0);       // saga_lighting.py:42
+  dflt(p.transmittance, 0.70);       // saga_lighting.py:44
+  dflt(p.hour_step, 0.25);           // saga_lighting.py:43
+  dflt(p.sensible_corr, 1.0);
+  dflt(p.latent_corr, 1.0);
+}
+
 // ---- early host pre-pass ----------------------------------------------------------------------
 // The per-step scalars depend on the forcing table, the parameters and the DEM around the AWS cell
 // only (not on the albedo / SWE rasters, unless the sub-surface model integrates the AWS cell).  So
@@ -475,18 +491,7 @@ int enrgy_set_params(enrgy_ctx* c, const enrgy_params* pin) {
   if (c->have_dem) return fail(ENRGY_ERR_ARG, "set_params must precede set_dem");
   drop_early_prepass(c);
   enrgy_params p = *pin;
-  auto dflt = [](double& v, double d) { if (std::isnan(v)) v = d; };
-  dflt(p.zm, 0.001);                 // turbo.py:273-274
-  dflt(p.z_h_or_e, p.zm / 10);       // turbo.py:275-277
-  dflt(p.emissivity, 0.98);          // model.py:541-542
-  dflt(p.max_ice_albedo, 0.45);      // model.py:325-326
-  dflt(p.snow_density, 387.0);       // var_classes.py:9
-  dflt(p.ice_density, 900.0);
-  dflt(p.solar_const, 1367.0);       // saga_lighting.py:42
-  dflt(p.transmittance, 0.70);       // saga_lighting.py:44
-  dflt(p.hour_step, 0.25);           // saga_lighting.py:43
-  dflt(p.sensible_corr, 1.0);
-  dflt(p.latent_corr, 1.0);
+  resolve_defaults(p);
   if (!(p.cell_size > 0)) return fail(ENRGY_ERR_ARG, "cell_size must be > 0");
   if (!(p.sensor_z > 0) || !(p.zm > 0) || !(p.z_h_or_e > 0)) return fail(ENRGY_ERR_ARG, "sensor_z, zm, z_h_or_e must be > 0");
   if (p.msm_layers < 0 || p.msm_layers > ENRGY_MAX_LAYERS - 1) return fail(ENRGY_ERR_ARG, "msm_layers outside 0..%d", ENRGY_MAX_LAYERS - 1);
@@ -858,6 +863,45 @@ int enrgy_prepass(enrgy_ctx* c) {
   const int urc = c->precision == ENRGY_F32 ? upload_tables<float>(c) : upload_tables<double>(c);
   if (urc != ENRGY_OK) return urc;
   c->prepass_done = true;
+  return ENRGY_OK;
+}
+
+int enrgy_host_prepass(const enrgy_params* pin, int precision, int rows, int cols, const float* dem, int n_steps,
+                       const double* forcing, const double* pot_aws, double* point_out) {
+  if (!pin || !dem || (n_steps > 0 && (!forcing || !point_out))) return fail(ENRGY_ERR_ARG, "null argument");
+  if (precision != ENRGY_F32 && precision != ENRGY_F64) return fail(ENRGY_ERR_ARG, "precision must be 32 or 64");
+  if (rows <= 0 || cols <= 0 || n_steps < 0) return fail(ENRGY_ERR_ARG, "bad sizes");
+  PrepassInput in;
+  in.p = *pin;
+  resolve_defaults(in.p);
+  if (in.p.msm_layers > 0) return fail(ENRGY_ERR_ARG, "enrgy_host_prepass: the sub-surface model needs the cell state of a loaded handle");
+  if (in.p.insol_mode == ENRGY_INSOL_STREAMED && n_steps > 0 && !pot_aws) return fail(ENRGY_ERR_ARG, "pot_aws is needed in streamed mode");
+  if (in.p.aws_row < 0 || in.p.aws_row >= rows || in.p.aws_col < 0 || in.p.aws_col >= cols)
+    return fail(ENRGY_ERR_ARG, "AWS cell (%d, %d) outside the %d x %d raster", in.p.aws_row, in.p.aws_col, rows, cols);
+  in.precision = precision; in.rows = rows; in.cols = cols; in.dem = dem;
+  float zmax = -std::numeric_limits<float>::infinity();
+  for (size_t i = 0; i < (size_t)rows * cols; ++i) if (dem[i] == dem[i]) zmax = std::max(zmax, dem[i]);
+  in.zmax = zmax;
+  for (int dr = -1; dr <= 1; ++dr)
+    for (int dc = -1; dc <= 1; ++dc) {
+      const int r = in.p.aws_row + dr, x = in.p.aws_col + dc;
+      in.nbhd[(dr + 1) * 3 + (dc + 1)] = (r >= 0 && r < rows && x >= 0 && x < cols) ? dem[(size_t)r * cols + x]
+                                                                                 : std::numeric_limits<float>::quiet_NaN();
+    }
+  in.n_steps = n_steps; in.forcing = forcing;
+  std::vector<double> nan_pot(std::max(n_steps, 1), std::numeric_limits<double>::quiet_NaN());
+  in.pot_aws = pot_aws ? pot_aws : nan_pot.data();
+  if (in.p.insol_mode == ENRGY_INSOL_COMPUTED && in.p.shadow) { in.cap_steps = kShadowStepsPerBlock; in.cap_subs = kShadowSubsPerBlock; }
+  for (int i = 0; i < n_steps; ++i) {
+    const double* f = forcing + (size_t)i * ENRGY_F_COUNT;
+    if (!(f[ENRGY_F_RH] <= 1.0)) return fail(ENRGY_ERR_RANGE, "row %d: HUMID must be a 0..1 fraction here (helpers.py:74-87)", i);
+    if (!(f[ENRGY_F_DT] > 0)) return fail(ENRGY_ERR_RANGE, "row %d: time step must be > 0", i);
+  }
+  PrepassOutput out;
+  std::string err;
+  const int rc = run_prepass(in, out, err);
+  if (rc != ENRGY_OK) return fail(rc, "%s", err.c_str());
+  if (n_steps > 0) std::memcpy(point_out, out.point.data(), out.point.size() * sizeof(double));
   return ENRGY_OK;
 }
 

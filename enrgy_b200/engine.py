@@ -14,6 +14,61 @@ def _f32c(a):
     return a
 
 
+def make_params(*, cell_size, elev_aws, aws_row, aws_col, sensor_z=2.0, zm=None, z_h_or_e=None,
+                andreas=False, sensible_corr=1.0, latent_corr=1.0, emissivity=None,
+                const_albedo=None, max_ice_albedo=None, snow_density=None, ice_density=None,
+                insol_mode=_lib.INSOL_STREAMED, shadow=False, lat=0.0, lon=0.0, solar_const=None,
+                transmittance=None, hour_step=None, band_row0=0, band_rows=0, msm_depths=None):
+    """struct enrgy_params from keyword arguments; None = the reference's default (NaN in the struct)."""
+    nan = float("nan")
+    p = Params()
+    p.cell_size = cell_size
+    p.elev_aws = elev_aws
+    p.aws_row, p.aws_col = int(aws_row), int(aws_col)
+    p.sensor_z = sensor_z
+    p.zm = nan if zm is None else zm
+    p.z_h_or_e = nan if z_h_or_e is None else z_h_or_e
+    p.andreas = 1 if andreas else 0
+    p.sensible_corr, p.latent_corr = float(sensible_corr), float(latent_corr)
+    p.emissivity = nan if emissivity is None else emissivity
+    if const_albedo is not None:
+        p.albedo_const = 1
+        p.albedo_ice, p.albedo_snow = float(const_albedo[0]), float(const_albedo[1])
+    p.max_ice_albedo = nan if max_ice_albedo is None else max_ice_albedo
+    p.snow_density = nan if snow_density is None else snow_density
+    p.ice_density = nan if ice_density is None else ice_density
+    p.insol_mode = int(insol_mode)
+    p.shadow = int(shadow) if shadow in (0, 1, 2) else (1 if shadow else 0)   # 2: float-sample march
+    p.lat_deg, p.lon_deg = float(lat), float(lon)
+    p.solar_const = nan if solar_const is None else solar_const
+    p.transmittance = nan if transmittance is None else transmittance
+    p.hour_step = nan if hour_step is None else hour_step
+    p.band_row0, p.band_rows = int(band_row0), int(band_rows)
+    if msm_depths is not None:
+        if len(msm_depths) > _lib.MAX_LAYERS - 1:
+            raise ValueError("at most %d sub-surface layers" % (_lib.MAX_LAYERS - 1))
+        p.msm_layers = len(msm_depths)
+        for i, d in enumerate(msm_depths):
+            p.msm_depths[i] = float(d)
+    return p
+
+
+def host_prepass(dem, forcing, precision=_lib.F64, pot_aws=None, **params):
+    """The library's pre-pass on the host alone (enrgy_host_prepass: no device, no handle): per-row
+    scalars [T, P_COUNT] -- Monin-Obukhov length, CH, potential insolation and shortwave factor at the
+    AWS cell, sunlit sub-step count -- for a full DEM and a forcing table (forcing.build_forcing)."""
+    lib = _lib.load()
+    dem = np.ascontiguousarray(dem, dtype=np.float32)
+    forcing = np.ascontiguousarray(forcing, dtype=np.float64)
+    t = forcing.shape[0]
+    out = np.zeros((t, _lib.P_COUNT), dtype=np.float64)
+    pa = None if pot_aws is None else np.ascontiguousarray(pot_aws, dtype=np.float64)
+    p = make_params(**params)
+    check(lib.enrgy_host_prepass(C.byref(p), int(precision), dem.shape[0], dem.shape[1], dem.ctypes.data, t,
+                                 forcing.ctypes.data, None if pa is None else pa.ctypes.data, out.ctypes.data))
+    return out
+
+
 class Engine:
     def __init__(self, rows, cols, precision=_lib.F32, device=0):
         self.lib = _lib.load()
@@ -26,45 +81,13 @@ class Engine:
         self._keep = []
 
     # ---- configuration ------------------------------------------------------------------------
-    def set_params(self, *, cell_size, elev_aws, aws_row, aws_col, sensor_z=2.0, zm=None, z_h_or_e=None,
-                   andreas=False, sensible_corr=1.0, latent_corr=1.0, emissivity=None,
-                   const_albedo=None, max_ice_albedo=None, snow_density=None, ice_density=None,
-                   insol_mode=_lib.INSOL_STREAMED, shadow=False, lat=0.0, lon=0.0, solar_const=None,
-                   transmittance=None, hour_step=None, band_row0=0, band_rows=0, msm_depths=None):
-        nan = float("nan")
-        p = Params()
-        p.cell_size = cell_size
-        p.elev_aws = elev_aws
-        p.aws_row, p.aws_col = int(aws_row), int(aws_col)
-        p.sensor_z = sensor_z
-        p.zm = nan if zm is None else zm
-        p.z_h_or_e = nan if z_h_or_e is None else z_h_or_e
-        p.andreas = 1 if andreas else 0
-        p.sensible_corr, p.latent_corr = float(sensible_corr), float(latent_corr)
-        p.emissivity = nan if emissivity is None else emissivity
-        if const_albedo is not None:
-            p.albedo_const = 1
-            p.albedo_ice, p.albedo_snow = float(const_albedo[0]), float(const_albedo[1])
-        p.max_ice_albedo = nan if max_ice_albedo is None else max_ice_albedo
-        p.snow_density = nan if snow_density is None else snow_density
-        p.ice_density = nan if ice_density is None else ice_density
-        p.insol_mode = int(insol_mode)
-        p.shadow = int(shadow) if shadow in (0, 1, 2) else (1 if shadow else 0)   # 2: float-sample march
-        p.lat_deg, p.lon_deg = float(lat), float(lon)
-        p.solar_const = nan if solar_const is None else solar_const
-        p.transmittance = nan if transmittance is None else transmittance
-        p.hour_step = nan if hour_step is None else hour_step
-        p.band_row0, p.band_rows = int(band_row0), int(band_rows)
-        if msm_depths is not None:
-            if len(msm_depths) > _lib.MAX_LAYERS - 1:
-                raise ValueError("at most %d sub-surface layers" % (_lib.MAX_LAYERS - 1))
-            p.msm_layers = len(msm_depths)
-            for i, d in enumerate(msm_depths):
-                p.msm_depths[i] = float(d)
+    def set_params(self, **kw):
+        """Keyword arguments: see make_params()."""
+        p = make_params(**kw)
         self.msm_layers = int(p.msm_layers)
         check(self.lib.enrgy_set_params(self.h, C.byref(p)))
-        self.band_row0 = int(band_row0)
-        self.band_rows = int(band_rows) if band_rows else self.rows
+        self.band_row0 = int(p.band_row0)
+        self.band_rows = int(p.band_rows) if p.band_rows else self.rows
         self.params = p
 
     def set_dem(self, dem):

@@ -192,6 +192,14 @@ int enrgy_set_insolation(enrgy_ctx* ctx, int t0, int n, const float* pot);
 /* pre-pass: per-step scalars at the AWS cell (model.py:347-358, :500-530, turbo.py:88-137) */
 int enrgy_prepass(enrgy_ctx* ctx);
 int enrgy_get_point_scalars(enrgy_ctx* ctx, double* out /* [n_steps][ENRGY_P_COUNT] */);
+/* the same pre-pass WITHOUT a device or a handle (host arithmetic only): the per-row scalars of
+ * model.py:347-358 / :500-530 for a full host DEM [rows][cols] -- Monin-Obukhov length, CH, potential
+ * insolation and shortwave factor at the AWS cell, sunlit sub-step count.  pot_aws: potential
+ * insolation at the AWS cell per row [kWh m-2] in streamed mode, else NULL.  Not available with the
+ * sub-surface model (its pre-pass integrates the AWS cell from the loaded state). */
+int enrgy_host_prepass(const enrgy_params* params, int precision, int rows, int cols, const float* dem,
+                       int n_steps, const double* forcing, const double* pot_aws,
+                       double* point_out /* [n_steps][ENRGY_P_COUNT] */);
 
 /* the hot path: steps [t0, t1) of the time loop (model.py:183-261) as fused kernels.
  * stats_out: host [t1 - t0][ENRGY_S_COUNT] float64 or NULL. */

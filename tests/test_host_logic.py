@@ -120,3 +120,64 @@ def test_insolation_tables_match_oracle():
     for r in rows:
         assert abs(r["E"] ** 2 + r["N"] ** 2 + r["U"] ** 2 - 1.0) < 1e-12
         assert max(abs(r["dc_fix"]), abs(r["dr_fix"])) == 65536
+
+
+@pytest.mark.parametrize("f64", [True, False])
+@pytest.mark.parametrize("variant", ["default", "andreas", "gradient_calm"])
+def test_host_prepass_matches_oracle(f64, variant):
+    """The library's host pre-pass (C++: Monin-Obukhov solve, CH, shortwave factor; csrc/prepass.cu,
+    reached through enrgy_host_prepass WITHOUT a device) against the oracle's per-row scalars, which are
+    the reference's own (turbo.py:88-137, model.py:500-530).  No GPU, no kernel: host logic only."""
+    from enrgy_b200.engine import host_prepass
+    from tests import parity as P
+    kw = {}
+    case_kw = {}
+    if variant == "andreas":
+        kw = dict(andreas=True)
+    if variant == "gradient_calm":
+        case_kw = dict(with_gradient=True, calm_every=5)     # GRADIENT column, WIND_SPEED 0 -> 0.1
+        kw = dict(temp_lapse_rate="GRADIENT")
+    case = make_case(48, 30, w=56, seed=17, **case_kw)
+    pot = P.random_insolation(case, 30)
+    ora = P.run_oracle(case, pot, f64, **kw)
+    alb = P.clipped_albedo(case, np.float32)
+    table = build_forcing(case.aws_rows, list(alb), temp_lapse_rate=kw.get("temp_lapse_rate", -0.006))
+    pot_aws = np.asarray(pot, dtype=np.float64 if f64 else np.float32)[:, case.aws_rc[0], case.aws_rc[1]].astype(np.float64)
+    point = host_prepass(case.dem, table, precision=_lib.F64 if f64 else _lib.F32, pot_aws=pot_aws,
+                         cell_size=case.cell, elev_aws=case.elev_aws, aws_row=case.aws_rc[0], aws_col=case.aws_rc[1],
+                         sensor_z=1.6, zm=1e-3, z_h_or_e=1e-4, emissivity=0.98, andreas=kw.get("andreas", False),
+                         insol_mode=_lib.INSOL_STREAMED, lat=case.lat, lon=case.lon)
+    L_ref = np.array([r["L"] for r in ora["rows"]])
+    f_ref = np.array([r["factor"] for r in ora["rows"]])
+    assert np.max(np.abs(point[:, _lib.P_L] - L_ref) / np.abs(L_ref)) < (1e-9 if f64 else 1e-5)
+    assert np.max(np.abs(point[:, _lib.P_SW_FACTOR] - f_ref) / np.maximum(np.abs(f_ref), 1e-12)) < (1e-12 if f64 else 1e-6)
+
+
+def test_host_prepass_computed_insolation_and_errors():
+    """In-kernel insolation: the pre-pass's potential insolation at the AWS cell and its sub-step
+    counts against the insolation oracle (with and without the shading ray of the AWS cell); bad
+    input is refused with the library's error codes."""
+    from enrgy_b200.engine import host_prepass
+    from enrgy_b200._lib import EnrgyError
+    from oracle import insolation_oracle as I
+    from oracle.enrgy_oracle import time_step_seconds
+    case = make_case(64, 12, w=72, seed=19)
+    table = build_forcing(case.aws_rows, list(case.albedo_maps))
+    base = dict(cell_size=case.cell, elev_aws=case.elev_aws, aws_row=case.aws_rc[0], aws_col=case.aws_rc[1],
+                sensor_z=1.6, zm=1e-3, z_h_or_e=1e-4, insol_mode=_lib.INSOL_COMPUTED, lat=case.lat, lon=case.lon)
+    for shadow in (False, True):
+        point = host_prepass(case.dem, table, shadow=shadow, **base)
+        for i, row in enumerate(case.aws_rows):
+            dt = time_step_seconds(case.aws_rows, i)
+            want = I.potential_insolation(case.dem, case.cell, case.lat, case.lon, I.to_unix(row["DATE"]), dt,
+                                          shadow=shadow)[case.aws_rc]
+            got_kwh = point[i, _lib.P_POT_AWS] * dt / 3.6e6                 # W m-2 over the step -> kWh m-2
+            assert abs(got_kwh - want) <= 1e-9 * max(abs(want), 1e-6), (shadow, i)
+            n_sub = len(I.substep_table(I.to_unix(row["DATE"]), dt, case.lat, case.lon, case.cell))
+            assert int(point[i, _lib.P_NSUB]) == n_sub
+    with pytest.raises(EnrgyError):
+        host_prepass(case.dem, table, **dict(base, aws_row=999))
+    bad = table.copy()
+    bad[3, _lib.F_RH] = 55.0                                                   # per cent instead of a fraction
+    with pytest.raises(EnrgyError):
+        host_prepass(case.dem, bad, **base)
