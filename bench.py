@@ -251,7 +251,10 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = cell_steps / float(t_e.item())
-    h2d = dem_full.nbytes + case.swe.nbytes + sum(a.nbytes for a in case.albedo_maps.values()) + table.nbytes
+    # the DEM goes up whole only with shading (the rays leave the band); else the band + one row either side
+    m = case.meta
+    dem_rows_up = dem_full.shape[0] if SHADOW else (min(dem_full.shape[0], m["band_row0"] + case.dem.shape[0] + 1) - max(0, m["band_row0"] - 1))
+    h2d = dem_rows_up * dem_full.shape[1] * 4 + case.swe.nbytes + sum(a.nbytes for a in case.albedo_maps.values()) + table.nbytes
     d2h = 3 * case.dem.size * 4 + stats_h.numel() * 8
 
     result = None

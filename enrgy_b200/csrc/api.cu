@@ -548,8 +548,19 @@ int enrgy_set_dem(enrgy_ctx* c, const float* dem) {
   CU_TRY(c->d_dem.alloc(dem_elems));
   c->dem0 = c->d_dem.p + (size_t)kDemApron * c->dem_pitch + kDemApron;
   CU_TRY(cudaMemsetAsync(c->d_dem.p, 0xFF, dem_elems * sizeof(float), c->stream));
-  CU_TRY(cudaMemcpy2DAsync(c->dem0, (size_t)c->dem_pitch * sizeof(float), dem, (size_t)c->cols * sizeof(float),
-                           (size_t)c->cols * sizeof(float), c->rows, cudaMemcpyHostToDevice, c->stream));
+  {
+    // Only the shading rays read the DEM outside the band; without them the band plus one row on
+    // either side (terrain normals) is all the device needs -- on a multi-GPU run every rank then
+    // uploads its share instead of the whole raster.  The rest of the buffer stays NaN.
+    const bool need_all = c->p.insol_mode == ENRGY_INSOL_COMPUTED && c->p.shadow;
+    const int r_a = need_all ? 0 : std::max(0, c->band_row0 - 1);
+    const int r_b = need_all ? c->rows : std::min(c->rows, c->band_row0 + c->band_rows + 1);
+    if (r_b > r_a) {
+      CU_TRY(cudaMemcpy2DAsync(c->dem0 + (size_t)r_a * c->dem_pitch, (size_t)c->dem_pitch * sizeof(float),
+                               dem + (size_t)r_a * c->cols, (size_t)c->cols * sizeof(float),
+                               (size_t)c->cols * sizeof(float), r_b - r_a, cudaMemcpyHostToDevice, c->stream));
+    }
+  }
   {
     MaxPyramid& py = c->pyramid;
     py = MaxPyramid{};

@@ -163,7 +163,8 @@ int enrgy_set_params(enrgy_ctx* ctx, const enrgy_params* p);
 
 /* rasters: base DEM (model.py:74), albedo maps (model.py:160-165, already clipped to [0.001, 1]),
  * initial SWE (model.py:122-124; NULL = zeros, model.py:79).  The DEM passed here is the FULL
- * raster even for a row band (it is replicated for the shading rays). */
+ * raster even for a row band (it is replicated for the shading rays; without shading only
+ * the band and one row on either side are copied to the device). */
 int enrgy_set_dem(enrgy_ctx* ctx, const float* dem);
 int enrgy_set_albedo_maps(enrgy_ctx* ctx, int n_maps, const float* const* maps);
 int enrgy_set_swe(enrgy_ctx* ctx, const float* swe);
