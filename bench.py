@@ -277,7 +277,7 @@ def run_ours(args):
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": "C2: %dx%d 10 m synthetic DEM + 5 albedo maps per GPU, %d hourly steps, "
                                    "in-kernel insolation (4 sub-steps/step), %s" % (n, n, T, "shading ray march" if SHADOW else "no shading"),
-                       "raster": [n * world, n], "steps_per_pass": T, "parallelism": "row bands x%d, balanced by glacier cells" % world,
+                       "raster": [n * world, n], "steps_per_pass": T, "parallelism": "row bands x%d, balanced by visited tiles" % world,
                        "band_rows": [b[1] for b in case.meta["bands"]],
                        "l2": "per-pass inputs ~%.0f MB > 126 MB L2, no flush" % (bytes_per_launch / 1e6)},
             "roofline": {"bound": "fp32" if args.dtype == "f32" else "fp64",

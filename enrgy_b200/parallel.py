@@ -38,6 +38,20 @@ def row_bands(rows, world, align=16, valid_per_row=None):
     return [(edges[i], edges[i + 1] - edges[i]) for i in range(world)]
 
 
+def tile_cost_per_row(valid, tile_h=8, tile_w=128):
+    """Cost weights for row_bands(valid_per_row=...) in units of VISITED TILES: the fused kernel walks
+    tiles of tile_h x tile_w cells and a tile with one glacier cell costs as much as a full one, so a
+    band along the glacier margin is more expensive than its glacier-cell count says.  `valid` is the
+    boolean glacier mask [rows, cols]; every row gets 1 / tile_h of the tiles its row group touches."""
+    valid = np.asarray(valid, dtype=bool)
+    rows, cols = valid.shape
+    hp, wp = -(-rows // tile_h) * tile_h, -(-cols // tile_w) * tile_w
+    v = np.zeros((hp, wp), dtype=bool)
+    v[:rows, :cols] = valid
+    tiles = v.reshape(hp // tile_h, tile_h, wp // tile_w, tile_w).any(axis=(1, 3)).sum(axis=1)
+    return np.repeat(tiles / float(tile_h), tile_h)[:rows]
+
+
 def rebalance_bands(bands, seconds, valid_per_row, align=16):
     """New band edges from MEASURED per-band times: with the shading ray march the cost of a glacier
     cell depends on the terrain around it, so equal glacier-cell counts are not equal times.  The

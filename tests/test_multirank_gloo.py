@@ -13,7 +13,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from enrgy_b200 import _lib
-from enrgy_b200.parallel import allreduce_stats, means_from_sums, rebalance_bands, row_bands
+from enrgy_b200.parallel import allreduce_stats, means_from_sums, rebalance_bands, row_bands, tile_cost_per_row
 from enrgy_b200.synthetic import make_case
 from oracle import enrgy_oracle as O
 from tests import parity as P
@@ -131,3 +131,17 @@ def test_rebalance_bands_moves_rows_to_the_fast_ranks():
     cost = np.concatenate([np.full(n, t / n) for (_, n), t in zip(bands, [1.0, 2.0, 1.0, 1.0])])
     shares = [cost[r0:r0 + n].sum() for r0, n in nb]
     assert max(shares) - min(shares) < 0.1
+
+
+def test_tile_cost_weights():
+    """Bands cut by visited tiles: a ragged glacier margin (one valid cell per tile) weighs as much as
+    a filled interior, so the band holding it gets fewer rows than a cut by glacier cells gives it."""
+    valid = np.zeros((256, 512), dtype=bool)
+    valid[:128, :] = True                          # interior: every cell
+    valid[128:, ::128] = True                      # margin: one cell per 128-column tile
+    w = tile_cost_per_row(valid, tile_h=8, tile_w=128)
+    assert w.shape == (256,) and np.allclose(w, 4 / 8.0)          # 4 tiles per 8-row group everywhere
+    by_tiles = row_bands(256, 2, align=16, valid_per_row=w)
+    by_cells = row_bands(256, 2, align=16, valid_per_row=valid.sum(axis=1))
+    assert by_tiles == [(0, 128), (128, 128)]
+    assert by_cells[0][1] < 128                                    # cells alone would starve rank 0 of rows
