@@ -145,3 +145,30 @@ def test_tile_cost_weights():
     by_cells = row_bands(256, 2, align=16, valid_per_row=valid.sum(axis=1))
     assert by_tiles == [(0, 128), (128, 128)]
     assert by_cells[0][1] < 128                                    # cells alone would starve rank 0 of rows
+
+
+def test_band_cuts_properties_randomised():
+    """row_bands / rebalance_bands on random weights and times: bands tile the raster without gaps or
+    overlaps, edges are aligned, no band is negative, and re-cutting with the times a perfectly
+    uniform cost model would have produced leaves the bands unchanged."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 8), st.integers(1, 40), st.integers(0, 2**31 - 1), st.sampled_from([1, 8, 16]))
+    def check(world, groups, seed, align):
+        rows = groups * 16
+        rng = np.random.default_rng(seed)
+        w = rng.integers(0, 200, rows).astype(float)
+        w[rng.random(rows) < 0.3] = 0.0
+        bands = row_bands(rows, world, align=align, valid_per_row=w)
+        assert len(bands) == world and bands[0][0] == 0
+        assert all(n >= 0 for _, n in bands) and sum(n for _, n in bands) == rows
+        assert all(bands[i][0] + bands[i][1] == bands[i + 1][0] for i in range(world - 1))
+        assert all(r0 % align == 0 for r0, _ in bands[1:])
+        # times proportional to the weights the bands were cut with -> same cuts again
+        secs = [max(w[r0:r0 + n].sum(), 0.0) for r0, n in bands]
+        if min(secs) > 0:
+            again = rebalance_bands(bands, secs, w, align=align)
+            assert sum(n for _, n in again) == rows
+            assert max(abs(a[0] - b[0]) for a, b in zip(again, bands)) <= align
+    check()
