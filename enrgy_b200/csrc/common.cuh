@@ -51,7 +51,10 @@ constexpr int kShadowStepsPerBlock = ENRGY_SHADOW_STEPS_PER_BLOCK;  // with the 
 constexpr int kShadowSubsPerBlock = 4 * kShadowStepsPerBlock;
 constexpr int kDemApron = 64;                 // NaN cells around the DEM buffer: a ray-chunk window of a warp
                                               // whose last active ray is at the grid edge stays inside it
-constexpr int kRayChunk = 16;                 // ray steps marched (or skipped) at a time
+#ifndef ENRGY_RAY_CHUNK
+#define ENRGY_RAY_CHUNK 16
+#endif
+constexpr int kRayChunk = ENRGY_RAY_CHUNK;    // ray steps marched (or skipped) at a time (<= 32: one lane per step)
 constexpr int kMaxBlock = 16;                 // edge of the blocks of the DEM max grid
 
 // Statistics the kernel reduces per step (the rest of ENRGY_S_* is derived from these by

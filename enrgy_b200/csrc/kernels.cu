@@ -622,9 +622,10 @@ constexpr float kGstepEps = 0.01f;   // margin of the step-rise test [m]: above 
 #ifdef ENRGY_MARCH_STATS
 __device__ unsigned long long g_march_stats[32];
 #endif
-constexpr int kWinW = 52;                       // DEM window of a ray chunk: 32 columns + 16 steps + 3 (alignment)
-constexpr int kWinH = 24;                       //                            K <= 8 rows + 16 steps
-constexpr int kWinBytes = kWinW * kWinH * 4;    // 4992 B = 39 x 128 B
+constexpr int kWinW = 32 + kRayChunk + 4;        // DEM window of a ray chunk: 32 columns + chunk steps + 3 (alignment), 16 B multiple
+constexpr int kWinH = 8 + kRayChunk;            //                            K <= 8 rows + chunk steps
+constexpr int kWinBytes = (kWinW * kWinH * 4 + 127) / 128 * 128;   // 4992 B = 39 x 128 B at 16 steps
+static_assert(kWinW % 4 == 0 && kWinH % 2 == 0 && 2 * (kWinW / 4) <= 32 && kRayChunk <= 32, "window staging: two rows of 16 B chunks per pass of the warp");
 
 // order-preserving float <-> int key (for REDUX min/max on the integer pipe)
 __device__ __forceinline__ int float_key(float x) {
@@ -801,7 +802,7 @@ __device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem
 #pragma unroll
       for (int i = 0; i < K; ++i) under[i] = 0x7fffffff;
       const int* wkeys = reinterpret_cast<const int*>(win) + lane;
-#pragma unroll(kRayUnroll)
+#pragma unroll(kRayUnroll < kRayChunk ? kRayUnroll : kRayChunk)
       for (int j = 0; j < kRayChunk; ++j) {
         // step j of the chunk: window offset and rise come from lane j (two shuffles, one LEA)
         const int* p = wkeys + __shfl_sync(full, ab_l, j);
@@ -819,7 +820,7 @@ __device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem
 #pragma unroll
       for (int i = 0; i < K; ++i) over[i] = -INFINITY;
       const float* wlane = win + lane;
-#pragma unroll(kRayUnroll)
+#pragma unroll(kRayUnroll < kRayChunk ? kRayUnroll : kRayChunk)
       for (int j = 0; j < kRayChunk; ++j) {
         const float* p = wlane + __shfl_sync(full, ab_l, j);
         const float kdz = __shfl_sync(full, kdz_l, j);
