@@ -188,6 +188,10 @@ int upload_tables(enrgy_ctx* c) {
     d.c_sens = (R)s.c_sens; d.c_lat = (R)s.c_lat; d.c_lwd = (R)s.c_lwd; d.c_lwu = (R)s.c_lwu;
     d.c_sw = (R)s.c_sw; d.c_melt = (R)s.c_melt; d.alb_w = (R)s.alb_w; d.snow_alb = (R)s.snow_alb;
     d.dsum = (R)s.dsum; d.dt = (R)s.dt;
+    d.dir_u = (R)s.dir_u; d.dir_e = (R)s.dir_e; d.dir_n = (R)s.dir_n;
+    // (rounded DOWN into the kernel's precision: the test it feeds must stay conservative)
+    d.tan2_min = (R)s.tan2_min;
+    if ((double)d.tan2_min > s.tan2_min) d.tan2_min = std::nextafter(d.tan2_min, (R)-1);
     // the two integer codes travel as int32 bit patterns in the low word of their slots (no float -> int
     // conversion at the head of every step)
     const int32_t pair_code = (int32_t)s.alb_pair, sub_code = (int32_t)s.sub;

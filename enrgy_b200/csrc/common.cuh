@@ -73,7 +73,7 @@ struct MsmParams {
   R inv_snow_density;                         // snow depth = swe / snow_density (model.py:428, sic)
 };
 
-// ---- per-step record (16 values, staged per time block by a TMA bulk copy) ---------------------
+// ---- per-step record (20 values, staged per time block by a TMA bulk copy) ---------------------
 template <typename R>
 struct alignas(16) StepRec {
   R t_air;     // T_AIR at the AWS [deg C]
@@ -92,6 +92,10 @@ struct alignas(16) StepRec {
   R dt;        // time step [s]
   R alb_pair;  // i0 * 256 + i1; on the device an int32 bit pattern in the low word (step_code())
   R sub;       // (first sub-step index relative to the time block) * 256 + number of sub-steps; int32 bits on the device
+  // sums over the step's sunlit sub-steps of b * (u, e, n): where the sun stands above every slope of a
+  // patch for the whole step, max(cos i, 0) = cos i and the direct beam is dir_u + px dir_e + py dir_n
+  R dir_u, dir_e, dir_n;
+  R tan2_min;  // min over the sub-steps of tan^2(sun elevation); < 0: no sunlit sub-step
 };
 
 // ---- per-sub-step record (sun above the horizon only) ------------------------------------------

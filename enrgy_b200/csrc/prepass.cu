@@ -299,6 +299,7 @@ int run_prepass(const PrepassInput& in, PrepassOutput& out, std::string& err) {
       int n_sub = (int)std::ceil(dt_h / hs - 1e-9);
       if (n_sub < 1) n_sub = 1;
       double direct = 0.0, dsum = 0.0;
+      double dir_u = 0.0, dir_e = 0.0, dir_n = 0.0, tan2_min = std::numeric_limits<double>::infinity();
       for (int j = 0; j < n_sub; ++j) {
         const double w = std::min(hs, dt_h - j * hs);
         const double t_mid = f[ENRGY_F_TIME] + (j * hs + 0.5 * w) * 3600.0;
@@ -320,6 +321,11 @@ int run_prepass(const PrepassInput& in, PrepassOutput& out, std::string& err) {
         }
         sb.shade.kmax = std::max(in.rows, in.cols);
         out.subs.push_back(sb);
+        dir_u += sb.b * sb.u; dir_e += sb.b * sb.e; dir_n += sb.b * sb.n;
+        {
+          const double h2 = sb.e * sb.e + sb.n * sb.n;
+          if (h2 > 0.0) tan2_min = std::min(tan2_min, sb.u * sb.u / h2);
+        }
         const double cosi = nx * sb.e + ny * sb.n + nz * sb.u;
         double term = sb.b * std::max(cosi, 0.0);
         if (p.shadow && !host_lit(in.dem, in.rows, in.cols, p.aws_row, p.aws_col, sb.shade, zmax)) {
@@ -329,9 +335,13 @@ int run_prepass(const PrepassInput& in, PrepassOutput& out, std::string& err) {
         dsum = dsum + sb.d;
       }
       s.dsum = dsum;
+      s.dir_u = dir_u; s.dir_e = dir_e; s.dir_n = dir_n;
+      // no sunlit sub-step: never; all at the zenith: the (huge) finite maximum, not inf
+      s.tan2_min = (int)out.subs.size() == out.sub_first[i] ? -1.0 : std::min(tan2_min, 1e30);
       pot_aws_kwh = direct + dsum * (1.0 + nz);
     } else {
       s.dsum = 0.0;
+      s.dir_u = s.dir_e = s.dir_n = 0.0; s.tan2_min = -1.0;
       pot_aws_kwh = in.pot_aws ? in.pot_aws[i] : 0.0;
     }
     out.sub_count[i] = (int)out.subs.size() - out.sub_first[i];

@@ -69,3 +69,33 @@ def test_computed_insolation(f64, shadow):
     tol = 1e-9 if f64 else 1e-4
     for k, v in res.items():
         assert v < tol, (k, v)
+
+
+@pytest.mark.parametrize("f64", [True, False])
+def test_computed_insolation_high_sun_gentle_slopes(f64):
+    """Mid-latitude summer days on gentle slopes: for most rows the sun stands above every slope of a
+    patch in all sub-steps, where the kernel replaces the per-sub-step max(cos i, 0) sum by the row's
+    analytic sums; steeper patches, dawn and dusk take the sub-step path in the same run."""
+    case = make_case(128, 40, w=160, seed=43, start="20220620 03:00:00")
+    r, c = np.mgrid[0:128, 0:160].astype(np.float64)
+    nan = np.isnan(case.dem)
+    dem = 1500.0 + 1.2 * r + 30.0 * np.sin(c / 25.0) + 6.0 * np.cos(r / 7.0) + 0.15 * (case.dem.astype(np.float64) - np.nanmean(case.dem))
+    dem[:, 100:] += 3.5 * (c[:, 100:] - 100)          # a steep flank (35 % grade): its patches keep the sub-step path
+    dem[nan] = np.nan
+    case.dem[...] = dem.astype(np.float32)
+    case.elev_aws = float(case.dem[case.aws_rc])
+    case.lat, case.lon = 46.0, 8.0
+    res = P.compare_run(case, f64, computed=True, shadow=False)
+    print(f64, res)
+    tol = 1e-9 if f64 else 1e-4
+    for k, v in res.items():
+        assert v < tol, (k, v)
+    # both paths really occur: tan(sun elevation) runs from 0.02 at dawn to 2.3 at noon, the patches'
+    # steepest slopes from ~0.2 to ~0.5
+    from oracle import insolation_oracle as I
+    tan2 = []
+    for row in case.aws_rows:
+        tab = I.substep_table(I.to_unix(row["DATE"]), 3600, 46.0, 8.0, case.cell)
+        if tab:
+            tan2.append(min(s["U"] ** 2 / (s["E"] ** 2 + s["N"] ** 2) for s in tab))
+    assert max(tan2) > 1.0 and min(tan2) < 0.01
