@@ -37,7 +37,8 @@ N_STEPS = 2200
 # ez = e, exp(0) = 1, one reciprocal per quantity, analytic longwave sum, daily albedo blend, flux
 # scalars folded into the balance FMA chain): 77 FLOP = 46.5 FP32-pipe operations (FMA/ADD/MUL, two
 # cells per packed instruction) + 14 min/max/select/compare/MUFU/SHFL operations on the other pipes,
-# counted in the SASS of the hot basic block (346 instructions per 256 cell-steps).  Both are
+# counted in the SASS of the hot basic block (346 instructions per 256 cell-steps; rows that take the
+# analytic direct-beam path execute 40 packed instructions fewer, not credited here).  Both are
 # reported; `roofline.frac` uses the SURVEY figure as the contract asks.
 FLOP_PER_CELL_STEP = 141.0
 FLOP_EXECUTED_PER_CELL_STEP = 77.0
