@@ -64,6 +64,7 @@ _PROTOTYPES = {
     "enrgy_destroy": (C.c_int, [_P]),
     "enrgy_set_params": (C.c_int, [_P, C.POINTER(Params)]),
     "enrgy_set_dem": (C.c_int, [_P, _P]),
+    "enrgy_set_terrain": (C.c_int, [_P, _P]),
     "enrgy_set_albedo_maps": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
     "enrgy_set_swe": (C.c_int, [_P, _P]),
     "enrgy_set_msm": (C.c_int, [_P, _P, C.c_double]),
@@ -80,6 +81,12 @@ _PROTOTYPES = {
     "enrgy_get_substeps": (C.c_int, [_P, C.c_int, C.c_int, _P, C.POINTER(C.c_int)]),
     "enrgy_shade_masks": (C.c_int, [_P, C.c_int, C.c_int, _P, C.POINTER(C.c_int)]),
     "enrgy_potential_insolation": (C.c_int, [_P, C.c_int, _P]),
+    "enrgy_sub_range": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "enrgy_mask_words": (C.c_int64, [_P, C.c_int]),
+    "enrgy_shade_scan": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                   C.POINTER(_P), _P]),
+    "enrgy_run_masked": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
+    "enrgy_set_mask_budget": (C.c_int, [_P, C.c_int64]),
     "enrgy_get_state": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "enrgy_set_state": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "enrgy_get_layer_temps": (C.c_int, [_P, _P]),
@@ -88,6 +95,7 @@ _PROTOTYPES = {
     "enrgy_microbench": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
     "enrgy_launch_count": (C.c_int64, [_P]),
     "enrgy_last_kernel_ms": (C.c_double, [_P]),
+    "enrgy_last_sweep_ms": (C.c_double, [_P]),
     "enrgy_kernel_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                     C.POINTER(C.c_int)]),
 }

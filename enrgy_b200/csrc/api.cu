@@ -80,18 +80,24 @@ struct enrgy_ctx {
   size_t band_elems = 0;  // band_rows_pad * pitch
   // host copies
   std::vector<float> h_dem;       // full host copy, kept only when the AWS-cell shading ray needs it
-  float aws_nbhd[9] = {};         // DEM at the AWS cell and its 8 neighbours
-  float zmax = 0.f;               // top of the device max pyramid
+  std::vector<float> h_terrain;   // ... and the uncropped terrain, when one was set (enrgy_set_terrain)
+  float aws_nbhd[9] = {};         // terrain at the AWS cell and its 8 neighbours
   std::vector<double> forcing;
   int n_steps = 0;
   std::vector<double> pot_aws;
   PrepassOutput pre;
   // device rasters
-  DevBuf<float> d_dem, d_albedo, d_pot, d_tmp32, d_blockmax, d_gstep;
-  int pyr_stride = 0;
+  DevBuf<float> d_dem, d_terrain, d_albedo, d_pot, d_tmp32, d_scan, d_scan_t;
+  bool have_terrain = false;
   int dem_pitch = 0;
-  MaxPyramid pyramid{};
-  float* dem0 = nullptr;          // cell (0, 0) inside the apron buffer
+  float* dem0 = nullptr;          // cell (0, 0) of the DEM buffer
+  // shading: sunlit masks of a range of sub-steps, kept between runs (they depend on the terrain and
+  // the sub-step directions only -- ensemble members and repeated passes reuse them)
+  DevBuf<unsigned> d_maskbuf, d_masktmp;
+  DevBuf<SweepSub> d_sweepsubs;
+  int mask_sub0 = 0, mask_sub1 = 0;   // cached range [sub0, sub1) of d_maskbuf
+  size_t mask_budget = (size_t)16 << 30;
+  int64_t sweep_launches = 0;
   DevBuf<unsigned char> d_nx, d_ny, d_nz, d_swe, d_ts, d_ti, d_dump, d_stage, d_snap, d_layer_t;
   bool have_msm = false;
   std::vector<double> alb_aws, layer_t_aws;
@@ -105,18 +111,18 @@ struct enrgy_ctx {
   DevBuf<ShadeRec> d_shades;
   DevBuf<TimeBlock> d_blocks;
   DevBuf<int2> d_tiles;
-  DevBuf<int> d_counts, d_demkeys;
+  DevBuf<int> d_counts;
   // host pre-pass started ahead of enrgy_prepass (see start_early_prepass)
   std::thread pre_thread;
   PrepassOutput pre_early;
   int pre_early_rc = 0;
   std::string pre_early_err;
-  float dem_min = 0.f;       // lowest valid elevation (shading only)
-  bool dem_nonneg = false;   // no negative elevation: the shading samples use the integer copy (kInsolShadowKeys)
   DevBuf<double> d_stats, d_small;
   DevBuf<unsigned char> d_partials;
   DevBuf<unsigned long long> d_counters;
-  DevBuf<unsigned> d_masks;
+  std::vector<ShadeRec> mask_shades;   // directions the cached masks were swept for
+  void* ev_fused = nullptr;       // EventPairs around the fused kernels / the shading sweeps of the last run
+  void* ev_sweep = nullptr;
   // SWE statistics of the initial raster (first CSV row)
   double swe0_sum = 0.0, swe0_nsnow = 0.0, swe0_nvalid = 0.0;
   // runtime
@@ -201,15 +207,12 @@ int upload_tables(enrgy_ctx* c) {
   }
   const size_t ns = o.subs.size();
   std::vector<SubRec<R>> sb(std::max<size_t>(ns, 1));
-  std::vector<ShadeRec> sh(std::max<size_t>(ns, 1));
   for (size_t i = 0; i < ns; ++i) {
     sb[i].e = (R)o.subs[i].e; sb[i].n = (R)o.subs[i].n; sb[i].u = (R)o.subs[i].u; sb[i].b = (R)o.subs[i].b;
-    sh[i] = o.subs[i].shade;
   }
   CU_TRY(c->d_steps.alloc(std::max<size_t>(T, 1) * sizeof(StepRec<R>)));
   CU_TRY(c->d_steps64.alloc(std::max<size_t>(T, 1)));
   CU_TRY(c->d_subs.alloc(sb.size() * sizeof(SubRec<R>)));
-  CU_TRY(c->d_shades.alloc(sh.size()));
   CU_TRY(c->d_blocks.alloc(std::max<size_t>(o.blocks.size(), 1)));
   if (T) {
     CU_TRY(cudaMemcpyAsync(c->d_steps.p, st.data(), (size_t)T * sizeof(StepRec<R>), cudaMemcpyHostToDevice, c->stream));
@@ -218,7 +221,6 @@ int upload_tables(enrgy_ctx* c) {
   }
   if (ns) {
     CU_TRY(cudaMemcpyAsync(c->d_subs.p, sb.data(), ns * sizeof(SubRec<R>), cudaMemcpyHostToDevice, c->stream));
-    CU_TRY(cudaMemcpyAsync(c->d_shades.p, sh.data(), ns * sizeof(ShadeRec), cudaMemcpyHostToDevice, c->stream));
   }
   CU_TRY(cudaStreamSynchronize(c->stream));   // host vectors go out of scope
   return ENRGY_OK;
@@ -249,10 +251,10 @@ void resolve_defaults(enrgy_params& p) {
 void fill_prepass_input(enrgy_ctx* c, PrepassInput& in) {
   in.p = c->p; in.precision = c->precision; in.rows = c->rows; in.cols = c->cols;
   in.albedo_offset = c->albedo_offset;
-  in.dem = c->h_dem.empty() ? nullptr : c->h_dem.data(); in.n_steps = c->n_steps; in.forcing = c->forcing.data();
-  std::memcpy(in.nbhd, c->aws_nbhd, sizeof(in.nbhd)); in.zmax = c->zmax;
+  in.dem = c->have_terrain ? (c->h_terrain.empty() ? nullptr : c->h_terrain.data()) : (c->h_dem.empty() ? nullptr : c->h_dem.data());
+  in.n_steps = c->n_steps; in.forcing = c->forcing.data();
+  std::memcpy(in.nbhd, c->aws_nbhd, sizeof(in.nbhd));
   in.pot_aws = c->pot_aws.data();
-  if (c->p.insol_mode == ENRGY_INSOL_COMPUTED && c->p.shadow) { in.cap_steps = kShadowStepsPerBlock; in.cap_subs = kShadowSubsPerBlock; }
   in.alb_aws = c->alb_aws; in.swe_aws = c->swe_aws; in.layer_t_aws = c->layer_t_aws;
 }
 void drop_early_prepass(enrgy_ctx* c) {
@@ -275,11 +277,8 @@ int fill_args(enrgy_ctx* c, int t0, int t1, KernelArgs<R>& a) {
   a.rows_full = c->rows; a.cols = c->cols; a.pitch = c->pitch;
   a.band_row0 = c->band_row0; a.band_rows = c->band_rows; a.rows_pad_full = c->rows_pad_full;
   a.dem = c->dem0; a.dem_pitch = c->dem_pitch;
-  a.blockmax = c->d_blockmax.p; a.pyramid = c->pyramid;
-  // the step-rise test's margin (1 cm) assumes float32 ray heights below 16 km
-  a.gstep = (std::fabs(c->zmax) < 16000.f && c->dem_min > -16000.f) ? c->d_gstep.p : nullptr;
-  a.pyr_stride = c->pyr_stride;
-  a.dem_keys = c->d_demkeys.p ? c->d_demkeys.p + (size_t)kDemApron * c->dem_pitch + kDemApron : nullptr;
+  a.mask_words = c->pitch / 32;
+  a.mask_sub_stride = (size_t)c->band_rows_pad * a.mask_words;   // (rows_pad / 8) x words x 8
   a.nx = (const R*)c->d_nx.p; a.ny = (const R*)c->d_ny.p; a.nz = (const R*)c->d_nz.p;
   a.albedo = c->d_albedo.p;
   a.map_stride = c->band_elems;
@@ -288,7 +287,6 @@ int fill_args(enrgy_ctx* c, int t0, int t1, KernelArgs<R>& a) {
   a.albedo_offset = (R)c->albedo_offset;
   a.max_ice_albedo = c->p.albedo_const ? (R)INFINITY : (R)c->p.max_ice_albedo;
   a.elev_aws = (R)c->p.elev_aws;
-  a.zmax = (R)c->pre.zmax;
   a.swe = (R*)c->d_swe.p; a.total_snow = (R*)c->d_ts.p; a.total_ice = (R*)c->d_ti.p;
   a.pot = c->d_pot.p; a.pot_stride = c->band_elems; a.pot_t0 = c->pot_t0;
   a.layer_t = (R*)c->d_layer_t.p;
@@ -304,7 +302,6 @@ int fill_args(enrgy_ctx* c, int t0, int t1, KernelArgs<R>& a) {
   a.msm.inv_snow_density = (R)(1.0 / c->p.snow_density);
   a.steps = (const StepRec<R>*)c->d_steps.p;
   a.subs = (const SubRec<R>*)c->d_subs.p;
-  a.shades = c->d_shades.p;
   a.blocks = c->d_blocks.p;
   a.cap_steps = c->pre.cap_steps; a.cap_subs = c->pre.cap_subs;
   int b0 = 0;
@@ -320,8 +317,7 @@ int fill_args(enrgy_ctx* c, int t0, int t1, KernelArgs<R>& a) {
 
 int insol_variant(const enrgy_ctx* c) {
   if (c->p.insol_mode == ENRGY_INSOL_STREAMED) return kInsolStreamed;
-  if (!c->p.shadow) return kInsolComputed;
-  return c->dem_nonneg ? kInsolShadowKeys : kInsolShadow;
+  return c->p.shadow ? kInsolMasked : kInsolComputed;
 }
 
 int check_run_ready(enrgy_ctx* c, int t0, int t1) {
@@ -337,11 +333,177 @@ int check_run_ready(enrgy_ctx* c, int t0, int t1) {
   return ENRGY_OK;
 }
 
+// ---- CUDA event pairs around the kernels of the last run (several chunks -> several pairs) ---------
+struct EventPairs {
+  std::vector<cudaEvent_t> ev;   // begin, end, begin, end, ...
+  int used = 0;
+  bool pending = false;
+  double last_ms = 0.0;
+  void reset() { used = 0; pending = false; }
+  cudaError_t begin(cudaStream_t s) {
+    while ((int)ev.size() < used + 2) {
+      cudaEvent_t e;
+      cudaError_t rc = cudaEventCreate(&e);
+      if (rc != cudaSuccess) return rc;
+      ev.push_back(e);
+    }
+    return cudaEventRecord(ev[used], s);
+  }
+  cudaError_t end(cudaStream_t s) {
+    cudaError_t rc = cudaEventRecord(ev[used + 1], s);
+    used += 2;
+    pending = true;
+    return rc;
+  }
+  double collect() {
+    if (pending) {
+      double tot = 0.0;
+      for (int i = 0; i + 1 < used; i += 2) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(ev[i + 1]) == cudaSuccess && cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) tot += ms;
+      }
+      last_ms = tot;
+      pending = false;
+    }
+    return last_ms;
+  }
+  void destroy() {
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    ev.clear();
+  }
+};
+EventPairs& fused_events(enrgy_ctx* c);
+EventPairs& sweep_events(enrgy_ctx* c);
+
+EventPairs& fused_events(enrgy_ctx* c) {
+  if (!c->ev_fused) c->ev_fused = new EventPairs();
+  return *static_cast<EventPairs*>(c->ev_fused);
+}
+EventPairs& sweep_events(enrgy_ctx* c) {
+  if (!c->ev_sweep) c->ev_sweep = new EventPairs();
+  return *static_cast<EventPairs*>(c->ev_sweep);
+}
+
+// ---- shading: sunlit masks by the line sweep (shade.cu) -------------------------------------------
+// uint32 words of one sub-step's mask for a band of `rows` rows: [rows_pad / 8][pitch / 32][8]
+size_t mask_words_per_sub(const enrgy_ctx* c, int rows) { return (size_t)round_up(std::max(rows, 1), 16) * (c->pitch / 32); }
+
+// sweeps the sunlit sub-steps [sub0, sub1) of the run into the given destination segments
+int sweep_range(enrgy_ctx* c, int sub0, int sub1, int n_seg, const SweepSeg* segs, cudaStream_t stream) {
+  if (sub1 <= sub0) return ENRGY_OK;
+  if (!c->d_scan.p) return fail(ENRGY_ERR_ARG, "shading is off for this handle (params.shadow = 0)");
+  std::vector<SweepSub> row_subs, col_subs;
+  std::vector<int> zenith;
+  for (int i = sub0; i < sub1; ++i) {
+    const ShadeRec& sr = c->pre.subs[i].shade;
+    if (!std::isfinite(sr.dz) || (sr.dc_fix == 0 && sr.dr_fix == 0)) {   // sun at the zenith: nothing can shade
+      zenith.push_back(i - sub0);
+      continue;
+    }
+    bool row_type; int sigma, dfix;
+    line_geometry(sr.dc_fix, sr.dr_fix, &row_type, &sigma, &dfix);
+    SweepSub sw{};
+    sw.dfix = dfix; sw.sigma = sigma; sw.dz = (double)sr.dz; sw.out = i - sub0; sw.out2 = i - sub0;
+    (row_type ? row_subs : col_subs).push_back(sw);
+  }
+  // neighbours in the lists have similar directions: the Q warps of a CTA then sweep nearly the same
+  // cells and share the terrain rows through L1 (the same hour of consecutive days)
+  auto by_direction = [](const SweepSub& x, const SweepSub& y) { return x.sigma != y.sigma ? x.sigma < y.sigma : x.dfix < y.dfix; };
+  std::stable_sort(row_subs.begin(), row_subs.end(), by_direction);
+  std::stable_sort(col_subs.begin(), col_subs.end(), by_direction);
+  for (size_t i = 0; i < col_subs.size(); ++i) col_subs[i].out = (int)i;   // slot in the transposed temporary
+  SweepArgs a{};
+  a.rows = c->rows; a.cols = c->cols;
+  a.scan = c->d_scan.p + (size_t)kScanRowApron * scan_pitch(c->cols) + kScanColApron;
+  a.scan_t = c->d_scan_t.p + (size_t)kScanRowApron * scan_pitch(c->rows) + kScanColApron;
+  a.n_seg = n_seg;
+  for (int q = 0; q < n_seg; ++q) a.seg[q] = segs[q];
+  a.tmp_words = sweep_tmp_words(c->rows);
+  CU_TRY(c->d_sweepsubs.alloc(row_subs.size() + col_subs.size() + 1));
+  // (pageable source: the copy is staged before the call returns, the vectors may go out of scope)
+  if (!row_subs.empty()) CU_TRY(cudaMemcpyAsync(c->d_sweepsubs.p, row_subs.data(), row_subs.size() * sizeof(SweepSub), cudaMemcpyHostToDevice, stream));
+  if (!col_subs.empty()) CU_TRY(cudaMemcpyAsync(c->d_sweepsubs.p + row_subs.size(), col_subs.data(), col_subs.size() * sizeof(SweepSub), cudaMemcpyHostToDevice, stream));
+  a.row_subs = c->d_sweepsubs.p; a.n_row_subs = (int)row_subs.size();
+  a.col_subs = c->d_sweepsubs.p + row_subs.size(); a.n_col_subs = (int)col_subs.size();
+  if (!col_subs.empty()) {
+    CU_TRY(c->d_masktmp.alloc(col_subs.size() * (size_t)c->cols * a.tmp_words));
+    a.tmp = c->d_masktmp.p;
+  }
+  for (int z : zenith) {
+    for (int q = 0; q < n_seg; ++q) {
+      const size_t words = (size_t)segs[q].rg * segs[q].words * 8;
+      CU_TRY(cudaMemsetAsync(segs[q].ptr + (size_t)z * words, 0xFF, words * sizeof(unsigned), stream));
+    }
+  }
+  int n = 0;
+  CU_TRY(sweep_events(c).begin(stream));
+  CU_TRY(launch_sweep(a, c->sm_count, stream, &n));
+  CU_TRY(sweep_events(c).end(stream));
+  c->launches += n;
+  c->sweep_launches += n;
+  return ENRGY_OK;
+}
+
+// masks of [sub0, sub1) for this handle's own band in c->d_maskbuf (kept: they depend only on the
+// terrain and the sub-step directions, so later runs, ensemble members and debug views reuse them)
+int ensure_masks(enrgy_ctx* c, int sub0, int sub1, cudaStream_t stream) {
+  if (sub1 <= sub0) return ENRGY_OK;
+  bool hit = sub0 >= c->mask_sub0 && sub1 <= c->mask_sub1;
+  if (hit) {
+    for (int i = sub0; i < sub1 && hit; ++i) {
+      hit = std::memcmp(&c->mask_shades[i - c->mask_sub0], &c->pre.subs[i].shade, sizeof(ShadeRec)) == 0;
+    }
+  }
+  if (hit) return ENRGY_OK;
+  const size_t per = mask_words_per_sub(c, c->band_rows);
+  c->mask_sub0 = c->mask_sub1 = 0;
+  CU_TRY(c->d_maskbuf.alloc((size_t)(sub1 - sub0) * per));
+  SweepSeg sg{};
+  sg.row0 = c->band_row0; sg.rows = c->band_rows; sg.rg = c->band_rows_pad / 8; sg.words = c->pitch / 32;
+  sg.ptr = c->d_maskbuf.p;
+  if (int e = sweep_range(c, sub0, sub1, 1, &sg, stream)) return e;
+  c->mask_shades.resize(sub1 - sub0);
+  for (int i = sub0; i < sub1; ++i) c->mask_shades[i - sub0] = c->pre.subs[i].shade;
+  c->mask_sub0 = sub0; c->mask_sub1 = sub1;
+  return ENRGY_OK;
+}
+
+struct Chunk { int t0, t1, s0, s1; };
+// steps [t0, t1) cut so that the masks (and the transposed temporaries, worst case all of them) of a
+// chunk fit the budget; one chunk when everything fits
+std::vector<Chunk> plan_chunks(const enrgy_ctx* c, int t0, int t1) {
+  const size_t per_sub = (mask_words_per_sub(c, c->band_rows) + (size_t)c->cols * sweep_tmp_words(c->rows)) * sizeof(unsigned);
+  size_t budget = c->mask_budget;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+    // what is already held for masks counts as available
+    const size_t held = (c->d_maskbuf.n + c->d_masktmp.n) * sizeof(unsigned);
+    budget = std::min(budget, (free_b + held) / 2);
+  }
+  const int max_subs = (int)std::max<size_t>(budget / per_sub, 1);
+  std::vector<Chunk> out;
+  int t = t0;
+  while (t < t1) {
+    Chunk ch{t, t, c->pre.sub_first[t], c->pre.sub_first[t]};
+    while (ch.t1 < t1 && (ch.t1 == ch.t0 || ch.s1 - ch.s0 + c->pre.sub_count[ch.t1] <= max_subs)) {
+      ch.s1 += c->pre.sub_count[ch.t1];
+      ++ch.t1;
+    }
+    out.push_back(ch);
+    t = ch.t1;
+  }
+  return out;
+}
+
+// one launch of the fused kernel over [t0, t1) (+ statistics); masks: sunlit masks of this band, the
+// first one belonging to the run's sunlit sub-step number mask_sub0
 template <typename R>
-int run_typed(enrgy_ctx* c, int t0, int t1, double* d_stats, cudaStream_t stream) {
+int launch_range(enrgy_ctx* c, int t0, int t1, double* d_stats, cudaStream_t stream, const unsigned* masks, int mask_sub0) {
   KernelArgs<R> a;
   fill_args<R>(c, t0, t1, a);
+  a.masks = masks; a.mask_sub0 = mask_sub0;
   const int insol = insol_variant(c);
+  if (insol == kInsolMasked && masks == nullptr) return fail(ENRGY_ERR_ARG, "no sunlit masks for a run with shading");
   LaunchInfo li;
   const bool msm = c->p.msm_layers > 0;
   CU_TRY(energy_balance_grid<R>(insol, msm, false, c->sm_count, a.cap_steps, a.cap_subs, &li));
@@ -356,10 +518,9 @@ int run_typed(enrgy_ctx* c, int t0, int t1, double* d_stats, cudaStream_t stream
                                     a.total_snow, a.total_ice, stream));
     c->launches++;
   }
-  CU_TRY(cudaEventRecord(c->ev0, stream));
+  CU_TRY(fused_events(c).begin(stream));
   CU_TRY(launch_energy_balance<R>(a, nullptr, insol, false, c->sm_count, grid, &c->info, stream));
-  CU_TRY(cudaEventRecord(c->ev1, stream));
-  c->ev_pending = true;
+  CU_TRY(fused_events(c).end(stream));
   c->launches++;
   if (d_stats && n > 0) {
     FinalizeArgs f{};
@@ -377,39 +538,40 @@ int run_typed(enrgy_ctx* c, int t0, int t1, double* d_stats, cudaStream_t stream
 }
 
 template <typename R>
-int dump_typed(enrgy_ctx* c, int t0, int t1, double* out, unsigned* mask_host, int max_sub, int* n_sub_out) {
+int run_typed(enrgy_ctx* c, int t0, int t1, double* d_stats, cudaStream_t stream) {
+  fused_events(c).reset();
+  sweep_events(c).reset();
+  if (insol_variant(c) != kInsolMasked || t1 <= t0) return launch_range<R>(c, t0, t1, d_stats, stream, nullptr, 0);
+  // with shading: sweep the sunlit masks of a chunk of steps, then run the fused kernel over it
+  for (const Chunk& ch : plan_chunks(c, t0, t1)) {
+    if (int e = ensure_masks(c, ch.s0, ch.s1, stream)) return e;
+    const unsigned* m = c->d_maskbuf.p + (size_t)(ch.s0 - c->mask_sub0) * mask_words_per_sub(c, c->band_rows);
+    if (int e = launch_range<R>(c, ch.t0, ch.t1, d_stats ? d_stats + (size_t)(ch.t0 - t0) * ENRGY_S_COUNT : nullptr, stream,
+                                m, ch.s0))
+      return e;
+  }
+  return ENRGY_OK;
+}
+
+template <typename R>
+int dump_typed(enrgy_ctx* c, int t0, int t1, double* out) {
   KernelArgs<R> a;
   fill_args<R>(c, t0, t1, a);
   const int insol = insol_variant(c);
   const int n = t1 - t0;
   const size_t per_step = (size_t)ENRGY_D_COUNT * c->band_elems;
-  int n_sub = 0;
-  if (mask_host) {
-    if (!insol_shadow(insol)) return fail(ENRGY_ERR_ARG, "shade masks need insol_mode = COMPUTED with shadow = 1");
-    n_sub = c->pre.sub_count[t0];
-    if (n_sub > max_sub) return fail(ENRGY_ERR_ARG, "step has %d sunlit sub-steps, buffer holds %d", n_sub, max_sub);
-    a.mask_words = (c->cols + 31) / 32;
-    const size_t words = (size_t)std::max(n_sub, 1) * c->band_rows * a.mask_words;
-    CU_TRY(c->d_masks.alloc(words));
-    // off-glacier cells read "sunlit" (nothing marches from them); tiles without a glacier cell are
-    // never visited, so the buffer starts all-ones to give them the same value
-    CU_TRY(cudaMemsetAsync(c->d_masks.p, 0xFF, words * sizeof(unsigned), c->stream));
-    a.mask_out = c->d_masks.p;
-  } else {
-    CU_TRY(c->d_dump.alloc((size_t)n * per_step * sizeof(R)));
-    CU_TRY(cudaMemsetAsync(c->d_dump.p, 0xFF, (size_t)n * per_step * sizeof(R), c->stream));
-    a.dump = (R*)c->d_dump.p;
-    a.dump_field_stride = c->band_elems;
+  if (insol == kInsolMasked) {
+    const int s0 = c->pre.sub_first[t0], s1 = c->pre.sub_first[t1 - 1] + c->pre.sub_count[t1 - 1];
+    if (int e = ensure_masks(c, s0, s1, c->stream)) return e;
+    a.masks = c->d_maskbuf.p + (size_t)(s0 - c->mask_sub0) * mask_words_per_sub(c, c->band_rows);
+    a.mask_sub0 = s0;
   }
+  CU_TRY(c->d_dump.alloc((size_t)n * per_step * sizeof(R)));
+  CU_TRY(cudaMemsetAsync(c->d_dump.p, 0xFF, (size_t)n * per_step * sizeof(R), c->stream));
+  a.dump = (R*)c->d_dump.p;
+  a.dump_field_stride = c->band_elems;
   CU_TRY(launch_energy_balance<R>(a, nullptr, insol, true, c->sm_count, 0, nullptr, c->stream));
   c->launches++;
-  if (mask_host) {
-    const size_t words = (size_t)n_sub * c->band_rows * a.mask_words;
-    if (words) CU_TRY(cudaMemcpyAsync(mask_host, c->d_masks.p, words * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(cudaStreamSynchronize(c->stream));
-    if (n_sub_out) *n_sub_out = n_sub;
-    return ENRGY_OK;
-  }
   std::vector<R> h((size_t)n * per_step);
   CU_TRY(cudaMemcpyAsync(h.data(), c->d_dump.p, h.size() * sizeof(R), cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
@@ -481,7 +643,10 @@ int enrgy_destroy(enrgy_ctx* c) {
   c->d_ti.release(); c->d_dump.release(); c->d_stage.release(); c->d_steps.release(); c->d_subs.release();
   c->d_steps64.release(); c->d_shades.release(); c->d_blocks.release(); c->d_tiles.release();
   c->d_counts.release(); c->d_partials.release(); c->d_stats.release(); c->d_small.release();
-  c->d_counters.release(); c->d_masks.release(); c->d_snap.release(); c->d_blockmax.release(); c->d_layer_t.release(); c->d_demkeys.release(); c->d_gstep.release();
+  c->d_counters.release(); c->d_snap.release(); c->d_layer_t.release(); c->d_terrain.release(); c->d_scan.release();
+  c->d_scan_t.release(); c->d_maskbuf.release(); c->d_masktmp.release(); c->d_sweepsubs.release();
+  if (c->ev_fused) { fused_events(c).destroy(); delete static_cast<EventPairs*>(c->ev_fused); }
+  if (c->ev_sweep) { sweep_events(c).destroy(); delete static_cast<EventPairs*>(c->ev_sweep); }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -512,7 +677,7 @@ int enrgy_set_params(enrgy_ctx* c, const enrgy_params* pin) {
   c->band_row0 = p.band_row0;
   c->band_rows = p.band_rows;
   {
-    const int insol = p.insol_mode == ENRGY_INSOL_STREAMED ? kInsolStreamed : (p.shadow ? kInsolShadow : kInsolComputed);
+    const int insol = p.insol_mode == ENRGY_INSOL_STREAMED ? kInsolStreamed : (p.shadow ? kInsolMasked : kInsolComputed);
     if (c->precision == ENRGY_F32) {
       energy_balance_tile<float>(p.msm_layers > 0, insol, &c->tile_h, &c->tile_w);
     } else {
@@ -546,11 +711,16 @@ int enrgy_set_dem(enrgy_ctx* c, const float* dem) {
     c->h_dem.clear();
     c->h_dem.shrink_to_fit();
   }
-  // DEM buffer with a NaN apron of kDemApron cells on every side (ray chunks never leave it)
-  c->dem_pitch = c->pitch + 2 * kDemApron;
-  const size_t dem_elems = (size_t)(c->rows_pad_full + 2 * kDemApron) * c->dem_pitch;
+  c->have_terrain = false;
+  c->h_terrain.clear();
+  c->h_terrain.shrink_to_fit();
+  c->d_terrain.release();
+  c->mask_sub0 = c->mask_sub1 = 0;
+  // DEM buffer [rows_pad_full][pitch], padding cells NaN
+  c->dem_pitch = c->pitch;
+  const size_t dem_elems = (size_t)c->rows_pad_full * c->dem_pitch;
   CU_TRY(c->d_dem.alloc(dem_elems));
-  c->dem0 = c->d_dem.p + (size_t)kDemApron * c->dem_pitch + kDemApron;
+  c->dem0 = c->d_dem.p;
   CU_TRY(cudaMemsetAsync(c->d_dem.p, 0xFF, dem_elems * sizeof(float), c->stream));
   {
     // Only the shading rays read the DEM outside the band; without them the band plus one row on
@@ -565,54 +735,15 @@ int enrgy_set_dem(enrgy_ctx* c, const float* dem) {
                                (size_t)c->cols * sizeof(float), r_b - r_a, cudaMemcpyHostToDevice, c->stream));
     }
   }
-  {
-    MaxPyramid& py = c->pyramid;
-    py = MaxPyramid{};
-    int nbr = (c->rows + kMaxBlock - 1) / kMaxBlock, nbc = (c->cols + kMaxBlock - 1) / kMaxBlock, off = 0;
-    for (int l = 0; l < kMaxPyramidLevels; ++l) {
-      py.nbr[l] = nbr; py.nbc[l] = nbc; py.off[l] = off;
-      off += (nbr + 2) * (nbc + 2);
-      py.levels = l + 1;
-      if (nbr <= 1 && nbc <= 1) break;
-      nbr = (nbr + 1) / 2; nbc = (nbc + 1) / 2;
-    }
-    CU_TRY(c->d_blockmax.alloc((size_t)off));
-    CU_TRY(launch_blockmax(c->dem0, c->dem_pitch, c->rows, c->cols, py, c->d_blockmax.p, c->stream));
-    // the top level is one block: its value is the maximum of the valid DEM
-    const int top = py.levels - 1;
-    std::vector<float> tv((size_t)(py.nbr[top] + 2) * (py.nbc[top] + 2));
-    CU_TRY(cudaMemcpyAsync(tv.data(), c->d_blockmax.p + py.off[top], tv.size() * sizeof(float),
-                           cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(cudaStreamSynchronize(c->stream));
-    c->zmax = -std::numeric_limits<float>::infinity();
-    for (float v : tv) c->zmax = std::max(c->zmax, v);
-  }
-  c->launches++;
-  // shading: integer copy of the DEM buffer for the samples (march<K, KEYS>), used when no valid
-  // cell is negative
-  c->dem_nonneg = false;
+  // shading: scan copies of the terrain for the line sweep (shade.cu)
   if (c->p.insol_mode == ENRGY_INSOL_COMPUTED && c->p.shadow) {
-    // step-rise pyramids of the 8 ray octants (second skip test of the march)
-    c->pyr_stride = c->pyramid.off[c->pyramid.levels - 1] +
-                    (c->pyramid.nbr[c->pyramid.levels - 1] + 2) * (c->pyramid.nbc[c->pyramid.levels - 1] + 2);
-    CU_TRY(c->d_gstep.alloc((size_t)8 * c->pyr_stride));
-    CU_TRY(launch_gstep(c->dem0, c->dem_pitch, c->rows, c->cols, c->pyramid, c->pyr_stride, c->d_gstep.p, c->stream));
-    c->launches++;
-    CU_TRY(c->d_demkeys.alloc(dem_elems + 1));
-    int* d_min = c->d_demkeys.p + dem_elems;
-    const int int_max = 0x7fffffff;
-    CU_TRY(cudaMemcpyAsync(d_min, &int_max, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    CU_TRY(launch_dem_keys(c->d_dem.p, c->d_demkeys.p, dem_elems, d_min, c->stream));
-    c->launches++;
-    int min_key = 0;
-    CU_TRY(cudaMemcpyAsync(&min_key, d_min, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(cudaStreamSynchronize(c->stream));
-    c->dem_nonneg = min_key >= 0 && c->p.shadow != 2;
-    {
-      const int bits = min_key ^ ((min_key >> 31) & 0x7fffffff);     // key -> float bits
-      std::memcpy(&c->dem_min, &bits, sizeof(float));
-      if (min_key == 0x7fffffff) c->dem_min = 0.f;                    // no valid cell
-    }
+    CU_TRY(c->d_scan.alloc(scan_elems(c->rows, c->cols)));
+    CU_TRY(c->d_scan_t.alloc(scan_elems(c->cols, c->rows)));
+    CU_TRY(launch_scan_prepare(c->dem0, c->dem_pitch, c->rows, c->cols, c->d_scan.p, c->d_scan_t.p, c->stream));
+    c->launches += 3;
+  } else {
+    c->d_scan.release();
+    c->d_scan_t.release();
   }
   // active tiles of the band
   c->tiles_r = (c->band_rows + c->tile_h - 1) / c->tile_h;
@@ -677,10 +808,10 @@ int enrgy_set_dem(enrgy_ctx* c, const float* dem) {
     CU_TRY(c->d_ny.alloc(c->band_elems * rs));
     CU_TRY(c->d_nz.alloc(c->band_elems * rs));
     if (c->precision == ENRGY_F32) {
-      CU_TRY(launch_terrain<float>(c->dem0, c->dem_pitch, c->rows, c->cols, c->pitch, c->band_row0, c->band_rows_pad,
+      CU_TRY(launch_terrain<float>(c->dem0, c->dem0, c->dem_pitch, c->rows, c->cols, c->pitch, c->band_row0, c->band_rows_pad,
                                    c->p.cell_size, (float*)c->d_nx.p, (float*)c->d_ny.p, (float*)c->d_nz.p, c->stream));
     } else {
-      CU_TRY(launch_terrain<double>(c->dem0, c->dem_pitch, c->rows, c->cols, c->pitch, c->band_row0, c->band_rows_pad,
+      CU_TRY(launch_terrain<double>(c->dem0, c->dem0, c->dem_pitch, c->rows, c->cols, c->pitch, c->band_row0, c->band_rows_pad,
                                     c->p.cell_size, (double*)c->d_nx.p, (double*)c->d_ny.p, (double*)c->d_nz.p, c->stream));
     }
     c->launches++;
@@ -688,6 +819,66 @@ int enrgy_set_dem(enrgy_ctx* c, const float* dem) {
   CU_TRY(cudaStreamSynchronize(c->stream));
   c->have_dem = true;
   c->prepass_done = false;
+  return ENRGY_OK;
+}
+
+int enrgy_set_terrain(enrgy_ctx* c, const float* terrain) {
+  if (int e = use_device(c)) return e;
+  if (!c->have_dem) return fail(ENRGY_ERR_ARG, "set_dem must precede set_terrain");
+  if (!terrain) return fail(ENRGY_ERR_ARG, "terrain is null");
+  if (c->p.insol_mode != ENRGY_INSOL_COMPUTED) return fail(ENRGY_ERR_ARG, "the terrain only matters with insol_mode = COMPUTED");
+  drop_early_prepass(c);
+  const size_t n = (size_t)c->rows * c->cols;
+  {
+    // every glacier cell needs terrain under it
+    const int ar = c->p.aws_row, ac = c->p.aws_col;
+    if (!(terrain[(size_t)ar * c->cols + ac] == terrain[(size_t)ar * c->cols + ac]))
+      return fail(ENRGY_ERR_MASK, "the terrain raster is NaN at the AWS cell");
+  }
+  const size_t elems = (size_t)c->rows_pad_full * c->dem_pitch;
+  CU_TRY(c->d_terrain.alloc(elems));
+  CU_TRY(cudaMemsetAsync(c->d_terrain.p, 0xFF, elems * sizeof(float), c->stream));
+  CU_TRY(cudaMemcpy2DAsync(c->d_terrain.p, (size_t)c->dem_pitch * sizeof(float), terrain, (size_t)c->cols * sizeof(float),
+                           (size_t)c->cols * sizeof(float), c->rows, cudaMemcpyHostToDevice, c->stream));
+  // (the band's rows of the DEM are on the device in every mode; the mask check needs no more)
+  {
+    CU_TRY(c->d_counters.alloc(2));
+    CU_TRY(cudaMemsetAsync(c->d_counters.p, 0, 2 * sizeof(unsigned long long), c->stream));
+    CU_TRY(launch_mask_check(c->dem0, c->dem_pitch, c->d_terrain.p + (size_t)c->band_row0 * c->dem_pitch, c->dem_pitch,
+                             c->band_row0, c->band_rows, c->cols, c->d_counters.p, c->stream));
+    c->launches++;
+    unsigned long long h[2];
+    CU_TRY(cudaMemcpyAsync(h, c->d_counters.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (h[0] != 0) return fail(ENRGY_ERR_MASK, "the terrain raster is NaN at %llu glacier cells", h[0]);
+  }
+  for (int dr = -1; dr <= 1; ++dr)
+    for (int dc = -1; dc <= 1; ++dc) {
+      const int r = c->p.aws_row + dr, x = c->p.aws_col + dc;
+      c->aws_nbhd[(dr + 1) * 3 + (dc + 1)] = (r >= 0 && r < c->rows && x >= 0 && x < c->cols)
+                                                 ? terrain[(size_t)r * c->cols + x]
+                                                 : std::numeric_limits<float>::quiet_NaN();
+    }
+  const size_t rs = rsize(c);
+  (void)rs;
+  if (c->precision == ENRGY_F32) {
+    CU_TRY(launch_terrain<float>(c->dem0, c->d_terrain.p, c->dem_pitch, c->rows, c->cols, c->pitch, c->band_row0, c->band_rows_pad,
+                                 c->p.cell_size, (float*)c->d_nx.p, (float*)c->d_ny.p, (float*)c->d_nz.p, c->stream));
+  } else {
+    CU_TRY(launch_terrain<double>(c->dem0, c->d_terrain.p, c->dem_pitch, c->rows, c->cols, c->pitch, c->band_row0, c->band_rows_pad,
+                                  c->p.cell_size, (double*)c->d_nx.p, (double*)c->d_ny.p, (double*)c->d_nz.p, c->stream));
+  }
+  c->launches++;
+  if (c->p.shadow) {
+    c->h_terrain.assign(terrain, terrain + n);
+    CU_TRY(launch_scan_prepare(c->d_terrain.p, c->dem_pitch, c->rows, c->cols, c->d_scan.p, c->d_scan_t.p, c->stream));
+    c->launches += 3;
+  }
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  c->have_terrain = true;
+  c->mask_sub0 = c->mask_sub1 = 0;
+  c->prepass_done = false;
+  if (c->have_forcing) start_early_prepass(c);
   return ENRGY_OK;
 }
 
@@ -894,9 +1085,6 @@ int enrgy_host_prepass(const enrgy_params* pin, int precision, int rows, int col
   if (in.p.aws_row < 0 || in.p.aws_row >= rows || in.p.aws_col < 0 || in.p.aws_col >= cols)
     return fail(ENRGY_ERR_ARG, "AWS cell (%d, %d) outside the %d x %d raster", in.p.aws_row, in.p.aws_col, rows, cols);
   in.precision = precision; in.rows = rows; in.cols = cols; in.dem = dem;
-  float zmax = -std::numeric_limits<float>::infinity();
-  for (size_t i = 0; i < (size_t)rows * cols; ++i) if (dem[i] == dem[i]) zmax = std::max(zmax, dem[i]);
-  in.zmax = zmax;
   for (int dr = -1; dr <= 1; ++dr)
     for (int dc = -1; dc <= 1; ++dc) {
       const int r = in.p.aws_row + dr, x = in.p.aws_col + dc;
@@ -906,7 +1094,6 @@ int enrgy_host_prepass(const enrgy_params* pin, int precision, int rows, int col
   in.n_steps = n_steps; in.forcing = forcing;
   std::vector<double> nan_pot(std::max(n_steps, 1), std::numeric_limits<double>::quiet_NaN());
   in.pot_aws = pot_aws ? pot_aws : nan_pot.data();
-  if (in.p.insol_mode == ENRGY_INSOL_COMPUTED && in.p.shadow) { in.cap_steps = kShadowStepsPerBlock; in.cap_subs = kShadowSubsPerBlock; }
   for (int i = 0; i < n_steps; ++i) {
     const double* f = forcing + (size_t)i * ENRGY_F_COUNT;
     if (!(f[ENRGY_F_RH] <= 1.0)) return fail(ENRGY_ERR_RANGE, "row %d: HUMID must be a 0..1 fraction here (helpers.py:74-87)", i);
@@ -978,16 +1165,87 @@ int enrgy_dump_steps(enrgy_ctx* c, int t0, int t1, double* out) {
   if (int e = check_run_ready(c, t0, t1)) return e;
   if (!out) return fail(ENRGY_ERR_ARG, "out is null");
   if (t1 == t0) return ENRGY_OK;
-  return c->precision == ENRGY_F32 ? dump_typed<float>(c, t0, t1, out, nullptr, 0, nullptr)
-                                   : dump_typed<double>(c, t0, t1, out, nullptr, 0, nullptr);
+  return c->precision == ENRGY_F32 ? dump_typed<float>(c, t0, t1, out) : dump_typed<double>(c, t0, t1, out);
 }
 
 int enrgy_shade_masks(enrgy_ctx* c, int step, int max_sub, uint32_t* out, int* n_sub_out) {
   if (int e = use_device(c)) return e;
   if (int e = check_run_ready(c, step, step + 1)) return e;
   if (!out) return fail(ENRGY_ERR_ARG, "out is null");
-  return c->precision == ENRGY_F32 ? dump_typed<float>(c, step, step + 1, nullptr, out, max_sub, n_sub_out)
-                                   : dump_typed<double>(c, step, step + 1, nullptr, out, max_sub, n_sub_out);
+  if (insol_variant(c) != kInsolMasked) return fail(ENRGY_ERR_ARG, "shade masks need insol_mode = COMPUTED with shadow = 1");
+  const int s0 = c->pre.sub_first[step], n_sub = c->pre.sub_count[step];
+  if (n_sub > max_sub) return fail(ENRGY_ERR_ARG, "step has %d sunlit sub-steps, buffer holds %d", n_sub, max_sub);
+  if (n_sub_out) *n_sub_out = n_sub;
+  if (n_sub == 0) return ENRGY_OK;
+  if (int e = ensure_masks(c, s0, s0 + n_sub, c->stream)) return e;
+  const size_t per = mask_words_per_sub(c, c->band_rows);
+  std::vector<unsigned> h((size_t)n_sub * per);
+  CU_TRY(cudaMemcpyAsync(h.data(), c->d_maskbuf.p + (size_t)(s0 - c->mask_sub0) * per, h.size() * sizeof(unsigned),
+                         cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  // device layout [sub][row / 8][word][row % 8] -> [sub][row][word]; off-glacier cells and the bits
+  // beyond the last column read "sunlit"
+  const int words = (c->cols + 31) / 32, dwords = c->pitch / 32;
+  for (int j = 0; j < n_sub; ++j)
+    for (int r = 0; r < c->band_rows; ++r) {
+      uint32_t* dst = out + ((size_t)j * c->band_rows + r) * words;
+      for (int w = 0; w < words; ++w) {
+        unsigned v = h[(size_t)j * per + (((size_t)(r >> 3) * dwords + w) * 8) + (r & 7)];
+        const float* drow = c->h_dem.data() + (size_t)(r + c->band_row0) * c->cols;
+        for (int b = 0; b < 32; ++b) {
+          const int x = w * 32 + b;
+          if (x >= c->cols || !(drow[x] == drow[x])) v |= 1u << b;
+        }
+        dst[w] = v;
+      }
+    }
+  return ENRGY_OK;
+}
+
+int enrgy_sub_range(enrgy_ctx* c, int t0, int t1, int* sub0, int* sub1) {
+  if (!c || !sub0 || !sub1) return fail(ENRGY_ERR_ARG, "null argument");
+  if (!c->prepass_done) return fail(ENRGY_ERR_ARG, "prepass has not run");
+  if (t0 < 0 || t1 > c->n_steps || t0 > t1) return fail(ENRGY_ERR_ARG, "step range [%d, %d) outside [0, %d)", t0, t1, c->n_steps);
+  const int total = (int)c->pre.subs.size();
+  *sub0 = t0 < c->n_steps ? c->pre.sub_first[t0] : total;
+  *sub1 = t1 > t0 ? c->pre.sub_first[t1 - 1] + c->pre.sub_count[t1 - 1] : *sub0;
+  return ENRGY_OK;
+}
+
+int64_t enrgy_mask_words(enrgy_ctx* c, int rows) {
+  if (!c || rows <= 0) return 0;
+  return (int64_t)mask_words_per_sub(c, rows);
+}
+
+int enrgy_shade_scan(enrgy_ctx* c, int sub0, int sub1, int n_seg, const int* seg_row0, const int* seg_rows,
+                     void* const* seg_ptr, void* stream) {
+  if (int e = use_device(c)) return e;
+  if (!c->have_dem || !c->prepass_done) return fail(ENRGY_ERR_ARG, "set_dem / set_forcing / prepass must precede shade_scan");
+  if (insol_variant(c) != kInsolMasked) return fail(ENRGY_ERR_ARG, "shade_scan needs insol_mode = COMPUTED with shadow = 1");
+  if (sub0 < 0 || sub1 > (int)c->pre.subs.size() || sub0 > sub1) return fail(ENRGY_ERR_ARG, "sub-step range outside the run");
+  if (n_seg < 1 || n_seg > kMaxSweepSegs || !seg_row0 || !seg_rows || !seg_ptr) return fail(ENRGY_ERR_ARG, "1..%d row segments", kMaxSweepSegs);
+  SweepSeg segs[kMaxSweepSegs];
+  for (int q = 0; q < n_seg; ++q) {
+    if (seg_row0[q] < 0 || seg_rows[q] <= 0 || seg_row0[q] + seg_rows[q] > c->rows || (seg_row0[q] & 7) || !seg_ptr[q])
+      return fail(ENRGY_ERR_ARG, "segment %d: rows [%d, %d) must lie inside the raster and start on a multiple of 8", q, seg_row0[q], seg_row0[q] + seg_rows[q]);
+    segs[q].row0 = seg_row0[q]; segs[q].rows = seg_rows[q];
+    segs[q].rg = round_up(seg_rows[q], 16) / 8; segs[q].words = c->pitch / 32;
+    segs[q].ptr = static_cast<unsigned*>(seg_ptr[q]);
+  }
+  sweep_events(c).reset();
+  return sweep_range(c, sub0, sub1, n_seg, segs, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int enrgy_run_masked(enrgy_ctx* c, int t0, int t1, const void* d_masks, double* d_stats, void* stream) {
+  if (int e = use_device(c)) return e;
+  if (int e = check_run_ready(c, t0, t1)) return e;
+  if (insol_variant(c) != kInsolMasked) return fail(ENRGY_ERR_ARG, "run_masked needs insol_mode = COMPUTED with shadow = 1");
+  if (!d_masks && t1 > t0) return fail(ENRGY_ERR_ARG, "d_masks is null");
+  cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+  fused_events(c).reset();
+  const int sub0 = t0 < c->n_steps ? c->pre.sub_first[t0] : 0;
+  return c->precision == ENRGY_F32 ? launch_range<float>(c, t0, t1, d_stats, s, static_cast<const unsigned*>(d_masks), sub0)
+                                   : launch_range<double>(c, t0, t1, d_stats, s, static_cast<const unsigned*>(d_masks), sub0);
 }
 
 int enrgy_potential_insolation(enrgy_ctx* c, int step, double* out) {
@@ -1124,15 +1382,20 @@ int64_t enrgy_launch_count(enrgy_ctx* c) { return c ? c->launches : 0; }
 
 double enrgy_last_kernel_ms(enrgy_ctx* c) {
   if (!c) return 0.0;
-  if (c->ev_pending) {
-    cudaSetDevice(c->device);
-    if (cudaEventSynchronize(c->ev1) == cudaSuccess) {
-      float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_ms = ms;
-    }
-    c->ev_pending = false;
-  }
-  return c->last_ms;
+  cudaSetDevice(c->device);
+  return fused_events(c).collect();
+}
+
+double enrgy_last_sweep_ms(enrgy_ctx* c) {
+  if (!c) return 0.0;
+  cudaSetDevice(c->device);
+  return sweep_events(c).collect();
+}
+
+int enrgy_set_mask_budget(enrgy_ctx* c, int64_t bytes) {
+  if (!c || bytes <= 0) return fail(ENRGY_ERR_ARG, "bad mask budget");
+  c->mask_budget = (size_t)bytes;
+  return ENRGY_OK;
 }
 
 int enrgy_kernel_info(enrgy_ctx* c, int* regs, int* smem_bytes, int* ctas_per_sm, int* grid) {

@@ -42,20 +42,8 @@ constexpr int kStatsP = kStatsK + kStatsM;    // columns of a per-CTA partial ro
 #ifndef ENRGY_STEPS_PER_BLOCK
 #define ENRGY_STEPS_PER_BLOCK 64
 #endif
-#ifndef ENRGY_SHADOW_STEPS_PER_BLOCK
-#define ENRGY_SHADOW_STEPS_PER_BLOCK 16
-#endif
 constexpr int kStepsPerBlock = ENRGY_STEPS_PER_BLOCK;               // energy balance alone
 constexpr int kSubsPerBlock = 256;
-constexpr int kShadowStepsPerBlock = ENRGY_SHADOW_STEPS_PER_BLOCK;  // with the shading ray march (one-warp CTAs)
-constexpr int kShadowSubsPerBlock = 4 * kShadowStepsPerBlock;
-constexpr int kDemApron = 64;                 // NaN cells around the DEM buffer: a ray-chunk window of a warp
-                                              // whose last active ray is at the grid edge stays inside it
-#ifndef ENRGY_RAY_CHUNK
-#define ENRGY_RAY_CHUNK 16
-#endif
-constexpr int kRayChunk = ENRGY_RAY_CHUNK;    // ray steps marched (or skipped) at a time (<= 32: one lane per step)
-constexpr int kMaxBlock = 16;                 // edge of the blocks of the DEM max grid
 
 // Statistics the kernel reduces per step (the rest of ENRGY_S_* is derived from these by
 // linearity in finalize_stats_kernel; DESIGN.md "Statistics").
@@ -104,13 +92,22 @@ struct alignas(16) SubRec {
   R e, n, u;   // unit vector toward the sun (east, north, up)
   R b;         // S0 * tau^(1/u) * width_h / 1000   [kWh m-2 per unit cos(incidence)]
 };
-// shading direction of a sub-step (precision independent: the mask spec is float32 + integers)
+// shading direction of a sub-step (precision independent: the mask spec is integers + exact float64)
 struct alignas(16) ShadeRec {
   int32_t dc_fix;  // Q16 column step per ray step (east = +col)
   int32_t dr_fix;  // Q16 row step per ray step (north = -row)
   float dz;        // rise of the ray per step [m] (float32 of cell * u / max(|e|,|n|))
-  int32_t kmax;    // last ray step that can still be inside the grid
+  int32_t kmax;    // (unused, kept for the record size)
 };
+// scan-line family of a direction (oracle/insolation_oracle.py:line_geometry): row type sweeps along
+// the rows with u = sigma * row and the column sheared by dfix, column type the other way round
+ENRGY_HD void line_geometry(int dc_fix, int dr_fix, bool* row_type, int* sigma, int* dfix) {
+  const int adr = dr_fix < 0 ? -dr_fix : dr_fix, adc = dc_fix < 0 ? -dc_fix : dc_fix;
+  *row_type = adr >= adc;
+  if (*row_type) { *sigma = dr_fix > 0 ? 1 : -1; *dfix = dc_fix; }
+  else { *sigma = dc_fix > 0 ? 1 : -1; *dfix = dr_fix; }
+}
+ENRGY_HD int shear_q16(int u, int dfix) { return (u * dfix + 32768) >> 16; }
 
 // time block = consecutive steps whose records and sub-steps fit the smem staging buffers
 struct TimeBlock {

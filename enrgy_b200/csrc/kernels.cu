@@ -14,7 +14,7 @@
 //   model.py:533-545        longwave                                      -> balance(), finalize_stats_kernel
 //   model.py:298-337        albedo                                        -> daily blend + balance()
 //   model.py:464-497        shortwave from potential insolation           -> balance()
-//   saga_lighting.py:42-44  potential insolation incl. shadows (SAGA)     -> sub_step() / march()
+//   saga_lighting.py:42-44  potential insolation incl. shadows (SAGA)     -> sub_step(); sunlit masks from shade.cu
 //   model.py:411, :434-438  flux sum and clamp                            -> balance()
 //   msm.py:193-203          melt partition                                -> balance()
 //   msm.py:31-107           sub-surface conduction (MSM variants)         -> balance()
@@ -28,13 +28,7 @@
 
 #include "../../include/enrgy_b200.h"
 
-#ifndef ENRGY_RAY_UNROLL
-#define ENRGY_RAY_UNROLL 16
-#endif
-
 namespace enrgy {
-
-constexpr int kRayUnroll = ENRGY_RAY_UNROLL;   // ray steps in flight per thread in the sampling loop
 
 // =================================================================================================
 // small device helpers
@@ -228,9 +222,13 @@ __device__ __forceinline__ int stat_of_lane(int lane) {
 // terrain normal from the 4-neighbourhood; a missing neighbour is mirrored from the opposite one
 // (DESIGN.md "Insolation specification"; oracle/insolation_oracle.py:terrain_normals)
 template <typename R>
-__global__ void terrain_kernel(const float* __restrict__ dem, int dem_pitch, int rows_full, int cols,
-                               int pitch, int band_row0, int band_rows_pad, R inv2cell, R* __restrict__ nx,
+__global__ void terrain_kernel(const float* __restrict__ dem, const float* __restrict__ terr, int dem_pitch, int rows_full,
+                               int cols, int pitch, int band_row0, int band_rows_pad, R inv2cell, R* __restrict__ nx,
                                R* __restrict__ ny, R* __restrict__ nz) {
+  // `dem` decides which cells are glacier cells; the elevations of the cell and its neighbours come
+  // from `terr` -- the same raster, or the uncropped terrain (enrgy_set_terrain): SAGA is handed the
+  // uncropped DEM (reference model.py:469 -> saga_lighting.py:42), so slopes at the glacier margin see
+  // their real neighbours
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int rb = blockIdx.y;
   if (c >= pitch || rb >= band_rows_pad) return;
@@ -239,9 +237,10 @@ __global__ void terrain_kernel(const float* __restrict__ dem, int dem_pitch, int
   const float qnan = __int_as_float(0x7fc00000);
   auto at = [&](int rr, int cc) -> float {
     if (rr < 0 || rr >= rows_full || cc < 0 || cc >= cols) return qnan;
-    return dem[(size_t)rr * dem_pitch + cc];
+    return terr[(size_t)rr * dem_pitch + cc];
   };
-  const float zf = at(r, c);
+  const bool glacier = r < rows_full && c < cols && dem[(size_t)r * dem_pitch + c] == dem[(size_t)r * dem_pitch + c];
+  const float zf = glacier ? at(r, c) : qnan;
   if (!(zf == zf)) {
     nx[o] = (R)qnan; ny[o] = (R)qnan; nz[o] = (R)qnan;
     return;
@@ -264,16 +263,16 @@ __global__ void terrain_kernel(const float* __restrict__ dem, int dem_pitch, int
 }
 
 template <typename R>
-cudaError_t launch_terrain(const float* dem, int dem_pitch, int rows_full, int cols, int pitch,
+cudaError_t launch_terrain(const float* dem, const float* terr, int dem_pitch, int rows_full, int cols, int pitch,
                            int band_row0, int band_rows_pad, double cell, R* nx, R* ny, R* nz,
                            cudaStream_t stream) {
   dim3 grid((pitch + 255) / 256, band_rows_pad);
-  terrain_kernel<R><<<grid, 256, 0, stream>>>(dem, dem_pitch, rows_full, cols, pitch, band_row0, band_rows_pad,
+  terrain_kernel<R><<<grid, 256, 0, stream>>>(dem, terr, dem_pitch, rows_full, cols, pitch, band_row0, band_rows_pad,
                                               (R)(1.0 / (2.0 * cell)), nx, ny, nz);
   return cudaGetLastError();
 }
-template cudaError_t launch_terrain<float>(const float*, int, int, int, int, int, int, double, float*, float*, float*, cudaStream_t);
-template cudaError_t launch_terrain<double>(const float*, int, int, int, int, int, int, double, double*, double*, double*, cudaStream_t);
+template cudaError_t launch_terrain<float>(const float*, const float*, int, int, int, int, int, int, double, float*, float*, float*, cudaStream_t);
+template cudaError_t launch_terrain<double>(const float*, const float*, int, int, int, int, int, int, double, double*, double*, double*, cudaStream_t);
 
 // valid (non-NaN DEM) cells per tile
 __global__ void tile_scan_kernel(const float* __restrict__ dem, int pitch, int band_row0,
@@ -304,27 +303,6 @@ cudaError_t launch_tile_scan(const float* dem, int pitch, int band_row0, int ban
                              cudaStream_t stream) {
   tile_scan_kernel<<<dim3(tiles_c, tiles_r), 256, 0, stream>>>(dem, pitch, band_row0, band_rows, cols,
                                                                tile_h, tile_w, tiles_c, counts);
-  return cudaGetLastError();
-}
-
-// Integer copy of the DEM buffer (apron included) for the shading samples: -(bit pattern) of a valid
-// cell, +1 for NaN, so that "sample > ray height" reads "height bits + key < 0" for non-negative
-// floats.  min_key receives the order-preserving key of the lowest valid cell (negative iff the DEM
-// has a negative elevation, in which case the float samples are used instead).
-__global__ void dem_key_kernel(const float* __restrict__ dem, int* __restrict__ keys, size_t n, int* min_key) {
-  int lo = 0x7fffffff;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float z = dem[i];
-    const int b = __float_as_int(z);
-    const bool v = z == z;
-    keys[i] = v ? -b : 1;
-    if (v) lo = min(lo, b ^ ((b >> 31) & 0x7fffffff));
-  }
-  lo = __reduce_min_sync(0xffffffffu, lo);
-  if ((threadIdx.x & 31) == 0 && lo != 0x7fffffff) atomicMin(min_key, lo);
-}
-cudaError_t launch_dem_keys(const float* dem_buf, int* key_buf, size_t n, int* min_key, cudaStream_t stream) {
-  dem_key_kernel<<<1184, 256, 0, stream>>>(dem_buf, key_buf, n, min_key);
   return cudaGetLastError();
 }
 
@@ -492,371 +470,9 @@ template cudaError_t launch_nan_offglacier<float>(const float*, int, int, int, i
 template cudaError_t launch_nan_offglacier<double>(const float*, int, int, int, int, int, double*, double*, double*, cudaStream_t);
 
 // =================================================================================================
-// shading ray march (DESIGN.md "Shading"; oracle/insolation_oracle.py:shadow_mask)
-// =================================================================================================
-// Max pyramid of the DEM: level 0 = max of the valid cells of every 16 x 16 block, level l = max of
-// 2 x 2 blocks of level l-1; every level carries one ring of -inf blocks around the grid.
-__global__ void blockmax_kernel(const float* __restrict__ dem, int dem_pitch, int rows_full, int cols,
-                                int nbr, int nbc, float* __restrict__ blockmax) {
-  const int bc = (int)blockIdx.x - 1, br = (int)blockIdx.y - 1;
-  float m = -INFINITY;
-  if (br >= 0 && br < nbr && bc >= 0 && bc < nbc) {
-    for (int i = threadIdx.x; i < kMaxBlock * kMaxBlock; i += blockDim.x) {
-      const int r = br * kMaxBlock + i / kMaxBlock, c = bc * kMaxBlock + i % kMaxBlock;
-      if (r < rows_full && c < cols) {
-        const float z = dem[(size_t)r * dem_pitch + c];
-        if (z == z) m = fmaxf(m, z);
-      }
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  __shared__ float sh[8];
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, sh[w]);
-    blockmax[(size_t)blockIdx.y * (nbc + 2) + blockIdx.x] = m;
-  }
-}
-__global__ void blockmax_coarsen_kernel(const float* __restrict__ fine, int fnbr, int fnbc,
-                                        float* __restrict__ coarse, int nbr, int nbc) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= nbc + 2 || y >= nbr + 2) return;
-  const int bc = x - 1, br = y - 1;
-  float m = -INFINITY;
-  if (br >= 0 && br < nbr && bc >= 0 && bc < nbc) {
-    for (int dy = 0; dy < 2; ++dy)
-      for (int dx = 0; dx < 2; ++dx) {
-        const int fr = 2 * br + dy, fc = 2 * bc + dx;
-        if (fr < fnbr && fc < fnbc) m = fmaxf(m, fine[(size_t)(fr + 1) * (fnbc + 2) + (fc + 1)]);
-      }
-  }
-  coarse[(size_t)y * (nbc + 2) + x] = m;
-}
-cudaError_t launch_blockmax(const float* dem, int dem_pitch, int rows_full, int cols, const MaxPyramid& py,
-                            float* buffer, cudaStream_t stream) {
-  blockmax_kernel<<<dim3(py.nbc[0] + 2, py.nbr[0] + 2), 256, 0, stream>>>(dem, dem_pitch, rows_full, cols, py.nbr[0],
-                                                                         py.nbc[0], buffer + py.off[0]);
-  for (int l = 1; l < py.levels; ++l) {
-    blockmax_coarsen_kernel<<<dim3((py.nbc[l] + 2 + 127) / 128, py.nbr[l] + 2), 128, 0, stream>>>(
-        buffer + py.off[l - 1], py.nbr[l - 1], py.nbc[l - 1], buffer + py.off[l], py.nbr[l], py.nbc[l]);
-  }
-  return cudaGetLastError();
-}
-
-// Step-rise pyramids.  A ray advances one cell along its dominant axis per step and zero or one cell
-// along the other, so between consecutive steps the terrain under it rises by at most
-//   G(Q) = max(dem(Q + major) - dem(Q), dem(Q + major + minor) - dem(Q))
-// of the cell Q it leaves.  If G <= dz - eps for every cell a bundle of rays can leave during the
-// next n steps, and no ray has been hit so far, none can be hit in those n steps: the terrain
-// cannot catch up with a ray that rises dz per step (induction over the steps).
-// One max pyramid of G per octant (dominant axis, its sign, sign of the other axis), level 0 = max
-// over the cells of a 16 x 16 block, +inf if the block holds a NaN cell inside the grid (the chain
-// of differences breaks there), -inf for the ring of blocks outside the grid.
-__global__ void gstep_kernel(const float* __restrict__ dem, int dem_pitch, int rows_full, int cols, int nbr, int nbc,
-                             int stride, float* __restrict__ out) {
-  const int bc = (int)blockIdx.x - 1, br = (int)blockIdx.y - 1;
-  float g[8];
-#pragma unroll
-  for (int o = 0; o < 8; ++o) g[o] = -INFINITY;
-  bool has_nan = false;
-  if (br >= 0 && br < nbr && bc >= 0 && bc < nbc) {
-    auto at = [&](int r, int c) -> float {   // NaN outside the grid
-      return (r >= 0 && r < rows_full && c >= 0 && c < cols) ? dem[(long long)r * dem_pitch + c] : __int_as_float(0x7fc00000);
-    };
-    for (int i = threadIdx.x; i < kMaxBlock * kMaxBlock; i += blockDim.x) {
-      const int r = br * kMaxBlock + i / kMaxBlock, c = bc * kMaxBlock + i % kMaxBlock;
-      if (r >= rows_full || c >= cols) continue;
-      const float z = dem[(long long)r * dem_pitch + c];
-      if (!(z == z)) { has_nan = true; continue; }
-#pragma unroll
-      for (int o = 0; o < 8; ++o) {
-        const bool col_major = o & 4;
-        const int s_major = (o & 2) ? -1 : 1, s_minor = (o & 1) ? -1 : 1;
-        const int r1 = col_major ? r : r + s_major, c1 = col_major ? c + s_major : c;          // + major
-        const int r2 = col_major ? r + s_minor : r + s_major, c2 = col_major ? c + s_major : c + s_minor;   // + major + minor
-        // fmaxf ignores NaN: a ray cannot be hit by a cell outside the grid, and a NaN cell inside
-        // the grid marks its own block
-        g[o] = fmaxf(g[o], fmaxf(__fsub_ru(at(r1, c1), z), __fsub_ru(at(r2, c2), z)));
-      }
-    }
-  }
-  __shared__ float sh[8][8];
-  __shared__ int sh_nan;
-  if (threadIdx.x == 0) sh_nan = 0;
-  __syncthreads();
-  if (has_nan) sh_nan = 1;
-#pragma unroll
-  for (int o = 0; o < 8; ++o) {
-    float m = g[o];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
-    if ((threadIdx.x & 31) == 0) sh[o][threadIdx.x >> 5] = m;
-  }
-  __syncthreads();
-  if (threadIdx.x < 8) {
-    const int o = threadIdx.x;
-    float m = -INFINITY;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, sh[o][w]);
-    if (sh_nan) m = INFINITY;
-    out[(size_t)o * stride + (size_t)blockIdx.y * (nbc + 2) + blockIdx.x] = m;
-  }
-}
-cudaError_t launch_gstep(const float* dem, int dem_pitch, int rows_full, int cols, const MaxPyramid& py, int stride,
-                         float* buffer, cudaStream_t stream) {
-  gstep_kernel<<<dim3(py.nbc[0] + 2, py.nbr[0] + 2), 256, 0, stream>>>(dem, dem_pitch, rows_full, cols, py.nbr[0],
-                                                                       py.nbc[0], stride, buffer + py.off[0]);
-  for (int o = 0; o < 8; ++o) {
-    float* b = buffer + (size_t)o * stride;
-    for (int l = 1; l < py.levels; ++l) {
-      blockmax_coarsen_kernel<<<dim3((py.nbc[l] + 2 + 127) / 128, py.nbr[l] + 2), 128, 0, stream>>>(
-          b + py.off[l - 1], py.nbr[l - 1], py.nbc[l - 1], b + py.off[l], py.nbr[l], py.nbc[l]);
-    }
-  }
-  return cudaGetLastError();
-}
-constexpr float kGstepEps = 0.01f;   // margin of the step-rise test [m]: above the float32 rounding of ray heights
-                                     // below 16 km (2 ulp = 2e-3 m) and of the stored rises (rounded up)
-
-#ifdef ENRGY_MARCH_STATS
-__device__ unsigned long long g_march_stats[32];
-#endif
-constexpr int kWinW = 32 + kRayChunk + 4;        // DEM window of a ray chunk: 32 columns + chunk steps + 3 (alignment), 16 B multiple
-constexpr int kWinH = 8 + kRayChunk;            //                            K <= 8 rows + chunk steps
-constexpr int kWinBytes = (kWinW * kWinH * 4 + 127) / 128 * 128;   // 4992 B = 39 x 128 B at 16 steps
-static_assert(kWinW % 4 == 0 && kWinH % 2 == 0 && 2 * (kWinW / 4) <= 32 && kRayChunk <= 32, "window staging: two rows of 16 B chunks per pass of the warp");
-
-// order-preserving float <-> int key (for REDUX min/max on the integer pipe)
-__device__ __forceinline__ int float_key(float x) {
-  const int i = __float_as_int(x);
-  return i ^ ((i >> 31) & 0x7fffffff);
-}
-__device__ __forceinline__ float key_float(int k) {
-  return __int_as_float(k ^ ((k >> 31) & 0x7fffffff));
-}
-
-// All K cells of a thread and all 32 lanes step together, kRayChunk steps at a time; bit i of the
-// returned mask = cell i is sunlit.  float32 + integer arithmetic only, non-fused multiply/add, so
-// the mask is bit-identical to the NumPy statement whatever the precision of the energy balance.
-//
-// Per chunk the warp (a) retires rays that left the grid, were hit, or are above the DEM maximum,
-// (b) compares its LOWEST ray height at the chunk start with the maximum of the DEM blocks the
-// chunk can touch -- ray heights only grow, so if even that is above the terrain no sample of the
-// chunk can hit and the chunk is skipped without reading the DEM (result-preserving), else
-// (c) samples the chunk: one coalesced 128 B read of the replicated DEM per cell row and step.
-// The NaN apron of kDemApron = kRayChunk cells lets a chunk that starts inside the grid run
-// without per-sample bounds checks.
-//
-// KEYS: the samples come from the integer copy of the DEM (dem_key_kernel: minus the float's bit
-// pattern, +1 for NaN).  For non-negative floats the bit pattern orders like the value, so
-// "sample > ray height" is "height bits + key < 0" and the running test is ONE integer
-// add-and-minimum per sample (VIADDMNMX) instead of a subtract and a maximum.  The host picks this
-// path when the DEM has no negative elevation (ray heights only grow, so they are non-negative too).
-template <int K, bool KEYS>
-__device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem_pitch, float* win,
-                                          int rows_full, int cols,
-                                          const float* __restrict__ pyr, const float* __restrict__ gstep,
-                                          int pyr_stride, const MaxPyramid& py,
-                                          const int (&row)[K], const int (&col)[K], const float (&z0)[K],
-                                          unsigned start_bits, const ShadeRec s, float zmax, int lane) {
-  const unsigned full = 0xffffffffu;
-  unsigned lit = (1u << K) - 1u;
-  if (!(s.dz < 3.0e38f)) return lit;   // sun at the zenith
-  unsigned active = start_bits;
-  // the warp's patch: K consecutive rows x 32 columns (lane = column)
-  const int r_lo = __shfl_sync(full, row[0], 0), r_hi = r_lo + K - 1;
-  const int c_lo = __shfl_sync(full, col[0], 0), c_hi = c_lo + 31;
-  // lowest start height of the rays still marching.  Rounding is monotone, so the lowest ray at
-  // step k is exactly fl(z0min + fl(k * dz)); a stale (too large) active set only makes it lower.
-  auto lowest = [&](unsigned act) -> float {
-    float zl = INFINITY;
-#pragma unroll
-    for (int i = 0; i < K; ++i) zl = ((act >> i) & 1u) ? fminf(zl, z0[i]) : zl;
-    return key_float(__reduce_min_sync(full, float_key(zl)));
-  };
-  if (!__any_sync(full, active != 0u)) return lit;
-  float z0min = lowest(active);
-  // step-rise pyramid of this direction's octant (gstep_kernel)
-  const int adr = abs(s.dr_fix), adc = abs(s.dc_fix);
-  const bool col_major = adc > adr;
-  const int octant = (col_major ? 4 : 0) | ((col_major ? s.dc_fix : s.dr_fix) < 0 ? 2 : 0) |
-                     ((col_major ? s.dr_fix : s.dc_fix) < 0 ? 1 : 0);
-  const bool rise_test = gstep != nullptr;                 // (off for rasters beyond +-16 km, where its margin is too small)
-  const float* __restrict__ gpyr = gstep + (size_t)octant * pyr_stride;
-  const float g_limit = s.dz - kGstepEps;                  // terrain rising less than this per step cannot catch a ray
-  int level = 0;
-  int k = 1;
-  while (k < 32768) {                                      // rasters are at most 32767 cells wide
-    const int n = kRayChunk << level;                      // steps covered by this test
-    const float zlow = __fadd_rn(z0min, __fmul_rn((float)k, s.dz));
-    if (zlow > zmax) break;                                // every ray is above the terrain maximum
-    const int ke = min(k + n - 1, 32767);                  // (k * Q16 step stays inside int32)
-    const int ro_a = (k * s.dr_fix + 32768) >> 16, ro_b = (ke * s.dr_fix + 32768) >> 16;
-    const int co_a = (k * s.dc_fix + 32768) >> 16, co_b = (ke * s.dc_fix + 32768) >> 16;
-    const int ro_min = min(ro_a, ro_b), co_min = min(co_a, co_b);
-    const int rmin = r_lo + ro_min, rmax = r_hi + max(ro_a, ro_b);
-    const int cmin = c_lo + co_min, cmax = c_hi + max(co_a, co_b);
-    // the patch left the grid for good (offsets are monotone in k)
-    if (r_hi + ro_a < 0 || r_lo + ro_a >= rows_full || c_hi + co_a < 0 || c_lo + co_a >= cols) break;
-    // (b) can these n steps hit anything?  Two conservative tests on the blocks (edge 16 << level)
-    // under the bounding box swept from step k - 1 to step k + n - 1 (at most 4 x 4 blocks):
-    //   lanes 0-15  the max pyramid: nothing in reach is as high as the LOWEST ray, or
-    //   lanes 16-31 the step-rise pyramid: nowhere in reach does the terrain rise as fast as the rays
-    //               (none of which has been hit so far), so it cannot catch up with any of them.
-    // One block per lane, one REDUX each.
-    {
-      const int kp = k - 1;
-      const int ro_p = (kp * s.dr_fix + 32768) >> 16, co_p = (kp * s.dc_fix + 32768) >> 16;
-      const int sh = 4 + level;
-      const int br0 = min(rmin, r_lo + ro_p) >> sh, br1 = max(rmax, r_hi + ro_p) >> sh;
-      const int bc0 = min(cmin, c_lo + co_p) >> sh, bc1 = max(cmax, c_hi + co_p) >> sh;
-      const int nbr = py.nbr[level], nbc = py.nbc[level];
-      float m = -INFINITY;
-      const int l16 = lane & 15;
-      const int br = br0 + (l16 >> 2), bc = bc0 + (l16 & 3);
-      if (br <= br1 && bc <= bc1) {
-        const int cr = min(max(br, -1), nbr), cc = min(max(bc, -1), nbc);
-        const float* __restrict__ src = lane < 16 ? pyr : gpyr;
-        if (lane < 16 || rise_test) m = __ldg(src + py.off[level] + (size_t)(cr + 1) * (nbc + 2) + (cc + 1));
-      }
-      const int key = float_key(m);
-      const int region_key = __reduce_max_sync(full, lane < 16 ? key : (int)0x80000000);
-      const int rise_key = __reduce_max_sync(full, lane < 16 ? (int)0x80000000 : key);
-      const bool fits = br1 - br0 <= 3 && bc1 - bc0 <= 3;
-      if (fits && (float_key(zlow) > region_key || (rise_test && rise_key <= float_key(g_limit)))) {
-        k += n;
-        level = min(level + 1, py.levels - 1);
-        continue;
-      }
-    }
-    if (level > 0) {                                       // look closer before touching the DEM
-      --level;
-      continue;
-    }
-    // (a) about to sample: retire rays that are outside the grid at step k or above the maximum
-    {
-      const float kdz_a = __fmul_rn((float)k, s.dz);
-#pragma unroll
-      for (int i = 0; i < K; ++i) {
-        const float zk = __fadd_rn(z0[i], kdz_a);
-        const bool in = (unsigned)(row[i] + ro_a) < (unsigned)rows_full && (unsigned)(col[i] + co_a) < (unsigned)cols;
-        if (!in || zk > zmax) active &= ~(1u << i);
-      }
-      if (!__any_sync(full, active != 0u)) break;
-    }
-#ifdef ENRGY_MARCH_STATS
-    {
-      const unsigned n_act = __reduce_add_sync(full, __popc(active));
-      unsigned any_rows = 0;
-#pragma unroll
-      for (int i = 0; i < K; ++i) any_rows |= __any_sync(full, (active >> i) & 1u) ? (1u << i) : 0u;
-      if (lane == 0) {
-        atomicAdd(&g_march_stats[0], 1ull);
-        atomicAdd(&g_march_stats[1], (unsigned long long)n_act);
-        atomicAdd(&g_march_stats[2], (unsigned long long)(K - __popc(any_rows)));
-        atomicAdd(&g_march_stats[4 + min((k - 1) / kRayChunk, 11)], 1ull);
-        atomicAdd(&g_march_stats[16 + min((int)n_act / 32, 8)], 1ull);
-      }
-    }
-#endif
-    // (c) stage the chunk's DEM window (kWinH rows x kWinW columns, 16-byte aligned origin) in this
-    // warp's shared-memory buffer with asynchronous 16 B copies (cp.async / LDGSTS: 10 per lane, no
-    // registers, all in flight together), then sample it: a sample is LDS [idx + i * row pitch].
-    // Measured alternatives (profiles/r01_summary.md): direct L1 loads cost 7 instructions per
-    // sample against 4 here; one TMA bulk copy per row (UBLKCP) serialises 24 single-lane issues
-    // per window; tensor-map TMA (UTMALDG) raises "illegal instruction" on this pool's driver even
-    // for the libcu++ reference example (scratch/tma_tensor_repro.cu).
-    const int x_buf = cmin + kDemApron;                    // column of the window origin in the buffer
-    const int x_al = x_buf & ~3;                           // 16-byte aligned source address
-    const int shift = x_buf - x_al;
-    __syncwarp();                                          // every lane is done with the previous window
-    {
-      // lane -> 16-byte column chunk (lane % 13) of the rows (lane / 13) + 2 * it; 26 lanes, 12 copies
-      // each, one 64-bit add per copy
-      constexpr int kChunksPerRow = kWinW / 4;             // 13 x 16 B
-      const int rr = lane >= kChunksPerRow ? 1 : 0, cc = lane - rr * kChunksPerRow;
-      const float* src = dem + ((long long)(rmin + rr) * dem_pitch + (x_al - kDemApron) + cc * 4);
-      const uint32_t dst = smem_u32(win + rr * kWinW + cc * 4);
-      const long long stride = 2LL * dem_pitch;
-      if (lane < 2 * kChunksPerRow) {
-#pragma unroll
-        for (int it = 0; it < kWinH / 2; ++it) {
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + it * (2 * kWinW * 4)), "l"(src + it * stride)
-                       : "memory");
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    // offsets of this lane's step of the chunk (lanes >= kRayChunk are not read)
-    const int kl = k + lane;
-    const int ro_l = (kl * s.dr_fix + 32768) >> 16;
-    const int co_l = (kl * s.dc_fix + 32768) >> 16;
-    const int ab_l = (ro_l - ro_min) * kWinW + (co_l - co_min) + shift;
-    const float kdz_l = __fmul_rn((float)kl, s.dz);        // rise of the ray at this lane's step
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
-    unsigned hit = 0u;
-    if (KEYS) {
-      int under[K];                                        // min over the chunk of (height bits - sample bits)
-#pragma unroll
-      for (int i = 0; i < K; ++i) under[i] = 0x7fffffff;
-      const int* wkeys = reinterpret_cast<const int*>(win) + lane;
-#pragma unroll(kRayUnroll < kRayChunk ? kRayUnroll : kRayChunk)
-      for (int j = 0; j < kRayChunk; ++j) {
-        // step j of the chunk: window offset and rise come from lane j (two shuffles, one LEA)
-        const int* p = wkeys + __shfl_sync(full, ab_l, j);
-        const float kdz = __shfl_sync(full, kdz_l, j);
-#pragma unroll
-        for (int i = 0; i < K; ++i) {
-          const float zk = __fadd_rn(z0[i], kdz);
-          under[i] = min(under[i], __float_as_int(zk) + p[i * kWinW]);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < K; ++i) hit |= (under[i] < 0) ? (1u << i) : 0u;
-    } else {
-      float over[K];                                       // max over the chunk of (sample - ray height)
-#pragma unroll
-      for (int i = 0; i < K; ++i) over[i] = -INFINITY;
-      const float* wlane = win + lane;
-#pragma unroll(kRayUnroll < kRayChunk ? kRayUnroll : kRayChunk)
-      for (int j = 0; j < kRayChunk; ++j) {
-        const float* p = wlane + __shfl_sync(full, ab_l, j);
-        const float kdz = __shfl_sync(full, kdz_l, j);
-#pragma unroll
-        for (int i = 0; i < K; ++i) {
-          const float smp = p[i * kWinW];
-          const float zk = __fadd_rn(z0[i], kdz);
-          // smp > zk  <=>  smp - zk > 0 (IEEE subtraction keeps the sign; NaN samples never count)
-          over[i] = fmaxf(over[i], __fsub_rn(smp, zk));
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < K; ++i) hit |= (over[i] > 0.0f) ? (1u << i) : 0u;
-    }
-    // samples of a retired ray do not count: it left the grid or cleared the terrain before
-    hit &= active;
-    lit &= ~hit;
-    active &= ~hit;
-    if (!__any_sync(full, active != 0u)) break;
-    z0min = lowest(active);
-    k += kRayChunk;
-  }
-  return lit;
-}
-
-// =================================================================================================
 // the fused energy-balance kernel
 // =================================================================================================
-// Warps per CTA.  The energy balance alone runs 8 warps that share one staged copy of the AWS
-// records (their end-of-time-block barrier costs ~1 % there).  With the shading ray march the
-// warps of a CTA finish their rays at very different times and a quarter of all stall samples sat
-// at that barrier (profiles/r01_summary.md), so every warp is its own CTA there: no coupling at
-// all, 7-8 independent warps per SM at up to 255 registers.
-#ifndef ENRGY_SHADOW_WARPS
-#define ENRGY_SHADOW_WARPS 1
-#endif
+// Warps per CTA: the warps of a CTA share one staged copy of the AWS records.
 #ifndef ENRGY_WARPS32
 #define ENRGY_WARPS32 4      // float32: 4 CTAs x 4 warps at 128 registers (profiles/r01_summary.md)
 #endif
@@ -864,31 +480,26 @@ __device__ __forceinline__ unsigned march(const float* __restrict__ dem, int dem
 #define ENRGY_WARPS64 4      // float64: 3 CTAs x 4 warps at 156 registers, no spills (profiles/r01_summary.md)
 #endif
 template <typename R, int INSOL>
-constexpr int kWarpsFor = insol_shadow(INSOL) ? ENRGY_SHADOW_WARPS : (sizeof(R) == 4 ? ENRGY_WARPS32 : ENRGY_WARPS64);
+constexpr int kWarpsFor = sizeof(R) == 4 ? ENRGY_WARPS32 : ENRGY_WARPS64;
 __host__ __device__ constexpr int warps_x(int w) { return w >= 4 ? 4 : w; }          // patches side by side in a tile
 
 // Shared-memory carve-up of a CTA.  The capacities of a time block (steps, sunlit sub-steps) are
-// run-time values chosen by the host: 64 / 256 for the energy balance alone, 16 / >= 64 with the
-// shading ray march, whose one-warp CTAs want many residents per SM rather than long time blocks.
+// run-time values chosen by the host (64 / 256, grown to the largest sub-step count of one step).
 template <typename R>
 struct SmemPlan {
-  int steps, subs, shades, slots, slots_m, full, win, total;   // byte offsets and the total size
+  int steps, subs, slots, slots_m, full, total;   // byte offsets and the total size
 };
 template <typename R>
-__host__ __device__ inline SmemPlan<R> smem_plan(int warps, int cap_steps, int cap_subs, bool with_subs,
-                                                 bool with_shades, bool msm) {
+__host__ __device__ inline SmemPlan<R> smem_plan(int warps, int cap_steps, int cap_subs, bool with_subs, bool msm) {
   SmemPlan<R> p;
   int o = 0;
   p.steps = o;   o += 2 * cap_steps * (int)sizeof(StepRec<R>);
   p.subs = o;    o += with_subs ? 2 * cap_subs * (int)sizeof(SubRec<R>) : 0;
-  p.shades = o;  o += with_shades ? 2 * cap_subs * (int)sizeof(ShadeRec) : 0;
   p.slots = o;   o += warps * cap_steps * kStatsK * (int)sizeof(R);
   p.slots_m = o; o += msm ? warps * cap_steps * kStatsM * (int)sizeof(R) : 0;
   o = (o + 15) / 16 * 16;
   p.full = o;    o += 16;
-  o = (o + 127) / 128 * 128;
-  p.win = o;     o += with_shades ? warps * kWinBytes : 0;
-  p.total = o;
+  p.total = (o + 127) / 128 * 128;
   return p;
 }
 
@@ -909,29 +520,21 @@ __host__ __device__ inline SmemPlan<R> smem_plan(int warps, int cap_steps, int c
 #ifndef ENRGY_SUB_UNROLL
 #define ENRGY_SUB_UNROLL 4
 #endif
-constexpr int kSubUnroll = ENRGY_SUB_UNROLL;   // unroll factor of the insolation sub-step loop (not with the inlined march)
-#ifndef ENRGY_MINB_SHADOW
-#define ENRGY_MINB_SHADOW 12
-#endif
+constexpr int kSubUnroll = ENRGY_SUB_UNROLL;   // unroll factor of the insolation sub-step loop
 template <typename R, int K, int INSOL, bool MSM, bool DUMP>
-__global__ void __launch_bounds__(32 * kWarpsFor<R, INSOL>, insol_shadow(INSOL)
-                                                            ? ENRGY_MINB_SHADOW
-                                                            : (sizeof(R) == 4 ? ENRGY_MINB32 : ENRGY_MINB64))
+__global__ void __launch_bounds__(32 * kWarpsFor<R, INSOL>, sizeof(R) == 4 ? ENRGY_MINB32 : ENRGY_MINB64)
 energy_balance_kernel(const KernelArgs<R> a) {
   constexpr int W = kWarpsFor<R, INSOL>;           // warps per CTA
   constexpr int WX = warps_x(W), WY = W / WX;      // patches of a tile: WX across, WY down
   constexpr int NT = 32 * W;                       // threads per CTA
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int cap_steps = a.cap_steps, cap_subs = a.cap_subs;
-  const SmemPlan<R> plan = smem_plan<R>(W, cap_steps, cap_subs, INSOL != kInsolStreamed, insol_shadow(INSOL), MSM);
+  const SmemPlan<R> plan = smem_plan<R>(W, cap_steps, cap_subs, INSOL != kInsolStreamed, MSM);
   StepRec<R>* const sm_steps = reinterpret_cast<StepRec<R>*>(smem_raw + plan.steps);     // [2][cap_steps]
   SubRec<R>* const sm_subs = reinterpret_cast<SubRec<R>*>(smem_raw + plan.subs);         // [2][cap_subs]
-  ShadeRec* const sm_shades = reinterpret_cast<ShadeRec*>(smem_raw + plan.shades);       // [2][cap_subs]
   R* const sm_slots = reinterpret_cast<R*>(smem_raw + plan.slots);                       // [W][cap_steps][kStatsK]
   R* const sm_slots_m = reinterpret_cast<R*>(smem_raw + plan.slots_m);                   // [W][cap_steps][kStatsM]
   uint64_t* const sm_full = reinterpret_cast<uint64_t*>(smem_raw + plan.full);           // [2]
-  // shading only: one DEM window per warp, behind the common layout
-  float* win_base = reinterpret_cast<float*>(smem_raw + plan.win);
 
   constexpr int TILE_H = WY * K, TILE_W = 32 * WX;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -944,9 +547,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
   }
   __syncthreads();
   unsigned phase[2] = {0u, 0u};
-  float* const my_win = win_base + (size_t)(tid >> 5) * (kWinBytes / sizeof(float));
 
-  const bool use_shades = insol_shadow(INSOL);
   auto issue_block = [&](int b, int buf) {
     // one elected thread: stage the per-step records (and sub-step records) of time block b
     const TimeBlock tb = a.blocks[b];
@@ -954,7 +555,6 @@ energy_balance_kernel(const KernelArgs<R> a) {
     const unsigned n_subs = (unsigned)(tb.sub_end - tb.sub_begin);
     unsigned bytes = n_steps * (unsigned)sizeof(StepRec<R>);
     if (INSOL != kInsolStreamed) bytes += n_subs * (unsigned)sizeof(SubRec<R>);
-    if (use_shades) bytes += n_subs * (unsigned)sizeof(ShadeRec);
     fence_proxy_async();
     mbar_expect_tx(&sm_full[buf], bytes);
     tma_bulk_g2s(sm_steps + buf * cap_steps, a.steps + tb.t_begin, n_steps * (unsigned)sizeof(StepRec<R>),
@@ -962,10 +562,6 @@ energy_balance_kernel(const KernelArgs<R> a) {
     if (INSOL != kInsolStreamed && n_subs) {
       tma_bulk_g2s(sm_subs + buf * cap_subs, a.subs + tb.sub_begin, n_subs * (unsigned)sizeof(SubRec<R>),
                    &sm_full[buf]);
-      if (use_shades) {
-        tma_bulk_g2s(sm_shades + buf * cap_subs, a.shades + tb.sub_begin, n_subs * (unsigned)sizeof(ShadeRec),
-                     &sm_full[buf]);
-      }
     }
   };
 
@@ -988,8 +584,6 @@ energy_balance_kernel(const KernelArgs<R> a) {
     const int row0 = tile.x * TILE_H + (warp / WX) * K;           // band-local row of cell 0
     const int colx = tile.y * TILE_W + (warp % WX) * 32 + lane;   // this lane's column
     V delta2[KP], pw2[KP], om2[KP], nx2[KP], ny2[KP], nz2[KP], swe2[KP], tic2[KP];
-    float z0[K];                   // shading: ray start heights
-    int rowf[K], col[K];           // shading: full-raster row, column
     R tl[K][NB];                   // sub-surface boundary temperatures [deg C] (MSM)
     // The reference's top boundary turns float64 after its first tick (NEP 50: float32 array +
     // float64 increment), so its round-off does not random-walk at float32 spacing; the float32
@@ -1005,14 +599,11 @@ energy_balance_kernel(const KernelArgs<R> a) {
       for (int h = 0; h < 2; ++h) {
         const int i = 2 * q + h;
         const int rowb = row0 + i;
-        col[i] = colx;
-        rowf[i] = rowb + a.band_row0;
         const size_t o = (size_t)rowb * a.pitch + colx;
         const bool inside = rowb < a.band_rows && colx < a.cols;
-        float z = inside ? __ldg(a.dem + (size_t)rowf[i] * a.dem_pitch + colx) : __int_as_float(0x7fc00000);
+        float z = inside ? __ldg(a.dem + (size_t)(rowb + a.band_row0) * a.dem_pitch + colx) : __int_as_float(0x7fc00000);
         const bool v = z == z;
         valid_bits |= v ? (1u << i) : 0u;
-        z0[i] = z;
         if (!v) z = (float)a.elev_aws;           // keep the arithmetic of masked cells finite
         d_[h] = (R)z - a.elev_aws;               // var_classes.py:114
         p_[h] = Num<R>::pow10(-d_[h] / (R)kVapourScale);   // var_classes.py:162
@@ -1063,6 +654,13 @@ energy_balance_kernel(const KernelArgs<R> a) {
     }
     keep_in_register(valid_bits);
     const bool patch_full = __all_sync(0xffffffffu, valid_bits == ((1u << K) - 1u));
+    // sunlit masks of this patch (INSOL == kInsolMasked): word of its 32 columns, its K rows
+    const unsigned lane_bit = 1u << lane;
+    const unsigned* const mask_patch =
+        INSOL == kInsolMasked
+            ? a.masks + ((size_t)(row0 >> 3) * a.mask_words + (size_t)((colx - lane) >> 5)) * 8 + (row0 & 7) -
+                  (size_t)a.mask_sub0 * a.mask_sub_stride
+            : nullptr;
 
     int buf = 0;
     if (tid == 0) issue_block(a.block_begin, 0);
@@ -1420,39 +1018,30 @@ energy_balance_kernel(const KernelArgs<R> a) {
             V c2[KP];
 #pragma unroll
             for (int q = 0; q < KP; ++q) c2[q] = fma2(ny2[q], n2, fma2(nx2[q], e2, u2));
-            unsigned lit = 0xffffffffu;
-            if (insol_shadow(INSOL)) {
-              // production runs skip cells that face away from the sun (direct beam = 0 whatever
-              // the mask says); the mask dump marches every glacier cell
-              unsigned start_bits = valid_bits;
-              if (!(DUMP && a.mask_out != nullptr)) {
-#pragma unroll
-                for (int q = 0; q < KP; ++q) {
-                  if (!(c2[q].lo() > (R)0)) start_bits &= ~(1u << (2 * q));
-                  if (!(c2[q].hi() > (R)0)) start_bits &= ~(1u << (2 * q + 1));
-                }
-              }
-              constexpr bool KEYS = INSOL == kInsolShadowKeys;
-              lit = march<K, KEYS>(KEYS ? reinterpret_cast<const float*>(a.dem_keys) : a.dem, a.dem_pitch, my_win,
-                                   a.rows_full, a.cols, a.blockmax, a.gstep, a.pyr_stride, a.pyramid, rowf, col, z0,
-                                   start_bits,
-                                   sm_shades[buf * cap_subs + j], (float)a.zmax, lane);
-              if (DUMP && a.mask_out != nullptr && t == a.t0) {
-#pragma unroll
-                for (int i = 0; i < K; ++i) {
-                  const unsigned word = __ballot_sync(0xffffffffu, (lit >> i) & 1u);
-                  if (lane == 0 && row0 + i < a.band_rows && colx < a.cols) {
-                    a.mask_out[((size_t)(j - j0) * a.band_rows + (row0 + i)) * a.mask_words + (colx >> 5)] = word;
-                  }
-                }
+            // sunlit bits of the patch's K rows for this sub-step: K consecutive words of the interleaved
+            // mask layout [sub-step][row / 8][column word][row % 8] written by the line sweep (shade.cu);
+            // the address is warp-uniform (one 32-byte sector per patch and sub-step), bit = lane
+            unsigned mw[K];
+            if (INSOL == kInsolMasked) {
+              const unsigned* mp = mask_patch + (size_t)(tb.sub_begin + j) * a.mask_sub_stride;
+              if (K == 8) {
+                const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mp)), m1 = __ldg(reinterpret_cast<const uint4*>(mp) + 1);
+                mw[0] = m0.x; mw[1] = m0.y; mw[2 % K] = m0.z; mw[3 % K] = m0.w;
+                mw[4 % K] = m1.x; mw[5 % K] = m1.y; mw[6 % K] = m1.z; mw[7 % K] = m1.w;
+              } else if (K == 4) {
+                const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mp));
+                mw[0] = m0.x; mw[1] = m0.y; mw[2 % K] = m0.z; mw[3 % K] = m0.w;
+              } else {
+                const uint2 m0 = __ldg(reinterpret_cast<const uint2*>(mp));
+                mw[0] = m0.x; mw[1] = m0.y;
               }
             }
 #pragma unroll
             for (int q = 0; q < KP; ++q) {
               R c_lo = fmax_(c2[q].lo(), (R)0), c_hi = fmax_(c2[q].hi(), (R)0);
-              if (insol_shadow(INSOL)) {
-                c_lo = ((lit >> (2 * q)) & 1u) ? c_lo : (R)0;
-                c_hi = ((lit >> (2 * q + 1)) & 1u) ? c_hi : (R)0;
+              if (INSOL == kInsolMasked) {
+                c_lo = (mw[2 * q] & lane_bit) ? c_lo : (R)0;
+                c_hi = (mw[2 * q + 1] & lane_bit) ? c_hi : (R)0;
               }
               direct2[q] = fma2(b2, V::make(c_lo, c_hi), direct2[q]);
             }
@@ -1460,8 +1049,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
           // hourly rows carry four sunlit sub-steps by day.  That case is straight-line code followed by
           // its own copy of the balance, so that insolation and balance of a step form one basic block
           // (the records load ahead, the chains of consecutive sub-steps and the first reciprocals of
-          // the balance interleave); every other count takes the loop.  With the ray march inlined in
-          // the sub-step only the loop exists.
+          // the balance interleave); every other count takes the loop.
           if (kAnalyticBeam && patch_g2 < s.tan2_min) {
             // the sun stands above every slope of the patch in every sub-step of the row:
             // max(cos i, 0) = cos i, and the sum over the sub-steps collapses to the row's three sums
@@ -1470,11 +1058,11 @@ energy_balance_kernel(const KernelArgs<R> a) {
 #pragma unroll
             for (int q = 0; q < KP; ++q) direct2[q] = fma2(ny2[q], dn, fma2(nx2[q], de, du));
             finish_step();
-          } else if (!insol_shadow(INSOL) && nj == 4) {
+          } else if (nj == 4) {
             sub_step(j0); sub_step(j0 + 1); sub_step(j0 + 2); sub_step(j0 + 3);
             finish_step();
           } else {
-#pragma unroll(insol_shadow(INSOL) ? 1 : kSubUnroll)
+#pragma unroll(kSubUnroll)
             for (int j = j0; j < j0 + nj; ++j) sub_step(j);
             finish_step();
           }
@@ -1540,7 +1128,8 @@ struct CellsPerThread {
 template <typename R>
 void energy_balance_tile(bool msm, int insol, int* tile_h, int* tile_w) {
   const int k = msm ? CellsPerThread<R, true>::value : CellsPerThread<R, false>::value;
-  const int w = insol_shadow(insol) ? kWarpsFor<R, kInsolShadow> : kWarpsFor<R, kInsolComputed>;
+  (void)insol;
+  const int w = kWarpsFor<R, kInsolComputed>;
   *tile_w = 32 * warps_x(w);
   *tile_h = (w / warps_x(w)) * k;
 }
@@ -1551,8 +1140,7 @@ template <typename R, int INSOL, bool MSM, bool DUMP>
 static cudaError_t configure(int sm_count, int cap_steps, int cap_subs, LaunchInfo* info) {
   constexpr int K = CellsPerThread<R, MSM>::value;
   auto kern = energy_balance_kernel<R, K, INSOL, MSM, DUMP>;
-  const int smem = smem_plan<R>(kWarpsFor<R, INSOL>, cap_steps, cap_subs, INSOL != kInsolStreamed,
-                                insol_shadow(INSOL), MSM).total;
+  const int smem = smem_plan<R>(kWarpsFor<R, INSOL>, cap_steps, cap_subs, INSOL != kInsolStreamed, MSM).total;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
@@ -1590,10 +1178,10 @@ template <typename R, typename F>
 static cudaError_t dispatch(int insol, bool msm, bool dump, F&& f) {
 #define ENRGY_CASE(I, M, D) \
   if (insol == I && msm == M && dump == D) return f(std::integral_constant<int, I>{}, std::integral_constant<bool, M>{}, std::integral_constant<bool, D>{});
-  ENRGY_CASE(0, false, false) ENRGY_CASE(1, false, false) ENRGY_CASE(2, false, false) ENRGY_CASE(3, false, false)
-  ENRGY_CASE(0, true, false) ENRGY_CASE(1, true, false) ENRGY_CASE(2, true, false) ENRGY_CASE(3, true, false)
-  ENRGY_CASE(0, false, true) ENRGY_CASE(1, false, true) ENRGY_CASE(2, false, true) ENRGY_CASE(3, false, true)
-  ENRGY_CASE(0, true, true) ENRGY_CASE(1, true, true) ENRGY_CASE(2, true, true) ENRGY_CASE(3, true, true)
+  ENRGY_CASE(0, false, false) ENRGY_CASE(1, false, false) ENRGY_CASE(2, false, false)
+  ENRGY_CASE(0, true, false) ENRGY_CASE(1, true, false) ENRGY_CASE(2, true, false)
+  ENRGY_CASE(0, false, true) ENRGY_CASE(1, false, true) ENRGY_CASE(2, false, true)
+  ENRGY_CASE(0, true, true) ENRGY_CASE(1, true, true) ENRGY_CASE(2, true, true)
 #undef ENRGY_CASE
   return cudaErrorInvalidValue;
 }
@@ -1818,11 +1406,6 @@ __global__ void finalize_stats_kernel(const FinalizeArgs f) {
   }
 }
 
-#ifdef ENRGY_MARCH_STATS
-extern "C" int enrgy_debug_march_stats(unsigned long long* out) {
-  return (int)cudaMemcpyFromSymbol(out, g_march_stats, sizeof(g_march_stats));
-}
-#endif
 cudaError_t launch_finalize(const FinalizeArgs& f, cudaStream_t stream) {
   if (f.n_steps <= 0) return cudaSuccess;
   finalize_stats_kernel<<<(f.n_steps + 3) / 4, 128, 0, stream>>>(f);      // four steps (warps) per block

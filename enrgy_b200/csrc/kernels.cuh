@@ -9,17 +9,7 @@ namespace enrgy {
 // insolation source of the fused kernel (template parameter)
 constexpr int kInsolStreamed = 0;  // per-step kWh m-2 raster streamed from HBM
 constexpr int kInsolComputed = 1;  // terrain normal . sun vector per sub-step, no shadows
-constexpr int kInsolShadow = 2;    // ... with the ray-marched sunlit mask
-constexpr int kInsolShadowKeys = 3;  // ... the same, sampling the integer copy of the DEM (no negative elevations)
-__host__ __device__ constexpr bool insol_shadow(int insol) { return insol >= kInsolShadow; }
-
-// Max pyramid of the DEM: level l holds the max of the valid cells of every (16 << l)^2 block as
-// [(nbr + 2)][(nbc + 2)] floats with one ring of -inf blocks, at offset off[l] of one buffer.
-constexpr int kMaxPyramidLevels = 12;   // 16 << 11 = 32768 >= the largest raster edge
-struct MaxPyramid {
-  int levels;
-  int off[kMaxPyramidLevels], nbr[kMaxPyramidLevels], nbc[kMaxPyramidLevels];
-};
+constexpr int kInsolMasked = 2;    // ... times the sunlit mask of the sub-step (line sweep, shade.cu)
 
 template <typename R>
 struct KernelArgs {
@@ -30,11 +20,12 @@ struct KernelArgs {
   const float* dem;               // full DEM (replicated for shading), pointing at cell (0, 0) of a
                                   // buffer with a NaN apron of kDemApron cells on every side
   int dem_pitch;                  // row stride of the DEM buffer
-  const int* dem_keys;            // same layout: -(bit pattern) of every valid cell, +1 for NaN (dem_key_kernel)
-  const float* blockmax;          // max pyramid of the DEM (shading early exit), see MaxPyramid
-  MaxPyramid pyramid;
-  const float* gstep;             // 8 step-rise pyramids (one per ray octant, same layout), see gstep_kernel
-  int pyr_stride;                 // floats per pyramid
+  // sunlit masks (kInsolMasked): bit-packed, [sub-step][band_rows_pad / 8][mask_words][8] uint32 -- the 8
+  // rows of a row group are adjacent, so a warp patch (32 columns x K <= 8 rows) reads one 32-byte sector
+  const unsigned* masks;
+  int mask_sub0;                  // global index (over all sunlit sub-steps of the run) of the first mask
+  int mask_words;                 // column words per row = pitch / 32
+  size_t mask_sub_stride;         // words between consecutive sub-steps
   const R* nx;                    // [band_rows_pad][pitch] terrain normal (computed insolation)
   const R* ny;
   const R* nz;
@@ -44,7 +35,6 @@ struct KernelArgs {
   R albedo_ice, albedo_snow, max_ice_albedo;
   R albedo_offset;                // ensemble member: added to the map values, clipped to [0.001, 1]
   R elev_aws;
-  R zmax;                         // max of the valid DEM, as float exactly
   // state, band-local [band_rows_pad][pitch]
   R* swe;
   R* total_snow;
@@ -60,7 +50,6 @@ struct KernelArgs {
   // tables
   const StepRec<R>* steps;        // [n_steps]
   const SubRec<R>* subs;          // [n_subs]
-  const ShadeRec* shades;         // [n_subs]
   const TimeBlock* blocks;        // [n_blocks] covering at least [t0, t1)
   int cap_steps, cap_subs;        // capacities the time blocks were cut for (smem staging buffers)
   int block_begin, block_end;     // blocks to process
@@ -73,9 +62,6 @@ struct KernelArgs {
   // dump mode: [t1 - t0][ENRGY_D_COUNT][band_rows_pad][pitch] R (may be null)
   R* dump;
   size_t dump_field_stride;
-  // shade-mask dump: [n_sub][band_rows][words] bit masks of step t0 (may be null)
-  unsigned* mask_out;
-  int mask_words;
 };
 
 struct FinalizeArgs {
@@ -95,17 +81,9 @@ struct FinalizeArgs {
 
 // launch helpers (defined in kernels.cu); all asynchronous on `stream`
 template <typename R>
-cudaError_t launch_terrain(const float* dem, int dem_pitch, int rows_full, int cols, int pitch,
+cudaError_t launch_terrain(const float* dem, const float* terrain, int dem_pitch, int rows_full, int cols, int pitch,
                            int band_row0, int band_rows_pad, double cell, R* nx, R* ny, R* nz,
                            cudaStream_t stream);
-cudaError_t launch_blockmax(const float* dem, int dem_pitch, int rows_full, int cols, const MaxPyramid& py,
-                            float* buffer, cudaStream_t stream);
-// integer copy of the DEM buffer for the shading samples + min of the valid cells (as float bits key)
-cudaError_t launch_dem_keys(const float* dem_buf, int* key_buf, size_t n, int* min_key /*device, preset INT_MAX*/,
-                            cudaStream_t stream);
-// step-rise pyramids of the 8 ray octants: buffer[oct * stride + pyramid layout], stride = floats per pyramid
-cudaError_t launch_gstep(const float* dem, int dem_pitch, int rows_full, int cols, const MaxPyramid& py, int stride,
-                         float* buffer, cudaStream_t stream);
 cudaError_t launch_tile_scan(const float* dem, int pitch, int band_row0, int band_rows, int cols,
                              int tile_h, int tile_w, int tiles_r, int tiles_c, int* counts,
                              cudaStream_t stream);
@@ -145,6 +123,46 @@ cudaError_t launch_msm_init(const float* dem, int dem_pitch, int pitch, int band
                             size_t layer_stride, cudaStream_t stream);
 
 cudaError_t launch_finalize(const FinalizeArgs& f, cudaStream_t stream);
+
+// ---- shading line sweep (shade.cu) ---------------------------------------------------------------
+// Scan copy of the terrain: float [na + 2 * kScanRowApron][pitch_s] with -inf for NaN cells and in the
+// aprons (kScanRowApron rows above and below, kScanColApron columns left and right), so the sweep
+// needs no bounds checks.  The transposed copy serves the column-type sub-steps.
+constexpr int kScanRowApron = 8;
+constexpr int kScanColApron = 288;
+inline int scan_pitch(int nb) { return (nb + 31) / 32 * 32 + 2 * kScanColApron; }
+inline size_t scan_elems(int na, int nb) { return (size_t)(na + 2 * kScanRowApron) * scan_pitch(nb); }
+// src: [rows][cols] device raster with row stride src_pitch (NaN = no terrain)
+cudaError_t launch_scan_prepare(const float* src, int src_pitch, int rows, int cols, float* scan, float* scan_t,
+                                cudaStream_t stream);
+
+struct SweepSub {            // one sunlit sub-step to sweep
+  int32_t dfix;              // Q16 step of the minor coordinate per step along the sweep axis
+  int32_t sigma;             // u = sigma * (index along the sweep axis) grows toward the sun
+  double dz;                 // rise of the rays per step [m] (the float32 of the ShadeRec, exactly)
+  int32_t out;               // row type: index of the sub-step in the output chunk; column type: index in tmp
+  int32_t out2;              // column type: index of the sub-step in the output chunk (transpose target)
+};
+constexpr int kMaxSweepSegs = 8;
+struct SweepSeg {            // rows [row0, row0 + rows) of the raster go to a band-local mask array at ptr
+  int32_t row0, rows;        // (row0 and rows multiples of 8, except the last segment's end)
+  int32_t rg;                // row groups of the destination = rows_pad / 8
+  int32_t words;             // column words per row of the destination
+  unsigned* ptr;             // [n_sub][rg][words][8]
+};
+struct SweepArgs {
+  const float* scan;         // cell (0, 0) of the scan copy swept along its rows (row type) ...
+  const float* scan_t;       // ... and of the transposed copy (column type)
+  int rows, cols;            // raster
+  const SweepSub* row_subs; int n_row_subs;
+  const SweepSub* col_subs; int n_col_subs;
+  int n_seg;
+  SweepSeg seg[kMaxSweepSegs];
+  unsigned* tmp;             // column type: [n_col_subs][cols][tmp_words] (bit = row % 32 of word row / 32)
+  int tmp_words;             // round_up(ceil(rows / 32), 8)
+};
+inline int sweep_tmp_words(int rows) { return ((rows + 31) / 32 + 7) / 8 * 8; }
+cudaError_t launch_sweep(const SweepArgs& a, int sm_count, cudaStream_t stream, int* n_launches);
 cudaError_t launch_microbench(int kind, int sm_count, int iters, void* scratch, double* ops_per_launch,
                               cudaStream_t stream);
 

@@ -156,19 +156,23 @@ void host_normal(const float* nb, double cell, double* nx, double* ny, double* n
   *nz = inv;
 }
 
-// the shading specification for ONE cell on the host (float32 + integers, see common.cuh)
-bool host_lit(const float* dem, int rows, int cols, int r, int c, const ShadeRec& s, float zmax) {
-  if (!std::isfinite(s.dz)) return true;
-  const float z0 = dem[(size_t)r * cols + c];
+// the shading specification for ONE cell on the host: the ray of the cell marched along its scan line
+// (oracle/insolation_oracle.py:trace_cells; the device sweeps whole lines, shade.cu)
+bool host_lit(const float* dem, int rows, int cols, int r, int c, const ShadeRec& s) {
+  if (!std::isfinite(s.dz) || (s.dc_fix == 0 && s.dr_fix == 0)) return true;
+  bool row_type; int sigma, dfix;
+  line_geometry(s.dc_fix, s.dr_fix, &row_type, &sigma, &dfix);
+  const double dz = (double)s.dz;
+  const int u0 = sigma * (row_type ? r : c);
+  const int line = (row_type ? c : r) - shear_q16(u0, dfix);
+  const double g0 = (double)dem[(size_t)r * cols + c] - (double)u0 * dz;
   for (int k = 1;; ++k) {
-    const int rr = r + ((k * s.dr_fix + 32768) >> 16);
-    const int cc = c + ((k * s.dc_fix + 32768) >> 16);
+    const int u = u0 + k;
+    const int major = sigma * u, minor = line + shear_q16(u, dfix);
+    const int rr = row_type ? major : minor, cc = row_type ? minor : major;
     if (rr < 0 || rr >= rows || cc < 0 || cc >= cols) return true;
-    volatile float prod = (float)k * s.dz;   // one rounded multiply, one rounded add
-    const float zk = z0 + prod;
-    if (zk > zmax) return true;
     const float smp = dem[(size_t)rr * cols + cc];
-    if (smp > zk) return false;
+    if (smp == smp && (double)smp - (double)u * dz > g0) return false;
   }
 }
 
@@ -185,9 +189,6 @@ int run_prepass(const PrepassInput& in, PrepassOutput& out, std::string& err) {
   out.sub_count.assign(T, 0);
   out.blocks.clear();
   out.point.assign((size_t)T * ENRGY_P_COUNT, 0.0);
-
-  const float zmax = in.zmax;
-  out.zmax = zmax;
 
   if (p.aws_row < 0 || p.aws_row >= in.rows || p.aws_col < 0 || p.aws_col >= in.cols) {
     err = "AWS cell outside the raster";
@@ -328,7 +329,7 @@ int run_prepass(const PrepassInput& in, PrepassOutput& out, std::string& err) {
         }
         const double cosi = nx * sb.e + ny * sb.n + nz * sb.u;
         double term = sb.b * std::max(cosi, 0.0);
-        if (p.shadow && !host_lit(in.dem, in.rows, in.cols, p.aws_row, p.aws_col, sb.shade, zmax)) {
+        if (p.shadow && !host_lit(in.dem, in.rows, in.cols, p.aws_row, p.aws_col, sb.shade)) {
           term = 0.0;
         }
         direct = direct + term;

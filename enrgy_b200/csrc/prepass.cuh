@@ -31,7 +31,6 @@ struct PrepassInput {
   int rows, cols;          // full raster
   const float* dem;        // full host DEM [rows][cols]; only needed (non-null) for the shading ray of the AWS cell
   float nbhd[9];           // DEM at the AWS cell and its 8 neighbours (row-major 3 x 3, NaN outside the grid)
-  float zmax;              // max of the valid DEM (top of the device max pyramid)
   int cap_steps = kStepsPerBlock;   // time-block capacities (smem staging buffers of the kernel)
   int cap_subs = kSubsPerBlock;     // ... grown to the largest sub-step count of a single step
   int n_steps;
@@ -51,7 +50,6 @@ struct PrepassOutput {
   std::vector<TimeBlock> blocks;
   int cap_steps = 0, cap_subs = 0;        // capacities the blocks were cut for
   std::vector<double> point;              // [n_steps][ENRGY_P_COUNT]
-  float zmax = 0.f;                       // max of the valid DEM (ray termination)
 };
 
 // Returns 0 or an ENRGY_ERR_* code with a message in err.

@@ -38,7 +38,7 @@ def make_params(*, cell_size, elev_aws, aws_row, aws_col, sensor_z=2.0, zm=None,
     p.snow_density = nan if snow_density is None else snow_density
     p.ice_density = nan if ice_density is None else ice_density
     p.insol_mode = int(insol_mode)
-    p.shadow = int(shadow) if shadow in (0, 1, 2) else (1 if shadow else 0)   # 2: float-sample march
+    p.shadow = 1 if shadow else 0
     p.lat_deg, p.lon_deg = float(lat), float(lon)
     p.solar_const = nan if solar_const is None else solar_const
     p.transmittance = nan if transmittance is None else transmittance
@@ -94,6 +94,13 @@ class Engine:
         dem = _f32c(dem)
         assert dem.shape == (self.rows, self.cols), dem.shape
         check(self.lib.enrgy_set_dem(self.h, dem.ctypes.data))
+
+    def set_terrain(self, terrain):
+        """The uncropped terrain on the model grid (shadow casters and slopes outside the glacier
+        outline); see enrgy_set_terrain."""
+        terrain = _f32c(terrain)
+        assert terrain.shape == (self.rows, self.cols), terrain.shape
+        check(self.lib.enrgy_set_terrain(self.h, terrain.ctypes.data))
 
     def set_albedo_maps(self, maps):
         maps = [_f32c(m) for m in maps]
@@ -158,6 +165,33 @@ class Engine:
 
     def run_async(self, t0, t1, d_stats_ptr=None, stream_ptr=None):
         check(self.lib.enrgy_run_async(self.h, int(t0), int(t1), d_stats_ptr, stream_ptr))
+
+    # ---- shading as separate steps (parallel.ShardedRun) ---------------------------------------
+    def sub_range(self, t0, t1):
+        a, b = C.c_int(0), C.c_int(0)
+        check(self.lib.enrgy_sub_range(self.h, int(t0), int(t1), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def mask_words(self, rows):
+        """uint32 words per sub-step of a mask array for a band of `rows` rows."""
+        return int(self.lib.enrgy_mask_words(self.h, int(rows)))
+
+    def shade_scan(self, sub0, sub1, segments, stream_ptr=None):
+        """Sweeps the sub-steps [sub0, sub1) over the full raster; segments = [(row0, rows, device_ptr)]."""
+        n = len(segments)
+        r0 = (C.c_int * n)(*[int(s[0]) for s in segments])
+        nr = (C.c_int * n)(*[int(s[1]) for s in segments])
+        ptr = (C.c_void_p * n)(*[int(s[2]) for s in segments])
+        check(self.lib.enrgy_shade_scan(self.h, int(sub0), int(sub1), n, r0, nr, ptr, stream_ptr))
+
+    def run_masked(self, t0, t1, d_masks_ptr, d_stats_ptr=None, stream_ptr=None):
+        check(self.lib.enrgy_run_masked(self.h, int(t0), int(t1), d_masks_ptr, d_stats_ptr, stream_ptr))
+
+    def set_mask_budget(self, n_bytes):
+        check(self.lib.enrgy_set_mask_budget(self.h, int(n_bytes)))
+
+    def last_sweep_ms(self):
+        return float(self.lib.enrgy_last_sweep_ms(self.h))
 
     def synchronize(self):
         check(self.lib.enrgy_synchronize(self.h))

@@ -1,10 +1,17 @@
 """Multi-GPU plumbing: one process per GPU, the raster cut into row bands.
 
-Cells are independent once the AWS-cell pre-pass has produced the per-step scalars, so the data
-path needs NO collective: every rank gets the full DEM (replicated, for the shading rays) and its
-own band of the albedo / SWE / state rasters.  The only exchange is the sum of the per-step area
-statistics (`[T, S_COUNT]` float64 sums and counts) -- one all-reduce per pass, NCCL for CUDA
-tensors (NVLink/NVSwitch), gloo on the CPU in the tests.
+Cells are independent once the AWS-cell pre-pass has produced the per-step scalars, so the energy
+balance needs NO collective: every rank runs the fused kernel on its own band of the albedo / SWE /
+state rasters, and the only exchange is the sum of the per-step area statistics (`[T, S_COUNT]`
+float64 sums and counts) -- one all-reduce per pass, NCCL for CUDA tensors (NVLink/NVSwitch), gloo on
+the CPU in the tests.
+
+Topographic shading is the one step that is NOT local to a band: a scan line runs through the whole
+raster, so the sunlit mask of a band depends on terrain in every other band.  The sweep therefore
+shards along a different axis -- the sunlit SUB-STEPS, which are independent of each other and cost
+the same whatever the terrain: every rank sweeps the full (replicated) terrain for 1/N of the
+sub-steps and an all-to-all over NVLink hands every rank the rows of its own band
+(`ShardedShading`).  Per cell and sub-step that exchange moves one bit.
 """
 from __future__ import annotations
 
@@ -25,6 +32,9 @@ def row_bands(rows, world, align=16, valid_per_row=None):
         weights = np.asarray(valid_per_row, dtype=np.float64)
         if weights.shape != (rows,):
             raise ValueError("valid_per_row must have one entry per raster row")
+    if rows < world * align:
+        # (an empty band would read as "whole raster" at the C ABI and double count the statistics)
+        raise ValueError("%d rows cannot give %d bands of at least %d rows" % (rows, world, align))
     cum = np.concatenate([[0.0], np.cumsum(weights)])
     total = cum[-1]
     edges = [0]
@@ -32,7 +42,8 @@ def row_bands(rows, world, align=16, valid_per_row=None):
         target = total * r / world
         e = int(np.searchsorted(cum, target))
         e = int(round(e / align)) * align
-        e = min(max(e, edges[-1]), rows)
+        # every band keeps at least `align` rows, also where the glacier occupies a few rows only
+        e = min(max(e, edges[-1] + align), rows - (world - r) * align)
         edges.append(e)
     edges.append(rows)
     return [(edges[i], edges[i + 1] - edges[i]) for i in range(world)]
@@ -68,6 +79,92 @@ def rebalance_bands(bands, seconds, valid_per_row, align=16):
         if n > 0:
             cost[r0:r0 + n] = (w[r0:r0 + n] * (float(t) / tot)) if tot > 0 else 0.0
     return row_bands(rows, len(bands), align=align, valid_per_row=cost)
+
+
+def split_even(lo, hi, parts):
+    """[lo, hi) cut into `parts` contiguous ranges whose sizes differ by at most one."""
+    n = hi - lo
+    edges = [lo + (n * p) // parts for p in range(parts + 1)]
+    return [(edges[p], edges[p + 1]) for p in range(parts)]
+
+
+def plan_step_chunks(sub_counts, t0, t1, max_subs):
+    """Steps [t0, t1) cut into chunks of at most max_subs sunlit sub-steps (at least one step each)."""
+    out, t = [], t0
+    while t < t1:
+        e, n = t, 0
+        while e < t1 and (e == t or n + sub_counts[e] <= max_subs):
+            n += sub_counts[e]
+            e += 1
+        out.append((t, e))
+        t = e
+    return out
+
+
+class ShardedShading:
+    """Row-band run WITH shading over `world` ranks (one Engine per rank, every one loaded with the
+    full terrain and its own band): per chunk of rows
+      1. rank p sweeps sub-steps p/N .. (p+1)/N of the chunk over the full raster, writing the rows of
+         band q into the q-th segment of its send buffer (enrgy_shade_scan),
+      2. one all_to_all_single (NCCL over NVLink) delivers to every rank the masks of ITS band for all
+         sub-steps of the chunk, already in the order the fused kernel reads them,
+      3. the fused kernels run on the band with these masks (enrgy_run_masked).
+    With world == 1 the sweep writes straight into the receive buffer.  Everything is enqueued on the
+    caller's torch stream; nothing synchronises the host."""
+
+    def __init__(self, engine, bands, rank, world, group=None, budget_bytes=8 << 30):
+        import torch
+        self.torch = torch
+        self.eng, self.bands, self.rank, self.world, self.group = engine, list(bands), int(rank), int(world), group
+        if len(self.bands) != self.world:
+            raise ValueError("one band per rank")
+        if any(r0 % 8 for r0, _ in self.bands):
+            raise ValueError("band starts must be multiples of 8 rows")
+        self.words = [engine.mask_words(n) for _, n in self.bands]       # uint32 per sub-step and band
+        self.budget = int(budget_bytes)
+        self.send = self.recv = None
+        self.exchange_bytes = 0
+
+    def _buffers(self, n_send_words, n_recv_words):
+        torch = self.torch
+        if self.send is None or self.send.numel() < n_send_words:
+            self.send = torch.empty(max(n_send_words, 1), dtype=torch.int32, device="cuda")
+        if self.recv is None or self.recv.numel() < n_recv_words:
+            self.recv = torch.empty(max(n_recv_words, 1), dtype=torch.int32, device="cuda")
+
+    def chunks(self, t0, t1, sub_counts):
+        per_sub = 4 * (sum(self.words) // self.world + self.words[self.rank]) + 1
+        return plan_step_chunks(sub_counts, t0, t1, max(1, self.budget // per_sub))
+
+    def run(self, t0, t1, d_stats_ptr, stream, sub_counts):
+        """Steps [t0, t1): statistics of this band into the device array at d_stats_ptr ([t1 - t0, S_COUNT]
+        float64, NOT yet reduced over ranks).  `stream` is the torch.cuda.Stream everything runs on."""
+        torch = self.torch
+        eng, me, world = self.eng, self.rank, self.world
+        sp = stream.cuda_stream
+        for (c0, c1) in self.chunks(t0, t1, sub_counts):
+            s0, s1 = eng.sub_range(c0, c1)
+            shares = split_even(s0, s1, world)
+            a, b = shares[me]
+            in_split = [(b - a) * w for w in self.words]                         # what I send to rank q
+            out_split = [(hi - lo) * self.words[me] for lo, hi in shares]        # what rank p sends me
+            self._buffers(sum(in_split), sum(out_split))
+            if world == 1:
+                eng.shade_scan(a, b, [(self.bands[0][0], self.bands[0][1], self.recv.data_ptr())], sp)
+            else:
+                segs, off = [], 0
+                for (r0, n), w in zip(self.bands, in_split):
+                    segs.append((r0, n, self.send.data_ptr() + 4 * off))
+                    off += w
+                if b > a:
+                    eng.shade_scan(a, b, segs, sp)
+                with torch.cuda.stream(stream):
+                    import torch.distributed as dist
+                    dist.all_to_all_single(self.recv[:sum(out_split)], self.send[:sum(in_split)], out_split, in_split,
+                                           group=self.group)
+                self.exchange_bytes += 4 * (sum(in_split) - in_split[me])
+            stats_ptr = None if d_stats_ptr is None else d_stats_ptr + 8 * _lib.S_COUNT * (c0 - t0)
+            eng.run_masked(c0, c1, self.recv.data_ptr(), stats_ptr, sp)
 
 
 def allreduce_stats(stats):

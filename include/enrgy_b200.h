@@ -129,9 +129,7 @@ typedef struct enrgy_params {
   double ice_density;    /* NaN = 900 */
   /* --- insolation (saga_lighting.py:42-44 options) --- */
   int32_t insol_mode;    /* ENRGY_INSOL_* */
-  int32_t shadow;        /* 1 = topographic shading ray march (SAGA -SHADOW); 2 = the same, forcing the
-                            float-sample variant of the march (the default picks it only for DEMs with
-                            negative elevations; masks are identical either way) */
+  int32_t shadow;        /* != 0: topographic shading (SAGA -SHADOW), a line sweep over the terrain per sub-step */
   double lat_deg;        /* grid reference latitude / longitude for the sun position */
   double lon_deg;
   double solar_const;    /* NaN = 1367 */
@@ -166,6 +164,12 @@ int enrgy_set_params(enrgy_ctx* ctx, const enrgy_params* p);
  * raster even for a row band (it is replicated for the shading rays; without shading only
  * the band and one row on either side are copied to the device). */
 int enrgy_set_dem(enrgy_ctx* ctx, const float* dem);
+/* optional: the UNCROPPED terrain on the model grid, [rows][cols], NaN = no terrain.  The reference
+ * hands SAGA the uncropped DEM file (model.py:469 -> saga_lighting.py:42) and only crops the result,
+ * so relief outside the glacier outline shades the glacier and shapes the slopes at its margin.
+ * Without this call the (cropped) DEM is its own terrain: off-glacier cells then never cast a shadow.
+ * Call after enrgy_set_dem; glacier cells must have terrain under them (ENRGY_ERR_MASK). */
+int enrgy_set_terrain(enrgy_ctx* ctx, const float* terrain);
 int enrgy_set_albedo_maps(enrgy_ctx* ctx, int n_maps, const float* const* maps);
 int enrgy_set_swe(enrgy_ctx* ctx, const float* swe);
 /* initial sub-surface boundary temperatures at the AWS reference elevation (model.py:126-143):
@@ -224,6 +228,26 @@ int enrgy_shade_masks(enrgy_ctx* ctx, int step, int max_sub, uint32_t* out, int*
  * (the file saga_lighting.py:7-53 would have produced; insolation_pickler.py:12-25 layout) */
 int enrgy_potential_insolation(enrgy_ctx* ctx, int step, double* out);
 
+/* ---- shading as separate steps (multi-GPU: the sweep shards by sub-step, the fused kernel by row
+ * band, with an exchange of mask rows in between -- enrgy_b200/parallel.py) -------------------------
+ * The sunlit sub-steps of the whole run are numbered 0 .. n-1 in row order (enrgy_get_substeps lists
+ * those of one row); enrgy_sub_range gives the numbers [sub0, sub1) belonging to the rows [t0, t1).
+ * A mask array of a band of `rows` rows holds enrgy_mask_words(ctx, rows) uint32 per sub-step, laid out
+ * [round_up(rows, 16) / 8][pitch / 32][8]: bit (col % 32) of word [row / 8][col / 32][row % 8] = lit. */
+int enrgy_sub_range(enrgy_ctx* ctx, int t0, int t1, int* sub0, int* sub1);
+int64_t enrgy_mask_words(enrgy_ctx* ctx, int rows);
+/* sweeps the sub-steps [sub0, sub1) over the FULL raster and writes, for every segment q, the rows
+ * [seg_row0[q], seg_row0[q] + seg_rows[q]) into the DEVICE array seg_ptr[q] (which may live on a peer
+ * GPU) as [sub1 - sub0] band-local masks; seg_row0 must be multiples of 8; at most 8 segments. */
+int enrgy_shade_scan(enrgy_ctx* ctx, int sub0, int sub1, int n_seg, const int* seg_row0, const int* seg_rows,
+                     void* const* seg_ptr, void* stream);
+/* the fused kernels over the rows [t0, t1) with the caller's masks of this handle's band for exactly
+ * the sub-steps of enrgy_sub_range(t0, t1); otherwise like enrgy_run_async */
+int enrgy_run_masked(enrgy_ctx* ctx, int t0, int t1, const void* d_masks, double* d_stats, void* stream);
+/* device memory enrgy_run may spend on the masks of one chunk of rows (default 16 GiB; a season that
+ * does not fit is processed in chunks: sweep, fused kernels, sweep, ...) */
+int enrgy_set_mask_budget(enrgy_ctx* ctx, int64_t bytes);
+
 /* state rasters (model.py:76-80, :258-261): dtype 32 -> float*, 64 -> double*; any may be NULL */
 int enrgy_get_state(enrgy_ctx* ctx, int dtype, void* swe, void* total_snow, void* total_ice);
 int enrgy_set_state(enrgy_ctx* ctx, int dtype, const void* swe, const void* total_snow,
@@ -247,7 +271,8 @@ int enrgy_microbench(enrgy_ctx* ctx, int kind, double* result);
 
 /* introspection for bench.py / tests: kernels launched so far, device time of the last run [ms] */
 int64_t enrgy_launch_count(enrgy_ctx* ctx);
-double enrgy_last_kernel_ms(enrgy_ctx* ctx);
+double enrgy_last_kernel_ms(enrgy_ctx* ctx);   /* fused kernels of the last run */
+double enrgy_last_sweep_ms(enrgy_ctx* ctx);    /* shading sweeps of the last run / enrgy_shade_scan */
 int enrgy_kernel_info(enrgy_ctx* ctx, int* regs, int* smem_bytes, int* ctas_per_sm, int* grid);
 
 #ifdef __cplusplus

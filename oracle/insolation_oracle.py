@@ -20,11 +20,23 @@ Specification (all angles radians, time base UTC, one sun position per sub-step 
   direct       S0 * tau^(1/U) * max(0, n . s) * lit          (tau = 0.70; `beer_lambert.py:82-95`
                functional form flux*exp(-k*thickness) with k = -ln tau, thickness = 1/U)
   diffuse      S0 * (0.271 - 0.294 * tau^(1/U)) * U * (1 + n_z) / 2
-  shadow       slim ray trace from the cell toward the sun: step k = 1, 2, ... lands on cell
-               (r + ((k*dr_fix + 32768) >> 16), c + ((k*dc_fix + 32768) >> 16)) with Q16 fixed-point
-               direction (dominant axis = +-65536); ray height z_k = dem + float32(k) * dz in float32
-               (one rounded multiply, one rounded add); shaded iff some in-grid, non-NaN sample is
-               > z_k; the ray stops at the grid edge or once z_k > max(dem).
+  shadow       line-sweep ray trace.  All rays of one sub-step share one direction, so the raster is
+               cut into sheared scan LINES and every ray runs along its cell's line:
+                 direction in Q16 fixed point as before (dominant axis = +-65536);
+                 |dr_fix| >= |dc_fix| ("row type"):  u = sign(dr_fix) * row   (u grows toward the sun)
+                     line l holds the cells (row, l + sh(u)),  sh(u) = (u * dc_fix + 32768) >> 16
+                 else ("column type"):               u = sign(dc_fix) * col
+                     line l holds the cells (l + sh(u), col),  sh(u) = (u * dr_fix + 32768) >> 16
+               so the ray of a cell visits, k = 1, 2, ... steps toward the sun, the cell of its own line
+               at u + k (one cell per step along the dominant axis; the other coordinate deviates from
+               the straight line by less than one cell).  Heights are compared in float64:
+                 g(cell) = float64(dem) - float64(u) * float64(dz)      (dz: float32 rise per step)
+               (product and difference are exact for any real DEM: 15 + 24 and < 53 significant bits)
+               and a cell is SHADED iff some in-grid, non-NaN cell further along its line toward the sun
+               has g > g(cell)  <=>  dem_k - dem_0 > k * dz.  Rays end at the grid edge.  Because g does
+               not depend on the ray, the mask of a whole sub-step is ONE running maximum per line,
+               swept from the sunward edge: lit = not (M > g); M = max(M, g)  -- O(H*W) whatever the
+               terrain, which is what the CUDA path does.
   result       sum_j (direct_j + diffuse_j) * w_j / 1000   [kWh m-2]; NaN where the DEM is NaN.
 """
 from __future__ import annotations
@@ -132,66 +144,83 @@ def terrain_normals(dem, cell):
     return nx, ny, nz
 
 
+def line_geometry(dc_fix, dr_fix):
+    """(row_type, sigma, dfix): scan-line family of a Q16 direction (module docstring, "shadow")."""
+    row_type = abs(dr_fix) >= abs(dc_fix)
+    if row_type:
+        return True, (1 if dr_fix > 0 else -1), int(dc_fix)
+    return False, (1 if dc_fix > 0 else -1), int(dr_fix)
+
+
+def shear(u, dfix):
+    """sh(u) = (u * dfix + 32768) >> 16 (floor), for Python ints or int64 arrays."""
+    return (u * dfix + 32768) >> 16
+
+
 def shadow_mask(dem32, dc_fix, dr_fix, dz32, zmax32=None):
-    """lit [H, W] bool (True = sunlit) by the slim ray trace of the specification."""
+    """lit [H, W] bool (True = sunlit) by the line sweep of the specification.  `zmax32` is accepted
+    for call compatibility and ignored (rays end at the grid edge)."""
     dem32 = np.asarray(dem32, dtype=np.float32)
     h, w = dem32.shape
-    if zmax32 is None:
-        zmax32 = np.float32(np.nanmax(dem32))
-    valid = ~np.isnan(dem32)
     lit = np.ones((h, w), dtype=bool)
-    if not np.isfinite(dz32):
+    if not np.isfinite(dz32) or (dc_fix == 0 and dr_fix == 0):
         return lit
-    active = valid.copy()
-    dz32 = np.float32(dz32)
-    k = 1
-    while active.any():
-        ro = (k * dr_fix + 32768) >> 16
-        co = (k * dc_fix + 32768) >> 16
-        if abs(ro) >= h or abs(co) >= w:
-            break
-        zk = dem32 + np.float32(k) * dz32                     # float32 multiply, float32 add
-        # sample[r, c] = dem32[r + ro, c + co] where inside, else NaN (ray left the grid)
-        sample = np.full((h, w), np.nan, dtype=np.float32)
-        r0, r1 = max(0, -ro), min(h, h - ro)
-        c0, c1 = max(0, -co), min(w, w - co)
-        sample[r0:r1, c0:c1] = dem32[r0 + ro:r1 + ro, c0 + co:c1 + co]
-        inside = np.zeros((h, w), dtype=bool)
-        inside[r0:r1, c0:c1] = True
+    row_type, sigma, dfix = line_geometry(dc_fix, dr_fix)
+    z = dem32.astype(np.float64)
+    if not row_type:
+        z = z.T                                         # sweep axis first
+    na, nb = z.shape
+    dz = float(np.float32(dz32))
+    out = np.ones((na, nb), dtype=bool)
+    us = sigma * np.arange(na, dtype=np.int64)
+    sh = shear(us, dfix)
+    l_off = int(sh.max())                               # line l lives at index l + l_off
+    m = np.full(nb + int(sh.max() - sh.min()), -np.inf)
+    b = np.arange(nb, dtype=np.int64)
+    for a in np.argsort(-us, kind="stable"):            # from the sunward edge (largest u) away from the sun
+        u = int(us[a])
+        idx = b - int(sh[a]) + l_off
+        hrow = z[a]
+        ok = ~np.isnan(hrow)
+        g = hrow - float(u) * dz
+        mm = m[idx]
         with np.errstate(invalid="ignore"):
-            active &= inside & ~(zk > zmax32)
-            hit = active & (sample > zk)
-        lit[hit] = False
-        active &= ~hit
-        k += 1
+            out[a] = ~(mm > g)
+        m[idx] = np.where(ok, np.maximum(mm, np.where(ok, g, -np.inf)), mm)
+    lit = out if row_type else out.T
+    lit = lit.copy()
+    lit[np.isnan(dem32)] = True                         # off-glacier cells read "sunlit"
     return lit
 
 
 def trace_cells(dem32, rows, cols, dc_fix, dr_fix, dz32, zmax32=None):
-    """Same ray trace for a list of cells only (spot checks at sizes the full mask is too slow for)."""
+    """The same specification cell by cell (the ray of each listed cell marched along its own line):
+    an independent formulation of shadow_mask, and the spot check at sizes where full masks are slow."""
     dem32 = np.asarray(dem32, dtype=np.float32)
     h, w = dem32.shape
-    if zmax32 is None:
-        zmax32 = np.float32(np.nanmax(dem32))
-    rows = np.asarray(rows)
-    cols = np.asarray(cols)
-    z0 = dem32[rows, cols]
+    rows = np.asarray(rows, dtype=np.int64)
+    cols = np.asarray(cols, dtype=np.int64)
     lit = np.ones(rows.shape, dtype=bool)
-    if not np.isfinite(dz32):
+    if not np.isfinite(dz32) or (dc_fix == 0 and dr_fix == 0):
         return lit
+    row_type, sigma, dfix = line_geometry(dc_fix, dr_fix)
+    dz = float(np.float32(dz32))
+    z0 = dem32[rows, cols].astype(np.float64)
+    u0 = sigma * (rows if row_type else cols)
+    line = (cols if row_type else rows) - shear(u0, dfix)
+    g0 = z0 - u0.astype(np.float64) * dz
     active = ~np.isnan(z0)
-    dz32 = np.float32(dz32)
     k = 1
     while active.any():
-        ro = (k * dr_fix + 32768) >> 16
-        co = (k * dc_fix + 32768) >> 16
-        r2, c2 = rows + ro, cols + co
+        u = u0 + k
+        major = sigma * u
+        minor = line + shear(u, dfix)
+        r2, c2 = (major, minor) if row_type else (minor, major)
         inside = (r2 >= 0) & (r2 < h) & (c2 >= 0) & (c2 < w)
-        zk = z0 + np.float32(k) * dz32
+        active &= inside                                # both coordinates are monotone along a ray
+        smp = dem32[np.clip(r2, 0, h - 1), np.clip(c2, 0, w - 1)].astype(np.float64)
         with np.errstate(invalid="ignore"):
-            active &= inside & ~(zk > zmax32)
-            sample = dem32[np.clip(r2, 0, h - 1), np.clip(c2, 0, w - 1)]
-            hit = active & (sample > zk)
+            hit = active & ((smp - u.astype(np.float64) * dz) > g0)
         lit[hit] = False
         active &= ~hit
         k += 1
@@ -223,6 +252,35 @@ def potential_insolation(dem32, cell, lat, lon, t_unix, dt_s, shadow=True, norma
     pot[np.isnan(dem32)] = np.nan
     if return_masks:
         return pot, masks, table
+    return pot
+
+
+def potential_insolation_window(dem32, cell, lat, lon, t_unix, dt_s, window, shadow=True,
+                                s0=S0, tau=TAU, hour_step=HOUR_STEP):
+    """potential_insolation for the cells of window = (r0, r1, c0, c1) of a LARGE raster: terrain normals
+    from the window plus a one-cell halo, sunlit masks by marching the rays of the window's cells
+    through the full raster (trace_cells).  Same values as the full computation, at a cost that does
+    not depend on the size of the raster."""
+    dem32 = np.asarray(dem32, dtype=np.float32)
+    h, w = dem32.shape
+    r0, r1, c0, c1 = window
+    ra, rb, ca, cb = max(r0 - 1, 0), min(r1 + 1, h), max(c0 - 1, 0), min(c1 + 1, w)
+    nx, ny, nz = terrain_normals(dem32[ra:rb, ca:cb], cell)
+    sl = (slice(r0 - ra, r0 - ra + (r1 - r0)), slice(c0 - ca, c0 - ca + (c1 - c0)))
+    nx, ny, nz = nx[sl], ny[sl], nz[sl]
+    rr, cc = np.mgrid[r0:r1, c0:c1]
+    direct = np.zeros(nz.shape, dtype=np.float64)
+    dsum = 0.0
+    for sub in substep_table(t_unix, dt_s, lat, lon, cell, s0, tau, hour_step):
+        cosi = nx * sub["E"] + ny * sub["N"] + nz * sub["U"]
+        term = sub["B"] * np.maximum(cosi, 0.0)
+        if shadow:
+            lit = trace_cells(dem32, rr.ravel(), cc.ravel(), sub["dc_fix"], sub["dr_fix"], sub["dz"]).reshape(nz.shape)
+            term = np.where(lit, term, 0.0)
+        direct = direct + term
+        dsum = dsum + sub["D"]
+    pot = direct + dsum * (1.0 + nz)
+    pot[np.isnan(dem32[r0:r1, c0:c1])] = np.nan
     return pot
 
 

@@ -113,33 +113,65 @@ def test_c2_split_runs_and_row_bands_bit_identical(c2_case):
     assert np.allclose(total[1:, cols], s_one[1:, cols], rtol=2e-6, atol=1e-6)
 
 
-def test_c3_size_shading_bands_and_rays():
-    """8192-row raster with the shading ray march (config C3's size along the band axis): two row
-    bands give bit-identical rasters to the whole raster -- rays cross the cut -- and 12000 rays
-    traced one by one with the specification agree with the masks."""
+def test_c3_full_raster_shading_bands_rays_and_window():
+    """Config C3 at its full raster: 8192 x 8192 with shading, 24 hourly rows (one day: the sun goes all
+    the way round at 78 N).  (a) Two row bands give bit-identical rasters and statistics sums to the whole
+    raster (the lines cross the cut); (b) the full masks of two rows against the oracle's sweep, and
+    60000 cells ray-traced one by one along their scan lines; (c) the energy balance of a window around
+    the AWS cell against the oracle for all 24 rows, its insolation computed by the oracle with rays
+    through the full raster."""
     from oracle.enrgy_oracle import time_step_seconds
-    case = make_case(8192, 6, w=1024, seed=11, start="20220615 18:00:00")
+    n, t = 8192, 24
+    case = make_case(n, t, seed=11, start="20220615 00:00:00")
+    valid = ~np.isnan(case.dem)
     whole = _engine(case, False, shadow=True)
     try:
-        whole.run(0, 6)
+        s_whole = whole.run(0, t)
         st = whole.state(np.float32)
-        step = 3
-        table = I.substep_table(I.to_unix(case.aws_rows[step]["DATE"]), time_step_seconds(case.aws_rows, step),
-                                case.lat, case.lon, case.cell)
-        masks = whole.shade_masks(step)
+        tables, masks = {}, {}
+        for step in (3, 14):
+            tables[step] = I.substep_table(I.to_unix(case.aws_rows[step]["DATE"]), time_step_seconds(case.aws_rows, step),
+                                           case.lat, case.lon, case.cell)
+            masks[step] = whole.shade_masks(step)
     finally:
         whole.close()
-    for band in ((0, 4000), (4000, 4192)):
+    # (a) row bands (the cut is a multiple of the patch height)
+    total = np.zeros_like(s_whole)
+    for band in ((0, 4112), (4112, n - 4112)):
         eng = _engine(case, False, shadow=True, band=band)
-        eng.run(0, 6)
+        total += eng.run(0, t)
         part = eng.state(np.float32)
         eng.close()
         for a, b in zip(part, st):
             assert np.array_equal(a, b[band[0]:band[0] + band[1]], equal_nan=True)
+    cols = [_lib.S_RS, _lib.S_SENS, _lib.S_LAT, _lib.S_MELT, _lib.S_SNOW, _lib.S_ICE]
+    assert np.allclose(total[1:, cols], s_whole[1:, cols], rtol=2e-6, atol=1e-6)
+    # (b) masks
     rng = np.random.default_rng(1)
-    rr, cc = rng.integers(0, 8192, 12000), rng.integers(0, 1024, 12000)
-    ok = ~np.isnan(case.dem[rr, cc])
+    rr, cc = rng.integers(0, n, 80000), rng.integers(0, n, 80000)
+    ok = valid[rr, cc]
     rr, cc = rr[ok], cc[ok]
-    for j, sub in enumerate(table):
-        lit = I.trace_cells(case.dem, rr, cc, sub["dc_fix"], sub["dr_fix"], sub["dz"])
-        assert np.array_equal(masks[j][rr, cc], lit), j
+    assert rr.size >= 50000
+    n_traced = 0
+    for step, table in tables.items():
+        assert masks[step].shape[0] == len(table) == 4
+        for j, sub in enumerate(table):
+            full = I.shadow_mask(case.dem, sub["dc_fix"], sub["dr_fix"], sub["dz"])
+            assert np.array_equal(masks[step][j][valid], full[valid]), (step, j)
+            lit = I.trace_cells(case.dem, rr, cc, sub["dc_fix"], sub["dr_fix"], sub["dz"])
+            assert np.array_equal(masks[step][j][rr, cc], lit), (step, j)
+            assert 0.01 < 1.0 - lit.mean() < 0.99
+            n_traced += rr.size
+    assert n_traced >= 400000
+    # (c) window vs oracle, all rows, with shading
+    win, sl = _window(case, 24)
+    r0, c0 = sl[0].start, sl[1].start
+    pot = np.stack([I.potential_insolation_window(case.dem, case.cell, case.lat, case.lon, I.to_unix(row["DATE"]),
+                                                  time_step_seconds(case.aws_rows, i),
+                                                  (r0, sl[0].stop, c0, sl[1].stop), shadow=True)
+                    for i, row in enumerate(case.aws_rows)])
+    ora = P.run_oracle(win, pot.astype(np.float32), False)
+    inner = (slice(1, -1), slice(1, -1))
+    for got, name in zip(st, ("swe", "total_snow", "total_ice")):
+        err = P.max_rel_err(got[sl][inner].astype(np.float64), np.asarray(ora[name], dtype=np.float64)[inner], 1e-3)
+        assert err < 1e-4, (name, err)

@@ -104,10 +104,20 @@ def test_two_rank_band_reduction(tmp_path):
 
 
 def test_row_bands_properties():
-    for rows, world in ((2048, 8), (100, 3), (16, 4), (8192, 8)):
+    for rows, world in ((2048, 8), (100, 3), (64, 4), (8192, 8)):
         b = row_bands(rows, world)
         assert b[0][0] == 0 and sum(n for _, n in b) == rows
         assert all(b[i][0] + b[i][1] == b[i + 1][0] for i in range(world - 1))
+        assert all(n > 0 for _, n in b)
+    # no empty bands, ever: an empty band reads as "whole raster" at the C ABI
+    for rows, world in ((16, 4), (100, 8)):
+        with pytest.raises(ValueError):
+            row_bands(rows, world, align=16)
+    w = np.zeros(512)
+    w[200:216] = 1.0                                 # the glacier occupies sixteen rows only
+    b = row_bands(512, 4, align=16, valid_per_row=w)
+    assert all(n >= 16 for _, n in b) and sum(n for _, n in b) == 512
+    assert rebalance_bands(b, [1.0, 0.0, 0.0, 0.0], w) and all(n >= 16 for _, n in rebalance_bands(b, [1.0, 0.0, 0.0, 0.0], w))
     w = np.zeros(256)
     w[64:192] = 1.0                                  # glacier only in the middle half
     b = row_bands(256, 2, align=16, valid_per_row=w)
@@ -149,7 +159,7 @@ def test_tile_cost_weights():
 
 def test_band_cuts_properties_randomised():
     """row_bands / rebalance_bands on random weights and times: bands tile the raster without gaps or
-    overlaps, edges are aligned, no band is negative, and re-cutting with the times a perfectly
+    overlaps, edges are aligned, no band is empty, and re-cutting with the times a perfectly
     uniform cost model would have produced leaves the bands unchanged."""
     from hypothesis import given, settings, strategies as st
 
@@ -160,9 +170,13 @@ def test_band_cuts_properties_randomised():
         rng = np.random.default_rng(seed)
         w = rng.integers(0, 200, rows).astype(float)
         w[rng.random(rows) < 0.3] = 0.0
+        if rows < world * align:
+            with pytest.raises(ValueError):
+                row_bands(rows, world, align=align, valid_per_row=w)
+            return
         bands = row_bands(rows, world, align=align, valid_per_row=w)
         assert len(bands) == world and bands[0][0] == 0
-        assert all(n >= 0 for _, n in bands) and sum(n for _, n in bands) == rows
+        assert all(n >= align for _, n in bands) and sum(n for _, n in bands) == rows
         assert all(bands[i][0] + bands[i][1] == bands[i + 1][0] for i in range(world - 1))
         assert all(r0 % align == 0 for r0, _ in bands[1:])
         # times proportional to the weights the bands were cut with -> same cuts again
