@@ -23,7 +23,7 @@ MAX_LAYERS = 8
 (S_RS, S_LWD, S_LWU, S_SENS, S_LAT, S_ATMO, S_G, S_MELT, S_SNOW, S_ICE, S_SWE, S_NSNOW, S_NSWE,
  S_NVALID, S_COUNT) = range(15)
 # point scalars (enum ENRGY_P_*)
-(P_L, P_CH, P_POT_AWS, P_SW_FACTOR, P_TSURF_AWS, P_QH_AWS, P_NSUB, P_COUNT) = range(8)
+(P_L, P_CH, P_POT_AWS, P_SW_FACTOR, P_TSURF_AWS, P_QH_AWS, P_NSUB, P_SENS_AWS, P_LAT_AWS, P_COUNT) = range(10)
 # dump fields (enum ENRGY_D_*)
 (D_RS, D_LWD, D_LWU, D_SENS, D_LAT, D_ATMO, D_MELT, D_SNOW, D_ICE, D_ALBEDO, D_POT, D_G,
  D_COUNT) = range(13)
@@ -73,6 +73,8 @@ _PROTOTYPES = {
     "enrgy_set_insolation": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "enrgy_prepass": (C.c_int, [_P]),
     "enrgy_get_point_scalars": (C.c_int, [_P, _P]),
+    "enrgy_get_point_layers": (C.c_int, [_P, _P]),
+    "enrgy_set_aws_cell": (C.c_int, [_P, C.c_int, _P, C.c_double]),
     "enrgy_host_prepass": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P]),
     "enrgy_run": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "enrgy_run_async": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
@@ -87,6 +89,7 @@ _PROTOTYPES = {
                                    C.POINTER(_P), _P]),
     "enrgy_run_masked": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "enrgy_set_mask_budget": (C.c_int, [_P, C.c_int64]),
+    "enrgy_defer_snow_total": (C.c_int, [_P, C.c_int]),
     "enrgy_get_state": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "enrgy_set_state": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "enrgy_get_layer_temps": (C.c_int, [_P, _P]),

@@ -97,6 +97,9 @@ struct enrgy_ctx {
   DevBuf<SweepSub> d_sweepsubs;
   int mask_sub0 = 0, mask_sub1 = 0;   // cached range [sub0, sub1) of d_maskbuf
   size_t mask_budget = (size_t)16 << 30;
+  // a run cut into several launches: SWE at its start (total_snow = start - end is added by the last)
+  DevBuf<unsigned char> d_swe_ref;
+  int defer = 0;                  // 0 off, 1 deferring (launches leave total_snow alone), 2 the next launch applies
   int64_t sweep_launches = 0;
   DevBuf<unsigned char> d_nx, d_ny, d_nz, d_swe, d_ts, d_ti, d_dump, d_stage, d_snap, d_layer_t;
   bool have_msm = false;
@@ -288,6 +291,8 @@ int fill_args(enrgy_ctx* c, int t0, int t1, KernelArgs<R>& a) {
   a.max_ice_albedo = c->p.albedo_const ? (R)INFINITY : (R)c->p.max_ice_albedo;
   a.elev_aws = (R)c->p.elev_aws;
   a.swe = (R*)c->d_swe.p; a.total_snow = (R*)c->d_ts.p; a.total_ice = (R*)c->d_ti.p;
+  a.swe_ref = c->defer ? (const R*)c->d_swe_ref.p : nullptr;
+  a.update_total_snow = c->defer == 1 ? 0 : 1;
   a.pot = c->d_pot.p; a.pot_stride = c->band_elems; a.pot_t0 = c->pot_t0;
   a.layer_t = (R*)c->d_layer_t.p;
   a.layer_stride = c->band_elems;
@@ -495,6 +500,18 @@ std::vector<Chunk> plan_chunks(const enrgy_ctx* c, int t0, int t1) {
   return out;
 }
 
+// A run cut into several launches: defer_begin copies the SWE raster (stream-ordered), the launches that
+// follow leave total_snow alone, and after defer_last the next launch adds swe(start of the run) -
+// swe(end) -- exactly what a single launch over the whole range does.
+int defer_begin(enrgy_ctx* c, cudaStream_t stream) {
+  const size_t bytes = c->band_elems * rsize(c);
+  CU_TRY(c->d_swe_ref.alloc(bytes));
+  CU_TRY(cudaMemcpyAsync(c->d_swe_ref.p, c->d_swe.p, bytes, cudaMemcpyDeviceToDevice, stream));
+  c->defer = 1;
+  return ENRGY_OK;
+}
+void defer_last(enrgy_ctx* c) { if (c->defer == 1) c->defer = 2; }
+
 // one launch of the fused kernel over [t0, t1) (+ statistics); masks: sunlit masks of this band, the
 // first one belonging to the run's sunlit sub-step number mask_sub0
 template <typename R>
@@ -522,6 +539,7 @@ int launch_range(enrgy_ctx* c, int t0, int t1, double* d_stats, cudaStream_t str
   CU_TRY(launch_energy_balance<R>(a, nullptr, insol, false, c->sm_count, grid, &c->info, stream));
   CU_TRY(fused_events(c).end(stream));
   c->launches++;
+  if (c->defer == 2) c->defer = 0;
   if (d_stats && n > 0) {
     FinalizeArgs f{};
     f.partials = c->d_partials.p; f.n_ctas = grid; f.n_steps = n; f.t0 = t0;
@@ -543,7 +561,13 @@ int run_typed(enrgy_ctx* c, int t0, int t1, double* d_stats, cudaStream_t stream
   sweep_events(c).reset();
   if (insol_variant(c) != kInsolMasked || t1 <= t0) return launch_range<R>(c, t0, t1, d_stats, stream, nullptr, 0);
   // with shading: sweep the sunlit masks of a chunk of steps, then run the fused kernel over it
-  for (const Chunk& ch : plan_chunks(c, t0, t1)) {
+  const std::vector<Chunk> chunks = plan_chunks(c, t0, t1);
+  if (chunks.size() > 1 && c->defer == 0) {
+    if (int e = defer_begin(c, stream)) return e;
+  }
+  for (size_t q = 0; q < chunks.size(); ++q) {
+    const Chunk& ch = chunks[q];
+    if (q + 1 == chunks.size() && chunks.size() > 1) defer_last(c);
     if (int e = ensure_masks(c, ch.s0, ch.s1, stream)) return e;
     const unsigned* m = c->d_maskbuf.p + (size_t)(ch.s0 - c->mask_sub0) * mask_words_per_sub(c, c->band_rows);
     if (int e = launch_range<R>(c, ch.t0, ch.t1, d_stats ? d_stats + (size_t)(ch.t0 - t0) * ENRGY_S_COUNT : nullptr, stream,
@@ -644,7 +668,7 @@ int enrgy_destroy(enrgy_ctx* c) {
   c->d_steps64.release(); c->d_shades.release(); c->d_blocks.release(); c->d_tiles.release();
   c->d_counts.release(); c->d_partials.release(); c->d_stats.release(); c->d_small.release();
   c->d_counters.release(); c->d_snap.release(); c->d_layer_t.release(); c->d_terrain.release(); c->d_scan.release();
-  c->d_scan_t.release(); c->d_maskbuf.release(); c->d_masktmp.release(); c->d_sweepsubs.release();
+  c->d_scan_t.release(); c->d_maskbuf.release(); c->d_masktmp.release(); c->d_sweepsubs.release(); c->d_swe_ref.release();
   if (c->ev_fused) { fused_events(c).destroy(); delete static_cast<EventPairs*>(c->ev_fused); }
   if (c->ev_sweep) { sweep_events(c).destroy(); delete static_cast<EventPairs*>(c->ev_sweep); }
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1114,6 +1138,28 @@ int enrgy_get_point_scalars(enrgy_ctx* c, double* out) {
   return ENRGY_OK;
 }
 
+int enrgy_get_point_layers(enrgy_ctx* c, double* out) {
+  if (!c || !out) return fail(ENRGY_ERR_ARG, "null argument");
+  if (!c->prepass_done) return fail(ENRGY_ERR_ARG, "prepass has not run");
+  if (c->p.msm_layers <= 0) return fail(ENRGY_ERR_ARG, "the sub-surface model is off");
+  const int nb = c->p.msm_layers + 1;
+  for (int i = 0; i < c->n_steps; ++i)
+    for (int l = 0; l < nb; ++l) out[(size_t)i * nb + l] = c->pre.point_layers[(size_t)i * (kMaxLayers + 1) + l];
+  return ENRGY_OK;
+}
+
+int enrgy_set_aws_cell(enrgy_ctx* c, int n_maps, const double* albedo_at_aws, double swe_at_aws) {
+  if (!c) return fail(ENRGY_ERR_ARG, "null context");
+  if (!c->have_dem) return fail(ENRGY_ERR_ARG, "set_dem must precede set_aws_cell");
+  if (n_maps < 0 || (n_maps > 0 && !albedo_at_aws)) return fail(ENRGY_ERR_ARG, "bad albedo list");
+  if (n_maps > 0 && c->n_maps > 0 && n_maps != c->n_maps) return fail(ENRGY_ERR_ARG, "%d albedo values for %d maps", n_maps, c->n_maps);
+  drop_early_prepass(c);
+  c->alb_aws.assign(albedo_at_aws, albedo_at_aws + n_maps);
+  c->swe_aws = swe_at_aws;
+  c->prepass_done = false;
+  return ENRGY_OK;
+}
+
 int enrgy_get_substeps(enrgy_ctx* c, int step, int max_sub, double* out, int* n_out) {
   if (!c || !out || !n_out) return fail(ENRGY_ERR_ARG, "null argument");
   if (!c->prepass_done) return fail(ENRGY_ERR_ARG, "prepass has not run");
@@ -1305,7 +1351,9 @@ int enrgy_set_state(enrgy_ctx* c, int dtype, const void* swe, const void* total_
     CU_TRY(cudaMemcpyAsync(dsts[q], host.data(), host.size(), cudaMemcpyHostToDevice, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
   }
-  c->state_advanced = true;   // a restart: the first-row SWE quirk no longer applies
+  // a restart from a SWE raster of an earlier run: the first-row SWE quirk no longer applies (seeding
+  // the totals alone, as Energy.model does for repeated calls, leaves it in force)
+  if (swe) c->state_advanced = true;
   return ENRGY_OK;
 }
 
@@ -1390,6 +1438,14 @@ double enrgy_last_sweep_ms(enrgy_ctx* c) {
   if (!c) return 0.0;
   cudaSetDevice(c->device);
   return sweep_events(c).collect();
+}
+
+int enrgy_defer_snow_total(enrgy_ctx* c, int on) {
+  if (int e = use_device(c)) return e;
+  if (!c->have_dem) return fail(ENRGY_ERR_ARG, "no state before set_dem");
+  if (on) return defer_begin(c, c->stream);
+  defer_last(c);
+  return ENRGY_OK;
 }
 
 int enrgy_set_mask_budget(enrgy_ctx* c, int64_t bytes) {

@@ -1101,10 +1101,12 @@ energy_balance_kernel(const KernelArgs<R> a) {
           const bool v = (valid_bits >> i) & 1u;
           const R swe_i = (i & 1) ? swe2[i / 2].hi() : swe2[i / 2].lo();
           const R tic_i = (i & 1) ? tic2[i / 2].hi() : tic2[i / 2].lo();
-          // total_snow grows by swe(start) - swe(end); the start value is still in HBM
-          const R swe_start = v ? a.swe[o] : (R)0;
+          // total_snow grows by swe(start) - swe(end); the start value is still in HBM -- or, when a run
+          // is cut into several launches (chunks of rows), in the copy taken at its start, and only the
+          // last launch adds the difference: the result does not depend on the cuts
+          const R swe_start = v ? (a.swe_ref ? a.swe_ref[o] : a.swe[o]) : (R)0;
           a.swe[o] = v ? swe_i : qnan;
-          a.total_snow[o] = v ? a.total_snow[o] + (swe_start - swe_i) : qnan;
+          if (a.update_total_snow) a.total_snow[o] = v ? a.total_snow[o] + (swe_start - swe_i) : qnan;
           a.total_ice[o] = v ? tic_i : qnan;
           if (MSM) {
 #pragma unroll

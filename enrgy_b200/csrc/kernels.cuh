@@ -39,6 +39,8 @@ struct KernelArgs {
   R* swe;
   R* total_snow;
   R* total_ice;
+  const R* swe_ref;               // SWE at the start of a run cut into several launches (null: a.swe itself)
+  int update_total_snow;          // 0: an earlier launch of such a run (total_snow is added by the last one)
   // sub-surface model: boundary temperatures [layers + 1][band_rows_pad][pitch] (deg C)
   R* layer_t;
   size_t layer_stride;

@@ -189,6 +189,7 @@ int run_prepass(const PrepassInput& in, PrepassOutput& out, std::string& err) {
   out.sub_count.assign(T, 0);
   out.blocks.clear();
   out.point.assign((size_t)T * ENRGY_P_COUNT, 0.0);
+  out.point_layers.assign(p.msm_layers > 0 ? (size_t)T * (kMaxLayers + 1) : 0, 0.0);
 
   if (p.aws_row < 0 || p.aws_row >= in.rows || p.aws_col < 0 || p.aws_col >= in.cols) {
     err = "AWS cell outside the raster";
@@ -364,17 +365,21 @@ int run_prepass(const PrepassInput& in, PrepassOutput& out, std::string& err) {
     }
     s.c_sw = 3.6 * 1000000 / dt * factor;
 
+    // turbulent fluxes of the distributed pass at the AWS cell itself (debug_point_output, model.py:441-448)
+    const double t_air_c = t_air + delta_cell * f[ENRGY_F_LAPSE];
+    const double tz_c = t_air_c + 273.15;
+    const double tsk = ts_aws_c + 273.15;
+    const double p_c = p_hpa + delta_cell * kPressureLapse;
+    const double r_rt = 1.0 / (kRair * tz_c);
+    const double sens = (s.c_sens * p_c) * (r_rt * (tz_c - tsk));
+    const double f_p = 1.0016 + 3.15 * 1e-6 * p_c - 0.074 / p_c;
+    const double es = 611.2 * std::exp((17.62 * ts_aws_c) / (243.12 + ts_aws_c)) * f_p;
+    const double lat = (s.c_lat * r_rt) * (e_aws * pw_cell - es);
+    pt[ENRGY_P_SENS_AWS] = sens;
+    pt[ENRGY_P_LAT_AWS] = lat;
     if (msm) {
       // the AWS cell's own energy balance and conduction step (same arithmetic as the kernel)
-      const double t_air_c = t_air + delta_cell * f[ENRGY_F_LAPSE];
-      const double tz_c = t_air_c + 273.15;
-      const double tsk = tl[0] + 273.15;
-      const double p_c = p_hpa + delta_cell * kPressureLapse;
-      const double r_rt = 1.0 / (kRair * tz_c);
-      const double sens = (s.c_sens * p_c) * (r_rt * (tz_c - tsk));
-      const double f_p = 1.0016 + 3.15 * 1e-6 * p_c - 0.074 / p_c;
-      const double es = 611.2 * std::exp((17.62 * tl[0]) / (243.12 + tl[0])) * f_p;
-      const double lat = (s.c_lat * r_rt) * (e_aws * pw_cell - es);
+      for (int lyr = 0; lyr <= nl; ++lyr) out.point_layers[(size_t)i * (kMaxLayers + 1) + lyr] = tl[lyr];
       const double lwd = s.c_lwd * (tz_c * tz_c) * (tz_c * tz_c);
       const double lwu = s.c_lwu * (tsk * tsk) * (tsk * tsk);
       double alb;

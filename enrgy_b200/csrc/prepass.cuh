@@ -50,6 +50,7 @@ struct PrepassOutput {
   std::vector<TimeBlock> blocks;
   int cap_steps = 0, cap_subs = 0;        // capacities the blocks were cut for
   std::vector<double> point;              // [n_steps][ENRGY_P_COUNT]
+  std::vector<double> point_layers;       // MSM: [n_steps][kMaxLayers + 1] boundary temperatures of the AWS cell BEFORE each row's update
 };
 
 // Returns 0 or an ENRGY_ERR_* code with a message in err.

@@ -153,6 +153,15 @@ class Engine:
         check(self.lib.enrgy_get_point_scalars(self.h, out.ctypes.data))
         return out
 
+    def point_layers(self):
+        out = np.empty((self.n_steps, self.msm_layers + 1), dtype=np.float64)
+        check(self.lib.enrgy_get_point_layers(self.h, out.ctypes.data))
+        return out
+
+    def set_aws_cell(self, albedo_at_aws, swe_at_aws):
+        a = np.ascontiguousarray(albedo_at_aws if albedo_at_aws is not None else [], dtype=np.float64)
+        check(self.lib.enrgy_set_aws_cell(self.h, int(a.size), a.ctypes.data if a.size else None, float(swe_at_aws)))
+
     # ---- the hot path -------------------------------------------------------------------------
     def run(self, t0=0, t1=None, want_stats=True):
         t1 = self.n_steps if t1 is None else t1
@@ -186,6 +195,9 @@ class Engine:
 
     def run_masked(self, t0, t1, d_masks_ptr, d_stats_ptr=None, stream_ptr=None):
         check(self.lib.enrgy_run_masked(self.h, int(t0), int(t1), d_masks_ptr, d_stats_ptr, stream_ptr))
+
+    def defer_snow_total(self, on):
+        check(self.lib.enrgy_defer_snow_total(self.h, 1 if on else 0))
 
     def set_mask_budget(self, n_bytes):
         check(self.lib.enrgy_set_mask_budget(self.h, int(n_bytes)))

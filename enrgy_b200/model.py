@@ -15,6 +15,15 @@ Differences, all additive:
     the GPU; without it the reference shells out to SAGA GIS per step (saga_lighting.py:7-53) --
     here the fused kernel computes insolation and the shading ray march itself.
   * no PNG previews (matplotlib, raster_utils.py:9-32) and no CPU fallback.
+  * several GPUs: under `torchrun` (torch.distributed initialised, one process per GPU) every rank
+    builds the same Energy object and calls model(); the raster is cut into row bands balanced by
+    visited tiles, every rank runs its band, the per-row area sums are all-reduced, rank 0 writes the
+    CSV files and exports, and every rank ends up with the full state rasters.  With shading the sweep
+    is sharded by sub-step and the mask rows are exchanged (parallel.ShardedShading).
+  * terrain outside the glacier outline: the reference hands SAGA the UNCROPPED DEM (model.py:469 ->
+    saga_lighting.py:42), so valley walls shade the glacier.  With GDAL the uncropped raster is read
+    on the model grid automatically; for `.npy` rasters call `add_terrain(path_or_array)` -- without
+    it only the glacier's own relief casts shadows.
 """
 from __future__ import annotations
 
@@ -30,31 +39,7 @@ from .geo import coords_to_index, get_value_by_real_coords, grid_centre_latlon
 from .helpers import fill_header
 from .raster_utils import export_array_as_geotiff, load_raster, show_me  # noqa: F401
 
-# var_classes.py:7-15 -- kept as a mutable module global because reference code reads it that way
-PARAMS = {
-    "ice_density": 900.0,
-    "snow_density": 387.0,
-    "latent_heat_of_fusion": 3.34 * 10 ** 5,
-    "specific_heat_capacity_ice": 2097.0,
-    "thermal_diffusivity_ice": 1.16 * 10 ** -6,
-    "thermal_diffusivity_snow": 0.40 * 10 ** -6,
-    "g": 9.81,
-}
-
-
-class OutputRow:
-    """Area means of one step, printed like reference var_classes.py:45-56."""
-
-    def __init__(self, date_time_str, means, point_t_surf):
-        self.date_time_str = date_time_str
-        (self.mean_rs, self.mean_rl, self.mean_lwd, self.mean_sensible, self.mean_latent, self.mean_atmo,
-         self.mean_g, self.mean_melt) = [float(x) for x in means]
-        self.point_t_surf = point_t_surf
-
-    def __repr__(self):
-        return "%s,%.1f,%.1f,%.1f,%.1f,%.1f,%.1f,%.1f,%.1f,%.2f" % (
-            self.date_time_str, self.mean_rs, self.mean_rl, self.mean_lwd, self.mean_sensible,
-            self.mean_latent, self.mean_atmo, self.mean_g, self.mean_melt, self.point_t_surf)
+from .var_classes import PARAMS, AwsVars, DistributedVars, OutputRow  # noqa: F401  (same names as var_classes.py)
 
 
 def _div(a, b):
@@ -62,7 +47,7 @@ def _div(a, b):
 
 
 class Energy:
-    def __init__(self, base_dem_path, glacier_outlines_path, out_dir, res=None, precision="f32", device=0):
+    def __init__(self, base_dem_path, glacier_outlines_path, out_dir, res=None, precision="f32", device=None):
         self.params = PARAMS
         self.current_date_str = None
         self.input_list = []
@@ -98,9 +83,16 @@ class Energy:
         self.lat = None                 # grid reference latitude / longitude; None = grid centre, UTM 33N
         self.lon = None
         self.max_resident_insolation_bytes = 4 << 30
-        self.stats = None               # [T, S_COUNT] sums of the last model() call
+        self.stats = None               # [T, S_COUNT] sums of the last model() call (all ranks: reduced)
         self.point_scalars = None
+        self.vars = None                # DistributedVars of the last processed row (model.py:232), lazy NumPy
+        self.albedo = None              # albedo / incoming shortwave rasters of the last row (model.py:235, :408)
+        self.incoming_shortwave = None  #   ... filled when debug_views is on
+        self.debug_views = None         # None: on for rasters up to 4 Mi cells; True / False to force
+        self.bands = None               # row bands of the last model() call [(row0, rows)] (one per rank)
+        self.terrain_array = None       # uncropped terrain on the model grid (add_terrain)
         self._engine = None
+        self._engine_factory = Engine   # (tests inject a stand-in here)
         self._last = None
 
         print("Loading base DEM...")
@@ -109,7 +101,12 @@ class Energy:
         self.total_snow_melt_array = np.zeros_like(self.base_dem_array, dtype=np.float32)
         self.total_ice_melt_array = np.zeros_like(self.base_dem_array, dtype=np.float32)
         self.swe_array = np.zeros_like(self.base_dem_array, dtype=np.float32)
-        self._swe_given = False
+        # SAGA sees the uncropped DEM (model.py:469): read it on the model grid where GDAL can
+        if not isinstance(base_dem_path, np.ndarray) and not str(base_dem_path).endswith(".npy"):
+            try:
+                self.add_terrain(None)
+            except Exception as e:                                   # pragma: no cover  (needs GDAL)
+                print("uncropped terrain not loaded (%s): only the glacier's own relief will cast shadows" % e)
 
     # ---- configuration, same semantics as model.py:84-153 -----------------------------------------
     def set_density(self, snow=None, ice=None):
@@ -153,7 +150,20 @@ class Energy:
     def add_snow(self, swe_map_path):
         print("Initialized snow cover state (SWE) from %s" % swe_map_path)
         self.swe_array = load_raster(swe_map_path, self.outlines_path, self.res, v=False)[0]
-        self._swe_given = True
+
+    def add_terrain(self, terrain=None):
+        """The UNCROPPED terrain on the model grid: shadow casters and slope neighbours outside the
+        glacier outline (the reference gives SAGA the uncropped DEM file, model.py:469 ->
+        saga_lighting.py:42, and crops the result).  `terrain`: an array or a `.npy` path on the model
+        grid; None re-reads `base_dem_path` without the cutline onto the cropped raster's grid (GDAL)."""
+        if terrain is None:
+            from .raster_utils import load_uncropped_like
+            arr = load_uncropped_like(self.base_dem_path, self.geotransform, self.base_dem_array.shape)
+        else:
+            arr = load_raster(terrain, None, self.res, v=False)[0]
+        if arr.shape != self.base_dem_array.shape:
+            raise ValueError("terrain raster %s does not match the model grid %s" % (arr.shape, self.base_dem_array.shape))
+        self.terrain_array = np.ascontiguousarray(arr, dtype=np.float32)
 
     def add_msm(self, depths, temperatures, elev_aws):
         """Sub-surface model set-up, reference model.py:126-149: `depths` are layer THICKNESSES,
@@ -177,6 +187,27 @@ class Energy:
         self.result_export_dates = [s + " 12:00:00" for s in date_str_list]
 
     # ---- the model run ----------------------------------------------------------------------------
+    @staticmethod
+    def _dist():
+        """(world, rank, torch.distributed or None): several ranks only under an initialised process group."""
+        try:
+            import torch.distributed as dist
+        except Exception:                                            # pragma: no cover
+            return 1, 0, None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist.get_world_size(), dist.get_rank(), dist
+        return 1, 0, None
+
+    def _collective_device(self, dist):
+        """Tensors of a collective live on the GPU with NCCL, on the host with gloo."""
+        import torch
+        return torch.device("cuda", self._device_index()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+    def _device_index(self):
+        if self.device is not None:
+            return int(self.device)
+        return int(os.environ.get("LOCAL_RANK", "0"))
+
     def model(self, aws_file=None, albedo_maps=None, z=2.0, elev_aws=0.0, xy_aws=None,
               zm=None, z_h_or_e=None, andreas=False,
               solar_only=False, const_albedo=None, temp_lapse_rate=-0.006, last_snowfall=None,
@@ -186,16 +217,35 @@ class Energy:
         if solar_only:
             raise NotImplementedError("solar_only is a debugging mode of the reference (model.py:400-405); "
                                       "not part of the accelerated path")
+        world, rank, dist = self._dist()
+        writer = rank == 0                                          # rank 0 writes every file
         if albedo_maps is not None:
             self.albedo_arrays = {}
             for key in albedo_maps:
                 self.albedo_arrays[key] = load_raster(albedo_maps[key], self.outlines_path, self.res,
                                                       remove_outliers=True, v=v)[0]
         out_file = os.path.join(self.out_dir, "heat_fluxes.csv")
-        fill_header(out_file)
-        if self.debug_point_output is not None:
+        if writer:
+            fill_header(out_file)
+        if self.use_msm and self.msm_xy is not None and self.debug_point_output is not None:
+            if coords_to_index(self.geotransform, *self.msm_xy) != coords_to_index(self.geotransform, *xy_aws):
+                raise NotImplementedError("debug_point_output prints the layer temperatures at msm_xy (model.py:421-426); "
+                                          "the accelerated path keeps them per step for the AWS cell only")
+        if self.debug_point_output is not None and writer:           # model.py:170-180
+            header = ""
             with open(os.path.join(self.out_dir, self.debug_point_output), "a") as f:
-                f.write("SENSIBLE,LATENT")
+                if self.use_msm:
+                    cur_depth = 0.0
+                    header += f"{cur_depth},"
+                    for layer_thickness in self.layer_depths:
+                        cur_depth += layer_thickness
+                        header += f"{cur_depth},"
+                header += "SENSIBLE,LATENT"
+                f.write(header)
+        if not self.use_msm and self.layer_temperatures is not None:
+            if any(np.nanmax(np.abs(t)) > 0 for t in self.layer_temperatures[:1]):
+                raise NotImplementedError("a hand-set surface temperature without add_msm (model.py:207-210) is not "
+                                          "supported: without the sub-surface model the surface is at 0 degC")
 
         self.input_list = read_input_file(aws_file)
         rows = self.input_list
@@ -211,10 +261,21 @@ class Energy:
         if not (0 <= aws_row < h and 0 <= aws_col < w):
             raise IndexError("AWS coordinates fall outside the model grid")
         streamed = bool(self.use_precomputed)
+        shading = bool(self.shadow) and not streamed
         lat, lon = self.lat, self.lon
         if not streamed and (lat is None or lon is None):
             lat, lon = grid_centre_latlon(self.geotransform, h, w)
-        eng = Engine(h, w, precision=_lib.F64 if self.precision == "f64" else _lib.F32, device=self.device)
+        # row bands, one per rank: equal numbers of visited tiles
+        if world > 1:
+            from .parallel import row_bands, tile_cost_per_row
+            bands = row_bands(h, world, align=16, valid_per_row=tile_cost_per_row(~np.isnan(self.base_dem_array)))
+        else:
+            bands = [(0, h)]
+        self.bands = bands
+        r0, nr = bands[rank]
+        band = slice(r0, r0 + nr)
+        eng = self._engine_factory(h, w, precision=_lib.F64 if self.precision == "f64" else _lib.F32,
+                                   device=self._device_index())
         self._engine = eng
         try:
             eng.set_params(cell_size=abs(self.geotransform[1]), elev_aws=elev_aws, aws_row=aws_row,
@@ -223,16 +284,26 @@ class Energy:
                            emissivity=emissivity, const_albedo=const_albedo, max_ice_albedo=max_ice_albedo,
                            snow_density=self.params["snow_density"], ice_density=self.params["ice_density"],
                            insol_mode=_lib.INSOL_STREAMED if streamed else _lib.INSOL_COMPUTED,
-                           shadow=self.shadow, lat=lat or 0.0, lon=lon or 0.0,
-                           msm_depths=self.layer_depths if self.use_msm else None)
+                           shadow=shading, lat=lat or 0.0, lon=lon or 0.0,
+                           msm_depths=self.layer_depths if self.use_msm else None,
+                           band_row0=r0 if world > 1 else 0, band_rows=nr if world > 1 else 0)
             eng.set_dem(self.base_dem_array)
+            if self.terrain_array is not None and not streamed:
+                eng.set_terrain(self.terrain_array)
             if self.use_msm:
                 eng.set_msm(self._msm_point_temps, self._msm_elev)
             eng.set_forcing(table)    # the library starts its host pre-pass here, under the raster uploads
             if keys is not None:
-                eng.set_albedo_maps([self.albedo_arrays[k] for k in keys])
-            if self._swe_given:
-                eng.set_swe(self.swe_array)
+                eng.set_albedo_maps([self.albedo_arrays[k][band] for k in keys])
+            # the SWE raster as it stands (model.py:245-258 reads self.swe_array; zeros by default) and the
+            # melt totals of earlier model() calls (model.py:260-261 accumulates across calls)
+            eng.set_swe(self.swe_array[band])
+            if np.any(np.nan_to_num(self.total_snow_melt_array) != 0) or np.any(np.nan_to_num(self.total_ice_melt_array) != 0):
+                eng.set_state(total_snow=self.total_snow_melt_array[band], total_ice=self.total_ice_melt_array[band])
+            if self.use_msm and world > 1:
+                # every rank integrates the AWS cell in its pre-pass: hand it that cell's own values
+                eng.set_aws_cell([float(self.albedo_arrays[k][aws_row, aws_col]) for k in keys] if keys else None,
+                                 float(self.swe_array[aws_row, aws_col]))
 
             # step ranges: cut at the checkpoint rows (model.py:279-283) and, for streamed
             # insolation, at the residency limit
@@ -243,7 +314,7 @@ class Energy:
                         cuts.add(i + 1)
             max_chunk = n_steps
             if streamed:
-                max_chunk = max(1, int(self.max_resident_insolation_bytes // (h * w * 4)))
+                max_chunk = max(1, int(self.max_resident_insolation_bytes // (nr * w * 4)))
             ranges, t = [], 0
             for c in sorted(cuts):
                 while t < c:
@@ -255,32 +326,108 @@ class Energy:
             if not streamed:
                 eng.prepass()
                 point = eng.point_scalars()
+            sharded = None
+            if shading and world > 1:
+                import torch
+                from .parallel import ShardedShading
+                stream = torch.cuda.Stream(self._device_index())
+                eng.set_stream(stream.cuda_stream)
+                sharded = (ShardedShading(eng, bands, rank, world), stream,
+                           point[:, _lib.P_NSUB].astype(int))
+            want_views = self.debug_views if self.debug_views is not None else (h * w <= (1 << 22))
             solar_file = os.path.join(self.out_dir, "solar_output.csv")
+            layers_pt = eng.point_layers() if (self.use_msm and self.debug_point_output is not None and not streamed) else None
             for (t0, t1) in ranges:
                 if streamed:
-                    eng.set_insolation(t0, self._read_insolation(rows, t0, t1, v))
+                    eng.set_insolation(t0, self._read_insolation(rows, t0, t1, v)[:, band])
                     eng.prepass()
                     point = eng.point_scalars()
-                stats[t0:t1] = eng.run(t0, t1)
-                self._write_rows(rows, t0, t1, stats, point, out_file, solar_file, table)
+                    if self.use_msm and self.debug_point_output is not None:
+                        layers_pt = eng.point_layers()
+                last = t1 == n_steps and want_views and sharded is None
+                if last and t1 - 1 > t0:
+                    eng.defer_snow_total(True)       # two launches, rasters as from one
+                    stats[t0:t1 - 1] = eng.run(t0, t1 - 1)
+                    eng.defer_snow_total(False)
+                if last:
+                    self._last_views(eng, t1 - 1, band, world, dist)
+                    stats[t1 - 1:t1] = eng.run(t1 - 1, t1)
+                elif sharded is not None:
+                    stats[t0:t1] = self._run_sharded(eng, sharded, t0, t1)
+                else:
+                    stats[t0:t1] = eng.run(t0, t1)
+                if world > 1:
+                    stats[t0:t1] = self._allreduce(stats[t0:t1], dist)
+                if writer:
+                    self._write_rows(rows, t0, t1, stats, point, out_file, solar_file, table, layers_pt)
                 self.current_date_str = rows[t1 - 1]["DATE"]
                 if self.result_export_dates is not None and self.current_date_str in self.result_export_dates:
-                    self._pull_state(eng)
-                    self.export_result()
-                    if self.stake_df is not None:
-                        self.sample_stakes()
-                        self.write_stakes(out_file)
-            self._pull_state(eng)
+                    self._pull_state(eng, bands, rank, dist)
+                    if writer:
+                        self.export_result()
+                        if self.stake_df is not None:
+                            self.sample_stakes()
+                            self.write_stakes(out_file)
+            self._pull_state(eng, bands, rank, dist)
             if self.use_msm:
-                self.layer_temperatures = [t.astype(np.float32) for t in eng.layer_temps()]
+                lt = eng.layer_temps()
+                self.layer_temperatures = [self._gather_rows(t.astype(np.float32), bands, rank, dist) for t in lt]
             self.stats = stats
             self.point_scalars = point
+            # the AwsVars / DistributedVars of the last row, as the reference leaves them behind (model.py:229-232)
+            f = table[-1]
+            t_surf = self.layer_temperatures[0] if self.use_msm else np.zeros(self.base_dem_array.shape)
+            self.aws = AwsVars(f[_lib.F_T_AIR], f[_lib.F_WIND], f[_lib.F_PRESSURE], f[_lib.F_RH], f[_lib.F_CLOUD],
+                               f[_lib.F_SWD], t_surf, f[_lib.F_LAPSE], elev_aws, xy_aws[0], xy_aws[1], z)
+            self.vars = DistributedVars(self.aws, self.base_dem_array, self.current_date_str, False)
         finally:
             eng.close()
             self._engine = None
-        self.export_result()                                        # model.py:285-286
+        if writer:
+            self.export_result()                                    # model.py:285-286
 
     # ---- helpers ------------------------------------------------------------------------------------
+    def _run_sharded(self, eng, sharded, t0, t1):
+        """Rows [t0, t1) with shading over several GPUs: this band's statistics sums (not yet reduced)."""
+        import torch
+        sh, stream, sub_counts = sharded
+        d_stats = torch.zeros((t1 - t0, _lib.S_COUNT), dtype=torch.float64, device="cuda:%d" % self._device_index())
+        stream.wait_stream(torch.cuda.current_stream(self._device_index()))
+        sh.run(t0, t1, d_stats.data_ptr(), stream, sub_counts)
+        stream.synchronize()
+        return d_stats.cpu().numpy()
+
+    def _allreduce(self, arr, dist):
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(arr)).to(self._collective_device(dist))
+        dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    def _gather_rows(self, part, bands, rank, dist):
+        """The full raster from every rank's band (all ranks get it)."""
+        if dist is None:
+            return part
+        import torch
+        dev = self._collective_device(dist)
+        mx = max(n for _, n in bands)
+        buf = torch.full((mx, part.shape[1]), float("nan"), dtype=torch.from_numpy(part).dtype, device=dev)
+        buf[:part.shape[0]] = torch.from_numpy(np.ascontiguousarray(part)).to(dev)
+        out = [torch.empty_like(buf) for _ in bands]
+        dist.all_gather(out, buf)
+        return np.concatenate([o[:n].cpu().numpy() for o, (_, n) in zip(out, bands)], axis=0)
+
+    def _last_views(self, eng, step, band, world, dist):
+        """Albedo and incoming shortwave rasters of the last row (model.py:235-236, :408), from the
+        debug view of the kernel's own arithmetic."""
+        d = eng.dump_steps(step, step + 1)[0]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            alb = d[_lib.D_ALBEDO]
+            inc = d[_lib.D_RS] / (1.0 - alb)                        # rs = incoming * (1 - albedo), model.py:497
+        if world > 1:
+            alb = self._gather_rows(alb, self.bands, dist.get_rank(), dist)
+            inc = self._gather_rows(inc, self.bands, dist.get_rank(), dist)
+        self.albedo, self.incoming_shortwave = alb, inc
+
     def _read_insolation(self, rows, t0, t1, v):
         """Per-step potential insolation rasters [kWh m-2], read where model.py:465-481 reads them."""
         h, w = self.base_dem_array.shape
@@ -294,8 +441,11 @@ class Energy:
                 out[i - t0] = np.load(os.path.join(self.pickle_dir, f"{os.path.basename(path)}.npy"))
         return out
 
-    def _write_rows(self, rows, t0, t1, stats, point, out_file, solar_file, table):
+    def _write_rows(self, rows, t0, t1, stats, point, out_file, solar_file, table, layers_pt=None):
         f32 = self.precision != "f64"
+        dbg = None
+        if self.debug_point_output is not None:
+            dbg = open(os.path.join(self.out_dir, self.debug_point_output), "a")
         with open(out_file, "a") as output, open(solar_file, "a") as solar:
             for i in range(t0, t1):
                 s = stats[i]
@@ -313,9 +463,20 @@ class Energy:
                 pot = point[i, _lib.P_POT_AWS]
                 pot = np.float32(pot) if f32 and self.use_precomputed else pot
                 solar.write("\n%s,%s,%s" % (rows[i]["DATE"], pot, table[i, _lib.F_SWD]))   # model.py:519-520
+                if dbg is not None:                                  # model.py:413, :421-426, :441-448
+                    line = "\n%s" % rows[i]["DATE"]
+                    if self.use_msm and self.msm_xy is not None and layers_pt is not None:
+                        for tl in layers_pt[i]:
+                            line += ",%.2f" % tl
+                    line += ",%.1f,%.1f" % (point[i, _lib.P_SENS_AWS], point[i, _lib.P_LAT_AWS])
+                    dbg.write(line)
+        if dbg is not None:
+            dbg.close()
 
-    def _pull_state(self, eng):
+    def _pull_state(self, eng, bands=None, rank=0, dist=None):
         swe, tsn, tic = eng.state(np.float32)
+        if dist is not None:
+            swe, tsn, tic = (self._gather_rows(a, bands, rank, dist) for a in (swe, tsn, tic))
         self.swe_array, self.total_snow_melt_array, self.total_ice_melt_array = swe, tsn, tic
 
     def export_result(self):
@@ -329,7 +490,7 @@ class Energy:
 
     # ---- config_template.json -------------------------------------------------------------------------
     @classmethod
-    def from_config(cls, config, precision="f32", device=0):
+    def from_config(cls, config, precision="f32", device=None):
         """Builds an Energy object and the keyword arguments of model() from a dict / JSON file laid
         out like the reference's config_template.json (which the reference itself never loads,
         SURVEY.md F6).  Returns (energy, model_kwargs)."""

@@ -142,7 +142,12 @@ class ShardedShading:
         torch = self.torch
         eng, me, world = self.eng, self.rank, self.world
         sp = stream.cuda_stream
-        for (c0, c1) in self.chunks(t0, t1, sub_counts):
+        chunks = self.chunks(t0, t1, sub_counts)
+        if len(chunks) > 1:
+            eng.defer_snow_total(True)            # the rasters must not depend on where the run is cut
+        for q, (c0, c1) in enumerate(chunks):
+            if len(chunks) > 1 and q == len(chunks) - 1:
+                eng.defer_snow_total(False)
             s0, s1 = eng.sub_range(c0, c1)
             shares = split_even(s0, s1, world)
             a, b = shares[me]

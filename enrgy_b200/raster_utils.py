@@ -82,6 +82,25 @@ def load_raster(raster_path, crop_path, res, remove_negatives=False, remove_outl
     return array, gt, proj
 
 
+def load_uncropped_like(raster_path, geotransform, shape):
+    """`raster_path` warped to UTM 33N onto the grid (geotransform, shape) of an already loaded cropped
+    raster, WITHOUT the cutline: the terrain SAGA sees around the glacier (the reference passes it the
+    uncropped DEM file, model.py:469 -> saga_lighting.py:42).  Needs GDAL."""
+    gdal = _gdal()
+    if gdal is None:
+        raise ImportError("GDAL (osgeo) is needed to re-read %r without the cutline" % (raster_path,))
+    rows, cols = shape
+    ulx, dx, _, uly, _, dy = geotransform
+    bounds = (ulx, uly + rows * dy, ulx + cols * dx, uly)           # (minX, minY, maxX, maxY); dy < 0
+    ds = gdal.Warp("", gdal.Open(raster_path), dstSRS=UTM33N, format="VRT", outputType=gdal.GDT_Float32,
+                   xRes=abs(dx), yRes=abs(dy), outputBounds=bounds)
+    band = ds.GetRasterBand(1)
+    nodata = band.GetNoDataValue()
+    array = band.ReadAsArray()
+    array[array == nodata] = np.nan
+    return array
+
+
 def export_array_as_geotiff(array_to_export, geotransform, projection, path, scale_mult=None):
     """Float32 GeoTIFF with nodata -9999 (Int16 / -32768 when scale_mult is given),
     raster_utils.py:56-82.  Without GDAL the same array is written to `<path>.npy`."""

@@ -180,8 +180,9 @@ def make_case(n=256, n_steps=24, seed=0, cell=10.0, glacier_mask=True, albedo_da
 
 
 def make_band_case(n, n_steps, world=1, rank=0, seed=0, cell=10.0, glacier_mask=True,
-                   albedo_dates=None, step_s=3600, start="20220601 00:00:00", balance=True):
-    """Weak-scaling workload: a (world*n) x n raster cut into `world` row bands.
+                   albedo_dates=None, step_s=3600, start="20220601 00:00:00", balance=True, rows_full=None):
+    """Weak-scaling workload: a (world*n) x n raster cut into `world` row bands -- or, with
+    `rows_full`, STRONG scaling: a fixed rows_full x n raster cut into `world` row bands.
 
     With `balance` the band edges are placed so that every rank visits the same number of TILES
     (off-glacier tiles cost nothing, a tile on the glacier margin costs as much as a full one;
@@ -190,11 +191,14 @@ def make_band_case(n, n_steps, world=1, rank=0, seed=0, cell=10.0, glacier_mask=
     maps / SWE of `rank` and the AWS description of the FULL raster (aws_rc in full-raster
     coordinates); `dem_full` is the whole DEM (replicated on every rank)."""
     from .parallel import row_bands, tile_cost_per_row
-    rows_full = n * world
+    strong = rows_full is not None
+    rows_full = n * world if rows_full is None else int(rows_full)
     dem_full = make_dem(rows_full, n, seed=seed, cell=cell, glacier_mask=glacier_mask)
     if balance and world > 1:
         # equal numbers of visited tiles (a tile on the glacier margin costs as much as a full one)
         bands = row_bands(rows_full, world, align=16, valid_per_row=tile_cost_per_row(~np.isnan(dem_full)))
+    elif strong:
+        bands = row_bands(rows_full, world, align=16)
     else:
         bands = [(r * n, n) for r in range(world)]
     r0, nrows = bands[rank]

@@ -90,6 +90,8 @@ enum {
   ENRGY_P_TSURF_AWS,    /* surface temperature at the AWS cell [deg C]    model.py:347 */
   ENRGY_P_QH_AWS,       /* point sensible flux of the last iteration */
   ENRGY_P_NSUB,         /* number of sunlit sub-steps of the row */
+  ENRGY_P_SENS_AWS,     /* distributed sensible flux at the AWS cell [W m-2]  model.py:443 */
+  ENRGY_P_LAT_AWS,      /* distributed latent flux at the AWS cell [W m-2]    model.py:444 */
   ENRGY_P_COUNT
 };
 
@@ -197,6 +199,13 @@ int enrgy_set_insolation(enrgy_ctx* ctx, int t0, int n, const float* pot);
 /* pre-pass: per-step scalars at the AWS cell (model.py:347-358, :500-530, turbo.py:88-137) */
 int enrgy_prepass(enrgy_ctx* ctx);
 int enrgy_get_point_scalars(enrgy_ctx* ctx, double* out /* [n_steps][ENRGY_P_COUNT] */);
+/* sub-surface model: boundary temperatures of the AWS cell BEFORE each row's update (the columns
+ * debug_point_output prints when msm_xy is the AWS cell, model.py:421-426); out [n_steps][msm_layers + 1] */
+int enrgy_get_point_layers(enrgy_ctx* ctx, double* out);
+/* the AWS cell's own values for a handle whose row band does not hold it (the sub-surface pre-pass
+ * integrates that cell on every rank): its albedo-map values and initial SWE.  Call after
+ * enrgy_set_albedo_maps / enrgy_set_swe. */
+int enrgy_set_aws_cell(enrgy_ctx* ctx, int n_maps, const double* albedo_at_aws, double swe_at_aws);
 /* the same pre-pass WITHOUT a device or a handle (host arithmetic only): the per-row scalars of
  * model.py:347-358 / :500-530 for a full host DEM [rows][cols] -- Monin-Obukhov length, CH, potential
  * insolation and shortwave factor at the AWS cell, sunlit sub-step count.  pot_aws: potential
@@ -244,6 +253,11 @@ int enrgy_shade_scan(enrgy_ctx* ctx, int sub0, int sub1, int n_seg, const int* s
 /* the fused kernels over the rows [t0, t1) with the caller's masks of this handle's band for exactly
  * the sub-steps of enrgy_sub_range(t0, t1); otherwise like enrgy_run_async */
 int enrgy_run_masked(enrgy_ctx* ctx, int t0, int t1, const void* d_masks, double* d_stats, void* stream);
+/* A run the CALLER cuts into several enrgy_run_masked / enrgy_run_async calls (chunks of rows): call with
+ * on = 1 before the first and with on = 0 before the last.  The snow-melt total is then formed once, as
+ * SWE(start of the run) - SWE(end), exactly as a single call over the whole range forms it, so the
+ * rasters do not depend on where the run was cut (enrgy_run does the same for its own chunks). */
+int enrgy_defer_snow_total(enrgy_ctx* ctx, int on);
 /* device memory enrgy_run may spend on the masks of one chunk of rows (default 16 GiB; a season that
  * does not fit is processed in chunks: sweep, fused kernels, sweep, ...) */
 int enrgy_set_mask_budget(enrgy_ctx* ctx, int64_t bytes);

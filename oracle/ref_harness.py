@@ -27,7 +27,20 @@ import contextlib
 
 import numpy as np
 
-REFERENCE_DIR = os.environ.get("ENRGY_REFERENCE_DIR", "/root/reference")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference():
+    """The reference checkout (build container), else the unmodified copy __graft_entry__.build() puts
+    under baseline/_ref/ (git-ignored; it travels to the GPU box, where bench.py --impl reference and
+    the cpu_baseline leg time it)."""
+    for d in (os.environ.get("ENRGY_REFERENCE_DIR"), "/root/reference", os.path.join(_ROOT, "baseline", "_ref")):
+        if d and os.path.isfile(os.path.join(d, "model.py")):
+            return d
+    return os.environ.get("ENRGY_REFERENCE_DIR", "/root/reference")
+
+
+REFERENCE_DIR = _find_reference()
 
 
 def reference_available():
@@ -187,12 +200,15 @@ def run_reference(case, insolation, *, f64=False, const_albedo=None, use_albedo_
             amaps = None
             if const_albedo is None and use_albedo_maps:
                 amaps = {k: "alb_" + k for k in case.albedo_maps}
+            import time as _time
             with _Recorder(ref, keep_steps) as rec:
+                _t_model = _time.perf_counter()
                 e.model(aws_file=aws_csv, albedo_maps=amaps, z=z, elev_aws=case.elev_aws,
                         xy_aws=case.xy_aws, zm=zm, z_h_or_e=z_h_or_e, andreas=andreas,
                         const_albedo=const_albedo, temp_lapse_rate=temp_lapse_rate,
                         last_snowfall=last_snowfall, max_ice_albedo=max_ice_albedo,
                         emissivity=emissivity, v=False)
+                _t_model = _time.perf_counter() - _t_model
         with open(os.path.join(out_dir, "heat_fluxes.csv")) as f:
             stats_csv = f.read()
         with open(os.path.join(out_dir, "solar_output.csv")) as f:
@@ -201,7 +217,7 @@ def run_reference(case, insolation, *, f64=False, const_albedo=None, use_albedo_
                     swe=np.array(e.swe_array), total_snow=np.array(e.total_snow_melt_array),
                     total_ice=np.array(e.total_ice_melt_array), exported=exported,
                     layer_temperatures=None if msm is None else [np.array(t) for t in e.layer_temperatures],
-                    numpy=np.__version__, n_steps=n_steps)
+                    numpy=np.__version__, n_steps=n_steps, model_seconds=_t_model)
     finally:
         m.load_raster, m.show_me, m.export_array_as_geotiff = saved
         ref.var_classes.PARAMS.clear()

@@ -89,27 +89,117 @@ def test_in_kernel_insolation_replaces_saga(tmp_path):
     assert P.max_rel_err(e.total_snow_melt_array, ora["total_snow"], 1e-3) < 2e-7
 
 
-def test_from_config(tmp_path):
-    case = make_case(48, 12, w=64, seed=19)
+def test_from_config_against_the_oracle(tmp_path):
+    """config_template.json layout -> Energy + model() keyword arguments; the run against the oracle
+    given the same knobs by hand (GRADIENT column as the lapse rate, snow ageing, ice-albedo cap,
+    correction factors, cloud correction, snow density, checkpoints, stakes)."""
+    import json
+    case = make_case(48, 30, w=64, seed=19, with_gradient=True)
     d = str(tmp_path)
     dem, swe, alb, aws = _write_case(case, d)
+    stakes = os.path.join(d, "stakes.csv")
+    pts = [(10, 20), (24, 32), (40, 50), (0, 0)]                    # the last one is off-glacier (NaN)
+    with open(stakes, "w") as f:
+        f.write("name,easting,northing\n")
+        for k, (r, c) in enumerate(pts):
+            f.write("s%d,%.1f,%.1f\n" % (k, case.geotransform[0] + (c + 0.5) * case.cell,
+                                        case.geotransform[3] - (r + 0.5) * case.cell))
     cfg = {
         "input": {"dem": dem, "outlines": None,
                   "aws": {"file": aws, "elev": case.elev_aws, "xy": list(case.xy_aws), "sensor_z": 1.6},
-                  "vertical_lapse_rates": {"t_air": -0.0065}},
-        "output": {"out_dir": os.path.join(d, "out"), "resolution": 10, "verbose": False, "png_export": 720},
+                  "vertical_lapse_rates": {"t_air": "GRADIENT"}},
+        "output": {"out_dir": os.path.join(d, "out"), "resolution": 10, "verbose": False, "png_export": 720,
+                   "dates": ["20220601"], "stake_coords": stakes, "debug_point_output": "point.csv"},
         "albedo": {"use_const": False, "last_snowfall": "20220522", "max_ice_albedo": 0.38, "albedo_maps": alb},
         "solar": {"use_precomputed": False},
-        "turbo": {"zm": 0.001, "z_h_or_e": 0.0001, "andreas": False, "sensible_corr_factor": 1, "latent_corr_factor": 1},
-        "longwave": {"emissivity": 0.98, "cloud_corr": 0.0},
-        "snow": {"use": True, "density": 387.0, "swe_grid": swe},
+        "turbo": {"zm": 0.001, "z_h_or_e": 0.0001, "andreas": True, "sensible_corr_factor": 1.1, "latent_corr_factor": 0.9},
+        "longwave": {"emissivity": 0.97, "cloud_corr": 0.1},
+        "snow": {"use": True, "density": 350.0, "swe_grid": swe},
         "msm": {"use": False},
     }
-    e, kw = Energy.from_config(cfg, precision="f32")
+    cfg_path = os.path.join(d, "config.json")
+    with open(cfg_path, "w") as f:
+        json.dump(cfg, f)
+    e, kw = Energy.from_config(cfg_path, precision="f64")
     e.lat, e.lon = case.lat, case.lon
     e.model(**kw)
-    assert e.stats.shape == (12, _lib_count())
-    assert np.isfinite(np.nanmean(e.total_ice_melt_array))
+    pot = I.insolation_series(case, shadow=True, dtype=np.float64)
+    okw = dict(temp_lapse_rate="GRADIENT", last_snowfall="20220522", max_ice_albedo=0.38, andreas=True,
+               sensible_corr=1.1, latent_corr=0.9, emissivity=0.97, cloud_corr=0.1, snow_density=350.0)
+    ora = P.run_oracle(case, pot, True, **okw)
+    assert e.stats.shape == (30, _lib_count())
+    assert P.max_rel_err(e.total_ice_melt_array, ora["total_ice"], 1e-3) < 2e-7
+    assert P.max_rel_err(e.total_snow_melt_array, ora["total_snow"], 1e-3) < 2e-7
+    assert P.max_rel_err(e.swe_array, ora["swe"], 1e-3) < 2e-7
+    got, want = _csv_numbers(open(os.path.join(d, "out", "heat_fluxes.csv")).read()), _csv_numbers(ora["stats_csv"])
+    assert [g[0] for g in got] == [w[0] for w in want]
+    lim = [0.1001] * 8 + [0.0101] + [0.00011] * 3 + [1.001]
+    for (_, a), (_, b) in zip(got, want):
+        assert all(abs(x - y) <= l for x, y, l in zip(a, b, lim)), (a, b)
+    # debug_point_output (model.py:170-180, :441-448): header + "DATE,sensible,latent" at the AWS cell per row
+    lines = open(os.path.join(d, "out", "point.csv")).read().split("\n")
+    assert lines[0] == "SENSIBLE,LATENT" and len(lines) == 31
+    r, c = case.aws_rc
+    for i, line in enumerate(lines[1:]):
+        date, sens, lat = line.split(",")
+        assert date == case.aws_rows[i]["DATE"]
+        assert abs(float(sens) - float(ora["rows"][i]["sens"][r, c])) <= 0.0501
+        assert abs(float(lat) - float(ora["rows"][i]["lat"][r, c])) <= 0.0501
+    # stakes sampled at the checkpoint row (model.py:102-120, :279-283): ice melt after the first 13 rows
+    k = [row["DATE"] for row in case.aws_rows].index("20220601 12:00:00") + 1
+    import dataclasses
+    part = dataclasses.replace(case, aws_rows=case.aws_rows[:k + 1])     # (one more row: same time step for row k-1)
+    out = open(os.path.join(d, "out", "ice_melt_point.csv")).read().strip().split("\n")
+    assert out[0] == "name,20220601 12:00:00" and len(out) == 5
+    ora_full = P.run_oracle(part, pot[:k + 1], True, **okw)
+    ice_k = np.asarray(ora_full["total_ice"], dtype=np.float64) - np.asarray(ora_full["melt"][k][1], dtype=np.float64)
+    for line, (rr, cc) in zip(out[1:], pts):
+        name, val = line.split(",")
+        if np.isnan(case.dem[rr, cc]):
+            assert val == ""                                          # NaN -> empty field, as pandas writes it
+        else:
+            assert abs(float(val) - ice_k[rr, cc]) <= 0.0011
+
+
+def test_views_left_behind_and_repeated_calls(tmp_path):
+    """After model(): `aws`, `vars` (DistributedVars of the last row), `albedo`, `incoming_shortwave`
+    (model.py:229-236, :408); a second model() call continues from the state of the first
+    (model.py:258-261 accumulates in place)."""
+    import dataclasses
+    case = make_case(56, 24, w=72, seed=43)
+    d = str(tmp_path)
+    dem, swe, alb, aws = _write_case(case, d)
+    first, second = dataclasses.replace(case, aws_rows=case.aws_rows[:12]), dataclasses.replace(case, aws_rows=case.aws_rows[12:])
+    aws1, aws2 = first.write_aws_csv(os.path.join(d, "aws1.csv")), second.write_aws_csv(os.path.join(d, "aws2.csv"))
+    kw = dict(albedo_maps=alb, z=1.6, elev_aws=case.elev_aws, xy_aws=case.xy_aws, zm=1e-3, z_h_or_e=1e-4,
+              emissivity=0.98, v=False)
+    e = Energy(dem, None, os.path.join(d, "out"), res=10, precision="f64")
+    e.lat, e.lon = case.lat, case.lon
+    e.add_snow(swe)
+    e.model(aws_file=aws1, **kw)
+    pot = I.insolation_series(case, shadow=True, dtype=np.float64)
+    o1 = P.run_oracle(first, pot[:12], True)
+    valid = ~np.isnan(case.dem)
+    # views of the last row of the first call
+    last = o1["rows"][-1]
+    assert np.allclose(e.albedo[valid], np.asarray(last["albedo"])[valid], rtol=1e-9)
+    inc = np.asarray(last["rs"])[valid] / (1.0 - np.asarray(last["albedo"])[valid])
+    assert np.allclose(e.incoming_shortwave[valid], inc, rtol=1e-9, atol=1e-9)
+    row = first.aws_rows[-1]
+    assert e.aws.Tz == float(row["T_AIR"]) + 273.15 and e.aws.P == float(row["PRESSURE"]) * 100
+    t_air = float(row["T_AIR"]) + (case.dem.astype(np.float64) - case.elev_aws) * -0.006
+    assert np.allclose(e.vars.t_air[valid], t_air[valid]) and np.allclose(e.vars.Tz[valid], t_air[valid] + 273.15)
+    assert np.allclose(e.vars.pressure[valid], (float(row["PRESSURE"]) + (case.dem - case.elev_aws) * -0.1145)[valid])
+    assert e.vars.rel_humidity.shape == case.dem.shape and e.vars.wind_speed.dtype == np.float32
+    # second call: starts from the first call's SWE, melt totals keep growing
+    e.model(aws_file=aws2, **kw)
+    second_case = dataclasses.replace(second, swe=np.asarray(o1["swe"], dtype=np.float32))
+    o2 = P.run_oracle(second_case, pot[12:], True)
+    tot_ice = np.asarray(o1["total_ice"], dtype=np.float64) + np.asarray(o2["total_ice"], dtype=np.float64)
+    tot_snow = np.asarray(o1["total_snow"], dtype=np.float64) + np.asarray(o2["total_snow"], dtype=np.float64)
+    assert P.max_rel_err(e.total_ice_melt_array, tot_ice, 1e-3) < 5e-7
+    assert P.max_rel_err(e.total_snow_melt_array, tot_snow, 1e-3) < 5e-7
+    assert P.max_rel_err(e.swe_array, o2["swe"], 1e-3) < 5e-7
 
 
 def _lib_count():

@@ -186,3 +186,78 @@ def test_band_cuts_properties_randomised():
             assert sum(n for _, n in again) == rows
             assert max(abs(a[0] - b[0]) for a, b in zip(again, bands)) <= align
     check()
+
+
+# ---- Energy.model over two ranks (gloo), the per-band numbers from an oracle-backed engine stand-in ----
+def _energy_worker(rank, world, port, d):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from enrgy_b200 import Energy
+        from tests.fake_engine import FakeEngine
+        case = make_case(96, 8, seed=31, w=48)
+        pot = np.load(os.path.join(d, "pot.npy"))
+        keys = list(case.albedo_maps)
+
+        def factory(rows, cols, precision, device):
+            f = FakeEngine(rows, cols, precision, device)
+            f.aws_rows, f.geotransform, f.xy_aws, f.albedo_keys = case.aws_rows, case.geotransform, case.xy_aws, keys
+            f.pot_aws = [float(pot[i][case.aws_rc]) for i in range(len(case.aws_rows))]
+            return f
+        e = Energy(os.path.join(d, "dem.npy"), None, os.path.join(d, "out"), res=10, precision="f64")
+        e._engine_factory = factory
+        e.debug_views = False
+        e.use_precomputed = True
+        e.add_pickle_dir(os.path.join(d, "pickle"))
+        e.add_snow(os.path.join(d, "swe.npy"))
+        e.add_checkpoints(["20220601"])
+        e.model(aws_file=os.path.join(d, "aws.csv"), albedo_maps={k: os.path.join(d, "alb_%s.npy" % k) for k in keys},
+                z=1.6, elev_aws=case.elev_aws, xy_aws=case.xy_aws, zm=1e-3, z_h_or_e=1e-4, emissivity=0.98, v=False)
+        np.save(os.path.join(d, "ice_rank%d.npy" % rank), e.total_ice_melt_array)
+        np.save(os.path.join(d, "swe_rank%d.npy" % rank), e.swe_array)
+        if rank == 0:
+            np.save(os.path.join(d, "bands.npy"), np.array(e.bands))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_energy_model_two_ranks(tmp_path):
+    """`Energy.model` under a 2-rank process group: bands cut by visited tiles, each rank feeds its band,
+    statistics all-reduced, rank 0 writes heat_fluxes.csv, every rank ends with the full rasters --
+    equal to the single-process oracle on the whole raster."""
+    from enrgy_b200.raster_utils import save_npy_raster
+    d = str(tmp_path)
+    case = make_case(96, 8, seed=31, w=48)
+    pot = P.random_insolation(case, 8, seed=2)
+    np.save(os.path.join(d, "pot.npy"), pot)
+    save_npy_raster(os.path.join(d, "dem.npy"), case.dem, case.geotransform)
+    save_npy_raster(os.path.join(d, "swe.npy"), case.swe, case.geotransform)
+    for k, a in case.albedo_maps.items():
+        save_npy_raster(os.path.join(d, "alb_%s.npy" % k), a, case.geotransform)
+    case.write_aws_csv(os.path.join(d, "aws.csv"))
+    os.makedirs(os.path.join(d, "pickle", "10"))
+    for i, row in enumerate(case.aws_rows):
+        np.save(os.path.join(d, "pickle", "10", "%s_total.sdat.npy" % row["DATE"]), pot[i])
+    world = 2
+    mp.spawn(_energy_worker, args=(world, _free_port(), d), nprocs=world, join=True)
+    bands = np.load(os.path.join(d, "bands.npy"))
+    assert len(bands) == 2 and bands[0][0] == 0 and bands[1][0] % 16 == 0 and bands[1][0] + bands[1][1] == 96
+    whole = P.run_oracle(case, pot, True)
+    for rank in range(world):
+        ice = np.load(os.path.join(d, "ice_rank%d.npy" % rank))
+        swe = np.load(os.path.join(d, "swe_rank%d.npy" % rank))
+        assert ice.shape == case.dem.shape and ice.dtype == np.float32
+        assert P.max_rel_err(ice, whole["total_ice"], 1e-6) < 1e-6
+        assert P.max_rel_err(swe, whole["swe"], 1e-6) < 1e-6
+    text = open(os.path.join(d, "out", "heat_fluxes.csv")).read()
+    got = [line.split(",") for line in text.split("\n") if line[:2] == "20"]
+    want = [line.split(",") for line in whole["stats_csv"].split("\n") if line[:2] == "20"]
+    assert len(got) == len(want) == 8
+    for g, w in zip(got, want):
+        assert g[0] == w[0]
+        lim = [0.1001] * 8 + [0.0101] + [0.00011] * 3 + [1.001]
+        assert all(abs(float(x) - float(y)) <= l for x, y, l in zip(g[1:], w[1:], lim)), (g, w)
+    files = os.listdir(os.path.join(d, "out"))
+    # one export (the final one, written by rank 0 only; without GDAL a .npy + its side-car json)
+    assert sum("remaining_snow_cover" in f and f.endswith(".npy") for f in files) == 1
