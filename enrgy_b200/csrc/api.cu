@@ -519,6 +519,8 @@ int launch_range(enrgy_ctx* c, int t0, int t1, double* d_stats, cudaStream_t str
   KernelArgs<R> a;
   fill_args<R>(c, t0, t1, a);
   a.masks = masks; a.mask_sub0 = mask_sub0;
+  a.mask_sub_last = t1 > t0 ? c->pre.sub_first[t1 - 1] + c->pre.sub_count[t1 - 1] - 1 : mask_sub0;
+  if (a.mask_sub_last < mask_sub0) a.mask_sub_last = mask_sub0;
   const int insol = insol_variant(c);
   if (insol == kInsolMasked && masks == nullptr) return fail(ENRGY_ERR_ARG, "no sunlit masks for a run with shading");
   LaunchInfo li;
@@ -589,6 +591,7 @@ int dump_typed(enrgy_ctx* c, int t0, int t1, double* out) {
     if (int e = ensure_masks(c, s0, s1, c->stream)) return e;
     a.masks = c->d_maskbuf.p + (size_t)(s0 - c->mask_sub0) * mask_words_per_sub(c, c->band_rows);
     a.mask_sub0 = s0;
+    a.mask_sub_last = std::max(s1 - 1, s0);
   }
   CU_TRY(c->d_dump.alloc((size_t)n * per_step * sizeof(R)));
   CU_TRY(cudaMemsetAsync(c->d_dump.p, 0xFF, (size_t)n * per_step * sizeof(R), c->stream));

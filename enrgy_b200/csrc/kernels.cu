@@ -521,6 +521,10 @@ __host__ __device__ inline SmemPlan<R> smem_plan(int warps, int cap_steps, int c
 #define ENRGY_SUB_UNROLL 4
 #endif
 constexpr int kSubUnroll = ENRGY_SUB_UNROLL;   // unroll factor of the insolation sub-step loop
+#ifndef ENRGY_MASK_AHEAD
+#define ENRGY_MASK_AHEAD 4
+#endif
+constexpr int kMaskAhead = ENRGY_MASK_AHEAD;   // sunlit masks are prefetched this many sub-steps ahead
 template <typename R, int K, int INSOL, bool MSM, bool DUMP>
 __global__ void __launch_bounds__(32 * kWarpsFor<R, INSOL>, sizeof(R) == 4 ? ENRGY_MINB32 : ENRGY_MINB64)
 energy_balance_kernel(const KernelArgs<R> a) {
@@ -1024,6 +1028,11 @@ energy_balance_kernel(const KernelArgs<R> a) {
             unsigned mw[K];
             if (INSOL == kInsolMasked) {
               const unsigned* mp = mask_patch + (size_t)(tb.sub_begin + j) * a.mask_sub_stride;
+              // the sector of the sub-step one row ahead goes to L1 now (no register, one lane)
+              if (lane == 0) {
+                const unsigned* ahead = mask_patch + (size_t)min(tb.sub_begin + j + kMaskAhead, a.mask_sub_last) * a.mask_sub_stride;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(ahead));
+              }
               if (K == 8) {
                 const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mp)), m1 = __ldg(reinterpret_cast<const uint4*>(mp) + 1);
                 mw[0] = m0.x; mw[1] = m0.y; mw[2 % K] = m0.z; mw[3 % K] = m0.w;

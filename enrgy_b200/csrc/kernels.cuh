@@ -24,6 +24,7 @@ struct KernelArgs {
   // rows of a row group are adjacent, so a warp patch (32 columns x K <= 8 rows) reads one 32-byte sector
   const unsigned* masks;
   int mask_sub0;                  // global index (over all sunlit sub-steps of the run) of the first mask
+  int mask_sub_last;              // ... and of the last one (prefetches are clamped to it)
   int mask_words;                 // column words per row = pitch / 32
   size_t mask_sub_stride;         // words between consecutive sub-steps
   const R* nx;                    // [band_rows_pad][pitch] terrain normal (computed insolation)

@@ -22,6 +22,10 @@
 
 #include <cstdio>
 
+#ifndef ENRGY_SWEEP_PIPE
+#define ENRGY_SWEEP_PIPE 1
+#endif
+
 namespace enrgy {
 
 namespace {
@@ -118,14 +122,12 @@ __global__ void __launch_bounds__(32 * Q) sweep_kernel(const SweepArgs a) {
   const double dz = s.dz;
   const int words_needed = (nb + 31) >> 5;
   // current destination segment (row type)
-  int seg_lo = 0, seg_hi = 0, seg_rg = 0, seg_words = 0;
-  unsigned* seg_ptr = nullptr;
+  int seg_lo = 0, seg_words = 0;
 
-  for (int u0 = ub; u0 >= ua; u0 -= U) {
-    // loads of U rows first (addresses do not depend on the running maxima); rows past ua are inside
-    // the -inf aprons or harmless (nothing is emitted for them)
-    float h[U][V];
-    int col0[U];
+  // U rows per iteration; the loads of the NEXT iteration are issued before the current one is worked
+  // on (two register buffers, the loop body exists twice), so a warp hides a full iteration of memory
+  // latency by itself.  Rows past ua are inside the -inf aprons or harmless (nothing is emitted).
+  auto load_rows = [&](int u0, float (&h)[U][V], int (&col0)[U]) {
 #pragma unroll
     for (int i = 0; i < U; ++i) {
       const int u = u0 - i;
@@ -134,6 +136,19 @@ __global__ void __launch_bounds__(32 * Q) sweep_kernel(const SweepArgs a) {
 #pragma unroll
       for (int v = 0; v < V; ++v) h[i][v] = __ldg(rowp + 32 * v);
     }
+  };
+  // Emission: the V ballots of a row cover the cells col0 .. col0 + 32 V - 1; the words aligned to 32
+  // cells start o = -col0 mod 32 bits in, so word j is a funnel shift of ballots j and j + 1.  Every lane
+  // holds all ballots, but "ballot number `lane`" is a register indexed by the lane id -- a select chain
+  // that cost more than the sweep itself (r2c profile: 60 % of the instructions).  Instead the ballots of
+  // the U rows go through a 32-byte row of shared memory per warp (every lane writes the same words),
+  // and lane j reads words j, j + 1 back: two vector stores, two loads and one funnel shift per row.
+  __shared__ __align__(16) unsigned s_ballots[Q][U][V];
+  unsigned (*my_b)[V] = s_ballots[warp];
+  // destination of the current segment and sub-step (row type) / of this sub-step (column type)
+  unsigned* out_base = ROW ? nullptr : a.tmp + (size_t)s.out * a.cols * a.tmp_words;
+  int seg_n = 0;
+  auto process = [&](int u0, const float (&h)[U][V], const int (&col0)[U]) {
 #pragma unroll
     for (int i = 0; i < U; ++i) {
       const int u = u0 - i;
@@ -146,38 +161,66 @@ __global__ void __launch_bounds__(32 * Q) sweep_kernel(const SweepArgs a) {
         M[v] = shaded ? M[v] : g;
         B[v] = __ballot_sync(full, !shaded);
       }
-      if (u < ua) continue;                        // (warp-uniform)
-      // the V ballots cover the cells col0 .. col0 + 32 V - 1; words aligned to 32 cells start o bits in
-      const int o = (-col0[i]) & 31;
-      const int cw0 = (col0[i] + o) >> 5;
-      unsigned w = 0;
+      if (V % 4 == 0) {
 #pragma unroll
-      for (int j = 0; j < V - 1; ++j) {
-        const unsigned wj = __funnelshift_r(B[j], B[j + 1], o);
-        w = lane == j ? wj : w;
+        for (int v = 0; v < V; v += 4) *reinterpret_cast<uint4*>(&my_b[i][v]) = make_uint4(B[v], B[v + 1], B[(v + 2) % V], B[(v + 3) % V]);
+      } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) my_b[i][v] = B[v];
       }
-      const int cw = cw0 + lane;
-      const bool mine = lane < V - 1 && (unsigned)cw < (unsigned)words_needed;
+    }
+    __syncwarp();
+    const int jl = min(lane, V - 2);
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const int u = u0 - i;
+      const int o = (-col0[i]) & 31;
+      const int cw = ((col0[i] + o) >> 5) + lane;
+      const unsigned w = __funnelshift_r(my_b[i][jl], my_b[i][jl + 1], o);
+      const bool mine = lane < V - 1 && (unsigned)cw < (unsigned)words_needed && u >= ua;
       const int idx = s.sigma * u;                 // row (row type) / column (column type)
       if (ROW) {
-        if (idx < seg_lo || idx >= seg_hi) {
-          seg_ptr = nullptr; seg_lo = 0; seg_hi = 0;
+        if ((unsigned)(idx - seg_lo) >= (unsigned)seg_n) {          // (warp-uniform, rare: a new segment)
+          out_base = nullptr; seg_lo = 0; seg_n = 0;
           for (int q = 0; q < a.n_seg; ++q) {
             if (idx >= a.seg[q].row0 && idx < a.seg[q].row0 + a.seg[q].rows) {
-              seg_lo = a.seg[q].row0; seg_hi = seg_lo + a.seg[q].rows;
-              seg_rg = a.seg[q].rg; seg_words = a.seg[q].words; seg_ptr = a.seg[q].ptr;
+              seg_lo = a.seg[q].row0; seg_n = a.seg[q].rows; seg_words = a.seg[q].words;
+              out_base = a.seg[q].ptr + (size_t)s.out * a.seg[q].rg * a.seg[q].words * 8;
             }
           }
         }
-        if (mine && seg_ptr != nullptr) {
+        if (mine && out_base != nullptr) {
           const int local = idx - seg_lo;
-          seg_ptr[(((size_t)s.out * seg_rg + (local >> 3)) * seg_words + cw) * 8 + (local & 7)] = w;
+          out_base[(((local >> 3) * seg_words + cw) << 3) + (local & 7)] = w;
         }
       } else {
-        if (mine) a.tmp[((size_t)s.out * a.cols + idx) * a.tmp_words + cw] = w;
+        if (mine) out_base[idx * a.tmp_words + cw] = w;
       }
     }
+    __syncwarp();
+  };
+#if ENRGY_SWEEP_PIPE
+  {
+    float ha[U][V], hb[U][V];
+    int ca[U], cb[U];
+    load_rows(ub, ha, ca);
+    for (int u0 = ub; u0 >= ua; u0 -= 2 * U) {
+      const bool more = u0 - U >= ua;
+      if (more) load_rows(u0 - U, hb, cb);
+      process(u0, ha, ca);
+      if (!more) break;
+      if (u0 - 2 * U >= ua) load_rows(u0 - 2 * U, ha, ca);
+      process(u0 - U, hb, cb);
+    }
   }
+#else
+  for (int u0 = ub; u0 >= ua; u0 -= U) {
+    float h[U][V];
+    int col0[U];
+    load_rows(u0, h, col0);
+    process(u0, h, col0);
+  }
+#endif
 }
 
 // ---- 32 x 32 bit blocks of the column-type temporaries turned around --------------------------------

@@ -13,8 +13,8 @@ mkdir -p $root/scratch/variants
 # sources include "../../include/enrgy_b200.h": compile in place of the tree layout
 mkdir -p $tmp/a/b && cp $tmp/*.cu $tmp/*.cuh $tmp/a/b/ && mkdir -p $tmp/include && cp $root/include/enrgy_b200.h $tmp/include/
 cd $tmp/a/b
-for f in kernels prepass api; do $NVCC $FLAGS "$@" ${PTXAS_V:+-Xptxas -v} -c $f.cu -o $f.o & done
+for f in kernels shade prepass api; do $NVCC $FLAGS "$@" ${PTXAS_V:+-Xptxas -v} -c $f.cu -o $f.o & done
 wait
-$NVCC -shared -o $root/scratch/variants/$name.so kernels.o prepass.o api.o -cudart static
+$NVCC -shared -o $root/scratch/variants/$name.so kernels.o shade.o prepass.o api.o -cudart static
 rm -rf $tmp
 echo built scratch/variants/$name.so

@@ -120,9 +120,15 @@ def test_from_config_against_the_oracle(tmp_path):
     cfg_path = os.path.join(d, "config.json")
     with open(cfg_path, "w") as f:
         json.dump(cfg, f)
-    e, kw = Energy.from_config(cfg_path, precision="f64")
-    e.lat, e.lon = case.lat, case.lon
-    e.model(**kw)
+    from enrgy_b200.model import PARAMS
+    saved = dict(PARAMS)               # set_density changes the module global, as in the reference (model.py:84-88)
+    try:
+        e, kw = Energy.from_config(cfg_path, precision="f64")
+        e.lat, e.lon = case.lat, case.lon
+        e.model(**kw)
+    finally:
+        PARAMS.clear()
+        PARAMS.update(saved)
     pot = I.insolation_series(case, shadow=True, dtype=np.float64)
     okw = dict(temp_lapse_rate="GRADIENT", last_snowfall="20220522", max_ice_albedo=0.38, andreas=True,
                sensible_corr=1.1, latent_corr=0.9, emissivity=0.97, cloud_corr=0.1, snow_density=350.0)
