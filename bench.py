@@ -360,7 +360,6 @@ def bench_c3(ctx, args):
     ctx.barrier()
     log("rank %d: C3 setup %.1f s, kernel %s" % (ctx.rank, time.time() - t_setup, eng.kernel_info()))
     steps = max(3, min(args.steps, 5))
-    sh.exchange_bytes = 0
     ms_step = ctx.timed(one_pass, 2, steps)
     per_rank = ctx.gather([eng.last_sweep_ms(), eng.last_kernel_ms(), case.dem.shape[0]])
     n_sub = int(sub_counts.sum())
@@ -371,8 +370,8 @@ def bench_c3(ctx, args):
                        "topographic shading; %d row bands" % (n, n, T, n_sub, world),
            "sweep_ms_per_rank": [p[0] for p in per_rank], "fused_ms_per_rank": [p[1] for p in per_rank],
            "band_rows": [int(p[2]) for p in per_rank],
-           "exchange_bytes_per_pass_per_rank": int(sh.exchange_bytes // max(steps, 1)),
-           "sub_steps": n_sub}
+           "exchange": sh.exchange, "exchange_bytes_per_pass_per_rank": int(sh.bytes_sent_last_run),
+           "chunks_per_pass": len(sh.chunks(0, T, sub_counts)), "sub_steps": n_sub}
     if ctx.rank == 0:
         sweep_ms = max(p[0] for p in per_rank)
         mhz = 1965.0
@@ -653,7 +652,7 @@ def main():
     ap.add_argument("--no-configs", dest="configs", action="store_false", help="headline only")
     ap.add_argument("--no-single-core", dest="single_core", action="store_false")
     ap.add_argument("--c3-n", type=int, default=8192)
-    ap.add_argument("--c3-t", type=int, default=96)
+    ap.add_argument("--c3-t", type=int, default=384)
     ap.add_argument("--c5-n", type=int, default=4096)
     ap.add_argument("--c5-members", type=int, default=8, help="ensemble members per GPU")
     args = ap.parse_args()

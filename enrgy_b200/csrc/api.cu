@@ -196,7 +196,7 @@ int upload_tables(enrgy_ctx* c) {
     d.t_air = (R)s.t_air; d.lapse = (R)s.lapse; d.p_hpa = (R)s.p_hpa; d.e_aws = (R)s.e_aws;
     d.c_sens = (R)s.c_sens; d.c_lat = (R)s.c_lat; d.c_lwd = (R)s.c_lwd; d.c_lwu = (R)s.c_lwu;
     d.c_sw = (R)s.c_sw; d.c_melt = (R)s.c_melt; d.alb_w = (R)s.alb_w; d.snow_alb = (R)s.snow_alb;
-    d.dsum = (R)s.dsum; d.dt = (R)s.dt;
+    d.dsum = (R)s.dsum; d.dt = (R)s.dt; d.inv_dt = (R)s.inv_dt; d.c_lw0 = (R)s.c_lw0; d.c_lw1 = (R)s.c_lw1;
     d.dir_u = (R)s.dir_u; d.dir_e = (R)s.dir_e; d.dir_n = (R)s.dir_n;
     // (rounded DOWN into the kernel's precision: the test it feeds must stay conservative)
     d.tan2_min = (R)s.tan2_min;

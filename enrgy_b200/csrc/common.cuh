@@ -61,7 +61,7 @@ struct MsmParams {
   R inv_snow_density;                         // snow depth = swe / snow_density (model.py:428, sic)
 };
 
-// ---- per-step record (20 values, staged per time block by a TMA bulk copy) ---------------------
+// ---- per-step record (24 values, staged per time block by a TMA bulk copy) ---------------------
 template <typename R>
 struct alignas(16) StepRec {
   R t_air;     // T_AIR at the AWS [deg C]
@@ -84,6 +84,10 @@ struct alignas(16) StepRec {
   // patch for the whole step, max(cos i, 0) = cos i and the direct beam is dir_u + px dir_e + py dir_n
   R dir_u, dir_e, dir_n;
   R tan2_min;  // min over the sub-steps of tan^2(sun elevation); < 0: no sunlit sub-step
+  R inv_dt;    // 1 / dt (sub-surface model: the cold content of the surface layer per second)
+  R c_lw0;     // float32, no MSM: c_lwd * K0^4 - lwu with K0 = float(273.15) (net longwave of a cell at K0)
+  R c_lw1;     //                  c_lwd * K0^4
+  R pad_;
 };
 
 // ---- per-sub-step record (sun above the horizon only) ------------------------------------------

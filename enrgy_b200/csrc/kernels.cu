@@ -610,7 +610,11 @@ energy_balance_kernel(const KernelArgs<R> a) {
         valid_bits |= v ? (1u << i) : 0u;
         if (!v) z = (float)a.elev_aws;           // keep the arithmetic of masked cells finite
         d_[h] = (R)z - a.elev_aws;               // var_classes.py:114
-        p_[h] = Num<R>::pow10(-d_[h] / (R)kVapourScale);   // var_classes.py:162
+        // var_classes.py:162.  float32: the reference's power is NumPy's float32 power of a float32
+        // exponent (libm, correctly rounded in practice); powf here may be a few ulp off, which the
+        // vapour-pressure difference e - es amplifies into the largest float32 error of the whole
+        // balance (4e-5 W m-2) -- so the power is taken in float64 and rounded once (prologue only)
+        p_[h] = (R)pow(10.0, (double)(-d_[h] / (R)kVapourScale));
         if (INSOL != kInsolStreamed) {
           x_[h] = v ? a.nx[o] : (R)0;
           y_[h] = v ? a.ny[o] : (R)0;
@@ -859,55 +863,95 @@ energy_balance_kernel(const KernelArgs<R> a) {
           // rs + lwd - lwu + sens + lat as one FMA chain; the area sum of lwd is not reduced here: Tz
           // is linear in the elevation, so it follows from the first four moments of
           // (dem - elev_aws), see finalize_stats_kernel
-          const V lwu_neg = V::make(-lwu.lo(), -lwu.hi());
-          const V atmo = fma2(c_lat, x_lat, fma2(c_sens, x_sens, fma2(c_sw, x_rs, fma2(c_lwd, tz4, lwu_neg))));
+          V rl;                                             // lwd - lwu
+          if (sizeof(R) == 4 && !MSM) {
+            // float32: both terms are ~300 W m-2 and Tz^4 alone would cost 4e-5 W m-2 of rounding.
+            // With the (rounded, as in the reference) Tz = K0 + d_t, K0 = float(273.15) and d_t exact:
+            //   c_lwd Tz^4 - lwu = (c_lwd K0^4 - lwu) + c_lwd K0^4 ((1 + y)^4 - 1),  y = d_t / K0
+            // -- a per-row scalar from the float64 pre-pass plus a term of at most ~30 W m-2
+            const V y = mul2(d_t, V::splat((R)(1.0 / (double)273.15f)));
+            const V poly = mul2(y, fma2(y, fma2(y, add2(y, V::splat((R)4)), V::splat((R)6)), V::splat((R)4)));
+            rl = fma2(V::splat(s.c_lw1), poly, V::splat(s.c_lw0));
+          } else {
+            const V lwu_neg = V::make(-lwu.lo(), -lwu.hi());
+            rl = fma2(c_lwd, tz4, lwu_neg);
+          }
+          const V atmo = fma2(c_lat, x_lat, fma2(c_sens, x_sens, fma2(c_sw, x_rs, rl)));
           V mf, gfl = V::splat((R)0);
           if (MSM) {
-            R mfh[2], gh[2];
+            // explicit conduction through the layer stack and the surface-layer melt gate,
+            // msm.py:31-107 (snow depth = swe / snow_density, model.py:428)
+            const MsmParams<R>& m = a.msm;
+            const R dt = s.dt, inv_dt = s.inv_dt;
+            R mfh[2], gh[2], grad0[2], sd1[2];
+            // surface layer, msm.py:80-101 (per cell: its snow share sets conductivity and density)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int i = 2 * q + h;
-              // explicit conduction through the layer stack and the surface-layer melt gate,
-              // msm.py:31-107 (snow depth = swe / snow_density, model.py:428)
-              const MsmParams<R>& m = a.msm;
               const R atmo_h = h ? atmo.hi() : atmo.lo();
-              R sd = (h ? swe2[q].hi() : swe2[q].lo()) * m.inv_snow_density;
-              R grad_prev = (R)0, t_next = tl[i][0];
-              const R dt = s.dt;
-              const R inv_dt = (R)1 / dt;
-              R mfv = (R)0, gv = (R)0;
+              const R sd = (h ? swe2[q].hi() : swe2[q].lo()) * m.inv_snow_density;
+              const R t_here = tl[i][0];
+              const R grad = (tl[i][1] - t_here) * m.inv_d[0];              // msm.py:18-28
+              const R ratio = sd > m.d[0] ? (R)1 : sd * m.inv_d[0];         // msm.py:63
+              const R kap = ratio * m.k_snow + ((R)1 - ratio) * m.k_ice;
+              const R rho = ratio * m.rho_snow + ((R)1 - ratio) * m.rho_ice;
+              sd1[h] = fmax_(sd - m.d[0], (R)0);
+              const R gv = kap * grad * m.c_ice * rho;
+              const R full = atmo_h + gv;
+              const R crd = m.c_ice * rho * m.d[0];
+              const R q0 = -t_here * crd * inv_dt;
+              const R mfv = fmax_(full - q0, (R)0);
+              const R dlt = (full - mfv) * Num<R>::rcp(crd);
+              grad0[h] = grad; mfh[h] = mfv; gh[h] = gv;
+              if (sizeof(R) == 4) {
+                t0_acc[i] += (double)(dlt * dt);
+                tl[i][0] = (R)t0_acc[i];
+              } else {
+                tl[i][0] = t_here + dlt * dt;
+              }
+            }
+            // deeper layers, msm.py:103.  Snow that reaches below the surface layer is rare (it takes
+            // swe / snow_density > d[0]): where no cell of the warp has any, conductivity is that of ice
+            // in every deeper layer (ratio = 0 gives exactly k_ice) and the pair runs packed; the general
+            // per-cell loop is the same arithmetic with the snow share carried along.
+            if (!__any_sync(0xffffffffu, sd1[0] > (R)0 || sd1[1] > (R)0)) {
+              V gp = V::make(grad0[0], grad0[1]);
+              V t_h = V::make(tl[2 * q][1], tl[2 * q + 1][1]);
+              const V k_ice2 = V::splat(m.k_ice), dt2 = V::splat(dt);
 #pragma unroll
-              for (int l = 0; l < kMaxLayers; ++l) {
+              for (int l = 1; l < kMaxLayers; ++l) {
                 if (l < m.layers) {
-                  const R t_here = t_next;
-                  t_next = tl[i][l + 1];
-                  const R grad = (t_next - t_here) * m.inv_d[l];            // msm.py:18-28
-                  const R ratio = sd > m.d[l] ? (R)1 : sd * m.inv_d[l];     // msm.py:63
-                  const R kap = ratio * m.k_snow + ((R)1 - ratio) * m.k_ice;
-                  const R rho = ratio * m.rho_snow + ((R)1 - ratio) * m.rho_ice;
-                  sd = fmax_(sd - m.d[l], (R)0);
-                  R dlt;
-                  if (l == 0) {                                             // surface layer, msm.py:80-101
-                    gv = kap * grad * m.c_ice * rho;
-                    const R full = atmo_h + gv;
-                    const R crd = m.c_ice * rho * m.d[0];
-                    const R q0 = -t_here * crd * inv_dt;
-                    mfv = fmax_(full - q0, (R)0);
-                    dlt = (full - mfv) * Num<R>::rcp(crd);
-                  } else {
-                    dlt = kap * (grad - grad_prev) * m.inv_d[l];            // msm.py:103
-                  }
-                  grad_prev = grad;
-                  if (l == 0 && sizeof(R) == 4) {
-                    t0_acc[i] += (double)(dlt * dt);
-                    tl[i][0] = (R)t0_acc[i];
-                  } else {
+                  const V t_n = V::make(tl[2 * q][l + 1], tl[2 * q + 1][l + 1]);
+                  const V inv_d2 = V::splat(m.inv_d[l]);
+                  const V grad = mul2(sub2(t_n, t_h), inv_d2);
+                  const V dlt = mul2(mul2(k_ice2, sub2(grad, gp)), inv_d2);
+                  const V t_new = fma2(dlt, dt2, t_h);
+                  tl[2 * q][l] = t_new.lo();
+                  tl[2 * q + 1][l] = t_new.hi();
+                  gp = grad;
+                  t_h = t_n;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int i = 2 * q + h;
+                R sd = sd1[h], grad_prev = grad0[h], t_next = tl[i][1];
+#pragma unroll
+                for (int l = 1; l < kMaxLayers; ++l) {
+                  if (l < m.layers) {
+                    const R t_here = t_next;
+                    t_next = tl[i][l + 1];
+                    const R grad = (t_next - t_here) * m.inv_d[l];
+                    const R ratio = sd > m.d[l] ? (R)1 : sd * m.inv_d[l];
+                    const R kap = ratio * m.k_snow + ((R)1 - ratio) * m.k_ice;
+                    sd = fmax_(sd - m.d[l], (R)0);
+                    const R dlt = kap * (grad - grad_prev) * m.inv_d[l];
+                    grad_prev = grad;
                     tl[i][l] = t_here + dlt * dt;
                   }
                 }
               }
-              mfh[h] = mfv;
-              gh[h] = gv;
             }
             mf = V::make(mfh[0], mfh[1]);
             gfl = V::make(gh[0], gh[1]);

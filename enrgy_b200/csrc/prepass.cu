@@ -276,8 +276,16 @@ int run_prepass(const PrepassInput& in, PrepassOutput& out, std::string& err) {
     } else {
       s.c_lwu = p.emissivity * kSigma * std::pow(ts_k, 4.0);
     }
+    {
+      const double k0 = (double)273.15f, k04 = (k0 * k0) * (k0 * k0);
+      // (float32 kernel: its c_lwd is the float32 of the value above)
+      const double c_lwd_k = mirror32 ? (double)(float)s.c_lwd : s.c_lwd;
+      s.c_lw1 = c_lwd_k * k04;
+      s.c_lw0 = s.c_lw1 - (mirror32 ? (double)(float)s.c_lwu : s.c_lwu);
+    }
     s.c_melt = dt / kLf / 1000;
     s.dt = dt;
+    s.inv_dt = 1.0 / dt;
 
     // albedo schedule, interpolator.py:5-20 and model.py:311-320
     const int i0 = (int)f[ENRGY_F_ALB_I0], i1 = (int)f[ENRGY_F_ALB_I1];

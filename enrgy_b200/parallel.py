@@ -103,16 +103,20 @@ def plan_step_chunks(sub_counts, t0, t1, max_subs):
 
 class ShardedShading:
     """Row-band run WITH shading over `world` ranks (one Engine per rank, every one loaded with the
-    full terrain and its own band): per chunk of rows
-      1. rank p sweeps sub-steps p/N .. (p+1)/N of the chunk over the full raster, writing the rows of
-         band q into the q-th segment of its send buffer (enrgy_shade_scan),
-      2. one all_to_all_single (NCCL over NVLink) delivers to every rank the masks of ITS band for all
-         sub-steps of the chunk, already in the order the fused kernel reads them,
+    full terrain and its own band).  Per chunk of rows
+      1. rank p sweeps sub-steps p/N .. (p+1)/N of the chunk over the full raster and writes the rows of
+         band q for rank q (enrgy_shade_scan with one destination segment per rank),
+      2. every rank ends up with the masks of ITS band for all sub-steps of the chunk, already in the
+         order the fused kernel reads them,
       3. the fused kernels run on the band with these masks (enrgy_run_masked).
-    With world == 1 the sweep writes straight into the receive buffer.  Everything is enqueued on the
-    caller's torch stream; nothing synchronises the host."""
+    Step 2 is either ONE KERNEL WITH STEP 1 -- the sweep stores the mask words straight into the
+    other ranks' receive buffers over NVLink (peer pointers from torch symmetric memory; `exchange ==
+    "p2p"`), bracketed by two stream-ordered barriers -- or, where symmetric memory is not available, an
+    all_to_all_single on a side stream (`exchange == "all_to_all"`).  Chunks are double-buffered: the
+    sweep (and exchange) of chunk k + 1 is enqueued before the fused kernels of chunk k.
+    With world == 1 the sweep writes straight into the receive buffer.  Nothing synchronises the host."""
 
-    def __init__(self, engine, bands, rank, world, group=None, budget_bytes=8 << 30):
+    def __init__(self, engine, bands, rank, world, group=None, budget_bytes=8 << 30, p2p=True):
         import torch
         self.torch = torch
         self.eng, self.bands, self.rank, self.world, self.group = engine, list(bands), int(rank), int(world), group
@@ -122,54 +126,132 @@ class ShardedShading:
             raise ValueError("band starts must be multiples of 8 rows")
         self.words = [engine.mask_words(n) for _, n in self.bands]       # uint32 per sub-step and band
         self.budget = int(budget_bytes)
-        self.send = self.recv = None
-        self.exchange_bytes = 0
+        self.slots = [dict(send=None, recv=None, peers=None, ready=None) for _ in range(2)]
+        self.exchange = "none" if self.world == 1 else ("p2p" if p2p else "all_to_all")
+        self.comm = torch.cuda.Stream() if self.world > 1 else None
+        self.bytes_sent_last_run = 0
+        self._flag = torch.zeros(1, dtype=torch.int32, device="cuda") if self.world > 1 else None
+        self._symm_failed = False
 
-    def _buffers(self, n_send_words, n_recv_words):
+    # ---- buffers ---------------------------------------------------------------------------------
+    def _recv(self, slot, n_words):
+        """Receive buffer of a slot: symmetric memory (peer-addressable) for the p2p exchange."""
         torch = self.torch
-        if self.send is None or self.send.numel() < n_send_words:
-            self.send = torch.empty(max(n_send_words, 1), dtype=torch.int32, device="cuda")
-        if self.recv is None or self.recv.numel() < n_recv_words:
-            self.recv = torch.empty(max(n_recv_words, 1), dtype=torch.int32, device="cuda")
+        sl = self.slots[slot]
+        if sl["recv"] is not None and sl["recv"].numel() >= n_words:
+            return sl
+        if self.exchange == "p2p":
+            try:
+                import torch.distributed as dist
+                import torch.distributed._symmetric_memory as symm
+                # every rank must allocate the same size: the largest band times the sub-steps of a chunk
+                t = symm.empty(int(n_words), dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+                hdl = symm.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+                sl["recv"], sl["peers"] = t, [int(p) for p in hdl.buffer_ptrs]
+                sl["hdl"] = hdl
+                return sl
+            except Exception as e:                                    # pragma: no cover  (needs several GPUs)
+                import sys
+                print("symmetric memory unavailable (%s: %s); falling back to all_to_all" % (type(e).__name__, e), file=sys.stderr)
+                self.exchange = "all_to_all"
+                self._symm_failed = True
+        sl["recv"] = torch.empty(max(int(n_words), 1), dtype=torch.int32, device="cuda")
+        sl["peers"] = None
+        return sl
+
+    def _send(self, slot, n_words):
+        sl = self.slots[slot]
+        if sl["send"] is None or sl["send"].numel() < n_words:
+            sl["send"] = self.torch.empty(max(int(n_words), 1), dtype=self.torch.int32, device="cuda")
+        return sl["send"]
 
     def chunks(self, t0, t1, sub_counts):
-        per_sub = 4 * (sum(self.words) // self.world + self.words[self.rank]) + 1
-        return plan_step_chunks(sub_counts, t0, t1, max(1, self.budget // per_sub))
+        """Chunks of rows: within the memory budget, and (several ranks) at least a few of them so that the
+        exchange of one chunk hides behind the kernels of its neighbours."""
+        per_sub = 4 * (sum(self.words) // self.world + max(self.words)) * 2 + 1
+        total = int(sum(sub_counts[t0:t1]))
+        max_subs = max(1, self.budget // per_sub)
+        if self.world > 1:
+            max_subs = min(max_subs, max(64 * self.world, -(-total // 4)))
+        return plan_step_chunks(sub_counts, t0, t1, max_subs)
 
+    def _barrier(self, stream):
+        """Stream-ordered barrier over the ranks (a one-word all-reduce)."""
+        import torch.distributed as dist
+        with self.torch.cuda.stream(stream):
+            dist.all_reduce(self._flag, group=self.group)
+
+    # ---- the run ---------------------------------------------------------------------------------
     def run(self, t0, t1, d_stats_ptr, stream, sub_counts):
         """Steps [t0, t1): statistics of this band into the device array at d_stats_ptr ([t1 - t0, S_COUNT]
         float64, NOT yet reduced over ranks).  `stream` is the torch.cuda.Stream everything runs on."""
         torch = self.torch
         eng, me, world = self.eng, self.rank, self.world
         sp = stream.cuda_stream
-        chunks = self.chunks(t0, t1, sub_counts)
-        if len(chunks) > 1:
+        plan = self.chunks(t0, t1, sub_counts)
+        if len(plan) > 1:
             eng.defer_snow_total(True)            # the rasters must not depend on where the run is cut
-        for q, (c0, c1) in enumerate(chunks):
-            if len(chunks) > 1 and q == len(chunks) - 1:
-                eng.defer_snow_total(False)
+        # every rank needs the same receive size (symmetric allocation): largest band x largest chunk
+        max_chunk_subs = 0
+        for (c0, c1) in plan:
+            s0, s1 = eng.sub_range(c0, c1)
+            max_chunk_subs = max(max_chunk_subs, s1 - s0)
+        recv_words = max(self.words) * max_chunk_subs
+        self.bytes_sent_last_run = 0
+        staged = {}
+
+        def stage(k):
+            """Sweep of chunk k (and its exchange) into slot k % 2."""
+            c0, c1 = plan[k]
             s0, s1 = eng.sub_range(c0, c1)
             shares = split_even(s0, s1, world)
             a, b = shares[me]
-            in_split = [(b - a) * w for w in self.words]                         # what I send to rank q
-            out_split = [(hi - lo) * self.words[me] for lo, hi in shares]        # what rank p sends me
-            self._buffers(sum(in_split), sum(out_split))
+            sl = self._recv(k % 2, recv_words)
             if world == 1:
-                eng.shade_scan(a, b, [(self.bands[0][0], self.bands[0][1], self.recv.data_ptr())], sp)
+                eng.shade_scan(a, b, [(self.bands[0][0], self.bands[0][1], sl["recv"].data_ptr())], sp)
+            elif self.exchange == "p2p":
+                # all ranks are done with this slot (fused kernels of chunk k - 2) before anybody writes into it
+                if k >= 2:
+                    self._barrier(stream)
+                segs = [(r0, n, sl["peers"][q] + 4 * (a - s0) * self.words[q]) for q, (r0, n) in enumerate(self.bands)]
+                if b > a:
+                    eng.shade_scan(a, b, segs, sp)
+                self._barrier(stream)             # every rank's stores have landed
+                self.bytes_sent_last_run += 4 * (b - a) * (sum(self.words) - self.words[me])
             else:
+                in_split = [(b - a) * w for w in self.words]                         # what I send to rank q
+                out_split = [(hi - lo) * self.words[me] for lo, hi in shares]        # what rank p sends me
+                send = self._send(k % 2, sum(in_split))
                 segs, off = [], 0
                 for (r0, n), w in zip(self.bands, in_split):
-                    segs.append((r0, n, self.send.data_ptr() + 4 * off))
+                    segs.append((r0, n, send.data_ptr() + 4 * off))
                     off += w
                 if b > a:
                     eng.shade_scan(a, b, segs, sp)
-                with torch.cuda.stream(stream):
-                    import torch.distributed as dist
-                    dist.all_to_all_single(self.recv[:sum(out_split)], self.send[:sum(in_split)], out_split, in_split,
+                swept = torch.cuda.Event()
+                swept.record(stream)
+                import torch.distributed as dist
+                with torch.cuda.stream(self.comm):
+                    self.comm.wait_event(swept)
+                    dist.all_to_all_single(sl["recv"][:sum(out_split)], send[:sum(in_split)], out_split, in_split,
                                            group=self.group)
-                self.exchange_bytes += 4 * (sum(in_split) - in_split[me])
+                    done = torch.cuda.Event()
+                    done.record(self.comm)
+                sl["ready"] = done
+                self.bytes_sent_last_run += 4 * (sum(in_split) - in_split[me])
+            staged[k] = sl
+
+        stage(0)
+        for k, (c0, c1) in enumerate(plan):
+            if k + 1 < len(plan):
+                stage(k + 1)
+            sl = staged.pop(k)
+            if self.exchange == "all_to_all":
+                stream.wait_event(sl["ready"])
+            if len(plan) > 1 and k == len(plan) - 1:
+                eng.defer_snow_total(False)
             stats_ptr = None if d_stats_ptr is None else d_stats_ptr + 8 * _lib.S_COUNT * (c0 - t0)
-            eng.run_masked(c0, c1, self.recv.data_ptr(), stats_ptr, sp)
+            eng.run_masked(c0, c1, sl["recv"].data_ptr(), stats_ptr, sp)
 
 
 def allreduce_stats(stats):
