@@ -121,6 +121,11 @@ struct enrgy_ctx {
   int pre_early_rc = 0;
   std::string pre_early_err;
   DevBuf<double> d_stats, d_small;
+  // fused ensemble members (enrgy_run_members): state rasters [slots][3][band_elems], per-step member
+  // scalars [T][nm] of the group in flight, float64 master records per member [slots][T]
+  DevBuf<unsigned char> d_mstate, d_mrecs;
+  DevBuf<StepRec<double>> d_msteps64;
+  int member_slots = 0, members_last = 0;
   DevBuf<unsigned char> d_partials;
   DevBuf<unsigned long long> d_counters;
   std::vector<ShadeRec> mask_shades;   // directions the cached masks were swept for
@@ -612,6 +617,158 @@ int dump_typed(enrgy_ctx* c, int t0, int t1, double* out) {
   return ENRGY_OK;
 }
 
+
+// ---- fused ensemble members (BASELINE config C5) ---------------------------------------------------
+struct MemberSpec { double offset, zm, zhe, alb_ice, alb_snow; };
+
+template <typename R>
+int run_members_typed(enrgy_ctx* c, const std::vector<MemberSpec>& mem, const std::vector<PrepassOutput>& pres,
+                      int t0, int t1, double* d_stats /* [n][t1 - t0][S_COUNT] or null */, double* totals_out /* host [n][4] or null */,
+                      cudaStream_t stream) {
+  const int n_members = (int)mem.size(), n = t1 - t0, T = c->n_steps;
+  const int slots = (n_members + 1) / 2 * 2;                  // an odd count is padded by a copy of the last member
+  const size_t be = c->band_elems, bytes = be * sizeof(R);
+  const int insol = insol_variant(c);
+  // state of every member = the handle's current state
+  CU_TRY(c->d_mstate.alloc((size_t)slots * 3 * bytes));
+  R* const ms_swe = (R*)c->d_mstate.p;
+  R* const ms_ts = ms_swe + (size_t)slots * be;
+  R* const ms_ti = ms_ts + (size_t)slots * be;
+  if (n > 0 && !c->state_advanced) {
+    CU_TRY(launch_nan_offglacier<R>(c->dem0, c->dem_pitch, c->pitch, c->band_row0, c->band_rows, c->cols, (R*)c->d_swe.p,
+                                    (R*)c->d_ts.p, (R*)c->d_ti.p, stream));
+    c->launches++;
+  }
+  for (int m = 0; m < slots; ++m) {
+    CU_TRY(cudaMemcpyAsync(ms_swe + (size_t)m * be, c->d_swe.p, bytes, cudaMemcpyDeviceToDevice, stream));
+    CU_TRY(cudaMemcpyAsync(ms_ts + (size_t)m * be, c->d_ts.p, bytes, cudaMemcpyDeviceToDevice, stream));
+    CU_TRY(cudaMemcpyAsync(ms_ti + (size_t)m * be, c->d_ti.p, bytes, cudaMemcpyDeviceToDevice, stream));
+  }
+  c->member_slots = slots;
+  c->members_last = n_members;
+  // groups of 4 members, then one of 2
+  struct Group { int first, nm; };
+  std::vector<Group> groups;
+  for (int m = 0; m < slots;) {
+    const int nm = slots - m >= 4 ? 4 : 2;
+    groups.push_back({m, nm});
+    m += nm;
+  }
+  auto member_of = [&](int slot) { return std::min(slot, n_members - 1); };
+  // per-step member scalars [group][T][nm] and the float64 master records per member (finalize)
+  std::vector<MemberRec<R>> recs((size_t)slots * std::max(T, 1));
+  {
+    size_t o = 0;
+    for (const Group& g : groups)
+      for (int t = 0; t < T; ++t)
+        for (int k = 0; k < g.nm; ++k, ++o) {
+          const StepRec<double>& sr = pres[member_of(g.first + k)].steps[t];
+          recs[o].c_sens = (R)sr.c_sens;
+          recs[o].c_lat = (R)sr.c_lat;
+        }
+  }
+  CU_TRY(c->d_mrecs.alloc(recs.size() * sizeof(MemberRec<R>)));
+  CU_TRY(c->d_msteps64.alloc((size_t)n_members * std::max(T, 1)));
+  if (T) {
+    CU_TRY(cudaMemcpyAsync(c->d_mrecs.p, recs.data(), recs.size() * sizeof(MemberRec<R>), cudaMemcpyHostToDevice, stream));
+    for (int m = 0; m < n_members; ++m)
+      CU_TRY(cudaMemcpyAsync(c->d_msteps64.p + (size_t)m * T, pres[m].steps.data(), (size_t)T * sizeof(StepRec<double>),
+                             cudaMemcpyHostToDevice, stream));
+  }
+  fused_events(c).reset();
+  sweep_events(c).reset();
+  // with shading the sunlit masks of a chunk of steps are swept once and serve every group
+  std::vector<Chunk> chunks;
+  if (insol == kInsolMasked && n > 0) chunks = plan_chunks(c, t0, t1);
+  else chunks.push_back(Chunk{t0, t1, 0, 0});
+  const bool cut = chunks.size() > 1;
+  if (cut) {                                            // SWE of every member at the start of the run
+    CU_TRY(c->d_swe_ref.alloc((size_t)slots * bytes));
+    CU_TRY(cudaMemcpyAsync(c->d_swe_ref.p, ms_swe, (size_t)slots * bytes, cudaMemcpyDeviceToDevice, stream));
+  }
+  LaunchInfo li4{}, li2{};
+  for (size_t q = 0; q < chunks.size(); ++q) {
+    const Chunk& ch = chunks[q];
+    const unsigned* masks = nullptr;
+    if (insol == kInsolMasked && ch.t1 > ch.t0) {
+      if (int e = ensure_masks(c, ch.s0, ch.s1, stream)) return e;
+      masks = c->d_maskbuf.p + (size_t)(ch.s0 - c->mask_sub0) * mask_words_per_sub(c, c->band_rows);
+    }
+    const int nc = ch.t1 - ch.t0;
+    for (const Group& g : groups) {
+      KernelArgs<R> a;
+      fill_args<R>(c, ch.t0, ch.t1, a);
+      a.masks = masks; a.mask_sub0 = ch.s0;
+      a.mask_sub_last = nc > 0 ? std::max(c->pre.sub_first[ch.t1 - 1] + c->pre.sub_count[ch.t1 - 1] - 1, ch.s0) : ch.s0;
+      a.swe = ms_swe + (size_t)g.first * be;
+      a.total_snow = ms_ts + (size_t)g.first * be;
+      a.total_ice = ms_ti + (size_t)g.first * be;
+      a.swe_ref = cut ? (const R*)c->d_swe_ref.p + (size_t)g.first * be : nullptr;
+      a.update_total_snow = (!cut || q + 1 == chunks.size()) ? 1 : 0;
+      a.member_stride = be;
+      a.member_recs = (const MemberRec<R>*)c->d_mrecs.p + (size_t)g.first * T;     // groups are stored one after the other
+      for (int k = 0; k < g.nm; ++k) {
+        const MemberSpec& ms = mem[member_of(g.first + k)];
+        a.member_offset[k] = (R)ms.offset;
+        a.member_albedo_ice[k] = (R)ms.alb_ice;
+        a.member_albedo_snow[k] = (R)ms.alb_snow;
+      }
+      LaunchInfo& li = g.nm == 4 ? li4 : li2;
+      const bool with_stats = d_stats != nullptr;
+      if (li.grid == 0) CU_TRY(energy_balance_members_grid<R>(insol, g.nm, with_stats, c->sm_count, a.cap_steps, a.cap_subs, &li));
+      const int grid = std::min(li.grid, std::max(c->n_tiles, 1));
+      if (with_stats) {
+        const size_t partial_bytes = (size_t)grid * std::max(nc, 1) * g.nm * kStatsK * sizeof(R);
+        // (the launches are stream-ordered and finalize runs right behind its kernel: one buffer serves all)
+        CU_TRY(c->d_partials.alloc(partial_bytes));
+        CU_TRY(cudaMemsetAsync(c->d_partials.p, 0, partial_bytes, stream));
+        a.partials = (R*)c->d_partials.p;
+      }
+      CU_TRY(fused_events(c).begin(stream));
+      CU_TRY(launch_energy_balance_members<R>(a, insol, g.nm, with_stats, c->sm_count, grid, &c->info, stream));
+      CU_TRY(fused_events(c).end(stream));
+      c->launches++;
+      if (d_stats && nc > 0) {
+        for (int k = 0; k < g.nm; ++k) {
+          const int m = g.first + k;
+          if (m >= n_members) continue;                 // the padding copy
+          FinalizeArgs f{};
+          f.partials = c->d_partials.p; f.n_ctas = grid; f.n_steps = nc; f.t0 = ch.t0;
+          f.nm = g.nm; f.member = k;
+          f.n_valid = c->n_valid; f.f32_mode = c->precision == ENRGY_F32; f.msm = 0;
+          for (int z = 0; z < 5; ++z) f.mom[z] = c->mom[z];
+          f.steps64 = c->d_msteps64.p + (size_t)m * T;
+          f.stats = d_stats + ((size_t)m * n + (ch.t0 - t0)) * ENRGY_S_COUNT;
+          f.override_first = (ch.t0 == 0 && !c->state_advanced) ? 1 : 0;
+          f.swe0_sum = c->swe0_sum; f.swe0_nsnow = c->swe0_nsnow; f.swe0_nvalid = c->swe0_nvalid;
+          CU_TRY(launch_finalize(f, stream));
+          c->launches++;
+        }
+      }
+    }
+  }
+  if (totals_out) {
+    // glacier-wide means of the final rasters of every member (no per-step statistics needed)
+    constexpr int kBlocks = 128;
+    CU_TRY(c->d_small.alloc((size_t)n_members * kBlocks * 4));
+    CU_TRY(launch_member_totals<R>(c->dem0, c->dem_pitch, c->pitch, c->band_row0, c->band_rows, c->cols, ms_swe, ms_ts, ms_ti, be,
+                                   n_members, c->d_small.p, kBlocks, stream));
+    c->launches++;
+    std::vector<double> hb((size_t)n_members * kBlocks * 4);
+    CU_TRY(cudaMemcpyAsync(hb.data(), c->d_small.p, hb.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CU_TRY(cudaStreamSynchronize(stream));
+    for (int m = 0; m < n_members; ++m) {
+      double acc[4] = {0, 0, 0, 0};
+      for (int b = 0; b < kBlocks; ++b)
+        for (int q = 0; q < 4; ++q) acc[q] += hb[((size_t)m * kBlocks + b) * 4 + q];
+      for (int q = 0; q < 3; ++q) totals_out[m * 4 + q] = acc[3] > 0 ? acc[q] / acc[3] : NAN;
+      totals_out[m * 4 + 3] = acc[3];
+    }
+  }
+  CU_TRY(cudaStreamSynchronize(stream));                // `recs` goes out of scope
+  return ENRGY_OK;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -670,6 +827,7 @@ int enrgy_destroy(enrgy_ctx* c) {
   c->d_ti.release(); c->d_dump.release(); c->d_stage.release(); c->d_steps.release(); c->d_subs.release();
   c->d_steps64.release(); c->d_shades.release(); c->d_blocks.release(); c->d_tiles.release();
   c->d_counts.release(); c->d_partials.release(); c->d_stats.release(); c->d_small.release();
+  c->d_mstate.release(); c->d_mrecs.release(); c->d_msteps64.release();
   c->d_counters.release(); c->d_snap.release(); c->d_layer_t.release(); c->d_terrain.release(); c->d_scan.release();
   c->d_scan_t.release(); c->d_maskbuf.release(); c->d_masktmp.release(); c->d_sweepsubs.release(); c->d_swe_ref.release();
   if (c->ev_fused) { fused_events(c).destroy(); delete static_cast<EventPairs*>(c->ev_fused); }
@@ -1200,6 +1358,98 @@ int enrgy_run(enrgy_ctx* c, int t0, int t1, double* stats_out) {
   if (rc != ENRGY_OK) return rc;
   if (d_stats) CU_TRY(cudaMemcpyAsync(stats_out, d_stats, (size_t)n * ENRGY_S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
+  return ENRGY_OK;
+}
+
+int enrgy_run_members(enrgy_ctx* c, int n_members, const double* albedo_offset, const double* zm, const double* z_h_or_e,
+                      int t0, int t1, double* stats_out, double* totals_out) {
+  if (int e = use_device(c)) return e;
+  if (n_members < 1 || !albedo_offset) return fail(ENRGY_ERR_ARG, "run_members: at least one member with an albedo offset");
+  if (!c->have_dem || !c->have_forcing) return fail(ENRGY_ERR_ARG, "set_dem and set_forcing must precede run_members");
+  if (c->p.msm_layers > 0)
+    return fail(ENRGY_ERR_ARG, "run_members: the sub-surface model keeps 8 temperatures per cell and member -- run such members "
+                               "one after the other (enrgy_set_member + enrgy_run)");
+  drop_early_prepass(c);
+  // the handle's own member settings come back afterwards
+  const enrgy_params p_saved = c->p;
+  const double off_saved = c->albedo_offset;
+  auto clip = [](double a) { return std::min(std::max(a, 0.001), 1.0); };
+  std::vector<MemberSpec> mem(n_members);
+  std::vector<PrepassOutput> pres(n_members);
+  int rc = ENRGY_OK;
+  std::string err;
+  for (int m = 0; m < n_members && rc == ENRGY_OK; ++m) {
+    MemberSpec& ms = mem[m];
+    ms.offset = std::isnan(albedo_offset[m]) ? 0.0 : albedo_offset[m];
+    ms.zm = (zm && !std::isnan(zm[m])) ? zm[m] : p_saved.zm;
+    ms.zhe = (z_h_or_e && !std::isnan(z_h_or_e[m])) ? z_h_or_e[m] : p_saved.z_h_or_e;
+    if (!(ms.zm > 0) || !(ms.zhe > 0)) { rc = ENRGY_ERR_ARG; err = "run_members: roughness lengths must be > 0"; break; }
+    ms.alb_ice = ms.offset != 0.0 ? clip(c->base_albedo_ice + ms.offset) : c->base_albedo_ice;
+    ms.alb_snow = ms.offset != 0.0 ? clip(c->base_albedo_snow + ms.offset) : c->base_albedo_snow;
+    c->p = p_saved;
+    c->p.zm = ms.zm; c->p.z_h_or_e = ms.zhe;
+    if (c->p.albedo_const) { c->p.albedo_ice = ms.alb_ice; c->p.albedo_snow = ms.alb_snow; }
+    c->albedo_offset = ms.offset;
+    PrepassInput in;
+    fill_prepass_input(c, in);
+    rc = run_prepass(in, pres[m], err);
+  }
+  if (rc == ENRGY_OK) {
+    // the member-invariant records (forcing, insolation, time blocks) are those of the first member
+    c->p = p_saved;
+    c->p.zm = mem[0].zm; c->p.z_h_or_e = mem[0].zhe;
+    if (c->p.albedo_const) { c->p.albedo_ice = mem[0].alb_ice; c->p.albedo_snow = mem[0].alb_snow; }
+    c->albedo_offset = mem[0].offset;
+    c->pre = pres[0];
+    rc = c->precision == ENRGY_F32 ? upload_tables<float>(c) : upload_tables<double>(c);
+    if (rc == ENRGY_OK) { c->prepass_done = true; rc = check_run_ready(c, t0, t1); }
+    const int n = t1 - t0;
+    double* d_stats = nullptr;
+    if (rc == ENRGY_OK && stats_out && n > 0) {
+      cudaError_t ce = c->d_stats.alloc((size_t)n_members * n * ENRGY_S_COUNT);
+      if (ce != cudaSuccess) rc = fail(ENRGY_ERR_CUDA, "cudaMalloc of the member statistics failed: %s", cudaGetErrorString(ce));
+      d_stats = c->d_stats.p;
+    }
+    if (rc == ENRGY_OK)
+      rc = c->precision == ENRGY_F32 ? run_members_typed<float>(c, mem, pres, t0, t1, d_stats, totals_out, c->stream)
+                                     : run_members_typed<double>(c, mem, pres, t0, t1, d_stats, totals_out, c->stream);
+    if (rc == ENRGY_OK && d_stats) {
+      cudaError_t ce = cudaMemcpyAsync(stats_out, d_stats, (size_t)n_members * n * ENRGY_S_COUNT * sizeof(double),
+                                       cudaMemcpyDeviceToHost, c->stream);
+      if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
+      if (ce != cudaSuccess) rc = fail(ENRGY_ERR_CUDA, "download of the member statistics failed: %s", cudaGetErrorString(ce));
+    }
+  } else if (!err.empty()) {
+    rc = fail(rc, "%s", err.c_str());
+  }
+  // back to the handle's own settings: its tables must be rebuilt by the next enrgy_prepass
+  c->p = p_saved;
+  c->albedo_offset = off_saved;
+  c->prepass_done = false;
+  return rc;
+}
+
+int enrgy_get_member_state(enrgy_ctx* c, int member, int dtype, void* swe, void* total_snow, void* total_ice) {
+  if (int e = use_device(c)) return e;
+  if (member < 0 || member >= c->members_last) return fail(ENRGY_ERR_ARG, "member %d outside the last run_members (%d members)", member, c->members_last);
+  if (dtype != 32 && dtype != 64) return fail(ENRGY_ERR_ARG, "dtype must be 32 or 64");
+  const size_t n = (size_t)c->band_rows * c->cols;
+  const size_t osz = dtype == 32 ? 4 : 8;
+  CU_TRY(c->d_stage.alloc(n * osz));
+  void* dsts[3] = {swe, total_snow, total_ice};
+  const size_t be = c->band_elems * rsize(c);
+  for (int q = 0; q < 3; ++q) {
+    if (!dsts[q]) continue;
+    const unsigned char* src = c->d_mstate.p + ((size_t)q * c->member_slots + member) * be;
+    if (c->precision == ENRGY_F32) {
+      CU_TRY(launch_unpad_state<float>((const float*)src, c->pitch, c->band_rows, c->cols, dtype, c->d_stage.p, c->stream));
+    } else {
+      CU_TRY(launch_unpad_state<double>((const double*)src, c->pitch, c->band_rows, c->cols, dtype, c->d_stage.p, c->stream));
+    }
+    c->launches++;
+    CU_TRY(cudaMemcpyAsync(dsts[q], c->d_stage.p, n * osz, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+  }
   return ENRGY_OK;
 }
 

@@ -90,6 +90,13 @@ struct alignas(16) StepRec {
   R pad_;
 };
 
+// ---- per-step scalars of one ensemble member (fused members): what the roughness lengths change ----
+constexpr int kMaxFusedMembers = 4;
+template <typename R>
+struct alignas(8) MemberRec {
+  R c_sens, c_lat;
+};
+
 // ---- per-sub-step record (sun above the horizon only) ------------------------------------------
 template <typename R>
 struct alignas(16) SubRec {

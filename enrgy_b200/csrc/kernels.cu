@@ -487,15 +487,18 @@ __host__ __device__ constexpr int warps_x(int w) { return w >= 4 ? 4 : w; }     
 // run-time values chosen by the host (64 / 256, grown to the largest sub-step count of one step).
 template <typename R>
 struct SmemPlan {
-  int steps, subs, slots, slots_m, full, total;   // byte offsets and the total size
+  int steps, subs, members, slots, slots_m, full, total;   // byte offsets and the total size
 };
+// nm: ensemble members fused into one pass (1 = a plain run: no member records)
 template <typename R>
-__host__ __device__ inline SmemPlan<R> smem_plan(int warps, int cap_steps, int cap_subs, bool with_subs, bool msm) {
+__host__ __device__ inline SmemPlan<R> smem_plan(int warps, int cap_steps, int cap_subs, bool with_subs, bool msm,
+                                                 int nm = 1) {
   SmemPlan<R> p;
   int o = 0;
   p.steps = o;   o += 2 * cap_steps * (int)sizeof(StepRec<R>);
   p.subs = o;    o += with_subs ? 2 * cap_subs * (int)sizeof(SubRec<R>) : 0;
-  p.slots = o;   o += warps * cap_steps * kStatsK * (int)sizeof(R);
+  p.members = o; o += nm > 1 ? 2 * cap_steps * nm * (int)sizeof(MemberRec<R>) : 0;
+  p.slots = o;   o += warps * cap_steps * nm * kStatsK * (int)sizeof(R);
   p.slots_m = o; o += msm ? warps * cap_steps * kStatsM * (int)sizeof(R) : 0;
   o = (o + 15) / 16 * 16;
   p.full = o;    o += 16;
@@ -525,22 +528,38 @@ constexpr int kSubUnroll = ENRGY_SUB_UNROLL;   // unroll factor of the insolatio
 #define ENRGY_MASK_AHEAD 4
 #endif
 constexpr int kMaskAhead = ENRGY_MASK_AHEAD;   // sunlit masks are prefetched this many sub-steps ahead
-template <typename R, int K, int INSOL, bool MSM, bool DUMP>
-__global__ void __launch_bounds__(32 * kWarpsFor<R, INSOL>, sizeof(R) == 4 ? ENRGY_MINB32 : ENRGY_MINB64)
+// NM > 1: NM ensemble members (BASELINE config C5) in one pass.  Members differ in an albedo offset and
+// in the roughness lengths, i.e. in (1 - albedo) and in the two exchange-coefficient scalars of a step;
+// the terrain, the insolation of every sub-step (sunlit masks included), the lapse-rate meteorology, the
+// reciprocals, the flux factors and the net longwave term of a cell-step are member-invariant and are
+// computed ONCE, then each member adds its shortwave term, clamps, melts and updates ITS state
+// (swe, total_ice and 1 - albedo per member and cell in registers).  KT = rows of a warp patch in the
+// handle's tile list; a pass with fewer cells per thread (K < KT) walks the patch in KT / K parts.
+#ifndef ENRGY_MINB_MEMBERS
+#define ENRGY_MINB_MEMBERS 3
+#endif
+// STATS = false (fused members only): no per-step area statistics -- their adds and the warp butterfly
+// are a third of a member's share of a step; the season totals come from the final rasters instead.
+template <typename R, int K, int INSOL, bool MSM, bool DUMP, int NM = 1, int KT = K, bool STATS = true>
+__global__ void __launch_bounds__(32 * kWarpsFor<R, INSOL>, NM > 2 ? ENRGY_MINB_MEMBERS : sizeof(R) == 4 ? ENRGY_MINB32 : ENRGY_MINB64)
 energy_balance_kernel(const KernelArgs<R> a) {
+  static_assert(NM == 1 || (!MSM && !DUMP), "fused members: no sub-surface model, no dump");
+  static_assert(KT % K == 0, "a patch is walked in whole parts");
+  static_assert(STATS || NM > 1, "only fused members run without statistics");
   constexpr int W = kWarpsFor<R, INSOL>;           // warps per CTA
   constexpr int WX = warps_x(W), WY = W / WX;      // patches of a tile: WX across, WY down
   constexpr int NT = 32 * W;                       // threads per CTA
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int cap_steps = a.cap_steps, cap_subs = a.cap_subs;
-  const SmemPlan<R> plan = smem_plan<R>(W, cap_steps, cap_subs, INSOL != kInsolStreamed, MSM);
+  const SmemPlan<R> plan = smem_plan<R>(W, cap_steps, cap_subs, INSOL != kInsolStreamed, MSM, NM);
   StepRec<R>* const sm_steps = reinterpret_cast<StepRec<R>*>(smem_raw + plan.steps);     // [2][cap_steps]
   SubRec<R>* const sm_subs = reinterpret_cast<SubRec<R>*>(smem_raw + plan.subs);         // [2][cap_subs]
-  R* const sm_slots = reinterpret_cast<R*>(smem_raw + plan.slots);                       // [W][cap_steps][kStatsK]
+  MemberRec<R>* const sm_members = reinterpret_cast<MemberRec<R>*>(smem_raw + plan.members);  // [2][cap_steps][NM]
+  R* const sm_slots = reinterpret_cast<R*>(smem_raw + plan.slots);                       // [W][cap_steps][NM][kStatsK]
   R* const sm_slots_m = reinterpret_cast<R*>(smem_raw + plan.slots_m);                   // [W][cap_steps][kStatsM]
   uint64_t* const sm_full = reinterpret_cast<uint64_t*>(smem_raw + plan.full);           // [2]
 
-  constexpr int TILE_H = WY * K, TILE_W = 32 * WX;
+  constexpr int TILE_H = WY * KT, TILE_W = 32 * WX;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const R qnan = (R)__int_as_float(0x7fc00000);
 
@@ -559,6 +578,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
     const unsigned n_subs = (unsigned)(tb.sub_end - tb.sub_begin);
     unsigned bytes = n_steps * (unsigned)sizeof(StepRec<R>);
     if (INSOL != kInsolStreamed) bytes += n_subs * (unsigned)sizeof(SubRec<R>);
+    if (NM > 1) bytes += n_steps * NM * (unsigned)sizeof(MemberRec<R>);
     fence_proxy_async();
     mbar_expect_tx(&sm_full[buf], bytes);
     tma_bulk_g2s(sm_steps + buf * cap_steps, a.steps + tb.t_begin, n_steps * (unsigned)sizeof(StepRec<R>),
@@ -567,15 +587,25 @@ energy_balance_kernel(const KernelArgs<R> a) {
       tma_bulk_g2s(sm_subs + buf * cap_subs, a.subs + tb.sub_begin, n_subs * (unsigned)sizeof(SubRec<R>),
                    &sm_full[buf]);
     }
+    if (NM > 1) {
+      tma_bulk_g2s(sm_members + buf * cap_steps * NM, a.member_recs + (size_t)tb.t_begin * NM,
+                   n_steps * NM * (unsigned)sizeof(MemberRec<R>), &sm_full[buf]);
+    }
   };
 
   const int n_steps_run = a.t1 - a.t0;
   // this CTA's rows of per-step sums (in R: in float32 mode the 40 MB of rows stay L2-resident)
   constexpr int kRow = MSM ? kStatsP : kStatsK;
-  R* my_partials = a.partials ? a.partials + (size_t)blockIdx.x * n_steps_run * kRow : nullptr;
+  R* my_partials = a.partials ? a.partials + (size_t)blockIdx.x * n_steps_run * NM * kRow : nullptr;
   constexpr int NB = MSM ? kMaxLayers + 1 : 1;       // boundary temperatures kept per cell
 
-  for (int ti = blockIdx.x; ti < a.n_tiles; ti += gridDim.x) {
+  // per-member constants (NM == 1: the handle's own)
+  auto m_offset = [&](int m) -> R { return NM > 1 ? a.member_offset[m] : a.albedo_offset; };
+  auto m_alb_ice = [&](int m) -> R { return NM > 1 ? a.member_albedo_ice[m] : a.albedo_ice; };
+  const size_t m_stride = NM > 1 ? a.member_stride : 0;     // elements between the state rasters of members
+
+  for (int ti = blockIdx.x; ti < a.n_tiles; ti += gridDim.x)
+  for (int part = 0; part < KT / K; ++part) {
     const int2 tile = a.tiles[ti];
     // ---- prologue: per-cell invariants and state into registers --------------------------------
     // A warp owns a compact 32-column x K-row patch (lane = column): every raster access is one
@@ -585,9 +615,10 @@ energy_balance_kernel(const KernelArgs<R> a) {
     constexpr int KP = K / 2;
     static_assert(K % 2 == 0, "cells per thread come in pairs");
     using V = V2<R>;
-    const int row0 = tile.x * TILE_H + (warp / WX) * K;           // band-local row of cell 0
+    const int row0 = tile.x * TILE_H + (warp / WX) * KT + part * K;   // band-local row of cell 0
     const int colx = tile.y * TILE_W + (warp % WX) * 32 + lane;   // this lane's column
-    V delta2[KP], pw2[KP], om2[KP], nx2[KP], ny2[KP], nz2[KP], swe2[KP], tic2[KP];
+    V delta2[KP], pw2[KP], nx2[KP], ny2[KP], nz2[KP];
+    V om2[NM][KP], swe2[NM][KP], tic2[NM][KP];         // per member: 1 - albedo (ice surface), SWE, ice-melt total
     R tl[K][NB];                   // sub-surface boundary temperatures [deg C] (MSM)
     // The reference's top boundary turns float64 after its first tick (NEP 50: float32 array +
     // float64 increment), so its round-off does not random-walk at float32 spacing; the float32
@@ -598,7 +629,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
     R cur_w = (R)-1;
 #pragma unroll
     for (int q = 0; q < KP; ++q) {
-      R d_[2], p_[2], x_[2], y_[2], n_[2], s_[2], t_[2];
+      R d_[2], p_[2], x_[2], y_[2], n_[2], s_[NM][2], t_[NM][2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int i = 2 * q + h;
@@ -622,8 +653,11 @@ energy_balance_kernel(const KernelArgs<R> a) {
         } else {
           x_[h] = y_[h] = (R)0; n_[h] = (R)1;
         }
-        s_[h] = v ? a.swe[o] : (R)0;
-        t_[h] = v ? a.total_ice[o] : (R)0;
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+          s_[m][h] = v ? a.swe[m * m_stride + o] : (R)0;
+          t_[m][h] = v ? a.total_ice[m * m_stride + o] : (R)0;
+        }
         if (MSM) {
 #pragma unroll
           for (int l = 0; l < NB; ++l) {
@@ -640,10 +674,13 @@ energy_balance_kernel(const KernelArgs<R> a) {
       nx2[q] = V::make(x_[0], x_[1]);
       ny2[q] = V::make(y_[0], y_[1]);
       nz2[q] = V::make(n_[0], n_[1]);
-      swe2[q] = V::make(s_[0], s_[1]);
-      tic2[q] = V::make(t_[0], t_[1]);
-      // 1 - albedo of the ice surface: the constant, or the blend of the bracketing maps (set below)
-      om2[q] = V::splat(a.albedo_const ? (R)1 - a.albedo_ice : (R)0.5);
+#pragma unroll
+      for (int m = 0; m < NM; ++m) {
+        swe2[m][q] = V::make(s_[m][0], s_[m][1]);
+        tic2[m][q] = V::make(t_[m][0], t_[m][1]);
+        // 1 - albedo of the ice surface: the constant, or the blend of the bracketing maps (set below)
+        om2[m][q] = V::splat(a.albedo_const ? (R)1 - m_alb_ice(m) : (R)0.5);
+      }
     }
     // steepest slope of the patch, tan^2 (nx2, ny2 hold the gradient); with a safety factor it decides
     // per step whether the sun stands above every slope of the patch (analytic direct beam below)
@@ -721,18 +758,23 @@ energy_balance_kernel(const KernelArgs<R> a) {
             const float* m1 = a.albedo + (size_t)(pair & 255) * a.map_stride;
 #pragma unroll
             for (int q = 0; q < KP; ++q) {
-              R om[2];
+              R om[NM][2];
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const int i = 2 * q + h;
                 const size_t o = (size_t)(row0 + i) * a.pitch + colx;
                 const bool v = (valid_bits >> i) & 1u;
-                // + ensemble offset, clipped like the loader clips a raster (identity for offset 0)
-                const R x0 = v ? fmin_(fmax_((R)__ldg(m0 + o) + a.albedo_offset, (R)0.001f), (R)1) : (R)0.5;
-                const R x1 = v ? fmin_(fmax_((R)__ldg(m1 + o) + a.albedo_offset, (R)0.001f), (R)1) : (R)0.5;
-                om[h] = ((R)1 - x0) + alb_w * (x0 - x1);
+                const R y0 = v ? (R)__ldg(m0 + o) : (R)0.5, y1 = v ? (R)__ldg(m1 + o) : (R)0.5;
+#pragma unroll
+                for (int m = 0; m < NM; ++m) {
+                  // + ensemble offset, clipped like the loader clips a raster (identity for offset 0)
+                  const R x0 = v ? fmin_(fmax_(y0 + m_offset(m), (R)0.001f), (R)1) : (R)0.5;
+                  const R x1 = v ? fmin_(fmax_(y1 + m_offset(m), (R)0.001f), (R)1) : (R)0.5;
+                  om[m][h] = ((R)1 - x0) + alb_w * (x0 - x1);
+                }
               }
-              om2[q] = V::make(om[0], om[1]);
+#pragma unroll
+              for (int m = 0; m < NM; ++m) om2[m][q] = V::make(om[m][0], om[m][1]);
             }
           }
         }
@@ -752,17 +794,35 @@ energy_balance_kernel(const KernelArgs<R> a) {
         V pot2[KP];
         auto balance = [&]() {
         // ---- per-cell energy balance -------------------------------------------------------------
-        V acc_rs = V::splat((R)0), acc_sens = acc_rs, acc_lat = acc_rs, acc_mf = acc_rs, acc_snow = acc_rs,
-          acc_swe = acc_rs, acc_lwu = acc_rs, acc_g = acc_rs;
-        int n_snow = 0;
+        const V zero2 = V::splat((R)0);
+        V acc_sens = zero2, acc_lat = zero2;                 // member-invariant flux factors
+        V acc_rs[NM], acc_mf[NM], acc_snow[NM], acc_swe[NM], acc_lwu = zero2, acc_g = zero2;
+        int n_snow[NM];
+#pragma unroll
+        for (int m = 0; m < NM; ++m) { acc_rs[m] = acc_mf[m] = acc_snow[m] = acc_swe[m] = zero2; n_snow[m] = 0; }
         // albedo of snow-covered cells: the aged value when ageing is on, else the blended map
         // (uniform per step): (1 - alb_snow) = (1 - alb) * keep_map + snow_const
         const V keep_map = V::splat(s.snow_alb >= (R)0 ? (R)0 : (R)1);
-        const V snow_const = V::splat(s.snow_alb >= (R)0 ? (R)1 - s.snow_alb : (R)0);
         const R ice_floor = (R)1 - a.max_ice_albedo;      // 1 - cap (-inf with constant albedo)
         const V t_aws = V::splat(s.t_air), lapse2 = V::splat(s.lapse), p_aws = V::splat(s.p_hpa), e_aws = V::splat(s.e_aws);
-        const V c_sens = V::splat(s.c_sens), c_lat = V::splat(s.c_lat), c_lwd = V::splat(s.c_lwd), c_sw = V::splat(s.c_sw),
-                c_melt = V::splat(s.c_melt);
+        const V c_lwd = V::splat(s.c_lwd), c_sw = V::splat(s.c_sw), c_melt = V::splat(s.c_melt);
+        // per member: the exchange-coefficient scalars of the step (roughness lengths) and, with constant
+        // albedo, the snow albedo
+        V c_sens[NM], c_lat[NM], snow_const[NM];
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+          if (NM > 1) {
+            const MemberRec<R> mr = sm_members[(buf * cap_steps + (t - tb.t_begin)) * NM + m];
+            c_sens[m] = V::splat(mr.c_sens);
+            c_lat[m] = V::splat(mr.c_lat);
+            const R sa = a.albedo_const ? a.member_albedo_snow[m] : s.snow_alb;
+            snow_const[m] = V::splat(s.snow_alb >= (R)0 ? (R)1 - sa : (R)0);
+          } else {
+            c_sens[m] = V::splat(s.c_sens);
+            c_lat[m] = V::splat(s.c_lat);
+            snow_const[m] = V::splat(s.snow_alb >= (R)0 ? (R)1 - s.snow_alb : (R)0);
+          }
+        }
         const V k273 = V::splat((R)273.15), k_plapse = V::splat((R)kPressureLapse), k_rair = V::splat((R)kRair),
                 k_fp0 = V::splat((R)1.0016), k_fp1 = V::splat((R)(3.15 * 1e-6)), k_fp2 = V::splat((R)-0.074);
 #pragma unroll
@@ -850,20 +910,10 @@ energy_balance_kernel(const KernelArgs<R> a) {
             }
             lwu = V::make(x[0], x[1]);
           }
-          // albedo, model.py:298-337, as 1 - albedo.  Maps: blend of the bracketing maps; snow cells
-          // take the aged snow albedo when ageing is on; ice cells are capped.  Constant albedo rides
-          // the same formula: om = 1 - ice, snow_alb = snow (so keep_map = 0), cap = +inf.
-          const bool snow_lo = swe2[q].lo() > (R)0, snow_hi = swe2[q].hi() > (R)0;
-          const V om_snow = fma2(om2[q], keep_map, snow_const);
-          const V oma = V::make(snow_lo ? om_snow.lo() : fmax_(om2[q].lo(), ice_floor),
-                                snow_hi ? om_snow.hi() : fmax_(om2[q].hi(), ice_floor));
-          // shortwave, model.py:483-497: rs = potential * c_sw * (1 - albedo)
-          const V x_rs = mul2(pot2[q], oma);
-          // balance, clamp, melt partition: model.py:411, :434-438, msm.py:193-203
-          // rs + lwd - lwu + sens + lat as one FMA chain; the area sum of lwd is not reduced here: Tz
-          // is linear in the elevation, so it follows from the first four moments of
-          // (dem - elev_aws), see finalize_stats_kernel
-          V rl;                                             // lwd - lwu
+          // net longwave lwd - lwu.  The area sum of lwd is not reduced here: Tz is linear in the
+          // elevation, so it follows from the first four moments of (dem - elev_aws), see
+          // finalize_stats_kernel
+          V rl;
           if (sizeof(R) == 4 && !MSM) {
             // float32: both terms are ~300 W m-2 and Tz^4 alone would cost 4e-5 W m-2 of rounding.
             // With the (rounded, as in the reference) Tz = K0 + d_t, K0 = float(273.15) and d_t exact:
@@ -876,12 +926,38 @@ energy_balance_kernel(const KernelArgs<R> a) {
             const V lwu_neg = V::make(-lwu.lo(), -lwu.hi());
             rl = fma2(c_lwd, tz4, lwu_neg);
           }
-          const V atmo = fma2(c_lat, x_lat, fma2(c_sens, x_sens, fma2(c_sw, x_rs, rl)));
+          const bool v_lo = (valid_bits >> (2 * q)) & 1u, v_hi = (valid_bits >> (2 * q + 1)) & 1u;
+          // statistics of the member-invariant factors.  Off-glacier cells of a visited patch carry finite
+          // dummy values: they are zeroed before the packed adds, on patches that have any (warp-uniform test)
+          if (STATS) {
+            V m_sens = x_sens, m_lat = x_lat;
+            if (!FULL) {
+              m_sens = V::make(v_lo ? x_sens.lo() : (R)0, v_hi ? x_sens.hi() : (R)0);
+              m_lat = V::make(v_lo ? x_lat.lo() : (R)0, v_hi ? x_lat.hi() : (R)0);
+            }
+            // (the first pair starts the sums: q is a compile-time constant of the unrolled loop)
+            acc_sens = q == 0 ? m_sens : add2(acc_sens, m_sens);
+            acc_lat = q == 0 ? m_lat : add2(acc_lat, m_lat);
+          }
+#pragma unroll
+          for (int m = 0; m < NM; ++m) {
+          // albedo, model.py:298-337, as 1 - albedo.  Maps: blend of the bracketing maps; snow cells
+          // take the aged snow albedo when ageing is on; ice cells are capped.  Constant albedo rides
+          // the same formula: om = 1 - ice, snow_alb = snow (so keep_map = 0), cap = +inf.
+          const bool snow_lo = swe2[m][q].lo() > (R)0, snow_hi = swe2[m][q].hi() > (R)0;
+          const V om_snow = fma2(om2[m][q], keep_map, snow_const[m]);
+          const V oma = V::make(snow_lo ? om_snow.lo() : fmax_(om2[m][q].lo(), ice_floor),
+                                snow_hi ? om_snow.hi() : fmax_(om2[m][q].hi(), ice_floor));
+          // shortwave, model.py:483-497: rs = potential * c_sw * (1 - albedo)
+          const V x_rs = mul2(pot2[q], oma);
+          // balance, clamp, melt partition: model.py:411, :434-438, msm.py:193-203
+          // rs + lwd - lwu + sens + lat as one FMA chain
+          const V atmo = fma2(c_lat[m], x_lat, fma2(c_sens[m], x_sens, fma2(c_sw, x_rs, rl)));
           V mf, gfl = V::splat((R)0);
           if (MSM) {
             // explicit conduction through the layer stack and the surface-layer melt gate,
             // msm.py:31-107 (snow depth = swe / snow_density, model.py:428)
-            const MsmParams<R>& m = a.msm;
+            const MsmParams<R>& mp = a.msm;
             const R dt = s.dt, inv_dt = s.inv_dt;
             R mfh[2], gh[2], grad0[2], sd1[2];
             // surface layer, msm.py:80-101 (per cell: its snow share sets conductivity and density)
@@ -889,16 +965,16 @@ energy_balance_kernel(const KernelArgs<R> a) {
             for (int h = 0; h < 2; ++h) {
               const int i = 2 * q + h;
               const R atmo_h = h ? atmo.hi() : atmo.lo();
-              const R sd = (h ? swe2[q].hi() : swe2[q].lo()) * m.inv_snow_density;
+              const R sd = (h ? swe2[m][q].hi() : swe2[m][q].lo()) * mp.inv_snow_density;
               const R t_here = tl[i][0];
-              const R grad = (tl[i][1] - t_here) * m.inv_d[0];              // msm.py:18-28
-              const R ratio = sd > m.d[0] ? (R)1 : sd * m.inv_d[0];         // msm.py:63
-              const R kap = ratio * m.k_snow + ((R)1 - ratio) * m.k_ice;
-              const R rho = ratio * m.rho_snow + ((R)1 - ratio) * m.rho_ice;
-              sd1[h] = fmax_(sd - m.d[0], (R)0);
-              const R gv = kap * grad * m.c_ice * rho;
+              const R grad = (tl[i][1] - t_here) * mp.inv_d[0];              // msm.py:18-28
+              const R ratio = sd > mp.d[0] ? (R)1 : sd * mp.inv_d[0];         // msm.py:63
+              const R kap = ratio * mp.k_snow + ((R)1 - ratio) * mp.k_ice;
+              const R rho = ratio * mp.rho_snow + ((R)1 - ratio) * mp.rho_ice;
+              sd1[h] = fmax_(sd - mp.d[0], (R)0);
+              const R gv = kap * grad * mp.c_ice * rho;
               const R full = atmo_h + gv;
-              const R crd = m.c_ice * rho * m.d[0];
+              const R crd = mp.c_ice * rho * mp.d[0];
               const R q0 = -t_here * crd * inv_dt;
               const R mfv = fmax_(full - q0, (R)0);
               const R dlt = (full - mfv) * Num<R>::rcp(crd);
@@ -917,12 +993,12 @@ energy_balance_kernel(const KernelArgs<R> a) {
             if (!__any_sync(0xffffffffu, sd1[0] > (R)0 || sd1[1] > (R)0)) {
               V gp = V::make(grad0[0], grad0[1]);
               V t_h = V::make(tl[2 * q][1], tl[2 * q + 1][1]);
-              const V k_ice2 = V::splat(m.k_ice), dt2 = V::splat(dt);
+              const V k_ice2 = V::splat(mp.k_ice), dt2 = V::splat(dt);
 #pragma unroll
               for (int l = 1; l < kMaxLayers; ++l) {
-                if (l < m.layers) {
+                if (l < mp.layers) {
                   const V t_n = V::make(tl[2 * q][l + 1], tl[2 * q + 1][l + 1]);
-                  const V inv_d2 = V::splat(m.inv_d[l]);
+                  const V inv_d2 = V::splat(mp.inv_d[l]);
                   const V grad = mul2(sub2(t_n, t_h), inv_d2);
                   const V dlt = mul2(mul2(k_ice2, sub2(grad, gp)), inv_d2);
                   const V t_new = fma2(dlt, dt2, t_h);
@@ -939,14 +1015,14 @@ energy_balance_kernel(const KernelArgs<R> a) {
                 R sd = sd1[h], grad_prev = grad0[h], t_next = tl[i][1];
 #pragma unroll
                 for (int l = 1; l < kMaxLayers; ++l) {
-                  if (l < m.layers) {
+                  if (l < mp.layers) {
                     const R t_here = t_next;
                     t_next = tl[i][l + 1];
-                    const R grad = (t_next - t_here) * m.inv_d[l];
-                    const R ratio = sd > m.d[l] ? (R)1 : sd * m.inv_d[l];
-                    const R kap = ratio * m.k_snow + ((R)1 - ratio) * m.k_ice;
-                    sd = fmax_(sd - m.d[l], (R)0);
-                    const R dlt = kap * (grad - grad_prev) * m.inv_d[l];
+                    const R grad = (t_next - t_here) * mp.inv_d[l];
+                    const R ratio = sd > mp.d[l] ? (R)1 : sd * mp.inv_d[l];
+                    const R kap = ratio * mp.k_snow + ((R)1 - ratio) * mp.k_ice;
+                    sd = fmax_(sd - mp.d[l], (R)0);
+                    const R dlt = kap * (grad - grad_prev) * mp.inv_d[l];
                     grad_prev = grad;
                     tl[i][l] = t_here + dlt * dt;
                   }
@@ -959,34 +1035,29 @@ energy_balance_kernel(const KernelArgs<R> a) {
             mf = V::make(fmax_(atmo.lo(), (R)0), fmax_(atmo.hi(), (R)0));
           }
           const V we = mul2(mf, c_melt);
-          const V snow = V::make(fmin_(we.lo(), swe2[q].lo()), fmin_(we.hi(), swe2[q].hi()));
+          const V snow = V::make(fmin_(we.lo(), swe2[m][q].lo()), fmin_(we.hi(), swe2[m][q].hi()));
           const V ice = sub2(we, snow);
-          // statistics.  Off-glacier cells of a visited patch carry finite dummy values: they are
-          // zeroed before the packed adds, on patches that have any (warp-uniform test)
-          V m_rs = x_rs, m_sens = x_sens, m_lat = x_lat, m_mf = mf, m_lwu = lwu, m_g = gfl;
+          // statistics (off-glacier cells zeroed as above)
+          if (STATS) {
+          V m_rs = x_rs, m_mf = mf, m_lwu = lwu, m_g = gfl;
           if (!FULL) {
-            const bool v_lo = (valid_bits >> (2 * q)) & 1u, v_hi = (valid_bits >> (2 * q + 1)) & 1u;
             m_rs = V::make(v_lo ? x_rs.lo() : (R)0, v_hi ? x_rs.hi() : (R)0);
-            m_sens = V::make(v_lo ? x_sens.lo() : (R)0, v_hi ? x_sens.hi() : (R)0);
-            m_lat = V::make(v_lo ? x_lat.lo() : (R)0, v_hi ? x_lat.hi() : (R)0);
             m_mf = V::make(v_lo ? mf.lo() : (R)0, v_hi ? mf.hi() : (R)0);
             if (MSM) {
               m_lwu = V::make(v_lo ? lwu.lo() : (R)0, v_hi ? lwu.hi() : (R)0);
               m_g = V::make(v_lo ? gfl.lo() : (R)0, v_hi ? gfl.hi() : (R)0);
             }
           }
-          // (the first pair starts the sums: q is a compile-time constant of the unrolled loop)
-          acc_rs = q == 0 ? m_rs : add2(acc_rs, m_rs);
-          acc_sens = q == 0 ? m_sens : add2(acc_sens, m_sens);
-          acc_lat = q == 0 ? m_lat : add2(acc_lat, m_lat);
-          acc_mf = q == 0 ? m_mf : add2(acc_mf, m_mf);
-          acc_snow = q == 0 ? snow : add2(acc_snow, snow);        // masked cells: swe = 0 -> snow = 0
-          acc_swe = q == 0 ? swe2[q] : add2(acc_swe, swe2[q]);
+          acc_rs[m] = q == 0 ? m_rs : add2(acc_rs[m], m_rs);
+          acc_mf[m] = q == 0 ? m_mf : add2(acc_mf[m], m_mf);
+          acc_snow[m] = q == 0 ? snow : add2(acc_snow[m], snow);        // masked cells: swe = 0 -> snow = 0
+          acc_swe[m] = q == 0 ? swe2[m][q] : add2(acc_swe[m], swe2[m][q]);
           if (MSM) {
             acc_lwu = q == 0 ? m_lwu : add2(acc_lwu, m_lwu);
             acc_g = q == 0 ? m_g : add2(acc_g, m_g);
           }
-          n_snow += (snow_lo ? 1 : 0) + (snow_hi ? 1 : 0);
+          n_snow[m] += (snow_lo ? 1 : 0) + (snow_hi ? 1 : 0);
+          }
           if (DUMP && a.dump != nullptr) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -1012,22 +1083,28 @@ energy_balance_kernel(const KernelArgs<R> a) {
           }
           // state update, model.py:258-261.  total_snow is not accumulated here: it equals
           // swe(start) - swe(end) and is added once in the epilogue.
-          swe2[q] = sub2(swe2[q], snow);
-          tic2[q] = add2(tic2[q], ice);
+          swe2[m][q] = sub2(swe2[m][q], snow);
+          tic2[m][q] = add2(tic2[m][q], ice);
+          }  // members
         }
-        // ---- per-step statistics: warp butterfly, one slot per warp --------------------------------
-        if (!DUMP) {
-          R acc[kStatsK];
-          acc[K_RS] = acc_rs.lo() + acc_rs.hi();
-          acc[K_LWD] = (R)0;
-          acc[K_SENS] = acc_sens.lo() + acc_sens.hi();
-          acc[K_LAT] = acc_lat.lo() + acc_lat.hi();
-          acc[K_MELT] = acc_mf.lo() + acc_mf.hi();
-          acc[K_SNOW] = acc_snow.lo() + acc_snow.hi();
-          acc[K_SWE] = acc_swe.lo() + acc_swe.hi();
-          acc[K_NSNOW] = (R)n_snow;
-          const R tot = warp_reduce8<R>(acc, lane);
-          if ((lane & 3) == 0) sm_slots[(warp * cap_steps + (t - tb.t_begin)) * kStatsK + stat_of_lane(lane)] = tot;
+        // ---- per-step statistics: warp butterfly, one slot per warp (and member) -------------------
+        if (!DUMP && STATS) {
+          const R sum_sens = acc_sens.lo() + acc_sens.hi(), sum_lat = acc_lat.lo() + acc_lat.hi();
+#pragma unroll
+          for (int m = 0; m < NM; ++m) {
+            R acc[kStatsK];
+            acc[K_RS] = acc_rs[m].lo() + acc_rs[m].hi();
+            acc[K_LWD] = (R)0;
+            acc[K_SENS] = sum_sens;
+            acc[K_LAT] = sum_lat;
+            acc[K_MELT] = acc_mf[m].lo() + acc_mf[m].hi();
+            acc[K_SNOW] = acc_snow[m].lo() + acc_snow[m].hi();
+            acc[K_SWE] = acc_swe[m].lo() + acc_swe[m].hi();
+            acc[K_NSNOW] = (R)n_snow[m];
+            const R tot = warp_reduce8<R>(acc, lane);
+            if ((lane & 3) == 0)
+              sm_slots[((warp * cap_steps + (t - tb.t_begin)) * NM + m) * kStatsK + stat_of_lane(lane)] = tot;
+          }
           if (MSM) {
             R acc_m[kStatsM];
             acc_m[M_LWU] = acc_lwu.lo() + acc_lwu.hi();
@@ -1099,6 +1176,10 @@ energy_balance_kernel(const KernelArgs<R> a) {
               direct2[q] = fma2(b2, V::make(c_lo, c_hi), direct2[q]);
             }
           };
+          // (sub-surface model: ONE copy of the balance per loop -- three of them, each with the layer
+          // stack of every pair, made a step loop of 160 KB that no longer fitted the instruction caches:
+          // ncu showed 2.5 warps per issue waiting for instructions)
+          constexpr bool kOneBalance = MSM;
           // hourly rows carry four sunlit sub-steps by day.  That case is straight-line code followed by
           // its own copy of the balance, so that insolation and balance of a step form one basic block
           // (the records load ahead, the chains of consecutive sub-steps and the first reciprocals of
@@ -1110,15 +1191,16 @@ energy_balance_kernel(const KernelArgs<R> a) {
             const V du = V::splat(s.dir_u), de = V::splat(s.dir_e), dn = V::splat(s.dir_n);
 #pragma unroll
             for (int q = 0; q < KP; ++q) direct2[q] = fma2(ny2[q], dn, fma2(nx2[q], de, du));
-            finish_step();
+            if (!kOneBalance) finish_step();
           } else if (nj == 4) {
             sub_step(j0); sub_step(j0 + 1); sub_step(j0 + 2); sub_step(j0 + 3);
-            finish_step();
+            if (!kOneBalance) finish_step();
           } else {
 #pragma unroll(kSubUnroll)
             for (int j = j0; j < j0 + nj; ++j) sub_step(j);
-            finish_step();
+            if (!kOneBalance) finish_step();
           }
+          if (kOneBalance) finish_step();
         }
       }  // steps of the time block
       };
@@ -1126,19 +1208,20 @@ energy_balance_kernel(const KernelArgs<R> a) {
 
       // ---- flush the block's statistics into this CTA's partial rows (fixed order) ---------------
       __syncthreads();
-      if (!DUMP && my_partials != nullptr) {
+      if (!DUMP && STATS && my_partials != nullptr) {
+        // (fused members: a "step" of this loop is a (step, member) pair; rows are [step][member][kRow])
         constexpr int NQ = MSM ? kStatsP : kStatsK;
-        const int n = (te - ts) * NQ;
+        const int n = (te - ts) * NM * NQ;
         for (int idx = tid; idx < n; idx += NT) {
           const int step = idx / NQ, q = idx - step * NQ;
-          const int sl = ts - tb.t_begin + step;
+          const int sl = (ts - tb.t_begin) * NM + step;
           double sum = 0.0;
 #pragma unroll
           for (int w = 0; w < W; ++w) {
-            sum += q < kStatsK ? (double)sm_slots[(w * cap_steps + sl) * kStatsK + q]
+            sum += q < kStatsK ? (double)sm_slots[(w * cap_steps * NM + sl) * kStatsK + q]
                                : (double)sm_slots_m[(w * cap_steps + sl) * kStatsM + (q - kStatsK)];
           }
-          my_partials[(size_t)(ts - a.t0 + step) * kRow + q] += (R)sum;
+          my_partials[((size_t)(ts - a.t0) * NM + step) * kRow + q] += (R)sum;
         }
       }
       __syncthreads();
@@ -1152,15 +1235,19 @@ energy_balance_kernel(const KernelArgs<R> a) {
         if (rowb < a.band_rows && colx < a.cols) {
           const size_t o = (size_t)rowb * a.pitch + colx;
           const bool v = (valid_bits >> i) & 1u;
-          const R swe_i = (i & 1) ? swe2[i / 2].hi() : swe2[i / 2].lo();
-          const R tic_i = (i & 1) ? tic2[i / 2].hi() : tic2[i / 2].lo();
-          // total_snow grows by swe(start) - swe(end); the start value is still in HBM -- or, when a run
-          // is cut into several launches (chunks of rows), in the copy taken at its start, and only the
-          // last launch adds the difference: the result does not depend on the cuts
-          const R swe_start = v ? (a.swe_ref ? a.swe_ref[o] : a.swe[o]) : (R)0;
-          a.swe[o] = v ? swe_i : qnan;
-          if (a.update_total_snow) a.total_snow[o] = v ? a.total_snow[o] + (swe_start - swe_i) : qnan;
-          a.total_ice[o] = v ? tic_i : qnan;
+#pragma unroll
+          for (int m = 0; m < NM; ++m) {
+            const size_t om = m * m_stride + o;
+            const R swe_i = (i & 1) ? swe2[m][i / 2].hi() : swe2[m][i / 2].lo();
+            const R tic_i = (i & 1) ? tic2[m][i / 2].hi() : tic2[m][i / 2].lo();
+            // total_snow grows by swe(start) - swe(end); the start value is still in HBM -- or, when a run
+            // is cut into several launches (chunks of rows), in the copy taken at its start, and only the
+            // last launch adds the difference: the result does not depend on the cuts
+            const R swe_start = v ? (a.swe_ref ? a.swe_ref[om] : a.swe[om]) : (R)0;
+            a.swe[om] = v ? swe_i : qnan;
+            if (a.update_total_snow) a.total_snow[om] = v ? a.total_snow[om] + (swe_start - swe_i) : qnan;
+            a.total_ice[om] = v ? tic_i : qnan;
+          }
           if (MSM) {
 #pragma unroll
             for (int l = 0; l < NB; ++l) {
@@ -1170,7 +1257,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
         }
       }
     }
-  }  // tiles
+  }  // tiles (and parts of their patches)
 }
 
 // cells per thread: the sub-surface model carries 8 more registers per cell
@@ -1191,11 +1278,19 @@ void energy_balance_tile(bool msm, int insol, int* tile_h, int* tile_w) {
 template void energy_balance_tile<float>(bool, int, int*, int*);
 template void energy_balance_tile<double>(bool, int, int*, int*);
 
-template <typename R, int INSOL, bool MSM, bool DUMP>
+// fused members: half the cells per thread (their per-member state takes the registers), the handle's
+// tile list is walked in two parts
+template <typename R, bool MSM, int NM>
+struct PassShape {
+  static constexpr int KT = CellsPerThread<R, MSM>::value;
+  static constexpr int K = NM > 1 ? KT / 2 : KT;
+};
+
+template <typename R, int INSOL, bool MSM, bool DUMP, int NM = 1, bool STATS = true>
 static cudaError_t configure(int sm_count, int cap_steps, int cap_subs, LaunchInfo* info) {
-  constexpr int K = CellsPerThread<R, MSM>::value;
-  auto kern = energy_balance_kernel<R, K, INSOL, MSM, DUMP>;
-  const int smem = smem_plan<R>(kWarpsFor<R, INSOL>, cap_steps, cap_subs, INSOL != kInsolStreamed, MSM).total;
+  constexpr int K = PassShape<R, MSM, NM>::K, KT = PassShape<R, MSM, NM>::KT;
+  auto kern = energy_balance_kernel<R, K, INSOL, MSM, DUMP, NM, KT, STATS>;
+  const int smem = smem_plan<R>(kWarpsFor<R, INSOL>, cap_steps, cap_subs, INSOL != kInsolStreamed, MSM, NM).total;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
@@ -1213,20 +1308,96 @@ static cudaError_t configure(int sm_count, int cap_steps, int cap_subs, LaunchIn
   return cudaSuccess;
 }
 
-template <typename R, int INSOL, bool MSM, bool DUMP>
+template <typename R, int INSOL, bool MSM, bool DUMP, int NM = 1, bool STATS = true>
 static cudaError_t launch_one(const KernelArgs<R>& a, int sm_count, int forced_grid, LaunchInfo* info,
                               cudaStream_t stream) {
-  constexpr int K = CellsPerThread<R, MSM>::value;
+  constexpr int K = PassShape<R, MSM, NM>::K, KT = PassShape<R, MSM, NM>::KT;
   LaunchInfo li;
-  cudaError_t e = configure<R, INSOL, MSM, DUMP>(sm_count, a.cap_steps, a.cap_subs, &li);
+  cudaError_t e = configure<R, INSOL, MSM, DUMP, NM, STATS>(sm_count, a.cap_steps, a.cap_subs, &li);
   if (e != cudaSuccess) return e;
   int grid = forced_grid > 0 ? forced_grid : li.grid;
   li.grid = grid;
   if (info) *info = li;
   if (a.n_tiles == 0 || a.t1 <= a.t0) return cudaSuccess;
-  energy_balance_kernel<R, K, INSOL, MSM, DUMP><<<grid, 32 * kWarpsFor<R, INSOL>, li.smem_bytes, stream>>>(a);
+  energy_balance_kernel<R, K, INSOL, MSM, DUMP, NM, KT, STATS><<<grid, 32 * kWarpsFor<R, INSOL>, li.smem_bytes, stream>>>(a);
   return cudaGetLastError();
 }
+
+// fused ensemble members: (insol, nm, stats) -> template instance; nm = 2 or 4 members per pass
+template <typename R, typename F>
+static cudaError_t dispatch_members(int insol, int nm, bool stats, F&& f) {
+#define ENRGY_CASE(I, N, S) \
+  if (insol == I && nm == N && stats == S) \
+    return f(std::integral_constant<int, I>{}, std::integral_constant<int, N>{}, std::integral_constant<bool, S>{});
+  ENRGY_CASE(0, 2, true) ENRGY_CASE(1, 2, true) ENRGY_CASE(2, 2, true)
+  ENRGY_CASE(0, 4, true) ENRGY_CASE(1, 4, true) ENRGY_CASE(2, 4, true)
+  ENRGY_CASE(0, 2, false) ENRGY_CASE(1, 2, false) ENRGY_CASE(2, 2, false)
+  ENRGY_CASE(0, 4, false) ENRGY_CASE(1, 4, false) ENRGY_CASE(2, 4, false)
+#undef ENRGY_CASE
+  return cudaErrorInvalidValue;
+}
+template <typename R>
+cudaError_t energy_balance_members_grid(int insol, int nm, bool stats, int sm_count, int cap_steps, int cap_subs,
+                                        LaunchInfo* info) {
+  return dispatch_members<R>(insol, nm, stats, [&](auto i, auto n, auto st) {
+    return configure<R, decltype(i)::value, false, false, decltype(n)::value, decltype(st)::value>(sm_count, cap_steps,
+                                                                                                    cap_subs, info);
+  });
+}
+template cudaError_t energy_balance_members_grid<float>(int, int, bool, int, int, int, LaunchInfo*);
+template cudaError_t energy_balance_members_grid<double>(int, int, bool, int, int, int, LaunchInfo*);
+template <typename R>
+cudaError_t launch_energy_balance_members(const KernelArgs<R>& a, int insol, int nm, bool stats, int sm_count,
+                                          int forced_grid, LaunchInfo* info, cudaStream_t stream) {
+  return dispatch_members<R>(insol, nm, stats, [&](auto i, auto n, auto st) {
+    return launch_one<R, decltype(i)::value, false, false, decltype(n)::value, decltype(st)::value>(a, sm_count, forced_grid,
+                                                                                                     info, stream);
+  });
+}
+template cudaError_t launch_energy_balance_members<float>(const KernelArgs<float>&, int, int, bool, int, int, LaunchInfo*, cudaStream_t);
+template cudaError_t launch_energy_balance_members<double>(const KernelArgs<double>&, int, int, bool, int, int, LaunchInfo*, cudaStream_t);
+
+// glacier-wide means of the state rasters of fused members: block_out[(member * blocks + b) * 4 + {0..3}] =
+// {sum swe, sum total_snow, sum total_ice, count} over the band's glacier cells (summed on the host in
+// block order)
+template <typename R>
+__global__ void member_totals_kernel(const float* __restrict__ dem, int dem_pitch, int pitch, int band_row0, int band_rows,
+                                     int cols, const R* __restrict__ swe, const R* __restrict__ tsn,
+                                     const R* __restrict__ tic, size_t member_stride, double* __restrict__ block_out) {
+  const int m = blockIdx.y;
+  double acc[4] = {0, 0, 0, 0};
+  const size_t n = (size_t)band_rows * cols;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int rb = (int)(i / cols), c = (int)(i % cols);
+    const float z = dem[(size_t)(rb + band_row0) * dem_pitch + c];
+    if (z == z) {
+      const size_t o = m * member_stride + (size_t)rb * pitch + c;
+      acc[0] += (double)swe[o]; acc[1] += (double)tsn[o]; acc[2] += (double)tic[o]; acc[3] += 1.0;
+    }
+  }
+  __shared__ double sh[4][kThreads];
+  for (int q = 0; q < 4; ++q) sh[q][threadIdx.x] = acc[q];
+  __syncthreads();
+  for (int off = kThreads / 2; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) {
+      for (int q = 0; q < 4; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + off];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < 4; ++q) block_out[((size_t)m * gridDim.x + blockIdx.x) * 4 + q] = sh[q][0];
+  }
+}
+template <typename R>
+cudaError_t launch_member_totals(const float* dem, int dem_pitch, int pitch, int band_row0, int band_rows, int cols,
+                                 const R* swe, const R* tsn, const R* tic, size_t member_stride, int n_members,
+                                 double* block_out, int blocks, cudaStream_t stream) {
+  member_totals_kernel<R><<<dim3(blocks, n_members), kThreads, 0, stream>>>(dem, dem_pitch, pitch, band_row0, band_rows, cols,
+                                                                           swe, tsn, tic, member_stride, block_out);
+  return cudaGetLastError();
+}
+template cudaError_t launch_member_totals<float>(const float*, int, int, int, int, int, const float*, const float*, const float*, size_t, int, double*, int, cudaStream_t);
+template cudaError_t launch_member_totals<double>(const float*, int, int, int, int, int, const double*, const double*, const double*, size_t, int, double*, int, cudaStream_t);
 
 // runtime (insol, msm, dump) -> template instance
 template <typename R, typename F>
@@ -1402,8 +1573,9 @@ __global__ void finalize_stats_kernel(const FinalizeArgs f) {
   double k[kStatsP];
   for (int q = 0; q < kStatsP; ++q) k[q] = 0.0;
   const int row = f.msm ? kStatsP : kStatsK;
+  const int nm = f.nm > 1 ? f.nm : 1;                 // fused members: rows are [cta][step][member][row]
   for (int c = lane; c < f.n_ctas; c += 32) {
-    const size_t o = ((size_t)c * f.n_steps + t) * row;
+    const size_t o = (((size_t)c * f.n_steps + t) * nm + f.member) * row;
     if (f32_mode) {
       const float* p = static_cast<const float*>(f.partials) + o;
       for (int q = 0; q < row; ++q) k[q] += (double)p[q];

@@ -60,6 +60,13 @@ struct KernelArgs {
   // work list
   const int2* tiles;              // active tiles (tile row, tile col) of the band
   int n_tiles;
+  // fused ensemble members (kernel template NM > 1; BASELINE config C5): the state rasters of member m
+  // start member_stride elements after those of member m - 1, its two per-step scalars sit in
+  // member_recs[t * NM + m], its albedo offset / constants below
+  size_t member_stride;
+  const MemberRec<R>* member_recs;
+  R member_offset[kMaxFusedMembers];
+  R member_albedo_ice[kMaxFusedMembers], member_albedo_snow[kMaxFusedMembers];
   // statistics: per-CTA partial sums [gridDim.x][t1 - t0][kStatsP] float64
   R* partials;                    // [gridDim.x][t1 - t0][kStatsK (+ kStatsM with the sub-surface model)] in R
   // dump mode: [t1 - t0][ENRGY_D_COUNT][band_rows_pad][pitch] R (may be null)
@@ -71,6 +78,7 @@ struct FinalizeArgs {
   const void* partials;     // [n_ctas][n_steps][row], row = kStatsK (+ kStatsM with msm); float if f32_mode else double
   int msm;                  // sub-surface model on: lwu and g are summed per cell
   int n_ctas, n_steps, t0;
+  int nm, member;           // fused members: members per row group and the member to finalize (nm <= 1: plain rows)
   double n_valid;           // valid cells of the band
   double mom[5];            // sum over the band's glacier cells of (dem - elev_aws)^k, k = 0..4
   int f32_mode;             // round the per-step constants the way the float32 kernel saw them
@@ -114,6 +122,18 @@ struct LaunchInfo {
 template <typename R>
 cudaError_t launch_energy_balance(const KernelArgs<R>& a, const void* reserved, int insol, bool dump,
                                   int sm_count, int forced_grid, LaunchInfo* info, cudaStream_t stream);
+// nm = 2 or 4 ensemble members fused into one pass (no sub-surface model); stats = false: no per-step
+// statistics (a.partials unused)
+template <typename R>
+cudaError_t launch_energy_balance_members(const KernelArgs<R>& a, int insol, int nm, bool stats, int sm_count,
+                                          int forced_grid, LaunchInfo* info, cudaStream_t stream);
+template <typename R>
+cudaError_t energy_balance_members_grid(int insol, int nm, bool stats, int sm_count, int cap_steps, int cap_subs,
+                                        LaunchInfo* info);
+template <typename R>
+cudaError_t launch_member_totals(const float* dem, int dem_pitch, int pitch, int band_row0, int band_rows, int cols,
+                                 const R* swe, const R* tsn, const R* tic, size_t member_stride, int n_members,
+                                 double* block_out /*[n_members][blocks][4]*/, int blocks, cudaStream_t stream);
 template <typename R>
 void energy_balance_tile(bool msm, int insol, int* tile_h, int* tile_w);
 template <typename R>

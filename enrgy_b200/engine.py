@@ -134,6 +134,37 @@ class Engine:
         check(self.lib.enrgy_set_member(self.h, float(albedo_offset), nan if zm is None else float(zm),
                                         nan if z_h_or_e is None else float(z_h_or_e)))
 
+    def run_members(self, albedo_offsets, zm=None, z_h_or_e=None, t0=0, t1=None, want_stats=True):
+        """Ensemble members in fused passes of the kernel (enrgy_run_members): every member starts from
+        the handle's current state; returns (per-step statistics [members, t1 - t0, S_COUNT] or None -- the
+        passes skip them when they are not wanted --, totals [members, 4]: glacier-wide means of the final
+        swe, total_snow, total_ice rasters and the glacier cell count).
+        The handle needs prepass() again before a plain run()."""
+        t1 = self.n_steps if t1 is None else t1
+        off = np.ascontiguousarray(albedo_offsets, dtype=np.float64)
+        n = off.size
+
+        def opt(a):
+            if a is None:
+                return None
+            a = np.ascontiguousarray([np.nan if v is None else v for v in a], dtype=np.float64)
+            assert a.size == n
+            return a
+        zm_a, zh_a = opt(zm), opt(z_h_or_e)
+        stats = np.empty((n, t1 - t0, _lib.S_COUNT), dtype=np.float64) if want_stats else None
+        totals = np.empty((n, 4), dtype=np.float64)
+        check(self.lib.enrgy_run_members(self.h, n, off.ctypes.data, None if zm_a is None else zm_a.ctypes.data,
+                                         None if zh_a is None else zh_a.ctypes.data, int(t0), int(t1),
+                                         None if stats is None else stats.ctypes.data, totals.ctypes.data))
+        return stats, totals
+
+    def member_state(self, member, dtype=np.float32):
+        dt = np.dtype(dtype)
+        code = 32 if dt == np.float32 else 64
+        outs = [np.empty((self.band_rows, self.cols), dtype=dt) for _ in range(3)]
+        check(self.lib.enrgy_get_member_state(self.h, int(member), code, *[o.ctypes.data for o in outs]))
+        return tuple(outs)
+
     def set_forcing(self, table):
         table = np.ascontiguousarray(table, dtype=np.float64)
         assert table.ndim == 2 and table.shape[1] == _lib.F_COUNT

@@ -27,26 +27,52 @@ def shard(members, world, rank):
     return list(range(rank, len(members), world))
 
 
-def run_members(engine, members, indices=None, n_steps=None, keep_rasters=False):
-    """Runs the given members one after the other on a loaded Engine (DEM, albedo maps, SWE, forcing
-    set; state = initial).  Returns {index: dict(stats=[T, S_COUNT], mean_ice, mean_snow[, rasters])}."""
+def _result(stats, n_steps):
+    # glacier-wide melt totals from the per-step area sums (the melt rasters add up to exactly
+    # these, tests/test_gpu_full_size.py): no raster leaves the device unless it is asked for
+    n_valid = float(stats[-1, _lib.S_NVALID]) if n_steps else 0.0
+    return dict(stats=stats,
+                mean_ice=float(stats[:, _lib.S_ICE].sum() / n_valid) if n_valid else float("nan"),
+                mean_snow=float(stats[:, _lib.S_SNOW].sum() / n_valid) if n_valid else float("nan"))
+
+
+def run_members(engine, members, indices=None, n_steps=None, keep_rasters=False, fused=True, want_stats=True):
+    """Runs the given members on a loaded Engine (DEM, albedo maps, SWE, forcing set; state = initial);
+    every member starts from the engine's current state.  Returns {index: dict(stats=[T, S_COUNT],
+    mean_ice, mean_snow[, rasters])}.
+
+    fused (default): enrgy_run_members -- four members per pass of the kernel share everything a member
+    does not change (terrain, insolation and sunlit masks, lapse-rate meteorology, flux factors, net
+    longwave); the same state rasters as one run per member, bit for bit (float32 statistics to rounding:
+    the passes sum in another order).  want_stats=False skips the per-step statistics in the fused passes
+    (a third of a member's share of a step); mean_ice / mean_snow then come from the final rasters.
+    The sub-surface model (8 temperatures per cell and member) runs the members one after the other."""
     n_steps = engine.n_steps if n_steps is None else n_steps
-    indices = range(len(members)) if indices is None else indices
-    engine.snapshot(save=True)
+    indices = list(range(len(members)) if indices is None else indices)
     out = {}
+    if fused and getattr(engine, "msm_layers", 0) == 0 and indices:
+        sel = [members[i] for i in indices]
+        stats, totals = engine.run_members([m.get("albedo_offset", 0.0) for m in sel], [m.get("zm") for m in sel],
+                                           [m.get("z_h_or_e") for m in sel], 0, n_steps, want_stats=want_stats)
+        for k, i in enumerate(indices):
+            res = _result(stats[k], n_steps) if want_stats else dict(stats=None)
+            # (the season totals of the rasters; equal to the per-step sums added up, to rounding)
+            res.update(mean_ice_raster=float(totals[k, 2]), mean_snow_raster=float(totals[k, 1]))
+            if not want_stats:
+                res.update(mean_ice=float(totals[k, 2]), mean_snow=float(totals[k, 1]))
+            if keep_rasters:
+                swe, tsn, tic = engine.member_state(k, np.float32)
+                res.update(swe=swe, total_snow=tsn, total_ice=tic)
+            out[i] = res
+        return out
+    engine.snapshot(save=True)
     for i in indices:
         m = members[i]
         engine.snapshot(save=False)
         engine.synchronize()
         engine.set_member(m.get("albedo_offset", 0.0), m.get("zm"), m.get("z_h_or_e"))
         engine.prepass()
-        stats = engine.run(0, n_steps)
-        # glacier-wide melt totals from the per-step area sums (the melt rasters add up to exactly
-        # these, tests/test_gpu_full_size.py): no raster leaves the device unless it is asked for
-        n_valid = float(stats[-1, _lib.S_NVALID]) if n_steps else 0.0
-        res = dict(stats=stats,
-                   mean_ice=float(stats[:, _lib.S_ICE].sum() / n_valid) if n_valid else float("nan"),
-                   mean_snow=float(stats[:, _lib.S_SNOW].sum() / n_valid) if n_valid else float("nan"))
+        res = _result(engine.run(0, n_steps), n_steps)
         if keep_rasters:
             swe, tsn, tic = engine.state(np.float32)
             res.update(swe=swe, total_snow=tsn, total_ice=tic)

@@ -153,6 +153,28 @@ def make_aws_rows(n_steps, start="20220601 00:00:00", step_s=3600, seed=3, with_
     return rows
 
 
+def make_station_rows(case, elev, seed=11, lapse=-0.006):
+    """Series of an extra weather station (BASELINE config C4) on the case's time base: what the lapse
+    rates predict at `elev` from the primary station (seed None), plus seeded departures (temperature,
+    pressure, humidity, cloudiness) otherwise."""
+    rng = None if seed is None else np.random.default_rng(seed)
+    dz = elev - case.elev_aws
+    rows = []
+    for i, r in enumerate(case.aws_rows):
+        t = float(r["T_AIR"]) + dz * lapse
+        p = float(r["PRESSURE"]) + dz * -0.1145
+        h = float(r["HUMID"])
+        c = float(r["CLOUDINESS"])
+        if rng is not None:
+            t += 0.8 * math.sin(i / 19.0) + 0.3 * rng.standard_normal()
+            p += 0.6 * math.sin(i / 47.0)
+            h = float(np.clip(h + 8.0 * math.sin(i / 23.0 + 0.5), 30.0, 100.0))
+            c = float(np.clip(c + 0.35 * math.sin(i / 31.0 + 1.0), 0.0, 1.0))
+        rows.append({"DATE": r["DATE"], "T_AIR": "%.3f" % t, "PRESSURE": "%.2f" % p, "HUMID": "%.1f" % h,
+                     "CLOUDINESS": "%.2f" % c})
+    return rows
+
+
 def make_case(n=256, n_steps=24, seed=0, cell=10.0, glacier_mask=True, albedo_dates=None,
               step_s=3600, start="20220601 00:00:00", with_gradient=False, calm_every=0,
               w=None):

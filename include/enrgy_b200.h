@@ -186,6 +186,23 @@ int enrgy_set_msm(enrgy_ctx* ctx, const double* temps, double elev);
  * restore), enrgy_prepass and enrgy_run afterwards. */
 int enrgy_set_member(enrgy_ctx* ctx, double albedo_offset, double zm, double z_h_or_e);
 
+/* n_members ensemble members in FUSED passes of the kernel (4 members per pass, a remainder in pairs):
+ * everything a member does not change -- terrain, insolation of every sub-step incl. the sunlit masks,
+ * lapse-rate meteorology, flux factors, net longwave -- is computed once per cell-step and shared; each
+ * member keeps its own SWE / ice-melt total / (1 - albedo) per cell in registers.  Every member starts
+ * from the handle's current state and runs steps [t0, t1); the handle's own state is left alone.
+ * albedo_offset[n_members]; zm / z_h_or_e [n_members] or NULL (NaN entries = the handle's value);
+ * stats_out [n_members][t1 - t0][ENRGY_S_COUNT] or NULL: without it the passes skip the per-step area
+ * statistics altogether (a third of a member's share of a step).  totals_out [n_members][4] or NULL:
+ * glacier-wide means of the final swe, total_snow, total_ice rasters and the glacier cell count.
+ * The state rasters equal enrgy_set_member + enrgy_prepass + enrgy_run of each member on its own bit for
+ * bit; the float32 statistics agree to rounding (the passes sum in another order).  Not with the
+ * sub-surface model (ENRGY_ERR_ARG).  The handle needs enrgy_prepass again before a plain enrgy_run. */
+int enrgy_run_members(enrgy_ctx* ctx, int n_members, const double* albedo_offset, const double* zm,
+                      const double* z_h_or_e, int t0, int t1, double* stats_out, double* totals_out);
+/* state rasters of one member of the last enrgy_run_members (layout as enrgy_get_state) */
+int enrgy_get_member_state(enrgy_ctx* ctx, int member, int dtype, void* swe, void* total_snow, void* total_ice);
+
 /* forcing table [n_steps][ENRGY_F_COUNT] (model.py:182-230).  With in-kernel insolation and no
  * sub-surface model the host pre-pass needs nothing else besides the DEM, so it is started here on a
  * worker thread: call this right after enrgy_set_dem and the pre-pass runs while the albedo / SWE

@@ -427,8 +427,64 @@ CSV_HEADER = ("# DATE format is %Y%m%d, HEAT FLUXES are in W m-2"
 # ^ helpers.py:39-45 (the first two comment strings share one line)
 
 
+# ---- several weather stations + cloud transmissivity (BASELINE config C4) -----------------------
+# PARITY UNPINNED UPSTREAM: the reference supports exactly one AWS (model.py:155, var_classes.py:94-125)
+# and has no cloud term in the shortwave.  This is THIS REPO's specification; it is
+# built so that with no extra station it IS the reference's arithmetic, operation for operation
+# (tests/test_oracle_stations.py: bit-identical rasters), and the CUDA path is graded against it.
+#
+#   stations   k = 0 is the reference's AWS (cfg.elev_aws, cfg.xy_aws, aws_rows): wind, the Monin-Obukhov
+#              solve, the exchange coefficients, the lapse rate, the longwave cloudiness and the observed
+#              shortwave factor stay its own.  Extra stations k = 1.. carry (row, col) in cell units
+#              (cell centres; fractions allowed), an elevation and a series of T_AIR, PRESSURE, HUMID,
+#              CLOUDINESS on the same time base.
+#   weights    inverse squared distance in cell units, softened by half a cell:
+#                  q_k = 1 / ((r - r_k)^2 + (c - c_k)^2 + 0.25),   w_k = q_k / sum_j q_j
+#              (array arithmetic in the DEM's dtype; sums run k = 0, 1, ... left to right)
+#   reduction  every station value is brought to the cell's elevation with the reference's own
+#              formulas (var_classes.py:144-162) and the results are blended:
+#                  D      = sum_k w_k (dem - z_k)                  (replaces dem - elev_aws)
+#                  t_air  = sum_k w_k T_k + D * lapse
+#                  p      = sum_k w_k P_k + D * -0.1145
+#                  e      = sum_k e_k * V_k,   V_k = w_k * 10 ** (-(dem - z_k) / 6300)
+#              With one station w_0 = 1 exactly (q / q), so D = dem - elev_aws, t_air = T + D * lapse,
+#              e = e_0 * 10 ** (-D / 6300): the reference's expressions.
+#   cloud SW   Beer-Lambert attenuation by the cloud field relative to the primary station, where the
+#              shortwave factor was observed (model.py:500-530):
+#                  incoming = potential * factor * exp(-cloud_k * sum_k w_k (N_k - N_0))
+#              (N = cloudiness after cloud_corr and clamping; the k = 0 term is zero, so one station or
+#              equal cloudiness gives exp(0) = 1 exactly).
+def station_fields(dem, cfg, geotransform, stations):
+    """Time-invariant rasters of the station blend: (w [n], D, V [n]) in the DEM's dtype."""
+    dt = dem.dtype
+    h, w_ = dem.shape
+    ul_x, x_dist, _, ul_y, _, y_dist = geotransform
+    pixel = int((cfg.xy_aws[0] - ul_x) / x_dist)          # raster_utils.py:85-89
+    line = -int((ul_y - cfg.xy_aws[1]) / y_dist)
+    pos = [(float(line), float(pixel), cfg.elev_aws)] + [(float(s["row"]), float(s["col"]), float(s["elev"])) for s in stations]
+    rr = np.arange(h, dtype=dt)[:, None]
+    cc = np.arange(w_, dtype=dt)[None, :]
+    q = []
+    for (r_k, c_k, _) in pos:
+        dr = rr - dt.type(r_k)
+        dc = cc - dt.type(c_k)
+        q.append(dt.type(1) / (dr * dr + dc * dc + dt.type(0.25)))
+    tot = q[0]
+    for qk in q[1:]:
+        tot = tot + qk
+    wts = [qk / tot for qk in q]
+    D = None
+    V = []
+    for wk, (_, _, z_k) in zip(wts, pos):
+        dz = dem - z_k
+        term = wk * dz
+        D = term if D is None else D + term
+        V.append(wk * 10 ** (-dz / 6300))
+    return wts, D, V
+
+
 def run_model(dem, geotransform, aws_rows, insolation, cfg, *, swe=None, albedo_arrays=None,
-              state_dtype=np.float32, keep_steps=None, want_means=False):
+              state_dtype=np.float32, keep_steps=None, want_means=False, stations=None, cloud_k=None):
     """The reference's Energy.__init__ + model() on arrays (model.py:19-82, :155-286).
 
     dem            [H, W] float32 (as shipped) or float64 ("float64-injected")
@@ -442,6 +498,9 @@ def run_model(dem, geotransform, aws_rows, insolation, cfg, *, swe=None, albedo_
     params = default_params()
     if cfg.snow_density is not None:
         params["snow_density"] = cfg.snow_density
+    multi = stations is not None                          # (an empty list runs the blend with one station)
+    if multi:
+        st_w, st_D, st_V = station_fields(dem, cfg, geotransform, stations)
     total_snow = np.zeros_like(dem, dtype=state_dtype)
     total_ice = np.zeros_like(dem, dtype=state_dtype)
     if swe is None:
@@ -497,15 +556,42 @@ def run_model(dem, geotransform, aws_rows, insolation, cfg, *, swe=None, albedo_
 
         # DistributedVars.__post_init__, var_classes.py:113-125
         delta_dem = dem - cfg.elev_aws
-        d_t_air = t_air + delta_dem * grad_temp
+        if multi:                                         # station blend (specification above)
+            st_t, st_p, st_e, st_n = [t_air], [pressure], [aws_e], [cld]
+            for st in stations:
+                srow = st["rows"][i]
+                n_k = float(srow["CLOUDINESS"])
+                if cfg.cloud_corr is not None:
+                    n_k += cfg.cloud_corr
+                    n_k = 1.0 if n_k > 1.0 else n_k
+                    n_k = 0.0 if n_k < 0.0 else n_k
+                t_k, p_k = float(srow["T_AIR"]), float(srow["PRESSURE"])
+                st_t.append(t_k)
+                st_p.append(p_k)
+                st_e.append(unit_guess(float(srow["HUMID"]), 100) * e_max(t_k + 273.15, p_k * 100))
+                st_n.append(n_k)
+            mix_t = st_w[0] * st_t[0]
+            mix_p = st_w[0] * st_p[0]
+            d_e = st_e[0] * st_V[0]
+            mix_n = st_w[0] * (st_n[0] - st_n[0])
+            for k in range(1, len(st_t)):
+                mix_t = mix_t + st_w[k] * st_t[k]
+                mix_p = mix_p + st_w[k] * st_p[k]
+                d_e = d_e + st_e[k] * st_V[k]
+                mix_n = mix_n + st_w[k] * (st_n[k] - st_n[0])
+            delta_dem = st_D
+            d_t_air = mix_t + delta_dem * grad_temp
+            d_pressure = mix_p + delta_dem * -0.1145
+        else:
+            d_t_air = t_air + delta_dem * grad_temp
+            d_pressure = pressure + delta_dem * -0.1145
+            d_e = aws_e * 10 ** (-delta_dem / 6300)
         d_Tz = d_t_air + 273.15
         d_Tz_surf = t_surf + 273.15
         d_wind = np.zeros_like(dem, dtype=np.float32)     # :164-173, float32 on purpose (F10)
         d_wind[~np.isnan(dem)] = wind
         d_wind[np.isnan(dem)] = np.nan
-        d_pressure = pressure + delta_dem * -0.1145
         d_P = d_pressure * 100
-        d_e = aws_e * 10 ** (-delta_dem / 6300)
         d_emax = e_max(d_Tz, d_P)
         d_rh = np.divide(d_e, d_emax)
 
@@ -532,6 +618,8 @@ def run_model(dem, geotransform, aws_rows, insolation, cfg, *, swe=None, albedo_
         solar_lines.append("\n%s,%s,%s" % (date_str, pot_aws, swd))
         factor = 1 if pot_aws == 0 else swd / pot_aws
         incoming *= factor                    # in place, keeps the raster dtype (model.py:489)
+        if multi and cloud_k is not None:     # Beer-Lambert cloud attenuation relative to the primary station
+            incoming = incoming * np.exp(-cloud_k * mix_n)
         rs = incoming * (1 - albedo)
 
         atmo = rs + lwd - lwu + sens + lat                 # model.py:411

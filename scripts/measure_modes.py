@@ -39,6 +39,8 @@ def main():
     ap.add_argument("--size", dest="n", type=int, default=2048)
     ap.add_argument("--nsteps", dest="t", type=int, default=256)
     ap.add_argument("--dtype", default="f32")
+    ap.add_argument("--sequential", action="store_true", help="ensemble: one run per member instead of fused passes")
+    ap.add_argument("--shadow", action="store_true", help="ensemble: with topographic shading")
     a = ap.parse_args()
     prec = _lib.F32 if a.dtype == "f32" else _lib.F64
     if a.mode == "ensemble":
@@ -59,19 +61,19 @@ def main():
         eng = Engine(a.n, a.n, precision=prec, device=local)
         eng.set_params(cell_size=10.0, elev_aws=case.elev_aws, aws_row=case.aws_rc[0], aws_col=case.aws_rc[1],
                        sensor_z=1.6, zm=1e-3, z_h_or_e=1e-4, emissivity=0.98, lat=case.lat, lon=case.lon,
-                       insol_mode=_lib.INSOL_COMPUTED)
+                       insol_mode=_lib.INSOL_COMPUTED, shadow=a.shadow)
         eng.set_dem(dem)
         eng.set_albedo_maps([case.albedo_maps[k] for k in keys])
         eng.set_swe(case.swe)
         eng.set_forcing(build_forcing(case.aws_rows, keys))
         members = make_members(a.members)
         mine = shard(members, world, rank)
-        run_members(eng, members, indices=mine[:1])                  # warm-up
+        run_members(eng, members, indices=mine, fused=not a.sequential)   # warm-up (and the sunlit masks)
         if world > 1:
             torch.cuda.synchronize()
             dist.barrier()
         t0 = time.perf_counter()
-        out = run_members(eng, members, indices=mine)
+        out = run_members(eng, members, indices=mine, fused=not a.sequential)
         totals = np.zeros(a.members, dtype=np.float64)
         for i, o in out.items():
             totals[i] = o["mean_ice"]
@@ -83,7 +85,9 @@ def main():
         wall = time.perf_counter() - t0
         cells = float(a.n) * a.n * a.t * a.members
         if rank == 0:
-            print(json.dumps({"mode": "ensemble", "members": a.members, "gpus": world, "n": a.n, "t": a.t, "wall_s": wall,
+            print(json.dumps({"mode": "ensemble", "fused": not a.sequential, "shadow": a.shadow, "dtype": a.dtype,
+                              "kernel": eng.kernel_info(), "last_kernel_ms": eng.last_kernel_ms(), "last_sweep_ms": eng.last_sweep_ms(),
+                              "members": a.members, "gpus": world, "n": a.n, "t": a.t, "wall_s": wall,
                               "member_cell_steps_per_s": cells / wall,
                               "mean_ice_spread": float(np.std(totals))}))
         eng.close()

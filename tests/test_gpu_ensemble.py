@@ -42,3 +42,37 @@ def test_members_match_reference_on_perturbed_inputs(const):
         assert abs(got[i]["mean_ice"] - np.nanmean(got[i]["total_ice"])) < 1e-6 * max(np.nanmean(got[i]["total_ice"]), 1e-3), i
     assert abs(got[0]["mean_ice"] - got[3]["mean_ice"]) > 1e-6    # the perturbation really acts
     assert shard(members, 3, 1) == [1]
+
+
+@pytest.mark.parametrize("f64", [False, True])
+@pytest.mark.parametrize("mode", ["streamed", "computed", "shadow", "const"])
+def test_fused_members_equal_one_run_per_member(f64, mode):
+    """enrgy_run_members (four members per pass, a remainder in pairs, an odd one padded) gives the state
+    rasters of one enrgy_run per member bit for bit and its per-step statistics to rounding -- 5 members,
+    so that a group of four, a pair and the padding copy are all exercised; glacier margin included;
+    with and without the statistics."""
+    case = make_case(72, 30, w=150, seed=5)
+    pot = P.random_insolation(case, 30) if mode in ("streamed", "const") else None
+    kw = dict(const_albedo=(0.35, 0.75)) if mode == "const" else dict(last_snowfall="20220525") if mode == "computed" else {}
+    members = make_members(5, seed=3, albedo_sigma=0.08)
+    members[2] = dict(albedo_offset=0.9, zm=2e-3, z_h_or_e=1e-4)          # clipped at 1
+    eng = P.make_engine(case, f64, pot=pot, computed=mode in ("computed", "shadow"), shadow=mode == "shadow", **kw)
+    try:
+        one = run_members(eng, members, keep_rasters=True, fused=False)
+        eng.snapshot(save=False)
+        fused = run_members(eng, members, keep_rasters=True, fused=True)
+        nostat = run_members(eng, members, keep_rasters=True, fused=True, want_stats=False)
+        # a sub-range and a subset of the members, after the fused run: the handle's own state was left alone
+        eng.prepass()
+        stats_own = eng.run(0, 30)
+    finally:
+        eng.close()
+    for i in range(len(members)):
+        for k in ("swe", "total_snow", "total_ice"):
+            assert np.array_equal(one[i][k], fused[i][k], equal_nan=True), (i, k)
+            assert np.array_equal(one[i][k], nostat[i][k], equal_nan=True), (i, k)
+        # (the passes walk a patch in two halves: float32 sums in another order)
+        assert np.allclose(one[i]["stats"], fused[i]["stats"], rtol=1e-12 if f64 else 2e-6, atol=1e-9 if f64 else 1e-3), i
+        assert abs(fused[i]["mean_ice_raster"] - np.nanmean(fused[i]["total_ice"].astype(np.float64))) < 1e-6
+    assert np.isfinite(stats_own).all()
+    assert abs(fused[0]["mean_ice"] - fused[1]["mean_ice"]) > 1e-7
