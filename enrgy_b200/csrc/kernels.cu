@@ -175,6 +175,10 @@ __device__ __forceinline__ V2<double> lapse_product(V2<double> d, double g) { re
 __device__ __forceinline__ void keep_in_register(V2<float>& x) { asm volatile("" : "+l"(x.v)); }
 __device__ __forceinline__ void keep_in_register(V2<double>&) {}   // (float64 is short of registers: it may rematerialise)
 
+// x^2 + y^2 with fixed roundings (no contraction: the same value wherever it is formed)
+__device__ __forceinline__ float sq_sum(float x, float y) { return __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)); }
+__device__ __forceinline__ double sq_sum(double x, double y) { return __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)); }
+
 // single-instruction min / max (FMNMX / DMNMX); glacier cells never carry NaN here
 __device__ __forceinline__ float fmax_(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ float fmin_(float a, float b) { return fminf(a, b); }
@@ -690,8 +694,20 @@ energy_balance_kernel(const KernelArgs<R> a) {
     if (kAnalyticBeam) {
 #pragma unroll
       for (int q = 0; q < KP; ++q) {
-        patch_g2 = fmax_(patch_g2, fmax_(nx2[q].lo() * nx2[q].lo() + ny2[q].lo() * ny2[q].lo(),
-                                         nx2[q].hi() * nx2[q].hi() + ny2[q].hi() * ny2[q].hi()));
+        patch_g2 = fmax_(patch_g2, fmax_(sq_sum(nx2[q].lo(), ny2[q].lo()), sq_sum(nx2[q].hi(), ny2[q].hi())));
+      }
+      if (KT > K) {
+        // a pass that walks the patch in parts decides for the WHOLE patch, like a plain run does: the two
+        // forms of the direct beam differ in the last bits, and fused members must equal single runs
+        const int prow0 = row0 - part * K;
+        for (int i = 0; i < KT; ++i) {
+          const int rowb = prow0 + i;
+          if (rowb < a.band_rows && colx < a.cols && (i < part * K || i >= part * K + K)) {
+            const size_t o = (size_t)rowb * a.pitch + colx;
+            const R gx = a.nx[o], gy = a.ny[o];
+            if (gx == gx) patch_g2 = fmax_(patch_g2, sq_sum(gx, gy));
+          }
+        }
       }
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) patch_g2 = fmax_(patch_g2, __shfl_xor_sync(0xffffffffu, patch_g2, d));

@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--dtype", default="f32")
     ap.add_argument("--sequential", action="store_true", help="ensemble: one run per member instead of fused passes")
     ap.add_argument("--shadow", action="store_true", help="ensemble: with topographic shading")
+    ap.add_argument("--nostats", action="store_true", help="ensemble: fused passes without per-step statistics")
     a = ap.parse_args()
     prec = _lib.F32 if a.dtype == "f32" else _lib.F64
     if a.mode == "ensemble":
@@ -68,12 +69,12 @@ def main():
         eng.set_forcing(build_forcing(case.aws_rows, keys))
         members = make_members(a.members)
         mine = shard(members, world, rank)
-        run_members(eng, members, indices=mine, fused=not a.sequential)   # warm-up (and the sunlit masks)
+        run_members(eng, members, indices=mine, fused=not a.sequential, want_stats=not a.nostats)   # warm-up (and the sunlit masks)
         if world > 1:
             torch.cuda.synchronize()
             dist.barrier()
         t0 = time.perf_counter()
-        out = run_members(eng, members, indices=mine, fused=not a.sequential)
+        out = run_members(eng, members, indices=mine, fused=not a.sequential, want_stats=not a.nostats)
         totals = np.zeros(a.members, dtype=np.float64)
         for i, o in out.items():
             totals[i] = o["mean_ice"]
@@ -85,7 +86,7 @@ def main():
         wall = time.perf_counter() - t0
         cells = float(a.n) * a.n * a.t * a.members
         if rank == 0:
-            print(json.dumps({"mode": "ensemble", "fused": not a.sequential, "shadow": a.shadow, "dtype": a.dtype,
+            print(json.dumps({"mode": "ensemble", "fused": not a.sequential, "stats": not a.nostats, "lib": os.path.basename(_lib.LIB_PATH), "shadow": a.shadow, "dtype": a.dtype,
                               "kernel": eng.kernel_info(), "last_kernel_ms": eng.last_kernel_ms(), "last_sweep_ms": eng.last_sweep_ms(),
                               "members": a.members, "gpus": world, "n": a.n, "t": a.t, "wall_s": wall,
                               "member_cell_steps_per_s": cells / wall,
