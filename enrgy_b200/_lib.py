@@ -19,6 +19,8 @@ MAX_LAYERS = 8
 # forcing columns (enum ENRGY_F_*)
 (F_TIME, F_DT, F_T_AIR, F_WIND, F_PRESSURE, F_RH, F_CLOUD, F_SWD, F_LAPSE, F_ALB_I0, F_ALB_I1,
  F_ALB_DAYS, F_ALB_SPAN, F_SNOW_DAYS, F_COUNT) = range(15)
+# enrgy_station_col
+(ST_T_AIR, ST_PRESSURE, ST_RH, ST_CLOUD, ST_COUNT) = range(5)
 # statistics columns (enum ENRGY_S_*)
 (S_RS, S_LWD, S_LWU, S_SENS, S_LAT, S_ATMO, S_G, S_MELT, S_SNOW, S_ICE, S_SWE, S_NSNOW, S_NSWE,
  S_NVALID, S_COUNT) = range(15)
@@ -69,6 +71,7 @@ _PROTOTYPES = {
     "enrgy_set_swe": (C.c_int, [_P, _P]),
     "enrgy_set_msm": (C.c_int, [_P, _P, C.c_double]),
     "enrgy_set_member": (C.c_int, [_P, C.c_double, C.c_double, C.c_double]),
+    "enrgy_set_stations": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_double]),
     "enrgy_run_members": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "enrgy_get_member_state": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "enrgy_set_forcing": (C.c_int, [_P, C.c_int, _P]),

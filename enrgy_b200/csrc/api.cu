@@ -126,6 +126,13 @@ struct enrgy_ctx {
   DevBuf<unsigned char> d_mstate, d_mrecs;
   DevBuf<StepRec<double>> d_msteps64;
   int member_slots = 0, members_last = 0;
+  // station blend (enrgy_set_stations): extra weather stations and the cloud attenuation of the shortwave
+  bool stations_on = false;
+  int n_extra = 0;
+  double st_row[kMaxStations] = {}, st_col[kMaxStations] = {}, st_elev[kMaxStations] = {};
+  std::vector<double> st_series;   // [n_extra][n_steps][ENRGY_ST_COUNT]
+  double cloud_k = NAN;
+  DevBuf<unsigned char> d_strecs;  // StationRec<R> [n_steps][kMaxStations]
   DevBuf<unsigned char> d_partials;
   DevBuf<unsigned long long> d_counters;
   std::vector<ShadeRec> mask_shades;   // directions the cached masks were swept for
@@ -234,6 +241,46 @@ int upload_tables(enrgy_ctx* c) {
   return ENRGY_OK;
 }
 
+// per-step values of the stations (station blend): k = 0 the primary AWS, unused stations zero
+template <typename R>
+int upload_stations(enrgy_ctx* c) {
+  const int T = c->n_steps;
+  std::vector<StationRec<R>> recs((size_t)std::max(T, 1) * kMaxStations);
+  for (int i = 0; i < T; ++i) {
+    const StepRec<double>& s = c->pre.steps[i];
+    StationRec<R>* r = &recs[(size_t)i * kMaxStations];
+    r[0].t = (R)s.t_air; r[0].p = (R)s.p_hpa; r[0].e = (R)s.e_aws; r[0].cn = (R)0;
+    const double n0 = c->forcing[(size_t)i * ENRGY_F_COUNT + ENRGY_F_CLOUD];
+    for (int k = 1; k < kMaxStations; ++k) {
+      if (k <= c->n_extra) {
+        const double* v = &c->st_series[((size_t)(k - 1) * T + i) * ENRGY_ST_COUNT];
+        const double tk = v[ENRGY_ST_T_AIR], pk = v[ENRGY_ST_PRESSURE];
+        r[k].t = (R)tk;
+        r[k].p = (R)pk;
+        r[k].e = (R)(v[ENRGY_ST_RH] * sat_vapour_pressure(tk + 273.15, pk * 100));      // var_classes.py:83-85
+        r[k].cn = (R)(v[ENRGY_ST_CLOUD] - n0);
+      } else {
+        r[k].t = r[k].p = r[k].e = r[k].cn = (R)0;
+      }
+    }
+  }
+  CU_TRY(c->d_strecs.alloc(recs.size() * sizeof(StationRec<R>)));
+  CU_TRY(cudaMemcpyAsync(c->d_strecs.p, recs.data(), recs.size() * sizeof(StationRec<R>), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return ENRGY_OK;
+}
+template <typename R>
+void fill_station_args(const enrgy_ctx* c, KernelArgs<R>& a) {
+  a.n_stations = 1 + c->n_extra;
+  a.st_row[0] = (R)c->p.aws_row; a.st_col[0] = (R)c->p.aws_col; a.st_elev[0] = (R)c->p.elev_aws;
+  for (int k = 1; k < kMaxStations; ++k) {
+    a.st_row[k] = (R)c->st_row[k]; a.st_col[k] = (R)c->st_col[k]; a.st_elev[k] = (R)c->st_elev[k];
+  }
+  a.station_recs = (const StationRec<R>*)c->d_strecs.p;
+  a.cloud_on = std::isnan(c->cloud_k) ? 0 : 1;
+  a.cloud_neg_k = a.cloud_on ? (R)(-c->cloud_k) : (R)0;
+}
+
 // NaN fields of enrgy_params -> the reference's defaults
 void resolve_defaults(enrgy_params& p) {
   auto dflt = [](double& v, double d) { if (std::isnan(v)) v = d; };
@@ -335,6 +382,7 @@ int check_run_ready(enrgy_ctx* c, int t0, int t1) {
   if (t0 < 0 || t1 > c->n_steps || t0 > t1) return fail(ENRGY_ERR_ARG, "step range [%d, %d) outside [0, %d)", t0, t1, c->n_steps);
   if (!c->p.albedo_const && c->n_maps == 0) return fail(ENRGY_ERR_ARG, "albedo maps not set");
   if (c->p.msm_layers > 0 && !c->have_msm) return fail(ENRGY_ERR_ARG, "enrgy_set_msm must precede run when msm_layers > 0");
+  if (c->stations_on && c->p.msm_layers > 0) return fail(ENRGY_ERR_ARG, "the station blend does not run with the sub-surface model");
   if (c->p.insol_mode == ENRGY_INSOL_STREAMED && t1 > t0 &&
       (t0 < c->pot_t0 || t1 > c->pot_t0 + c->pot_n)) {
     return fail(ENRGY_ERR_ARG, "insolation rasters resident for steps [%d, %d), run asks [%d, %d)",
@@ -530,7 +578,12 @@ int launch_range(enrgy_ctx* c, int t0, int t1, double* d_stats, cudaStream_t str
   if (insol == kInsolMasked && masks == nullptr) return fail(ENRGY_ERR_ARG, "no sunlit masks for a run with shading");
   LaunchInfo li;
   const bool msm = c->p.msm_layers > 0;
-  CU_TRY(energy_balance_grid<R>(insol, msm, false, c->sm_count, a.cap_steps, a.cap_subs, &li));
+  if (c->stations_on) {
+    fill_station_args<R>(c, a);
+    CU_TRY(energy_balance_stations_grid<R>(insol, false, c->sm_count, a.cap_steps, a.cap_subs, &li));
+  } else {
+    CU_TRY(energy_balance_grid<R>(insol, msm, false, c->sm_count, a.cap_steps, a.cap_subs, &li));
+  }
   int grid = std::min(li.grid, std::max(c->n_tiles, 1));
   const int n = t1 - t0;
   const size_t partial_bytes = (size_t)grid * std::max(n, 1) * (msm ? kStatsP : kStatsK) * sizeof(R);
@@ -543,7 +596,11 @@ int launch_range(enrgy_ctx* c, int t0, int t1, double* d_stats, cudaStream_t str
     c->launches++;
   }
   CU_TRY(fused_events(c).begin(stream));
-  CU_TRY(launch_energy_balance<R>(a, nullptr, insol, false, c->sm_count, grid, &c->info, stream));
+  if (c->stations_on) {
+    CU_TRY(launch_energy_balance_stations<R>(a, insol, false, c->sm_count, grid, &c->info, stream));
+  } else {
+    CU_TRY(launch_energy_balance<R>(a, nullptr, insol, false, c->sm_count, grid, &c->info, stream));
+  }
   CU_TRY(fused_events(c).end(stream));
   c->launches++;
   if (c->defer == 2) c->defer = 0;
@@ -551,6 +608,7 @@ int launch_range(enrgy_ctx* c, int t0, int t1, double* d_stats, cudaStream_t str
     FinalizeArgs f{};
     f.partials = c->d_partials.p; f.n_ctas = grid; f.n_steps = n; f.t0 = t0;
     f.n_valid = c->n_valid; f.f32_mode = c->precision == ENRGY_F32; f.msm = msm ? 1 : 0;
+    f.lwd_summed = c->stations_on ? 1 : 0;
     for (int q = 0; q < 5; ++q) f.mom[q] = c->mom[q];
     f.steps64 = c->d_steps64.p; f.stats = d_stats;
     f.override_first = (t0 == 0 && !c->state_advanced) ? 1 : 0;
@@ -602,7 +660,12 @@ int dump_typed(enrgy_ctx* c, int t0, int t1, double* out) {
   CU_TRY(cudaMemsetAsync(c->d_dump.p, 0xFF, (size_t)n * per_step * sizeof(R), c->stream));
   a.dump = (R*)c->d_dump.p;
   a.dump_field_stride = c->band_elems;
-  CU_TRY(launch_energy_balance<R>(a, nullptr, insol, true, c->sm_count, 0, nullptr, c->stream));
+  if (c->stations_on) {
+    fill_station_args<R>(c, a);
+    CU_TRY(launch_energy_balance_stations<R>(a, insol, true, c->sm_count, 0, nullptr, c->stream));
+  } else {
+    CU_TRY(launch_energy_balance<R>(a, nullptr, insol, true, c->sm_count, 0, nullptr, c->stream));
+  }
   c->launches++;
   std::vector<R> h((size_t)n * per_step);
   CU_TRY(cudaMemcpyAsync(h.data(), c->d_dump.p, h.size() * sizeof(R), cudaMemcpyDeviceToHost, c->stream));
@@ -827,7 +890,7 @@ int enrgy_destroy(enrgy_ctx* c) {
   c->d_ti.release(); c->d_dump.release(); c->d_stage.release(); c->d_steps.release(); c->d_subs.release();
   c->d_steps64.release(); c->d_shades.release(); c->d_blocks.release(); c->d_tiles.release();
   c->d_counts.release(); c->d_partials.release(); c->d_stats.release(); c->d_small.release();
-  c->d_mstate.release(); c->d_mrecs.release(); c->d_msteps64.release();
+  c->d_mstate.release(); c->d_mrecs.release(); c->d_msteps64.release(); c->d_strecs.release();
   c->d_counters.release(); c->d_snap.release(); c->d_layer_t.release(); c->d_terrain.release(); c->d_scan.release();
   c->d_scan_t.release(); c->d_maskbuf.release(); c->d_masktmp.release(); c->d_sweepsubs.release(); c->d_swe_ref.release();
   if (c->ev_fused) { fused_events(c).destroy(); delete static_cast<EventPairs*>(c->ev_fused); }
@@ -1188,6 +1251,33 @@ int enrgy_set_member(enrgy_ctx* c, double albedo_offset, double zm, double z_h_o
   return ENRGY_OK;
 }
 
+int enrgy_set_stations(enrgy_ctx* c, int n_extra, const double* row, const double* col, const double* elev,
+                       const double* series, double cloud_k) {
+  if (int e = use_device(c)) return e;
+  if (n_extra < 0) {                      // back to the reference's single AWS
+    c->stations_on = false; c->n_extra = 0; c->st_series.clear(); c->cloud_k = NAN;
+    c->prepass_done = false;
+    return ENRGY_OK;
+  }
+  if (n_extra > kMaxStations - 1) return fail(ENRGY_ERR_ARG, "at most %d extra stations", kMaxStations - 1);
+  if (!c->have_forcing) return fail(ENRGY_ERR_ARG, "set_forcing must precede set_stations (the series share its time base)");
+  if (n_extra > 0 && (!row || !col || !elev || !series)) return fail(ENRGY_ERR_ARG, "set_stations: null arrays");
+  if (!std::isnan(cloud_k) && cloud_k < 0) return fail(ENRGY_ERR_ARG, "cloud_k must be >= 0 (NaN = no cloud attenuation)");
+  for (int k = 0; k < n_extra; ++k) {
+    if (!std::isfinite(row[k]) || !std::isfinite(col[k]) || !std::isfinite(elev[k])) return fail(ENRGY_ERR_ARG, "station %d: position not finite", k + 1);
+    c->st_row[k + 1] = row[k]; c->st_col[k + 1] = col[k]; c->st_elev[k + 1] = elev[k];
+  }
+  const size_t n = (size_t)n_extra * c->n_steps * ENRGY_ST_COUNT;
+  for (size_t i = 0; i < n; ++i)
+    if (!std::isfinite(series[i])) return fail(ENRGY_ERR_ARG, "station series: value %zu is not finite", i);
+  c->st_series.assign(series, series + n);
+  c->n_extra = n_extra;
+  c->cloud_k = cloud_k;
+  c->stations_on = true;
+  c->prepass_done = false;
+  return ENRGY_OK;
+}
+
 int enrgy_set_forcing(enrgy_ctx* c, int n_steps, const double* forcing) {
   if (int e = use_device(c)) return e;
   if (n_steps < 0 || (n_steps > 0 && !forcing)) return fail(ENRGY_ERR_ARG, "bad forcing table");
@@ -1253,6 +1343,12 @@ int enrgy_prepass(enrgy_ctx* c) {
   if (rc != ENRGY_OK) return fail(rc, "%s", err.c_str());
   const int urc = c->precision == ENRGY_F32 ? upload_tables<float>(c) : upload_tables<double>(c);
   if (urc != ENRGY_OK) return urc;
+  if (c->stations_on) {
+    if ((int)c->st_series.size() != c->n_extra * c->n_steps * ENRGY_ST_COUNT)
+      return fail(ENRGY_ERR_ARG, "station series were set for another forcing table: call enrgy_set_stations after enrgy_set_forcing");
+    const int src = c->precision == ENRGY_F32 ? upload_stations<float>(c) : upload_stations<double>(c);
+    if (src != ENRGY_OK) return src;
+  }
   c->prepass_done = true;
   return ENRGY_OK;
 }
@@ -1366,6 +1462,7 @@ int enrgy_run_members(enrgy_ctx* c, int n_members, const double* albedo_offset, 
   if (int e = use_device(c)) return e;
   if (n_members < 1 || !albedo_offset) return fail(ENRGY_ERR_ARG, "run_members: at least one member with an albedo offset");
   if (!c->have_dem || !c->have_forcing) return fail(ENRGY_ERR_ARG, "set_dem and set_forcing must precede run_members");
+  if (c->stations_on) return fail(ENRGY_ERR_ARG, "run_members: not with the station blend (enrgy_set_stations)");
   if (c->p.msm_layers > 0)
     return fail(ENRGY_ERR_ARG, "run_members: the sub-surface model keeps 8 temperatures per cell and member -- run such members "
                                "one after the other (enrgy_set_member + enrgy_run)");

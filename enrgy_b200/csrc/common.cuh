@@ -97,6 +97,16 @@ struct alignas(8) MemberRec {
   R c_sens, c_lat;
 };
 
+// ---- per-step values of one weather station (station blend, BASELINE config C4) ---------------------
+constexpr int kMaxStations = 4;               // the primary AWS + 3
+template <typename R>
+struct alignas(16) StationRec {
+  R t;     // T_AIR [deg C]
+  R p;     // PRESSURE [hPa]
+  R e;     // vapour pressure [Pa] = RH * e_max(T, P)           var_classes.py:85
+  R cn;    // cloudiness minus the primary station's (after cloud_corr and clamping)
+};
+
 // ---- per-sub-step record (sun above the horizon only) ------------------------------------------
 template <typename R>
 struct alignas(16) SubRec {

@@ -175,6 +175,13 @@ __device__ __forceinline__ V2<double> lapse_product(V2<double> d, double g) { re
 __device__ __forceinline__ void keep_in_register(V2<float>& x) { asm volatile("" : "+l"(x.v)); }
 __device__ __forceinline__ void keep_in_register(V2<double>&) {}   // (float64 is short of registers: it may rematerialise)
 
+// single IEEE operations (no contraction): the station weights follow NumPy's array arithmetic
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
 // x^2 + y^2 with fixed roundings (no contraction: the same value wherever it is formed)
 __device__ __forceinline__ float sq_sum(float x, float y) { return __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)); }
 __device__ __forceinline__ double sq_sum(double x, double y) { return __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)); }
@@ -491,17 +498,19 @@ __host__ __device__ constexpr int warps_x(int w) { return w >= 4 ? 4 : w; }     
 // run-time values chosen by the host (64 / 256, grown to the largest sub-step count of one step).
 template <typename R>
 struct SmemPlan {
-  int steps, subs, members, slots, slots_m, full, total;   // byte offsets and the total size
+  int steps, subs, members, stations, slots, slots_m, full, total;   // byte offsets and the total size
 };
-// nm: ensemble members fused into one pass (1 = a plain run: no member records)
+// nm: ensemble members fused into one pass (1 = a plain run: no member records); ns: weather stations
+// blended (1 = the reference's single AWS: no station records)
 template <typename R>
 __host__ __device__ inline SmemPlan<R> smem_plan(int warps, int cap_steps, int cap_subs, bool with_subs, bool msm,
-                                                 int nm = 1) {
+                                                 int nm = 1, int ns = 1) {
   SmemPlan<R> p;
   int o = 0;
   p.steps = o;   o += 2 * cap_steps * (int)sizeof(StepRec<R>);
   p.subs = o;    o += with_subs ? 2 * cap_subs * (int)sizeof(SubRec<R>) : 0;
   p.members = o; o += nm > 1 ? 2 * cap_steps * nm * (int)sizeof(MemberRec<R>) : 0;
+  p.stations = o; o += ns > 1 ? 2 * cap_steps * ns * (int)sizeof(StationRec<R>) : 0;
   p.slots = o;   o += warps * cap_steps * nm * kStatsK * (int)sizeof(R);
   p.slots_m = o; o += msm ? warps * cap_steps * kStatsM * (int)sizeof(R) : 0;
   o = (o + 15) / 16 * 16;
@@ -544,18 +553,25 @@ constexpr int kMaskAhead = ENRGY_MASK_AHEAD;   // sunlit masks are prefetched th
 #endif
 // STATS = false (fused members only): no per-step area statistics -- their adds and the warp butterfly
 // are a third of a member's share of a step; the season totals come from the final rasters instead.
-template <typename R, int K, int INSOL, bool MSM, bool DUMP, int NM = 1, int KT = K, bool STATS = true>
+// NS > 1: up to NS weather stations blended per cell (BASELINE config C4; specification in
+// oracle/enrgy_oracle.py "several weather stations"): inverse-squared-distance weights and the weights
+// folded with the vapour-pressure reduction live in registers per cell, the stations' per-step values are
+// staged like the AWS records; unused stations carry weight zero.  The shortwave is attenuated by the
+// cloud field relative to the primary station (Beer-Lambert, one exp per cell-step).
+template <typename R, int K, int INSOL, bool MSM, bool DUMP, int NM = 1, int KT = K, bool STATS = true, int NS = 1>
 __global__ void __launch_bounds__(32 * kWarpsFor<R, INSOL>, NM > 2 ? ENRGY_MINB_MEMBERS : sizeof(R) == 4 ? ENRGY_MINB32 : ENRGY_MINB64)
 energy_balance_kernel(const KernelArgs<R> a) {
   static_assert(NM == 1 || (!MSM && !DUMP), "fused members: no sub-surface model, no dump");
   static_assert(KT % K == 0, "a patch is walked in whole parts");
   static_assert(STATS || NM > 1, "only fused members run without statistics");
+  static_assert(NS == 1 || (NM == 1 && !MSM), "station blend: no fused members, no sub-surface model");
   constexpr int W = kWarpsFor<R, INSOL>;           // warps per CTA
   constexpr int WX = warps_x(W), WY = W / WX;      // patches of a tile: WX across, WY down
   constexpr int NT = 32 * W;                       // threads per CTA
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int cap_steps = a.cap_steps, cap_subs = a.cap_subs;
-  const SmemPlan<R> plan = smem_plan<R>(W, cap_steps, cap_subs, INSOL != kInsolStreamed, MSM, NM);
+  const SmemPlan<R> plan = smem_plan<R>(W, cap_steps, cap_subs, INSOL != kInsolStreamed, MSM, NM, NS);
+  StationRec<R>* const sm_stations = reinterpret_cast<StationRec<R>*>(smem_raw + plan.stations);  // [2][cap_steps][NS]
   StepRec<R>* const sm_steps = reinterpret_cast<StepRec<R>*>(smem_raw + plan.steps);     // [2][cap_steps]
   SubRec<R>* const sm_subs = reinterpret_cast<SubRec<R>*>(smem_raw + plan.subs);         // [2][cap_subs]
   MemberRec<R>* const sm_members = reinterpret_cast<MemberRec<R>*>(smem_raw + plan.members);  // [2][cap_steps][NM]
@@ -583,6 +599,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
     unsigned bytes = n_steps * (unsigned)sizeof(StepRec<R>);
     if (INSOL != kInsolStreamed) bytes += n_subs * (unsigned)sizeof(SubRec<R>);
     if (NM > 1) bytes += n_steps * NM * (unsigned)sizeof(MemberRec<R>);
+    if (NS > 1) bytes += n_steps * NS * (unsigned)sizeof(StationRec<R>);
     fence_proxy_async();
     mbar_expect_tx(&sm_full[buf], bytes);
     tma_bulk_g2s(sm_steps + buf * cap_steps, a.steps + tb.t_begin, n_steps * (unsigned)sizeof(StepRec<R>),
@@ -594,6 +611,10 @@ energy_balance_kernel(const KernelArgs<R> a) {
     if (NM > 1) {
       tma_bulk_g2s(sm_members + buf * cap_steps * NM, a.member_recs + (size_t)tb.t_begin * NM,
                    n_steps * NM * (unsigned)sizeof(MemberRec<R>), &sm_full[buf]);
+    }
+    if (NS > 1) {
+      tma_bulk_g2s(sm_stations + buf * cap_steps * NS, a.station_recs + (size_t)tb.t_begin * NS,
+                   n_steps * NS * (unsigned)sizeof(StationRec<R>), &sm_full[buf]);
     }
   };
 
@@ -621,7 +642,8 @@ energy_balance_kernel(const KernelArgs<R> a) {
     using V = V2<R>;
     const int row0 = tile.x * TILE_H + (warp / WX) * KT + part * K;   // band-local row of cell 0
     const int colx = tile.y * TILE_W + (warp % WX) * 32 + lane;   // this lane's column
-    V delta2[KP], pw2[KP], nx2[KP], ny2[KP], nz2[KP];
+    V delta2[KP], pw2[NS][KP], nx2[KP], ny2[KP], nz2[KP];   // pw2[k]: (weight of station k) x 10^(-(z - z_k) / 6300)
+    V wst2[NS > 1 ? NS : 1][KP];                           // weights of the stations (NS > 1)
     V om2[NM][KP], swe2[NM][KP], tic2[NM][KP];         // per member: 1 - albedo (ice surface), SWE, ice-melt total
     R tl[K][NB];                   // sub-surface boundary temperatures [deg C] (MSM)
     // The reference's top boundary turns float64 after its first tick (NEP 50: float32 array +
@@ -633,7 +655,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
     R cur_w = (R)-1;
 #pragma unroll
     for (int q = 0; q < KP; ++q) {
-      R d_[2], p_[2], x_[2], y_[2], n_[2], s_[NM][2], t_[NM][2];
+      R d_[2], p_[NS][2], w_[NS][2], x_[2], y_[2], n_[2], s_[NM][2], t_[NM][2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int i = 2 * q + h;
@@ -649,7 +671,32 @@ energy_balance_kernel(const KernelArgs<R> a) {
         // exponent (libm, correctly rounded in practice); powf here may be a few ulp off, which the
         // vapour-pressure difference e - es amplifies into the largest float32 error of the whole
         // balance (4e-5 W m-2) -- so the power is taken in float64 and rounded once (prologue only)
-        p_[h] = (R)pow(10.0, (double)(-d_[h] / (R)kVapourScale));
+        p_[0][h] = (R)pow(10.0, (double)(-d_[h] / (R)kVapourScale));
+        w_[0][h] = (R)1;
+        if (NS > 1) {
+          // inverse squared distance in cell units, softened by half a cell; w_k = q_k / sum_j q_j
+          R qk[NS];
+          const R rr = (R)(rowb + a.band_row0), cc = (R)colx;
+#pragma unroll
+          for (int k = 0; k < NS; ++k) {
+            const R dr = rr - a.st_row[k], dc = cc - a.st_col[k];
+            qk[k] = k < a.n_stations ? div_rn((R)1, add_rn(add_rn(mul_rn(dr, dr), mul_rn(dc, dc)), (R)0.25)) : (R)0;
+          }
+          R tot = qk[0];
+#pragma unroll
+          for (int k = 1; k < NS; ++k) tot = add_rn(tot, qk[k]);
+          R dsum = (R)0;
+#pragma unroll
+          for (int k = 0; k < NS; ++k) {
+            const R wk = div_rn(qk[k], tot);
+            const R dzk = (R)z - a.st_elev[k];
+            const R term = mul_rn(wk, dzk);
+            dsum = k == 0 ? term : add_rn(dsum, term);
+            w_[k][h] = wk;
+            p_[k][h] = mul_rn(wk, (R)pow(10.0, (double)(-dzk / (R)kVapourScale)));
+          }
+          d_[h] = dsum;                            // sum_k w_k (z - z_k) replaces z - elev_aws
+        }
         if (INSOL != kInsolStreamed) {
           x_[h] = v ? a.nx[o] : (R)0;
           y_[h] = v ? a.ny[o] : (R)0;
@@ -674,7 +721,11 @@ energy_balance_kernel(const KernelArgs<R> a) {
       // keep the elevation difference itself in registers: left alone, the compiler re-derives it (and
       // the validity test) from the raw elevation in every step, three extra instructions per cell-step
       keep_in_register(delta2[q]);
-      pw2[q] = V::make(p_[0], p_[1]);
+#pragma unroll
+      for (int k = 0; k < NS; ++k) {
+        pw2[k][q] = V::make(p_[k][0], p_[k][1]);
+        if (NS > 1) wst2[k][q] = V::make(w_[k][0], w_[k][1]);
+      }
       nx2[q] = V::make(x_[0], x_[1]);
       ny2[q] = V::make(y_[0], y_[1]);
       nz2[q] = V::make(n_[0], n_[1]);
@@ -812,6 +863,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
         // ---- per-cell energy balance -------------------------------------------------------------
         const V zero2 = V::splat((R)0);
         V acc_sens = zero2, acc_lat = zero2;                 // member-invariant flux factors
+        V acc_lwd = zero2;                                   // station blend: Tz^4 (no DEM-moment shortcut)
         V acc_rs[NM], acc_mf[NM], acc_snow[NM], acc_swe[NM], acc_lwu = zero2, acc_g = zero2;
         int n_snow[NM];
 #pragma unroll
@@ -846,7 +898,36 @@ energy_balance_kernel(const KernelArgs<R> a) {
           // lapse-rate distribution, var_classes.py:113-125.  float32 evaluates T + delta * lapse the
           // way NumPy float32 does (rounded product, rounded sum)
           // (the product is formed per cell with __fmul_rn: ptxas contracts a packed mul + add into FFMA2)
-          const V t_air = sizeof(R) == 4 ? add2(t_aws, lapse_product(delta2[q], s.lapse)) : fma2(delta2[q], lapse2, t_aws);
+          // station blend: T, p at the cell = sum_k w_k (station value) + D * lapse, e = sum_k e_k V_k
+          V t_st = t_aws, p_st = p_aws, e_st = zero2, cloud_fac = zero2;
+          if (NS > 1) {
+            const StationRec<R>* const sr = sm_stations + (buf * cap_steps + (t - tb.t_begin)) * NS;
+            V cn = zero2;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+              const StationRec<R> r = sr[k];
+              // float32: the temperature blend mirrors NumPy's float32 sequence (rounded products, rounded
+              // sums) -- one ulp of a Celsius value flips the rounding of the Kelvin value in 2 % of the
+              // cells, and Tz - Ts carries that into the sensible flux.  ptxas contracts a packed mul + add,
+              // so the products are formed per cell (lapse_product).
+              if (k == 0) {
+                t_st = sizeof(R) == 4 ? lapse_product(wst2[0][q], r.t) : mul2(wst2[0][q], V::splat(r.t));
+                p_st = mul2(wst2[0][q], V::splat(r.p));
+                e_st = mul2(pw2[0][q], V::splat(r.e));
+              } else {
+                t_st = sizeof(R) == 4 ? add2(t_st, lapse_product(wst2[k][q], r.t)) : fma2(wst2[k][q], V::splat(r.t), t_st);
+                p_st = fma2(wst2[k][q], V::splat(r.p), p_st);
+                e_st = fma2(pw2[k][q], V::splat(r.e), e_st);
+                cn = k == 1 ? mul2(wst2[1][q], V::splat(r.cn)) : fma2(wst2[k][q], V::splat(r.cn), cn);
+              }
+            }
+            // Beer-Lambert attenuation by the cloud field relative to the primary station
+            if (a.cloud_on) {
+              const V x = mul2(cn, V::splat(a.cloud_neg_k));
+              cloud_fac = V::make(Num<R>::exp_(x.lo()), Num<R>::exp_(x.hi()));
+            }
+          }
+          const V t_air = sizeof(R) == 4 ? add2(t_st, lapse_product(delta2[q], s.lapse)) : fma2(delta2[q], lapse2, t_st);
           const V tz = add2(t_air, k273);
           // surface temperature: 0 degC without the sub-surface model, else the top
           // boundary of the layer stack (model.py:207-210)
@@ -868,8 +949,8 @@ energy_balance_kernel(const KernelArgs<R> a) {
             }
             d_t = V::make(d[0], d[1]);
           }
-          const V p_hpa = fma2(delta2[q], k_plapse, p_aws);
-          const V e = mul2(pw2[q], e_aws);
+          const V p_hpa = fma2(delta2[q], k_plapse, p_st);
+          const V e = NS > 1 ? e_st : mul2(pw2[0][q], e_aws);
           // bulk fluxes, turbo.py:140-196 with rho = P / (R Tz) and rho / P = 1 / (R Tz);
           // c_sens carries CH * Cp * uz * 100 (Pa per hPa), c_lat carries CE * uz * 0.622 * Lv
           V r_rt, r_p;                                      // 1 / (R Tz) and 1 / p_hpa
@@ -934,7 +1015,9 @@ energy_balance_kernel(const KernelArgs<R> a) {
             // float32: both terms are ~300 W m-2 and Tz^4 alone would cost 4e-5 W m-2 of rounding.
             // With the (rounded, as in the reference) Tz = K0 + d_t, K0 = float(273.15) and d_t exact:
             //   c_lwd Tz^4 - lwu = (c_lwd K0^4 - lwu) + c_lwd K0^4 ((1 + y)^4 - 1),  y = d_t / K0
-            // -- a per-row scalar from the float64 pre-pass plus a term of at most ~30 W m-2
+            // -- a per-row scalar from the float64 pre-pass plus a term of at most ~30 W m-2.
+            // (Horner / Estrin forms in d_t with four per-row coefficients measured 1-2 % slower: the
+            // loop waits on dependent packed instructions, and the wider step record costs shared-memory loads)
             const V y = mul2(d_t, V::splat((R)(1.0 / (double)273.15f)));
             const V poly = mul2(y, fma2(y, fma2(y, add2(y, V::splat((R)4)), V::splat((R)6)), V::splat((R)4)));
             rl = fma2(V::splat(s.c_lw1), poly, V::splat(s.c_lw0));
@@ -954,6 +1037,10 @@ energy_balance_kernel(const KernelArgs<R> a) {
             // (the first pair starts the sums: q is a compile-time constant of the unrolled loop)
             acc_sens = q == 0 ? m_sens : add2(acc_sens, m_sens);
             acc_lat = q == 0 ? m_lat : add2(acc_lat, m_lat);
+            if (NS > 1) {
+              const V m_lwd = FULL ? tz4 : V::make(v_lo ? tz4.lo() : (R)0, v_hi ? tz4.hi() : (R)0);
+              acc_lwd = q == 0 ? m_lwd : add2(acc_lwd, m_lwd);
+            }
           }
 #pragma unroll
           for (int m = 0; m < NM; ++m) {
@@ -965,7 +1052,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
           const V oma = V::make(snow_lo ? om_snow.lo() : fmax_(om2[m][q].lo(), ice_floor),
                                 snow_hi ? om_snow.hi() : fmax_(om2[m][q].hi(), ice_floor));
           // shortwave, model.py:483-497: rs = potential * c_sw * (1 - albedo)
-          const V x_rs = mul2(pot2[q], oma);
+          const V x_rs = (NS > 1 && a.cloud_on) ? mul2(mul2(pot2[q], cloud_fac), oma) : mul2(pot2[q], oma);
           // balance, clamp, melt partition: model.py:411, :434-438, msm.py:193-203
           // rs + lwd - lwu + sens + lat as one FMA chain
           const V atmo = fma2(c_lat[m], x_lat, fma2(c_sens[m], x_sens, fma2(c_sw, x_rs, rl)));
@@ -1110,7 +1197,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
           for (int m = 0; m < NM; ++m) {
             R acc[kStatsK];
             acc[K_RS] = acc_rs[m].lo() + acc_rs[m].hi();
-            acc[K_LWD] = (R)0;
+            acc[K_LWD] = NS > 1 ? acc_lwd.lo() + acc_lwd.hi() : (R)0;
             acc[K_SENS] = sum_sens;
             acc[K_LAT] = sum_lat;
             acc[K_MELT] = acc_mf[m].lo() + acc_mf[m].hi();
@@ -1296,17 +1383,17 @@ template void energy_balance_tile<double>(bool, int, int*, int*);
 
 // fused members: half the cells per thread (their per-member state takes the registers), the handle's
 // tile list is walked in two parts
-template <typename R, bool MSM, int NM>
+template <typename R, bool MSM, int NM, int NS = 1>
 struct PassShape {
   static constexpr int KT = CellsPerThread<R, MSM>::value;
-  static constexpr int K = NM > 1 ? KT / 2 : KT;
+  static constexpr int K = (NM > 1 || NS > 1) ? KT / 2 : KT;
 };
 
-template <typename R, int INSOL, bool MSM, bool DUMP, int NM = 1, bool STATS = true>
+template <typename R, int INSOL, bool MSM, bool DUMP, int NM = 1, bool STATS = true, int NS = 1>
 static cudaError_t configure(int sm_count, int cap_steps, int cap_subs, LaunchInfo* info) {
-  constexpr int K = PassShape<R, MSM, NM>::K, KT = PassShape<R, MSM, NM>::KT;
-  auto kern = energy_balance_kernel<R, K, INSOL, MSM, DUMP, NM, KT, STATS>;
-  const int smem = smem_plan<R>(kWarpsFor<R, INSOL>, cap_steps, cap_subs, INSOL != kInsolStreamed, MSM, NM).total;
+  constexpr int K = PassShape<R, MSM, NM, NS>::K, KT = PassShape<R, MSM, NM, NS>::KT;
+  auto kern = energy_balance_kernel<R, K, INSOL, MSM, DUMP, NM, KT, STATS, NS>;
+  const int smem = smem_plan<R>(kWarpsFor<R, INSOL>, cap_steps, cap_subs, INSOL != kInsolStreamed, MSM, NM, NS).total;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
@@ -1324,18 +1411,18 @@ static cudaError_t configure(int sm_count, int cap_steps, int cap_subs, LaunchIn
   return cudaSuccess;
 }
 
-template <typename R, int INSOL, bool MSM, bool DUMP, int NM = 1, bool STATS = true>
+template <typename R, int INSOL, bool MSM, bool DUMP, int NM = 1, bool STATS = true, int NS = 1>
 static cudaError_t launch_one(const KernelArgs<R>& a, int sm_count, int forced_grid, LaunchInfo* info,
                               cudaStream_t stream) {
-  constexpr int K = PassShape<R, MSM, NM>::K, KT = PassShape<R, MSM, NM>::KT;
+  constexpr int K = PassShape<R, MSM, NM, NS>::K, KT = PassShape<R, MSM, NM, NS>::KT;
   LaunchInfo li;
-  cudaError_t e = configure<R, INSOL, MSM, DUMP, NM, STATS>(sm_count, a.cap_steps, a.cap_subs, &li);
+  cudaError_t e = configure<R, INSOL, MSM, DUMP, NM, STATS, NS>(sm_count, a.cap_steps, a.cap_subs, &li);
   if (e != cudaSuccess) return e;
   int grid = forced_grid > 0 ? forced_grid : li.grid;
   li.grid = grid;
   if (info) *info = li;
   if (a.n_tiles == 0 || a.t1 <= a.t0) return cudaSuccess;
-  energy_balance_kernel<R, K, INSOL, MSM, DUMP, NM, KT, STATS><<<grid, 32 * kWarpsFor<R, INSOL>, li.smem_bytes, stream>>>(a);
+  energy_balance_kernel<R, K, INSOL, MSM, DUMP, NM, KT, STATS, NS><<<grid, 32 * kWarpsFor<R, INSOL>, li.smem_bytes, stream>>>(a);
   return cudaGetLastError();
 }
 
@@ -1372,6 +1459,35 @@ cudaError_t launch_energy_balance_members(const KernelArgs<R>& a, int insol, int
 }
 template cudaError_t launch_energy_balance_members<float>(const KernelArgs<float>&, int, int, bool, int, int, LaunchInfo*, cudaStream_t);
 template cudaError_t launch_energy_balance_members<double>(const KernelArgs<double>&, int, int, bool, int, int, LaunchInfo*, cudaStream_t);
+
+// station blend (kMaxStations stations): (insol, dump) -> template instance
+template <typename R, typename F>
+static cudaError_t dispatch_stations(int insol, bool dump, F&& f) {
+#define ENRGY_CASE(I, D) \
+  if (insol == I && dump == D) return f(std::integral_constant<int, I>{}, std::integral_constant<bool, D>{});
+  ENRGY_CASE(0, false) ENRGY_CASE(1, false) ENRGY_CASE(2, false)
+  ENRGY_CASE(0, true) ENRGY_CASE(1, true) ENRGY_CASE(2, true)
+#undef ENRGY_CASE
+  return cudaErrorInvalidValue;
+}
+template <typename R>
+cudaError_t energy_balance_stations_grid(int insol, bool dump, int sm_count, int cap_steps, int cap_subs, LaunchInfo* info) {
+  return dispatch_stations<R>(insol, dump, [&](auto i, auto d) {
+    return configure<R, decltype(i)::value, false, decltype(d)::value, 1, true, kMaxStations>(sm_count, cap_steps, cap_subs, info);
+  });
+}
+template cudaError_t energy_balance_stations_grid<float>(int, bool, int, int, int, LaunchInfo*);
+template cudaError_t energy_balance_stations_grid<double>(int, bool, int, int, int, LaunchInfo*);
+template <typename R>
+cudaError_t launch_energy_balance_stations(const KernelArgs<R>& a, int insol, bool dump, int sm_count, int forced_grid,
+                                           LaunchInfo* info, cudaStream_t stream) {
+  return dispatch_stations<R>(insol, dump, [&](auto i, auto d) {
+    return launch_one<R, decltype(i)::value, false, decltype(d)::value, 1, true, kMaxStations>(a, sm_count, forced_grid, info,
+                                                                                              stream);
+  });
+}
+template cudaError_t launch_energy_balance_stations<float>(const KernelArgs<float>&, int, bool, int, int, LaunchInfo*, cudaStream_t);
+template cudaError_t launch_energy_balance_stations<double>(const KernelArgs<double>&, int, bool, int, int, LaunchInfo*, cudaStream_t);
 
 // glacier-wide means of the state rasters of fused members: block_out[(member * blocks + b) * 4 + {0..3}] =
 // {sum swe, sum total_snow, sum total_ice, count} over the band's glacier cells (summed on the host in
@@ -1625,7 +1741,8 @@ __global__ void finalize_stats_kernel(const FinalizeArgs f) {
     lwd_sum = c_lwd * (a2 * a2 * f.mom[0] + 4.0 * a2 * a * g * f.mom[1] + 6.0 * a2 * g2 * f.mom[2] +
                        4.0 * a * g2 * g * f.mom[3] + g2 * g2 * f.mom[4]);
   }
-  k[K_LWD] = lwd_sum;
+  // (station blend: Tz is no polynomial of one variable any more; the kernel summed Tz^4 itself)
+  k[K_LWD] = f.lwd_summed ? k[K_LWD] * (f32_mode ? (double)(float)s.c_lwd : s.c_lwd) : lwd_sum;
   o[ENRGY_S_RS] = k[K_RS];
   o[ENRGY_S_LWD] = k[K_LWD];
   o[ENRGY_S_LWU] = lwu;

@@ -67,6 +67,13 @@ struct KernelArgs {
   const MemberRec<R>* member_recs;
   R member_offset[kMaxFusedMembers];
   R member_albedo_ice[kMaxFusedMembers], member_albedo_snow[kMaxFusedMembers];
+  // station blend (kernel template NS > 1; BASELINE config C4): station k sits at (st_row, st_col) in cell
+  // units at elevation st_elev (k = 0: the primary AWS); its per-step values in station_recs[t * NS + k]
+  int n_stations;
+  R st_row[kMaxStations], st_col[kMaxStations], st_elev[kMaxStations];
+  const StationRec<R>* station_recs;
+  int cloud_on;                   // Beer-Lambert cloud attenuation of the shortwave on
+  R cloud_neg_k;                  // -cloud_k
   // statistics: per-CTA partial sums [gridDim.x][t1 - t0][kStatsP] float64
   R* partials;                    // [gridDim.x][t1 - t0][kStatsK (+ kStatsM with the sub-surface model)] in R
   // dump mode: [t1 - t0][ENRGY_D_COUNT][band_rows_pad][pitch] R (may be null)
@@ -78,6 +85,7 @@ struct FinalizeArgs {
   const void* partials;     // [n_ctas][n_steps][row], row = kStatsK (+ kStatsM with msm); float if f32_mode else double
   int msm;                  // sub-surface model on: lwu and g are summed per cell
   int n_ctas, n_steps, t0;
+  int lwd_summed;           // station blend: column K_LWD holds sum Tz^4 (else it follows from the DEM moments)
   int nm, member;           // fused members: members per row group and the member to finalize (nm <= 1: plain rows)
   double n_valid;           // valid cells of the band
   double mom[5];            // sum over the band's glacier cells of (dem - elev_aws)^k, k = 0..4
@@ -130,6 +138,12 @@ cudaError_t launch_energy_balance_members(const KernelArgs<R>& a, int insol, int
 template <typename R>
 cudaError_t energy_balance_members_grid(int insol, int nm, bool stats, int sm_count, int cap_steps, int cap_subs,
                                         LaunchInfo* info);
+// up to kMaxStations weather stations blended per cell (no sub-surface model, no fused members)
+template <typename R>
+cudaError_t launch_energy_balance_stations(const KernelArgs<R>& a, int insol, bool dump, int sm_count, int forced_grid,
+                                           LaunchInfo* info, cudaStream_t stream);
+template <typename R>
+cudaError_t energy_balance_stations_grid(int insol, bool dump, int sm_count, int cap_steps, int cap_subs, LaunchInfo* info);
 template <typename R>
 cudaError_t launch_member_totals(const float* dem, int dem_pitch, int pitch, int band_row0, int band_rows, int cols,
                                  const R* swe, const R* tsn, const R* tic, size_t member_stride, int n_members,

@@ -165,6 +165,27 @@ class Engine:
         check(self.lib.enrgy_get_member_state(self.h, int(member), code, *[o.ctypes.data for o in outs]))
         return tuple(outs)
 
+    def set_stations(self, stations, series, cloud_k=None):
+        """Extra weather stations (BASELINE config C4; enrgy_set_stations): stations = [(row, col, elev)] in
+        cell units of the full raster, series [n_extra, n_steps, ST_COUNT] (forcing.build_station_series),
+        cloud_k = Beer-Lambert coefficient of the cloud attenuation of the shortwave (None: off).
+        stations = [] runs the blend with the primary AWS alone; stations = None switches it off.
+        Call after set_forcing."""
+        if stations is None:
+            check(self.lib.enrgy_set_stations(self.h, -1, None, None, None, None, float("nan")))
+            return
+        n = len(stations)
+        ck = float("nan") if cloud_k is None else float(cloud_k)
+        if n == 0:
+            check(self.lib.enrgy_set_stations(self.h, 0, None, None, None, None, ck))
+            return
+        pos = np.ascontiguousarray(stations, dtype=np.float64)
+        rows, cols, elevs = [np.ascontiguousarray(pos[:, k]) for k in range(3)]
+        ser = np.ascontiguousarray(series, dtype=np.float64)
+        assert ser.shape == (n, self.n_steps, _lib.ST_COUNT), ser.shape
+        check(self.lib.enrgy_set_stations(self.h, n, rows.ctypes.data, cols.ctypes.data, elevs.ctypes.data,
+                                          ser.ctypes.data, ck))
+
     def set_forcing(self, table):
         table = np.ascontiguousarray(table, dtype=np.float64)
         assert table.ndim == 2 and table.shape[1] == _lib.F_COUNT

@@ -77,4 +77,5 @@ def run_members(engine, members, indices=None, n_steps=None, keep_rasters=False,
             swe, tsn, tic = engine.state(np.float32)
             res.update(swe=swe, total_snow=tsn, total_ice=tic)
         out[i] = res
+    engine.snapshot(save=False)          # like the fused passes: the engine's own state is left alone
     return out

@@ -110,3 +110,18 @@ def build_forcing(rows, albedo_keys=None, temp_lapse_rate=-0.006, cloud_corr=Non
                          - datetime.strptime(last_snowfall, "%Y%m%d"))
                 o[_lib.F_SNOW_DAYS] = delta.days if delta.days > 0 else 0
     return out
+
+
+def build_station_series(rows, cloud_corr=None):
+    """[n_rows, ST_COUNT] float64 series of an extra weather station for enrgy_set_stations (BASELINE
+    config C4): T_AIR, PRESSURE, HUMID as a fraction, CLOUDINESS after cloud_corr -- the row semantics of
+    model.py:197-204 applied to the station's own file."""
+    out = np.zeros((len(rows), _lib.ST_COUNT), dtype=np.float64)
+    for i, row in enumerate(rows):
+        cld = float(row["CLOUDINESS"])
+        if cloud_corr is not None:
+            cld += cloud_corr
+            cld = 1.0 if cld > 1.0 else cld
+            cld = 0.0 if cld < 0.0 else cld
+        out[i] = (float(row["T_AIR"]), float(row["PRESSURE"]), heuristic_unit_guesser(float(row["HUMID"]), 100), cld)
+    return out

@@ -203,6 +203,29 @@ int enrgy_run_members(enrgy_ctx* ctx, int n_members, const double* albedo_offset
 /* state rasters of one member of the last enrgy_run_members (layout as enrgy_get_state) */
 int enrgy_get_member_state(enrgy_ctx* ctx, int member, int dtype, void* swe, void* total_snow, void* total_ice);
 
+/* Several weather stations and cloud attenuation of the shortwave (BASELINE config C4).  The reference
+ * supports one AWS (model.py:155, var_classes.py:94-125) and has no cloud term in the shortwave: this is
+ * THIS REPO's specification, stated in oracle/enrgy_oracle.py ("several weather stations") and built so
+ * that without extra stations it is the reference's arithmetic.  Extra station k sits at (row[k], col[k])
+ * of the FULL raster in cell units (cell centres, fractions allowed) at elev[k] m and reports
+ * series[k][step][ENRGY_ST_*] on the forcing table's time base (call after enrgy_set_forcing).  Per cell:
+ * inverse-squared-distance weights (softened by half a cell) over the primary AWS and the extra stations;
+ * T, p, e reduced to the cell's elevation with the reference's lapse formulas and blended; wind, the
+ * Monin-Obukhov solve, exchange coefficients, lapse rate, longwave cloudiness and the observed shortwave
+ * factor stay the primary station's.  cloud_k >= 0: incoming shortwave times exp(-cloud_k * (blended
+ * cloudiness - the primary station's)); NaN: off.  n_extra = 0 runs the blend with the primary station
+ * alone (same rasters as a plain run); n_extra < 0 switches it off.  Not with the sub-surface model or
+ * enrgy_run_members.  At most 3 extra stations. */
+enum enrgy_station_col {
+  ENRGY_ST_T_AIR = 0,   /* T_AIR [deg C] */
+  ENRGY_ST_PRESSURE,    /* PRESSURE [hPa] */
+  ENRGY_ST_RH,          /* HUMID as a 0..1 fraction (after helpers.py:74-87) */
+  ENRGY_ST_CLOUD,       /* CLOUDINESS 0..1 after cloud_corr and clamping (model.py:200-204) */
+  ENRGY_ST_COUNT
+};
+int enrgy_set_stations(enrgy_ctx* ctx, int n_extra, const double* row, const double* col, const double* elev,
+                       const double* series, double cloud_k);
+
 /* forcing table [n_steps][ENRGY_F_COUNT] (model.py:182-230).  With in-kernel insolation and no
  * sub-surface model the host pre-pass needs nothing else besides the DEM, so it is started here on a
  * worker thread: call this right after enrgy_set_dem and the pre-pass runs while the albedo / SWE

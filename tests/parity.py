@@ -41,7 +41,8 @@ def run_oracle(case, pot, f64, keep_steps=None, **kw):
     return O.run_model(case.dem.astype(dt), case.geotransform, case.aws_rows,
                        pot if callable(pot) else np.asarray(pot, dtype=dt), cfg,
                        swe=case.swe.astype(dt) if kw.get("use_swe", True) else None,
-                       albedo_arrays=alb, state_dtype=dt, keep_steps=keep_steps, want_means=True)
+                       albedo_arrays=alb, state_dtype=dt, keep_steps=keep_steps, want_means=True,
+                       stations=kw.get("stations"), cloud_k=kw.get("cloud_k"))
 
 
 def run_oracle_arrays(case, pot, f64, **kw):
@@ -78,6 +79,12 @@ def make_engine(case, f64, pot=None, computed=False, shadow=False, device=0, **k
     table = build_forcing(case.aws_rows, keys, temp_lapse_rate=kw.get("temp_lapse_rate", -0.006),
                           cloud_corr=kw.get("cloud_corr"), last_snowfall=kw.get("last_snowfall"))
     eng.set_forcing(table)
+    if kw.get("stations") is not None:          # BASELINE config C4: extra weather stations, cloud attenuation
+        from enrgy_b200.forcing import build_station_series
+        st = kw["stations"]
+        eng.set_stations([(s_["row"], s_["col"], s_["elev"]) for s_ in st],
+                         [build_station_series(s_["rows"], cloud_corr=kw.get("cloud_corr")) for s_ in st],
+                         cloud_k=kw.get("cloud_k"))
     if not computed:
         eng.set_insolation(0, np.asarray(pot, dtype=np.float32))
     eng.prepass()
