@@ -14,7 +14,10 @@ With N > 1 GPUs the raster grows to (N*2048) x 2048 and is cut into N row bands,
   configs.c3_shadow  BASELINE configs[2]: 8192 x 8192 with topographic shading, STRONG scaling -- the
          raster is fixed, N row bands; the shading sweep shards by sub-step, an all-to-all over NVLink
          delivers every band its mask rows, the fused kernels run per band (parallel.ShardedShading)
-  configs.c5         BASELINE configs[4]: parameter ensemble on 4096 x 4096, 8 members per GPU
+  configs.c4_stations BASELINE configs[3]: 4096 x 4096, 15-minute rows, AWS + 3 stations blended per cell, cloud
+         attenuation of the shortwave (specification ours: the reference has one AWS)
+  configs.c5         BASELINE configs[4]: parameter ensemble on 4096 x 4096, 8 members per GPU; four members
+         per pass of the fused kernel (enrgy_run_members)
   --impl reference   the UNMODIFIED reference (baseline/_ref, copied by __graft_entry__.build()) run
          through oracle/ref_harness.py on the host cores -- per-step np.load of the insolation
          and CSV appends included -- one process per core on row bands, on a bounded sample of C2.
@@ -411,7 +414,7 @@ def bench_c5(ctx, args):
     out = {}
     for name, kw in (("one_pass_per_member", dict(fused=False)), ("fused_with_step_statistics", dict(fused=True)),
                      ("fused", dict(fused=True, want_stats=False))):
-        run_members(eng, members, mine[:2], **kw)        # warm-up
+        run_members(eng, members, mine, **kw)            # warm-up (the same kernels, buffers and tables)
         ctx.barrier()
         t0 = time.perf_counter()
         res = run_members(eng, members, mine, **kw)
@@ -431,6 +434,46 @@ def bench_c5(ctx, args):
             "variants": out, "mean_ice_melt_range_m": best["mean_ice_melt_range_m"]}
 
 
+def bench_c4(ctx, args):
+    """C4: 4096 x 4096 per GPU, 15-minute rows, three extra weather stations blended per cell and
+    Beer-Lambert cloud attenuation of the shortwave (enrgy_set_stations); weak scaling over row bands."""
+    torch, dist = ctx.torch, ctx.dist
+    from enrgy_b200 import _lib
+    from enrgy_b200.forcing import build_station_series
+    from enrgy_b200.synthetic import make_band_case, make_station_rows
+    n, T, world = args.c4_n, args.c4_t, ctx.world
+    case, dem_full = make_band_case(n, T, world=world, rank=ctx.rank, step_s=900)
+    eng, _ = build_engine(case, dem_full, _lib.F32, ctx.local_rank)
+    rows_full = case.meta["rows_full"]
+    spots = [(0.2 * rows_full, 0.3 * n, 150.0, 41), (0.75 * rows_full, 0.7 * n, -80.0, 42), (0.5 * rows_full, 0.9 * n, 60.0, 43)]
+    eng.set_stations([(r, c, case.elev_aws + dz) for (r, c, dz, _) in spots],
+                     [build_station_series(make_station_rows(case, case.elev_aws + dz, seed=sd)) for (_, _, dz, sd) in spots],
+                     cloud_k=0.7)
+    eng.prepass()
+    eng.set_stream(ctx.stream.cuda_stream)
+    stats = torch.zeros((T, _lib.S_COUNT), dtype=torch.float64, device="cuda")
+    eng.snapshot(save=True)
+
+    def one_pass():
+        eng.snapshot(save=False)
+        eng.run_async(0, T, stats.data_ptr(), None)
+        if world > 1:
+            with torch.cuda.stream(ctx.stream):
+                dist.all_reduce(stats)
+
+    ms_step = ctx.timed(one_pass, 2, max(3, min(args.steps, 5)))
+    kernel_ms = eng.last_kernel_ms()
+    info = eng.kernel_info()
+    st = stats.cpu().numpy()
+    eng.close()
+    return {"value": float(n) * n * world * T / (ms_step * 1e-3), "unit": "cell-timesteps/s", "scaling": "weak",
+            "ms_per_step": ms_step, "kernel_ms": kernel_ms, "dtype": "f32", "kernel": info,
+            "workload": "C4: %dx%d per GPU (%d row bands), %d rows of 15 minutes, the AWS + 3 extra weather stations blended "
+                        "per cell (inverse squared distance, lapse-rate reduction), Beer-Lambert cloud attenuation k = 0.7, "
+                        "in-kernel insolation (one sun position per row), no shading" % (n, n, world, T),
+            "check": {"mean_melt_flux_last_step": float(st[-1, _lib.S_MELT] / st[-1, _lib.S_NVALID])}}
+
+
 def run_ours(args):
     claim_stdout()
     ctx = Ctx(args)
@@ -440,6 +483,7 @@ def run_ours(args):
         other = "f64" if args.dtype == "f32" else "f32"
         for name, fn in (("c2_" + other, lambda: bench_c2(ctx, args, other, headline=False)),
                          ("c3_shadow", lambda: bench_c3(ctx, args)),
+                         ("c4_stations", lambda: bench_c4(ctx, args)),
                          ("c5", lambda: bench_c5(ctx, args))):
             try:
                 t0 = time.time()
@@ -662,6 +706,8 @@ def main():
     ap.add_argument("--no-single-core", dest="single_core", action="store_false")
     ap.add_argument("--c3-n", type=int, default=8192)
     ap.add_argument("--c3-t", type=int, default=384)
+    ap.add_argument("--c4-n", type=int, default=4096)
+    ap.add_argument("--c4-t", type=int, default=2200)
     ap.add_argument("--c5-n", type=int, default=4096)
     ap.add_argument("--c5-members", type=int, default=8, help="ensemble members per GPU")
     args = ap.parse_args()

@@ -120,6 +120,45 @@ class Energy:
             raise ValueError("cloud_corr value should be a float between [-1.0..+1.0]")
         self.cloud_corr = cloud_corr
 
+    # ---- beyond the reference (BASELINE config C4): several weather stations, cloud attenuation ------
+    def add_station(self, aws_file, xy, elev):
+        """An extra weather station: a CSV on the time base of the main AWS file with T_AIR, PRESSURE,
+        HUMID, CLOUDINESS columns, its real-world coordinates and elevation.  Temperature, pressure and
+        vapour pressure are then blended per cell over the main AWS and the extra stations (inverse
+        squared distance, each reduced to the cell's elevation with the reference's lapse formulas);
+        wind, exchange coefficients, longwave cloudiness and the observed shortwave factor stay the main
+        station's.  Specification: oracle/enrgy_oracle.py "several weather stations" (the reference has
+        one AWS, model.py:155).  At most three."""
+        if not hasattr(self, "stations"):
+            self.stations = []
+        if len(self.stations) >= 3:
+            raise ValueError("at most three extra stations")
+        self.stations.append(dict(aws_file=aws_file, xy=(float(xy[0]), float(xy[1])), elev=float(elev)))
+
+    def add_cloud_transmissivity(self, k):
+        """Beer-Lambert attenuation of the incoming shortwave by the blended cloud field relative to the
+        main station's cloudiness: x exp(-k (N_cell - N_aws)).  Needs at least one add_station to differ
+        from the reference."""
+        if float(k) < 0:
+            raise ValueError("cloud transmissivity coefficient must be >= 0")
+        self.cloud_k = float(k)
+
+    def _station_setup(self, n_steps):
+        """[(row, col, elev)] in cell units of the model grid (cell centres: the fractional position of the
+        station minus one half) and the series of every extra station."""
+        from .forcing import build_station_series
+        ul_x, x_dist, _, ul_y, _, y_dist = self.geotransform
+        pos, series = [], []
+        for st in getattr(self, "stations", []):
+            rows = read_input_file(st["aws_file"])
+            if len(rows) != n_steps:
+                raise ValueError("station file %s has %d rows, the main AWS file %d" % (st["aws_file"], len(rows), n_steps))
+            col = (st["xy"][0] - ul_x) / x_dist - 0.5
+            row = (st["xy"][1] - ul_y) / y_dist - 0.5
+            pos.append((row, col, st["elev"]))
+            series.append(build_station_series(rows, cloud_corr=self.cloud_corr))
+        return pos, series
+
     def add_pickle_dir(self, pickle_dir):
         self.pickle_dir = os.path.join(pickle_dir, str(self.res))
         if not os.path.exists(self.pickle_dir):
@@ -293,6 +332,9 @@ class Energy:
             if self.use_msm:
                 eng.set_msm(self._msm_point_temps, self._msm_elev)
             eng.set_forcing(table)    # the library starts its host pre-pass here, under the raster uploads
+            if getattr(self, "stations", None) or getattr(self, "cloud_k", None) is not None:
+                pos, series = self._station_setup(n_steps)
+                eng.set_stations(pos, series, cloud_k=getattr(self, "cloud_k", None))
             if keys is not None:
                 eng.set_albedo_maps([self.albedo_arrays[k][band] for k in keys])
             # the SWE raster as it stands (model.py:245-258 reads self.swe_array; zeros by default) and the

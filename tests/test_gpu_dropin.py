@@ -279,3 +279,44 @@ def test_add_msm_drop_in(tmp_path):
     want = _csv_numbers(ora["stats_csv"])
     for (_, a), (_, b) in zip(rows, want):
         assert abs(a[6] - b[6]) <= 0.1001 and abs(a[8] - b[8]) <= 0.0101      # in-glacier flux, POINT_T_SURF
+
+
+def test_extra_stations_through_the_energy_class(tmp_path):
+    """add_station / add_cloud_transmissivity (BASELINE config C4) on files: the station positions given in
+    real-world coordinates arrive in the kernel as the cell-unit positions the specification uses."""
+    import csv as _csv
+    from enrgy_b200.synthetic import make_station_rows
+    case = make_case(64, 20, w=80, seed=23)
+    d = str(tmp_path)
+    dem, swe, alb, aws = _write_case(case, d)
+    pot = I.insolation_series(case, shadow=False, dtype=np.float64)
+    pick = os.path.join(d, "pickle", "10")
+    os.makedirs(pick)
+    for i, row in enumerate(case.aws_rows):
+        np.save(os.path.join(pick, "%s_total.sdat.npy" % row["DATE"]), pot[i])
+    spots = [(12.0, 60.0, 110.0, 31), (50.0, 15.0, -70.0, 32)]
+    stations = []
+    e = Energy(dem, None, os.path.join(d, "out"), res=10, precision="f64")
+    e.use_precomputed = True
+    e.add_pickle_dir(os.path.join(d, "pickle"))
+    e.add_snow(swe)
+    e.add_cloud_corr(0.05)
+    ul_x, x_dist, _, ul_y, _, y_dist = case.geotransform
+    for k, (r, c, dz, sd) in enumerate(spots):
+        rows = make_station_rows(case, case.elev_aws + dz, seed=sd)
+        path = os.path.join(d, "station%d.csv" % k)
+        with open(path, "w", newline="") as f:
+            wr = _csv.DictWriter(f, fieldnames=list(rows[0]))
+            wr.writeheader()
+            wr.writerows(rows)
+        e.add_station(path, (ul_x + (c + 0.5) * x_dist, ul_y + (r + 0.5) * y_dist), case.elev_aws + dz)
+        stations.append(dict(row=r, col=c, elev=case.elev_aws + dz, rows=rows))
+    e.add_cloud_transmissivity(0.6)
+    e.model(aws_file=aws, albedo_maps=alb, z=1.6, elev_aws=case.elev_aws, xy_aws=case.xy_aws, zm=1e-3,
+            z_h_or_e=1e-4, emissivity=0.98, v=False)
+    ora = P.run_oracle(case, pot, True, stations=stations, cloud_k=0.6, cloud_corr=0.05)
+    # (the class keeps its state rasters in float32 like the reference, model.py:76-80)
+    assert P.max_rel_err(e.total_ice_melt_array, ora["total_ice"], 1e-3) < 1e-6
+    assert P.max_rel_err(e.swe_array, ora["swe"], 1e-3) < 1e-6
+    plain = P.run_oracle(case, pot, True, cloud_corr=0.05)
+    assert P.max_rel_err(e.total_ice_melt_array, plain["total_ice"], 1e-3) > 1e-3     # the stations really act
