@@ -350,7 +350,7 @@ def bench_c3(ctx, args):
     stats = torch.zeros((T, _lib.S_COUNT), dtype=torch.float64, device="cuda")
     eng.snapshot(save=True)
     sub_counts = eng.point_scalars()[:, _lib.P_NSUB].astype(int)
-    sh = ShardedShading(eng, case.meta["bands"], ctx.rank, world)
+    sh = ShardedShading(eng, case.meta["bands"], ctx.rank, world, p2p=os.environ.get("ENRGY_SHADE_EXCHANGE", "all_to_all") == "p2p")
 
     def one_pass():
         eng.snapshot(save=False)
@@ -485,6 +485,8 @@ def run_ours(args):
                          ("c3_shadow", lambda: bench_c3(ctx, args)),
                          ("c4_stations", lambda: bench_c4(ctx, args)),
                          ("c5", lambda: bench_c5(ctx, args))):
+            if args.only is not None and name != args.only:
+                continue
             try:
                 t0 = time.time()
                 configs[name] = fn()
@@ -704,8 +706,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-configs", dest="configs", action="store_false", help="headline only")
     ap.add_argument("--no-single-core", dest="single_core", action="store_false")
+    ap.add_argument("--only", default=None, help="run the headline and only this side config (c2_f64, c3_shadow, c4_stations, c5)")
     ap.add_argument("--c3-n", type=int, default=8192)
-    ap.add_argument("--c3-t", type=int, default=384)
+    ap.add_argument("--c3-t", type=int, default=768)
     ap.add_argument("--c4-n", type=int, default=4096)
     ap.add_argument("--c4-t", type=int, default=2200)
     ap.add_argument("--c5-n", type=int, default=4096)

@@ -109,14 +109,18 @@ class ShardedShading:
       2. every rank ends up with the masks of ITS band for all sub-steps of the chunk, already in the
          order the fused kernel reads them,
       3. the fused kernels run on the band with these masks (enrgy_run_masked).
-    Step 2 is either ONE KERNEL WITH STEP 1 -- the sweep stores the mask words straight into the
-    other ranks' receive buffers over NVLink (peer pointers from torch symmetric memory; `exchange ==
-    "p2p"`), bracketed by two stream-ordered barriers -- or, where symmetric memory is not available, an
-    all_to_all_single on a side stream (`exchange == "all_to_all"`).  Chunks are double-buffered: the
-    sweep (and exchange) of chunk k + 1 is enqueued before the fused kernels of chunk k.
+    Step 2 is an all_to_all_single (NCCL over NVLink / NVSwitch) on a side stream (`exchange ==
+    "all_to_all"`, the default) or ONE KERNEL WITH STEP 1 -- the sweep stores the mask words straight into
+    the other ranks' receive buffers over NVLink (peer pointers from torch symmetric memory; `exchange ==
+    "p2p"`), bracketed by two stream-ordered barriers.  Measured on 8192^2 (profiles/r02_summary.md): the
+    peer stores are single 4-byte words 32 bytes apart (the mask layout interleaves 8 rows so that the fused
+    kernel reads one sector per patch), which NVLink carries badly -- the sweep slows from 6.9 to 8-12 ms
+    per chunk on 8 GPUs -- so the bulk exchange wins (31.9 ms against 43.2 ms per pass) and is the default.
+    Chunks are double-buffered: the sweep (and exchange) of chunk k + 1 is enqueued before the fused
+    kernels of chunk k, so the exchange hides behind them.
     With world == 1 the sweep writes straight into the receive buffer.  Nothing synchronises the host."""
 
-    def __init__(self, engine, bands, rank, world, group=None, budget_bytes=8 << 30, p2p=True):
+    def __init__(self, engine, bands, rank, world, group=None, budget_bytes=8 << 30, p2p=False):
         import torch
         self.torch = torch
         self.eng, self.bands, self.rank, self.world, self.group = engine, list(bands), int(rank), int(world), group
@@ -172,7 +176,10 @@ class ShardedShading:
         total = int(sum(sub_counts[t0:t1]))
         max_subs = max(1, self.budget // per_sub)
         if self.world > 1:
-            max_subs = min(max_subs, max(64 * self.world, -(-total // 4)))
+            # a rank sweeps 1/world of a chunk's sub-steps in one launch, and a launch of fewer than ~200
+            # sub-steps leaves the GPU half empty in its tail (measured on 8192^2: 64 sub-steps per launch
+            # run at 6.2e11 cell-sub-steps/s, 192 at 1.05e12)
+            max_subs = min(max_subs, max(192 * self.world, -(-total // 4)))
         return plan_step_chunks(sub_counts, t0, t1, max_subs)
 
     def _barrier(self, stream):
