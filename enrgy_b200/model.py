@@ -13,7 +13,7 @@ Differences, all additive:
   * potential insolation: with `use_precomputed` the per-step rasters are read exactly where the
     reference reads them (pickle dir `.npy`, else `<dem_dir>/<DATE>_total.sdat`) and streamed to
     the GPU; without it the reference shells out to SAGA GIS per step (saga_lighting.py:7-53) --
-    here the fused kernel computes insolation and the shading ray march itself.
+    here the fused kernel computes the insolation and a line sweep (csrc/shade.cu) the shading masks.
   * no PNG previews (matplotlib, raster_utils.py:9-32) and no CPU fallback.
   * several GPUs: under `torchrun` (torch.distributed initialised, one process per GPU) every rank
     builds the same Energy object and calls model(); the raster is cut into row bands balanced by

@@ -64,8 +64,8 @@ def tile_cost_per_row(valid, tile_h=8, tile_w=128):
 
 
 def rebalance_bands(bands, seconds, valid_per_row, align=16):
-    """New band edges from MEASURED per-band times: with the shading ray march the cost of a glacier
-    cell depends on the terrain around it, so equal glacier-cell counts are not equal times.  The
+    """New band edges from MEASURED per-band times, for runs whose cost per glacier cell is not uniform
+    (tiles on the margin cost as much as full ones; streamed rasters).  The
     measured time of every band is spread over its rows in proportion to their glacier cells
     (piecewise-constant cost per glacier cell), and the cuts are placed at equal shares of that
     estimate.  One or two rounds settle (scripts/measure_modes.py strong)."""
