@@ -54,8 +54,7 @@ class Energy:
         self.output_row = None
         self.debug_point_output = None
         self.res = 100 if res is None else res                      # model.py:30-33
-        if not os.path.isdir(out_dir):
-            os.mkdir(out_dir)
+        os.makedirs(out_dir, exist_ok=True)                          # (every rank of a torchrun job gets here at once)
         self.out_dir = out_dir
         self.png_export = 1
         self.result_export_dates = None
