@@ -93,7 +93,24 @@ struct Num<float> {
 };
 template <>
 struct Num<double> {
-  static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+#ifndef ENRGY_F64_FAST_RCP
+#define ENRGY_F64_FAST_RCP 1
+#endif
+  // 1 / x for a normal, finite x far from the exponent limits (products of pressures and temperatures):
+  // MUFU.RCP64H seed (20 bits) and two Newton steps, without the IEEE division's slow-path test and
+  // fix-up (~1 ulp instead of correctly rounded; the float64 bar is 1e-9)
+  static __device__ __forceinline__ double rcp(double x) {
+#if ENRGY_F64_FAST_RCP
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / x;
+#endif
+  }
   static __device__ __forceinline__ double lapse(double t, double delta, double g) {
     return t + delta * g;
   }
@@ -959,7 +976,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
             if (sizeof(R) == 8) {
               // float64: one division serves both reciprocals (a DP division is ~20 instructions)
               const V den = mul2(rt, p_hpa);
-              const V inv = V::make((R)1 / den.lo(), (R)1 / den.hi());
+              const V inv = V::make(Num<R>::rcp(den.lo()), Num<R>::rcp(den.hi()));
               r_rt = mul2(inv, p_hpa);
               r_p = mul2(inv, rt);
             } else {

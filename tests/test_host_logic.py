@@ -62,6 +62,16 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "from oracle" not in src and "import oracle" not in src, f
                 assert "/root/reference" not in src, f
+                assert "from tests" not in src and "import tests" not in src, f      # (tests import the oracle)
+    # ... and following the imports: loading every module of the package pulls in neither
+    import subprocess
+    import sys
+    code = ("import sys, pkgutil, importlib, enrgy_b200\n"
+            "for m in pkgutil.walk_packages(enrgy_b200.__path__, 'enrgy_b200.'):\n"
+            "    importlib.import_module(m.name)\n"
+            "bad = [k for k in sys.modules if k == 'oracle' or k.startswith('oracle.') or k == 'tests' or k.startswith('tests.')]\n"
+            "assert not bad, bad\n")
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
 
 
 def test_forcing_matches_reference_row_logic():
