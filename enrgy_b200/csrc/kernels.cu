@@ -519,16 +519,27 @@ struct SmemPlan {
 };
 // nm: ensemble members fused into one pass (1 = a plain run: no member records); ns: weather stations
 // blended (1 = the reference's single AWS: no station records)
+// One barrier per time block instead of two: the warps' statistic slots are double-buffered, so the flush of
+// block b may still be running while block b + 1 fills the other set (ncu: 0.33 warps per issued
+// instruction waited at the two barriers).  float32 runs with sunlit masks only, where the warps of a CTA
+// drift apart on their mask loads (+5.8 %); without masks the extra 8 KB of shared memory per CTA cost 1 %.
+#ifndef ENRGY_ONE_BARRIER
+#define ENRGY_ONE_BARRIER 1
+#endif
+template <typename R, bool MSM, int NM, int INSOL>
+constexpr bool kOneBarrier = ENRGY_ONE_BARRIER && sizeof(R) == 4 && !MSM && NM == 1 && INSOL == kInsolMasked;
+
 template <typename R>
 __host__ __device__ inline SmemPlan<R> smem_plan(int warps, int cap_steps, int cap_subs, bool with_subs, bool msm,
-                                                 int nm = 1, int ns = 1) {
+                                                 int nm = 1, int ns = 1, bool with_masks = false) {
   SmemPlan<R> p;
   int o = 0;
   p.steps = o;   o += 2 * cap_steps * (int)sizeof(StepRec<R>);
   p.subs = o;    o += with_subs ? 2 * cap_subs * (int)sizeof(SubRec<R>) : 0;
   p.members = o; o += nm > 1 ? 2 * cap_steps * nm * (int)sizeof(MemberRec<R>) : 0;
   p.stations = o; o += ns > 1 ? 2 * cap_steps * ns * (int)sizeof(StationRec<R>) : 0;
-  p.slots = o;   o += warps * cap_steps * nm * kStatsK * (int)sizeof(R);
+  const bool two_sets = ENRGY_ONE_BARRIER && sizeof(R) == 4 && !msm && nm == 1 && with_masks;
+  p.slots = o;   o += (two_sets ? 2 : 1) * warps * cap_steps * nm * kStatsK * (int)sizeof(R);
   p.slots_m = o; o += msm ? warps * cap_steps * kStatsM * (int)sizeof(R) : 0;
   o = (o + 15) / 16 * 16;
   p.full = o;    o += 16;
@@ -587,12 +598,14 @@ energy_balance_kernel(const KernelArgs<R> a) {
   constexpr int NT = 32 * W;                       // threads per CTA
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int cap_steps = a.cap_steps, cap_subs = a.cap_subs;
-  const SmemPlan<R> plan = smem_plan<R>(W, cap_steps, cap_subs, INSOL != kInsolStreamed, MSM, NM, NS);
+  const SmemPlan<R> plan = smem_plan<R>(W, cap_steps, cap_subs, INSOL != kInsolStreamed, MSM, NM, NS, INSOL == kInsolMasked);
   StationRec<R>* const sm_stations = reinterpret_cast<StationRec<R>*>(smem_raw + plan.stations);  // [2][cap_steps][NS]
   StepRec<R>* const sm_steps = reinterpret_cast<StepRec<R>*>(smem_raw + plan.steps);     // [2][cap_steps]
   SubRec<R>* const sm_subs = reinterpret_cast<SubRec<R>*>(smem_raw + plan.subs);         // [2][cap_subs]
   MemberRec<R>* const sm_members = reinterpret_cast<MemberRec<R>*>(smem_raw + plan.members);  // [2][cap_steps][NM]
-  R* const sm_slots = reinterpret_cast<R*>(smem_raw + plan.slots);                       // [W][cap_steps][NM][kStatsK]
+  R* const sm_slots0 = reinterpret_cast<R*>(smem_raw + plan.slots);                      // [sets][W][cap_steps][NM][kStatsK]
+  constexpr bool ONE_BAR = kOneBarrier<R, MSM, NM, INSOL>;
+  unsigned slot_set = 0;                                                                 // flips per time block (ONE_BAR)
   R* const sm_slots_m = reinterpret_cast<R*>(smem_raw + plan.slots_m);                   // [W][cap_steps][kStatsM]
   uint64_t* const sm_full = reinterpret_cast<uint64_t*>(smem_raw + plan.full);           // [2]
 
@@ -796,6 +809,8 @@ energy_balance_kernel(const KernelArgs<R> a) {
 
     for (int b = a.block_begin; b < a.block_end; ++b, buf ^= 1) {
       if (tid == 0 && b + 1 < a.block_end) issue_block(b + 1, buf ^ 1);
+      R* const sm_slots = sm_slots0 + (ONE_BAR ? (size_t)(slot_set & 1u) * W * cap_steps * NM * kStatsK : 0);
+      slot_set ^= 1u;
       mbar_wait(&sm_full[buf], phase[buf]);
       phase[buf] ^= 1u;
       const TimeBlock tb = a.blocks[b];
@@ -1344,7 +1359,9 @@ energy_balance_kernel(const KernelArgs<R> a) {
           my_partials[((size_t)(ts - a.t0) * NM + step) * kRow + q] += (R)sum;
         }
       }
-      __syncthreads();
+      // (ONE_BAR: the next block fills the other set of slots and the other staging buffer; the barrier
+      // at ITS end orders this flush before anything of this block is overwritten)
+      if (!ONE_BAR) __syncthreads();
     }  // time blocks
 
     // ---- epilogue: state back to HBM (off-glacier cells become NaN, model.py:258) ---------------
@@ -1410,7 +1427,7 @@ template <typename R, int INSOL, bool MSM, bool DUMP, int NM = 1, bool STATS = t
 static cudaError_t configure(int sm_count, int cap_steps, int cap_subs, LaunchInfo* info) {
   constexpr int K = PassShape<R, MSM, NM, NS>::K, KT = PassShape<R, MSM, NM, NS>::KT;
   auto kern = energy_balance_kernel<R, K, INSOL, MSM, DUMP, NM, KT, STATS, NS>;
-  const int smem = smem_plan<R>(kWarpsFor<R, INSOL>, cap_steps, cap_subs, INSOL != kInsolStreamed, MSM, NM, NS).total;
+  const int smem = smem_plan<R>(kWarpsFor<R, INSOL>, cap_steps, cap_subs, INSOL != kInsolStreamed, MSM, NM, NS, INSOL == kInsolMasked).total;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;

@@ -37,7 +37,7 @@ def main():
                 mn = t.split()[0].split(".")[0]
                 if mn in WATCH:
                     h[mn] += 1
-            short = re.sub(r"\(.*", "", k).replace("enrgy::", "").replace("(anonymous namespace)::", "")
+            short = re.sub(r"\(.*", "", k.replace("(anonymous namespace)::", "")).replace("enrgy::", "")
             f.write("%-8d %s\n         %s\n" % (len(ins), short, "  ".join("%s %d" % (m, h[m]) for m in WATCH if h[m])))
         # hot block of the C2 float32 kernel: longest run without a branch / label-target in between
         key = next(k for k in funcs if "energy_balance_kernel<float, 8, 1, false, false, 1, 8, true, 1>" in k)

@@ -43,7 +43,8 @@ def test_station_blend_with_computed_insolation_and_shading(f64):
 @pytest.mark.parametrize("mode", ["streamed", "computed", "shadow"])
 def test_blend_with_the_primary_station_alone_equals_a_plain_run(f64, mode):
     """No extra station: the blend kernel (weights, folded vapour-pressure factors, exp(0) cloud factor,
-    half the cells per thread) must give the plain kernel's rasters bit for bit."""
+    half the cells per thread) must give the plain kernel's rasters: bit for bit in float32, to a few ulp in
+    float64."""
     case = make_case(72, 26, w=150, seed=5)
     pot = P.random_insolation(case, 26) if mode == "streamed" else None
     kw = dict(computed=mode != "streamed", shadow=mode == "shadow")
@@ -56,7 +57,12 @@ def test_blend_with_the_primary_station_alone_equals_a_plain_run(f64, mode):
         finally:
             eng.close()
     for a, b in zip(out[0][0], out[1][0]):
-        assert np.array_equal(a, b, equal_nan=True)
+        if f64:
+            # (float64 takes its reciprocals by Newton steps from a hardware seed: not correctly rounded, and
+            # the two instantiations are scheduled differently -- agreement to a few ulp, not bit for bit)
+            assert np.array_equal(np.isnan(a), np.isnan(b)) and np.allclose(a, b, rtol=1e-13, atol=1e-15, equal_nan=True)
+        else:
+            assert np.array_equal(a, b, equal_nan=True)
     # (the longwave area sum comes from the kernel instead of the DEM moments; float32 sums in another order)
     assert np.allclose(out[0][1], out[1][1], rtol=1e-11 if f64 else 3e-6, atol=1e-8 if f64 else 1e-2)
 
