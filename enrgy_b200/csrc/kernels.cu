@@ -511,11 +511,29 @@ template <typename R, int INSOL>
 constexpr int kWarpsFor = sizeof(R) == 4 ? ENRGY_WARPS32 : ENRGY_WARPS64;
 __host__ __device__ constexpr int warps_x(int w) { return w >= 4 ? 4 : w; }          // patches side by side in a tile
 
+// Option, OFF: sunlit masks through a per-warp ring in shared memory (float32 plain runs with masks, K = 8):
+// the 32-byte sector of sub-step j + kRingAhead is fetched by an asynchronous copy (two lanes, 16 bytes
+// each) while sub-step j is computed, and read back with two broadcast LDS.128.  Tried because ncu of the
+// LDG version shows 2.2 warps per issued instruction on the long scoreboard and an L1 hit rate of 50 % (the
+// CCTL.PF1 prefetch does not land, whatever its distance) -- but measured SLOWER: 16.14 against 15.75 ms
+// on 4096^2 x 384 steps; the commit / wait / syncwarp per sub-step cost more than the latency they hide,
+// which the other 15 warps of the SM already cover.
+#ifndef ENRGY_MASK_RING
+#define ENRGY_MASK_RING 0
+#endif
+constexpr int kRingSlots = 16, kRingAhead = 8;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // Shared-memory carve-up of a CTA.  The capacities of a time block (steps, sunlit sub-steps) are
 // run-time values chosen by the host (64 / 256, grown to the largest sub-step count of one step).
 template <typename R>
 struct SmemPlan {
-  int steps, subs, members, stations, slots, slots_m, full, total;   // byte offsets and the total size
+  int steps, subs, members, stations, slots, slots_m, ring, full, total;   // byte offsets and the total size
 };
 // nm: ensemble members fused into one pass (1 = a plain run: no member records); ns: weather stations
 // blended (1 = the reference's single AWS: no station records)
@@ -542,6 +560,7 @@ __host__ __device__ inline SmemPlan<R> smem_plan(int warps, int cap_steps, int c
   p.slots = o;   o += (two_sets ? 2 : 1) * warps * cap_steps * nm * kStatsK * (int)sizeof(R);
   p.slots_m = o; o += msm ? warps * cap_steps * kStatsM * (int)sizeof(R) : 0;
   o = (o + 15) / 16 * 16;
+  p.ring = o;    o += (ENRGY_MASK_RING && with_masks) ? warps * kRingSlots * 32 : 0;
   p.full = o;    o += 16;
   p.total = (o + 127) / 128 * 128;
   return p;
@@ -798,6 +817,9 @@ energy_balance_kernel(const KernelArgs<R> a) {
     const bool patch_full = __all_sync(0xffffffffu, valid_bits == ((1u << K) - 1u));
     // sunlit masks of this patch (INSOL == kInsolMasked): word of its 32 columns, its K rows
     const unsigned lane_bit = 1u << lane;
+    constexpr bool RING = ENRGY_MASK_RING && INSOL == kInsolMasked && K == 8;
+    uint4* const ring = reinterpret_cast<uint4*>(smem_raw + plan.ring) + warp * kRingSlots * 2;   // [kRingSlots][2]
+    int ring_next = -0x40000000;                    // next sub-step to fetch (not primed yet)
     const unsigned* const mask_patch =
         INSOL == kInsolMasked
             ? a.masks + ((size_t)(row0 >> 3) * a.mask_words + (size_t)((colx - lane) >> 5)) * 8 + (row0 & 7) -
@@ -1285,11 +1307,32 @@ energy_balance_kernel(const KernelArgs<R> a) {
             if (INSOL == kInsolMasked) {
               const unsigned* mp = mask_patch + (size_t)(tb.sub_begin + j) * a.mask_sub_stride;
               // the sector of the sub-step one row ahead goes to L1 now (no register, one lane)
-              if (lane == 0) {
+              if (!RING && lane == 0) {
                 const unsigned* ahead = mask_patch + (size_t)min(tb.sub_begin + j + kMaskAhead, a.mask_sub_last) * a.mask_sub_stride;
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(ahead));
               }
-              if (K == 8) {
+              if (RING) {
+                const int ms = tb.sub_begin + j;
+                auto fetch = [&](int x) {
+                  if (lane < 2 && x <= a.mask_sub_last)
+                    cp_async16(&ring[(x & (kRingSlots - 1)) * 2 + lane], mask_patch + (size_t)x * a.mask_sub_stride + 4 * lane);
+                  cp_async_commit();
+                };
+                if (ms != ring_next - kRingAhead) {          // first sub-step of the tile (or a jump): prime the ring
+                  cp_async_wait<0>();
+                  __syncwarp();
+#pragma unroll
+                  for (int p_ = 0; p_ < kRingAhead; ++p_) fetch(ms + p_);
+                  ring_next = ms + kRingAhead;
+                }
+                fetch(ring_next);
+                ++ring_next;
+                cp_async_wait<kRingAhead>();                 // the copy of sub-step ms has landed
+                __syncwarp();
+                const uint4 m0 = ring[(ms & (kRingSlots - 1)) * 2], m1 = ring[(ms & (kRingSlots - 1)) * 2 + 1];
+                mw[0] = m0.x; mw[1] = m0.y; mw[2 % K] = m0.z; mw[3 % K] = m0.w;
+                mw[4 % K] = m1.x; mw[5 % K] = m1.y; mw[6 % K] = m1.z; mw[7 % K] = m1.w;
+              } else if (K == 8) {
                 const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mp)), m1 = __ldg(reinterpret_cast<const uint4*>(mp) + 1);
                 mw[0] = m0.x; mw[1] = m0.y; mw[2 % K] = m0.z; mw[3 % K] = m0.w;
                 mw[4 % K] = m1.x; mw[5 % K] = m1.y; mw[6 % K] = m1.z; mw[7 % K] = m1.w;
