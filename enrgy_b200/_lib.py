@@ -71,6 +71,7 @@ _PROTOTYPES = {
     "enrgy_set_swe": (C.c_int, [_P, _P]),
     "enrgy_set_msm": (C.c_int, [_P, _P, C.c_double]),
     "enrgy_set_member": (C.c_int, [_P, C.c_double, C.c_double, C.c_double]),
+    "enrgy_set_insolation_aws": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "enrgy_set_stations": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_double]),
     "enrgy_run_members": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "enrgy_get_member_state": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),

@@ -1320,9 +1320,24 @@ int enrgy_set_insolation(enrgy_ctx* c, int t0, int n, const float* pot) {
   return ENRGY_OK;
 }
 
+int enrgy_set_insolation_aws(enrgy_ctx* c, int t0, int n, const double* pot_aws) {
+  if (!c) return fail(ENRGY_ERR_ARG, "null context");
+  if (!c->have_forcing) return fail(ENRGY_ERR_ARG, "set_forcing must precede set_insolation_aws");
+  if (t0 < 0 || n < 0 || t0 + n > c->n_steps || (n > 0 && !pot_aws)) return fail(ENRGY_ERR_ARG, "bad insolation window");
+  for (int i = 0; i < n; ++i) c->pot_aws[t0 + i] = pot_aws[i];
+  c->prepass_done = false;
+  return ENRGY_OK;
+}
+
 int enrgy_prepass(enrgy_ctx* c) {
   if (int e = use_device(c)) return e;
   if (!c->have_dem || !c->have_forcing) return fail(ENRGY_ERR_ARG, "set_dem and set_forcing must precede prepass");
+  if (c->p.insol_mode == ENRGY_INSOL_STREAMED) {
+    for (int i = c->pot_t0; i < c->pot_t0 + c->pot_n; ++i)
+      if (std::isnan(c->pot_aws[i]))
+        return fail(ENRGY_ERR_ARG, "step %d: no potential insolation at the AWS cell -- it lies outside this handle's row band "
+                                   "(hand its values in with enrgy_set_insolation_aws) or on a NaN cell of the rasters", i);
+  }
   if (c->p.msm_layers > 0 && !c->have_msm) return fail(ENRGY_ERR_ARG, "enrgy_set_msm must precede prepass when msm_layers > 0");
   if (c->p.msm_layers > 0 && !c->p.albedo_const && (int)c->alb_aws.size() != c->n_maps)
     return fail(ENRGY_ERR_ARG, "the AWS cell lies outside this handle's row band: its albedo/SWE are needed for the sub-surface pre-pass");

@@ -197,6 +197,12 @@ class Engine:
         assert pot.ndim == 3 and pot.shape[1:] == (self.band_rows, self.cols), pot.shape
         check(self.lib.enrgy_set_insolation(self.h, int(t0), pot.shape[0], pot.ctypes.data))
 
+    def set_insolation_aws(self, t0, pot_aws):
+        """Potential insolation at the AWS cell for steps t0.. (streamed mode on a row band that does not hold
+        the cell); see enrgy_set_insolation_aws."""
+        a = np.ascontiguousarray(pot_aws, dtype=np.float64)
+        check(self.lib.enrgy_set_insolation_aws(self.h, int(t0), int(a.size), a.ctypes.data))
+
     def prepass(self):
         check(self.lib.enrgy_prepass(self.h))
 

@@ -380,7 +380,10 @@ class Energy:
             layers_pt = eng.point_layers() if (self.use_msm and self.debug_point_output is not None and not streamed) else None
             for (t0, t1) in ranges:
                 if streamed:
-                    eng.set_insolation(t0, self._read_insolation(rows, t0, t1, v)[:, band])
+                    pot_rows = self._read_insolation(rows, t0, t1, v)
+                    eng.set_insolation(t0, pot_rows[:, band])
+                    if world > 1:                # the shortwave factor needs the AWS cell, whichever band holds it
+                        eng.set_insolation_aws(t0, pot_rows[:, aws_row, aws_col])
                     eng.prepass()
                     point = eng.point_scalars()
                     if self.use_msm and self.debug_point_output is not None:

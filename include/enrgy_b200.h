@@ -237,6 +237,11 @@ int enrgy_set_forcing(enrgy_ctx* ctx, int n_steps, const double* forcing);
 int enrgy_set_insolation(enrgy_ctx* ctx, int t0, int n, const float* pot);
 
 /* pre-pass: per-step scalars at the AWS cell (model.py:347-358, :500-530, turbo.py:88-137) */
+/* streamed insolation on a row band that does not hold the AWS cell: the potential insolation AT the AWS
+ * cell for steps [t0, t0 + n) [kWh m-2], which the observed / potential shortwave factor needs
+ * (model.py:500-530).  enrgy_set_insolation fills it by itself when the cell lies inside the band;
+ * enrgy_prepass fails if a resident step has none. */
+int enrgy_set_insolation_aws(enrgy_ctx* ctx, int t0, int n, const double* pot_aws);
 int enrgy_prepass(enrgy_ctx* ctx);
 int enrgy_get_point_scalars(enrgy_ctx* ctx, double* out /* [n_steps][ENRGY_P_COUNT] */);
 /* sub-surface model: boundary temperatures of the AWS cell BEFORE each row's update (the columns

@@ -63,6 +63,12 @@ class FakeEngine:
         for i in range(pot.shape[0]):
             self.pot[t0 + i] = np.asarray(pot[i], dtype=self.dt)
 
+    def set_insolation_aws(self, t0, pot_aws):
+        if not isinstance(getattr(self, "pot_aws", None), dict):
+            self.pot_aws = {}
+        for i, v in enumerate(np.asarray(pot_aws, dtype=np.float64)):
+            self.pot_aws[t0 + i] = float(v)
+
     def prepass(self):
         pass
 

@@ -54,8 +54,11 @@ def run_oracle_arrays(case, pot, f64, **kw):
                        swe=case.swe.astype(dt), albedo_arrays=alb, state_dtype=dt, want_means=True)
 
 
-def make_engine(case, f64, pot=None, computed=False, shadow=False, device=0, **kw):
+def make_engine(case, f64, pot=None, computed=False, shadow=False, device=0, band=None, **kw):
+    """band = (row0, rows): the engine of one row band of the case (every band-local raster is cut here)."""
     h, w = case.shape
+    r0, nr = band if band is not None else (0, h)
+    rows = slice(r0, r0 + nr)
     eng = Engine(h, w, precision=_lib.F64 if f64 else _lib.F32, device=device)
     eng.set_params(cell_size=case.cell, elev_aws=case.elev_aws, aws_row=case.aws_rc[0],
                    aws_col=case.aws_rc[1], sensor_z=kw.get("z", 1.6), zm=kw.get("zm", 1e-3),
@@ -65,7 +68,8 @@ def make_engine(case, f64, pot=None, computed=False, shadow=False, device=0, **k
                    max_ice_albedo=kw.get("max_ice_albedo"), snow_density=kw.get("snow_density"),
                    msm_depths=kw["msm"]["depths"] if kw.get("msm") else None,
                    insol_mode=_lib.INSOL_COMPUTED if computed else _lib.INSOL_STREAMED,
-                   shadow=shadow, lat=case.lat, lon=case.lon)
+                   shadow=shadow, lat=case.lat, lon=case.lon,
+                   band_row0=r0 if band is not None else 0, band_rows=nr if band is not None else 0)
     eng.set_dem(case.dem)
     if kw.get("msm"):
         eng.set_msm(kw["msm"]["temperatures"], kw["msm"]["elev"])
@@ -73,9 +77,9 @@ def make_engine(case, f64, pot=None, computed=False, shadow=False, device=0, **k
     if not kw.get("const_albedo"):
         alb = clipped_albedo(case, np.float32)
         keys = list(alb)
-        eng.set_albedo_maps([alb[k] for k in keys])
+        eng.set_albedo_maps([alb[k][rows] for k in keys])
     if kw.get("use_swe", True):
-        eng.set_swe(case.swe)
+        eng.set_swe(case.swe[rows])
     table = build_forcing(case.aws_rows, keys, temp_lapse_rate=kw.get("temp_lapse_rate", -0.006),
                           cloud_corr=kw.get("cloud_corr"), last_snowfall=kw.get("last_snowfall"))
     eng.set_forcing(table)
@@ -86,7 +90,9 @@ def make_engine(case, f64, pot=None, computed=False, shadow=False, device=0, **k
                          [build_station_series(s_["rows"], cloud_corr=kw.get("cloud_corr")) for s_ in st],
                          cloud_k=kw.get("cloud_k"))
     if not computed:
-        eng.set_insolation(0, np.asarray(pot, dtype=np.float32))
+        eng.set_insolation(0, np.ascontiguousarray(np.asarray(pot, dtype=np.float32)[:, rows]))
+        if band is not None:
+            eng.set_insolation_aws(0, np.asarray(pot, dtype=np.float32)[:, case.aws_rc[0], case.aws_rc[1]])
     eng.prepass()
     return eng
 

@@ -166,3 +166,30 @@ def test_error_codes():
     assert e.value.code == _lib.ERR_RANGE
     eng.close()
     assert lib.enrgy_destroy(None) == 0
+
+
+def test_streamed_band_without_the_aws_cell_needs_its_insolation():
+    """A row band that does not hold the AWS cell cannot form the shortwave factor from its own rasters: the
+    pre-pass fails loudly until the AWS-cell values are handed in (enrgy_set_insolation_aws), and then the
+    band gives the whole run's rasters bit for bit."""
+    from enrgy_b200._lib import EnrgyError
+    case = make_case(64, 10, w=72, seed=7)
+    pot = P.random_insolation(case, 10)
+    whole = P.make_engine(case, False, pot=pot)
+    try:
+        whole.run(0, 10)
+        ref = whole.state(np.float32)
+    finally:
+        whole.close()
+    band = (0, 16)                                   # the AWS cell sits in row 32
+    eng = P.make_engine(case, False, pot=pot, band=band)
+    try:
+        eng.run(0, 10)
+        got = eng.state(np.float32)
+        for a, b in zip(got, ref):
+            assert np.array_equal(a, b[:16], equal_nan=True)
+        eng.set_insolation_aws(0, np.full(10, np.nan))
+        with pytest.raises(EnrgyError):
+            eng.prepass()
+    finally:
+        eng.close()

@@ -76,3 +76,25 @@ def test_fused_members_equal_one_run_per_member(f64, mode):
         assert abs(fused[i]["mean_ice_raster"] - np.nanmean(fused[i]["total_ice"].astype(np.float64))) < 1e-6
     assert np.isfinite(stats_own).all()
     assert abs(fused[0]["mean_ice"] - fused[1]["mean_ice"]) > 1e-7
+
+
+def test_fused_members_on_row_bands():
+    """Fused members on two row bands (one engine per band, as one rank per GPU would hold them) give the
+    whole raster's member states bit for bit; with shading, so the bands see terrain outside themselves."""
+    case = make_case(80, 20, w=96, seed=9)
+    members = make_members(4, seed=2, albedo_sigma=0.05)
+    kw = dict(computed=True, shadow=True)
+    whole = P.make_engine(case, False, **kw)
+    try:
+        ref = run_members(whole, members, keep_rasters=True, want_stats=False)
+    finally:
+        whole.close()
+    for band in ((0, 32), (32, 48)):
+        eng = P.make_engine(case, False, band=band, **kw)
+        try:
+            got = run_members(eng, members, keep_rasters=True, want_stats=False)
+        finally:
+            eng.close()
+        for i in range(len(members)):
+            for k in ("swe", "total_snow", "total_ice"):
+                assert np.array_equal(got[i][k], ref[i][k][band[0]:band[0] + band[1]], equal_nan=True), (i, k, band)

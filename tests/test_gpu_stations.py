@@ -67,6 +67,34 @@ def test_blend_with_the_primary_station_alone_equals_a_plain_run(f64, mode):
     assert np.allclose(out[0][1], out[1][1], rtol=1e-11 if f64 else 3e-6, atol=1e-8 if f64 else 1e-2)
 
 
+@pytest.mark.parametrize("mode", ["streamed", "shadow"])
+def test_station_blend_on_row_bands(mode):
+    """Station positions are cells of the FULL raster: two row bands give the whole run's rasters bit for bit
+    (float32), and their area sums add up."""
+    case = make_case(80, 20, w=96, seed=9)
+    pot = P.random_insolation(case, 20) if mode == "streamed" else None
+    kw = dict(computed=mode != "streamed", shadow=mode == "shadow", stations=_stations(case, 3), cloud_k=0.8)
+    whole = P.make_engine(case, False, pot=pot, **kw)
+    try:
+        s_whole = whole.run(0, 20)
+        st_whole = whole.state(np.float32)
+    finally:
+        whole.close()
+    total = np.zeros_like(s_whole)
+    for band in ((0, 48), (48, 32)):
+        eng = P.make_engine(case, False, pot=pot, band=band, **kw)
+        try:
+            total += eng.run(0, 20)
+            part = eng.state(np.float32)
+        finally:
+            eng.close()
+        for a, b in zip(part, st_whole):
+            assert np.array_equal(a, b[band[0]:band[0] + band[1]], equal_nan=True)
+    from enrgy_b200 import _lib
+    cols = [_lib.S_RS, _lib.S_LWD, _lib.S_SENS, _lib.S_LAT, _lib.S_MELT, _lib.S_SNOW, _lib.S_ICE]
+    assert np.allclose(total[1:, cols], s_whole[1:, cols], rtol=3e-6, atol=1e-3)
+
+
 def test_station_errors():
     from enrgy_b200._lib import EnrgyError
     case = make_case(40, 6, w=56, seed=3)

@@ -203,7 +203,7 @@ def _energy_worker(rank, world, port, d):
         def factory(rows, cols, precision, device):
             f = FakeEngine(rows, cols, precision, device)
             f.aws_rows, f.geotransform, f.xy_aws, f.albedo_keys = case.aws_rows, case.geotransform, case.xy_aws, keys
-            f.pot_aws = [float(pot[i][case.aws_rc]) for i in range(len(case.aws_rows))]
+            # (the AWS-cell insolation reaches the engine through Energy.model -> set_insolation_aws)
             return f
         e = Energy(os.path.join(d, "dem.npy"), None, os.path.join(d, "out"), res=10, precision="f64")
         e._engine_factory = factory
