@@ -42,15 +42,16 @@ N_STEPS = 2200
 # counted) + 12 FLOP per insolation sub-step; C2 has 4 sub-steps per step -> 141 FLOP.  That is the
 # REFERENCE's arithmetic after hoisting per-cell invariants; the kernel executes less (DESIGN.md 4.1:
 # ez = e, exp(0) = 1, one reciprocal per quantity, analytic longwave sum, daily albedo blend, flux
-# scalars folded into the balance FMA chain): 77 FLOP = 46.5 FP32-pipe operations (FMA/ADD/MUL, two
-# cells per packed instruction) + 14 min/max/select/compare/MUFU/SHFL operations on the other pipes,
-# counted in the SASS of the hot basic block (346 instructions per 256 cell-steps; rows that take the
-# analytic direct-beam path execute 40 packed instructions fewer, not credited here).  Both are
-# reported; `roofline.frac` uses the SURVEY figure as the contract asks.
+# scalars folded into the balance FMA chain).  Counted in the SASS of the hot basic block (insolation +
+# balance + statistics of one step for the 8 cells of a thread, profiles/r02_sass.txt: 373 instructions,
+# of them FFMA2 96, FADD2 50, FMUL2 36, scalar FMUL 8, FADD 8): (96 x 4 + 50 x 2 + 36 x 2 + 16) / 8 = 71.5
+# FLOP, (182 x 2 + 16) / 8 = 47.5 FP32-pipe lane-operations and 373 / 8 = 46.6 issue slots per cell-step
+# (rows that take the analytic direct-beam path execute 40 packed instructions fewer, not credited here).
+# Both are reported; `roofline.frac` uses the SURVEY figure as the contract asks.
 FLOP_PER_CELL_STEP = 141.0
-FLOP_EXECUTED_PER_CELL_STEP = 77.0
-FP32_PIPE_OPS_PER_CELL_STEP = 46.5       # lane-operations on the FMA pipe (a packed FFMA2 is two)
-ISSUE_SLOTS_PER_CELL_STEP = 39.5         # 42.5 packed / 2 + 4 scalar FMA-pipe + 14 ALU/XU/SHFL instructions
+FLOP_EXECUTED_PER_CELL_STEP = 71.5
+FP32_PIPE_OPS_PER_CELL_STEP = 47.5       # lane-operations on the FMA pipe (a packed FFMA2 is two)
+ISSUE_SLOTS_PER_CELL_STEP = 46.6         # thread-instructions of the hot block per cell-step
 # Shading sweep (shade.cu), per terrain cell and sunlit sub-step: 4 B of terrain read + 1 bit of mask
 # written; executed thread-instructions from the SASS of the sweep loop
 SWEEP_BYTES_PER_CELL_SUB = 4.0 + 1.0 / 8.0
