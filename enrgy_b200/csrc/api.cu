@@ -358,6 +358,9 @@ int fill_args(enrgy_ctx* c, int t0, int t1, KernelArgs<R>& a) {
   a.msm.c_ice = (R)kCice; a.msm.k_ice = (R)kKappaIce; a.msm.k_snow = (R)kKappaSnow;
   a.msm.rho_ice = (R)c->p.ice_density; a.msm.rho_snow = (R)c->p.snow_density;
   a.msm.inv_snow_density = (R)(1.0 / c->p.snow_density);
+  a.msm.g0_ice = a.msm.k_ice * a.msm.c_ice * a.msm.rho_ice;
+  a.msm.crd_ice = a.msm.c_ice * a.msm.rho_ice * a.msm.d[0];
+  a.msm.inv_crd_ice = (R)1 / a.msm.crd_ice;
   a.steps = (const StepRec<R>*)c->d_steps.p;
   a.subs = (const SubRec<R>*)c->d_subs.p;
   a.blocks = c->d_blocks.p;

@@ -1117,6 +1117,36 @@ energy_balance_kernel(const KernelArgs<R> a) {
             const MsmParams<R>& mp = a.msm;
             const R dt = s.dt, inv_dt = s.inv_dt;
             R mfh[2], gh[2], grad0[2], sd1[2];
+            // Snow-free cells (the ablation zone for most of the season): the snow share of every layer is 0,
+            // conductivity and density are those of ice exactly, and the surface layer of the pair runs
+            // packed with per-run constants -- 8 packed operations instead of ~70 scalar ones.  Decided per
+            // warp, so a cell's arithmetic depends on its patch only (bit-identical across bands and cuts).
+            const bool bare = !__any_sync(0xffffffffu, snow_lo || snow_hi);
+            if (bare) {
+              const V t0v = V::make(tl[2 * q][0], tl[2 * q + 1][0]), t1v = V::make(tl[2 * q][1], tl[2 * q + 1][1]);
+              const V grad = mul2(sub2(t1v, t0v), V::splat(mp.inv_d[0]));            // msm.py:18-28
+              const V gv = mul2(grad, V::splat(mp.g0_ice));
+              const V full = add2(atmo, gv);
+              // melt gate: qm = full - q0, q0 = -t0 c rho d / dt (msm.py:88-93)
+              const V gate = fma2(t0v, V::splat(mp.crd_ice * inv_dt), full);
+              const V mfv = V::make(fmax_(gate.lo(), (R)0), fmax_(gate.hi(), (R)0));
+              const V dlt = mul2(sub2(full, mfv), V::splat(mp.inv_crd_ice));
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int i = 2 * q + h;
+                const R d_h = h ? dlt.hi() : dlt.lo();
+                grad0[h] = h ? grad.hi() : grad.lo();
+                mfh[h] = h ? mfv.hi() : mfv.lo();
+                gh[h] = h ? gv.hi() : gv.lo();
+                sd1[h] = (R)0;
+                if (sizeof(R) == 4) {
+                  t0_acc[i] += (double)(d_h * dt);
+                  tl[i][0] = (R)t0_acc[i];
+                } else {
+                  tl[i][0] = tl[i][0] + d_h * dt;
+                }
+              }
+            } else
             // surface layer, msm.py:80-101 (per cell: its snow share sets conductivity and density)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -1147,7 +1177,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
             // swe / snow_density > d[0]): where no cell of the warp has any, conductivity is that of ice
             // in every deeper layer (ratio = 0 gives exactly k_ice) and the pair runs packed; the general
             // per-cell loop is the same arithmetic with the snow share carried along.
-            if (!__any_sync(0xffffffffu, sd1[0] > (R)0 || sd1[1] > (R)0)) {
+            if (bare || !__any_sync(0xffffffffu, sd1[0] > (R)0 || sd1[1] > (R)0)) {
               V gp = V::make(grad0[0], grad0[1]);
               V t_h = V::make(tl[2 * q][1], tl[2 * q + 1][1]);
               const V k_ice2 = V::splat(mp.k_ice), dt2 = V::splat(dt);

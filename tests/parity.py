@@ -161,6 +161,18 @@ def compare_run(case, f64, pot=None, computed=False, shadow=False, **kw):
     finally:
         eng.close()
     ff, mfl, tfl = (1e-3, 1e-7, 1e-6) if f64 else (1.0, 1e-3, 1e-3)
+    msm_floor = 5.0
+    if kw.get("msm") and not f64:
+        # The bound for the melt gate in float32 is tied to the reference's OWN float32-vs-float64 gap on this
+        # very case: the as-shipped reference deviates from its float64-injected self by a few
+        # 1e-3 W m-2 in the melt flux (the gate carries the cold content of the surface layer, which integrates
+        # the float32 round-off of every earlier step).  1e-4 x 5 W m-2 = 5e-4 W m-2 must not be looser than that.
+        ora64 = run_oracle(case, pot_o if not computed else I.insolation_series(case, shadow=shadow, dtype=np.float64),
+                           True, **kw)
+        own_gap = max(float(np.nanmax(np.abs(np.asarray(a["mf"], dtype=np.float64) - b["mf"])))
+                      for a, b in zip(ora["rows"], ora64["rows"]))
+        assert 1e-4 * msm_floor <= own_gap, ("the float32 melt-flux bound is looser than the reference's own float32 "
+                                             "error on this case", own_gap)
     res = {}
     off = np.isnan(case.dem)
     for name in FLUX_FIELDS:
@@ -181,7 +193,7 @@ def compare_run(case, f64, pot=None, computed=False, shadow=False, **kw):
                 # of the surface layer, which integrates the float32 round-off of every earlier
                 # step's fluxes (3e-5 W m-2 per term, in the as-shipped reference too): the
                 # per-step melt flux agrees to ~5e-4 W m-2, the melt TOTALS to 1e-4 relative.
-                floor = 5.0
+                floor = msm_floor
             worst = max(worst, max_rel_err(dump[i, idx], ref, floor))
         res[name] = worst
     worst = 0.0
