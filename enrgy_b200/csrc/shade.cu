@@ -121,8 +121,6 @@ __global__ void __launch_bounds__(32 * Q) sweep_kernel(const SweepArgs a) {
   for (int v = 0; v < V; ++v) M[v] = -INFINITY;
   const double dz = s.dz;
   const int words_needed = (nb + 31) >> 5;
-  // current destination segment (row type)
-  int seg_lo = 0, seg_words = 0;
 
   // U rows per iteration; the loads of the NEXT iteration are issued before the current one is worked
   // on (two register buffers, the loop body exists twice), so a warp hides a full iteration of memory
@@ -137,17 +135,65 @@ __global__ void __launch_bounds__(32 * Q) sweep_kernel(const SweepArgs a) {
       for (int v = 0; v < V; ++v) h[i][v] = __ldg(rowp + 32 * v);
     }
   };
-  // Emission: the V ballots of a row cover the cells col0 .. col0 + 32 V - 1; the words aligned to 32
-  // cells start o = -col0 mod 32 bits in, so word j is a funnel shift of ballots j and j + 1.  Every lane
-  // holds all ballots, but "ballot number `lane`" is a register indexed by the lane id -- a select chain
-  // that cost more than the sweep itself (r2c profile: 60 % of the instructions).  Instead the ballots of
-  // the U rows go through a 32-byte row of shared memory per warp (every lane writes the same words),
-  // and lane j reads words j, j + 1 back: two vector stores, two loads and one funnel shift per row.
-  __shared__ __align__(16) unsigned s_ballots[Q][U][V];
-  unsigned (*my_b)[V] = s_ballots[warp];
-  // destination of the current segment and sub-step (row type) / of this sub-step (column type)
-  unsigned* out_base = ROW ? nullptr : a.tmp + (size_t)s.out * a.cols * a.tmp_words;
-  int seg_n = 0;
+  // Emission.  The V ballots of a row cover the cells col0 .. col0 + 32 V - 1; the words aligned to 32
+  // cells start o = -col0 mod 32 bits in, so word j is a funnel shift of ballots j and j + 1 (V - 1 full
+  // words per row).  Emitting row by row kept 25 of the 32 lanes idle through ~35 instructions per row (a
+  // third of the kernel's instructions) and stored single 4-byte words 32 bytes apart.  Instead the
+  // ballots and shears of the 8 rows of a ROW GROUP are parked in shared memory (every lane writes the
+  // same words), and when the sweep leaves the group all 32 lanes emit it at once: lane = (word column c,
+  // row pair), two funnel shifts each, one 8-byte store -- the four lanes of a column fill one 32-byte
+  // sector of the row-interleaved mask layout, the eight columns of a warp 256 contiguous bytes.
+  __shared__ __align__(16) unsigned s_bal[Q][8][V];
+  __shared__ int s_col0[Q][8];
+  unsigned (*bal)[V] = s_bal[warp];
+  int* const colv = s_col0[warp];
+  int cur_group = -1;                  // row group (index >> 3 along the sweep axis) being collected
+  unsigned present = 0;                // its rows seen so far
+  const int cidx = lane & 7, rp = lane >> 3;
+  auto flush = [&]() {
+    __syncwarp();
+    if (present != 0u) {
+      // smallest first word column of the group's rows (they differ by at most one: the shear moves the
+      // window by less than a cell per row)
+      const int c_l = colv[cidx];
+      const int base_l = ((present >> cidx) & 1u) ? ((c_l + ((-c_l) & 31)) >> 5) : 0x7fffffff;
+      const int cmin = __reduce_min_sync(full, base_l);
+      const int c = cmin + cidx;
+      unsigned w2[2];
+      bool ok[2];
+#pragma unroll
+      for (int z = 0; z < 2; ++z) {
+        const int rr = 2 * rp + z;
+        const int c0 = colv[rr];
+        const int o = (-c0) & 31;
+        const int j = c - ((c0 + o) >> 5);
+        ok[z] = ((present >> rr) & 1u) && j >= 0 && j <= V - 2 && (unsigned)c < (unsigned)words_needed;
+        const int jj = min(max(j, 0), V - 2);
+        w2[z] = __funnelshift_r(bal[rr][jj], bal[rr][jj + 1], o);
+      }
+      const int first = cur_group << 3;                // first row (row type) / column (column type) of the group
+      if (ROW) {
+        // destination segment of the group (band starts are multiples of 8 rows)
+        unsigned* out = nullptr;
+        for (int q = 0; q < a.n_seg; ++q) {
+          if (first >= a.seg[q].row0 && first < a.seg[q].row0 + a.seg[q].rows)
+            out = a.seg[q].ptr + ((size_t)s.out * a.seg[q].rg + ((first - a.seg[q].row0) >> 3)) * a.seg[q].words * 8;
+        }
+        if (out != nullptr) {
+          unsigned* p = out + ((size_t)c << 3) + 2 * rp;
+          if (ok[0] && ok[1]) *reinterpret_cast<uint2*>(p) = make_uint2(w2[0], w2[1]);
+          else if (ok[0]) p[0] = w2[0];
+          else if (ok[1]) p[1] = w2[1];
+        }
+      } else {
+        unsigned* out = a.tmp + (size_t)s.out * a.cols * a.tmp_words;
+#pragma unroll
+        for (int z = 0; z < 2; ++z)
+          if (ok[z]) out[(size_t)(first + 2 * rp + z) * a.tmp_words + c] = w2[z];
+      }
+    }
+    __syncwarp();
+  };
   auto process = [&](int u0, const float (&h)[U][V], const int (&col0)[U]) {
 #pragma unroll
     for (int i = 0; i < U; ++i) {
@@ -161,43 +207,25 @@ __global__ void __launch_bounds__(32 * Q) sweep_kernel(const SweepArgs a) {
         M[v] = shaded ? M[v] : g;
         B[v] = __ballot_sync(full, !shaded);
       }
-      if (V % 4 == 0) {
+      if (u >= ua) {                                   // (warp-uniform)
+        const int idx = s.sigma * u;                   // row (row type) / column (column type), >= 0
+        if ((idx >> 3) != cur_group) {
+          flush();
+          cur_group = idx >> 3;
+          present = 0;
+        }
+        const int pos = idx & 7;
+        if (V % 4 == 0) {
 #pragma unroll
-        for (int v = 0; v < V; v += 4) *reinterpret_cast<uint4*>(&my_b[i][v]) = make_uint4(B[v], B[v + 1], B[(v + 2) % V], B[(v + 3) % V]);
-      } else {
+          for (int v = 0; v < V; v += 4) *reinterpret_cast<uint4*>(&bal[pos][v]) = make_uint4(B[v], B[v + 1], B[(v + 2) % V], B[(v + 3) % V]);
+        } else {
 #pragma unroll
-        for (int v = 0; v < V; ++v) my_b[i][v] = B[v];
+          for (int v = 0; v < V; ++v) bal[pos][v] = B[v];
+        }
+        colv[pos] = col0[i];
+        present |= 1u << pos;
       }
     }
-    __syncwarp();
-    const int jl = min(lane, V - 2);
-#pragma unroll
-    for (int i = 0; i < U; ++i) {
-      const int u = u0 - i;
-      const int o = (-col0[i]) & 31;
-      const int cw = ((col0[i] + o) >> 5) + lane;
-      const unsigned w = __funnelshift_r(my_b[i][jl], my_b[i][jl + 1], o);
-      const bool mine = lane < V - 1 && (unsigned)cw < (unsigned)words_needed && u >= ua;
-      const int idx = s.sigma * u;                 // row (row type) / column (column type)
-      if (ROW) {
-        if ((unsigned)(idx - seg_lo) >= (unsigned)seg_n) {          // (warp-uniform, rare: a new segment)
-          out_base = nullptr; seg_lo = 0; seg_n = 0;
-          for (int q = 0; q < a.n_seg; ++q) {
-            if (idx >= a.seg[q].row0 && idx < a.seg[q].row0 + a.seg[q].rows) {
-              seg_lo = a.seg[q].row0; seg_n = a.seg[q].rows; seg_words = a.seg[q].words;
-              out_base = a.seg[q].ptr + (size_t)s.out * a.seg[q].rg * a.seg[q].words * 8;
-            }
-          }
-        }
-        if (mine && out_base != nullptr) {
-          const int local = idx - seg_lo;
-          out_base[(((local >> 3) * seg_words + cw) << 3) + (local & 7)] = w;
-        }
-      } else {
-        if (mine) out_base[idx * a.tmp_words + cw] = w;
-      }
-    }
-    __syncwarp();
   };
 #if ENRGY_SWEEP_PIPE
   {
@@ -221,6 +249,7 @@ __global__ void __launch_bounds__(32 * Q) sweep_kernel(const SweepArgs a) {
     process(u0, h, col0);
   }
 #endif
+  flush();                                             // the last row group
 }
 
 // ---- 32 x 32 bit blocks of the column-type temporaries turned around --------------------------------

@@ -112,10 +112,10 @@ class ShardedShading:
     Step 2 is an all_to_all_single (NCCL over NVLink / NVSwitch) on a side stream (`exchange ==
     "all_to_all"`, the default) or ONE KERNEL WITH STEP 1 -- the sweep stores the mask words straight into
     the other ranks' receive buffers over NVLink (peer pointers from torch symmetric memory; `exchange ==
-    "p2p"`), bracketed by two stream-ordered barriers.  Measured on 8192^2 (profiles/r02_summary.md): the
-    peer stores are single 4-byte words 32 bytes apart (the mask layout interleaves 8 rows so that the fused
-    kernel reads one sector per patch), which NVLink carries badly -- the sweep slows from 6.9 to 8-12 ms
-    per chunk on 8 GPUs -- so the bulk exchange wins (31.9 ms against 43.2 ms per pass) and is the default.
+    "p2p"`), bracketed by two stream-ordered barriers.  Measured on 8192^2 x 768 steps, 8 GPUs
+    (profiles/r02_summary.md): 47.4 ms per pass with the peer stores against 47.0 ms with the bulk exchange
+    -- the sweep emits whole 32-byte sectors, but stores over NVLink still slow it by 10 % -- so the bulk
+    exchange is the default.
     Chunks are double-buffered: the sweep (and exchange) of chunk k + 1 is enqueued before the fused
     kernels of chunk k, so the exchange hides behind them.
     With world == 1 the sweep writes straight into the receive buffer.  Nothing synchronises the host."""
