@@ -1146,31 +1146,40 @@ energy_balance_kernel(const KernelArgs<R> a) {
                   tl[i][0] = tl[i][0] + d_h * dt;
                 }
               }
-            } else
-            // surface layer, msm.py:80-101 (per cell: its snow share sets conductivity and density)
+            } else {
+              // surface layer, msm.py:80-101: the snow share of each cell sets conductivity and density;
+              // the pair runs packed (19 packed + 10 scalar instructions instead of ~70 scalar ones)
+              const V one2 = V::splat((R)1), d0_2 = V::splat(mp.d[0]), inv_d0 = V::splat(mp.inv_d[0]);
+              const V t0v = V::make(tl[2 * q][0], tl[2 * q + 1][0]), t1v = V::make(tl[2 * q][1], tl[2 * q + 1][1]);
+              const V sd = mul2(swe2[m][q], V::splat(mp.inv_snow_density));
+              const V share = mul2(sd, inv_d0);
+              const V ratio = V::make(sd.lo() > mp.d[0] ? (R)1 : share.lo(), sd.hi() > mp.d[0] ? (R)1 : share.hi());   // msm.py:63
+              const V omr = sub2(one2, ratio);
+              const V kap = fma2(ratio, V::splat(mp.k_snow), mul2(omr, V::splat(mp.k_ice)));
+              const V rho = fma2(ratio, V::splat(mp.rho_snow), mul2(omr, V::splat(mp.rho_ice)));
+              const V below = sub2(sd, d0_2);
+              const V grad = mul2(sub2(t1v, t0v), inv_d0);                                              // msm.py:18-28
+              const V c_ice2 = V::splat(mp.c_ice);
+              const V gv = mul2(mul2(mul2(kap, grad), c_ice2), rho);
+              const V full = add2(atmo, gv);
+              const V crd = mul2(mul2(c_ice2, rho), d0_2);
+              const V gate = fma2(mul2(t0v, crd), V::splat(inv_dt), full);          // full - q0, q0 = -t0 c rho d / dt
+              const V mfv = V::make(fmax_(gate.lo(), (R)0), fmax_(gate.hi(), (R)0));
+              const V dlt = mul2(sub2(full, mfv), V::make(Num<R>::rcp(crd.lo()), Num<R>::rcp(crd.hi())));
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int i = 2 * q + h;
-              const R atmo_h = h ? atmo.hi() : atmo.lo();
-              const R sd = (h ? swe2[m][q].hi() : swe2[m][q].lo()) * mp.inv_snow_density;
-              const R t_here = tl[i][0];
-              const R grad = (tl[i][1] - t_here) * mp.inv_d[0];              // msm.py:18-28
-              const R ratio = sd > mp.d[0] ? (R)1 : sd * mp.inv_d[0];         // msm.py:63
-              const R kap = ratio * mp.k_snow + ((R)1 - ratio) * mp.k_ice;
-              const R rho = ratio * mp.rho_snow + ((R)1 - ratio) * mp.rho_ice;
-              sd1[h] = fmax_(sd - mp.d[0], (R)0);
-              const R gv = kap * grad * mp.c_ice * rho;
-              const R full = atmo_h + gv;
-              const R crd = mp.c_ice * rho * mp.d[0];
-              const R q0 = -t_here * crd * inv_dt;
-              const R mfv = fmax_(full - q0, (R)0);
-              const R dlt = (full - mfv) * Num<R>::rcp(crd);
-              grad0[h] = grad; mfh[h] = mfv; gh[h] = gv;
-              if (sizeof(R) == 4) {
-                t0_acc[i] += (double)(dlt * dt);
-                tl[i][0] = (R)t0_acc[i];
-              } else {
-                tl[i][0] = t_here + dlt * dt;
+              for (int h = 0; h < 2; ++h) {
+                const int i = 2 * q + h;
+                const R d_h = h ? dlt.hi() : dlt.lo();
+                grad0[h] = h ? grad.hi() : grad.lo();
+                mfh[h] = h ? mfv.hi() : mfv.lo();
+                gh[h] = h ? gv.hi() : gv.lo();
+                sd1[h] = fmax_(h ? below.hi() : below.lo(), (R)0);
+                if (sizeof(R) == 4) {
+                  t0_acc[i] += (double)(d_h * dt);
+                  tl[i][0] = (R)t0_acc[i];
+                } else {
+                  tl[i][0] = tl[i][0] + d_h * dt;
+                }
               }
             }
             // deeper layers, msm.py:103.  Snow that reaches below the surface layer is rare (it takes
