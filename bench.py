@@ -351,7 +351,7 @@ def bench_c3(ctx, args):
     stats = torch.zeros((T, _lib.S_COUNT), dtype=torch.float64, device="cuda")
     eng.snapshot(save=True)
     sub_counts = eng.point_scalars()[:, _lib.P_NSUB].astype(int)
-    sh = ShardedShading(eng, case.meta["bands"], ctx.rank, world, p2p=os.environ.get("ENRGY_SHADE_EXCHANGE", "all_to_all") == "p2p")
+    sh = ShardedShading(eng, case.meta["bands"], ctx.rank, world, exchange=os.environ.get("ENRGY_SHADE_EXCHANGE") or None)
 
     def one_pass():
         eng.snapshot(save=False)
@@ -375,11 +375,13 @@ def bench_c3(ctx, args):
            "sweep_ms_per_rank": [p[0] for p in per_rank], "fused_ms_per_rank": [p[1] for p in per_rank],
            "band_rows": [int(p[2]) for p in per_rank],
            "exchange": sh.exchange, "exchange_bytes_per_pass_per_rank": int(sh.bytes_sent_last_run),
-           "chunks_per_pass": len(sh.chunks(0, T, sub_counts)), "sub_steps": n_sub}
+           "chunks_per_pass": len(sh.chunks(0, T, sub_counts)), "sub_steps": n_sub,
+           "per_rank_times": "sweep / fused kernel time of the LAST chunk of a pass (%d sub-steps swept by rank 0)" % sh.subs_last_scan,
+           "check": {"melt_flux_sum_W_m2_cells": float(stats.cpu().numpy()[:, _lib.S_MELT].sum())}}
     if ctx.rank == 0:
         sweep_ms = max(p[0] for p in per_rank)
         mhz = 1965.0
-        swept = float(n) * n * n_sub / world            # cell-sub-steps this rank sweeps per pass
+        swept = float(n) * n * sh.subs_last_scan        # cell-sub-steps of the scan that sweep_ms times (the last chunk's)
         out["roofline_sweep"] = {
             "bound": "issue", "kernel_ms": sweep_ms,
             "issue_slots": {"achieved": SWEEP_SLOTS_PER_CELL_SUB * swept / (sweep_ms * 1e-3) / 1e12,

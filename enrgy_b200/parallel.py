@@ -109,18 +109,21 @@ class ShardedShading:
       2. every rank ends up with the masks of ITS band for all sub-steps of the chunk, already in the
          order the fused kernel reads them,
       3. the fused kernels run on the band with these masks (enrgy_run_masked).
-    Step 2 is an all_to_all_single (NCCL over NVLink / NVSwitch) on a side stream (`exchange ==
-    "all_to_all"`, the default) or ONE KERNEL WITH STEP 1 -- the sweep stores the mask words straight into
-    the other ranks' receive buffers over NVLink (peer pointers from torch symmetric memory; `exchange ==
-    "p2p"`), bracketed by two stream-ordered barriers.  Measured on 8192^2 x 768 steps, 8 GPUs
-    (profiles/r02_summary.md): 47.4 ms per pass with the peer stores against 47.0 ms with the bulk exchange
-    -- the sweep emits whole 32-byte sectors, but stores over NVLink still slow it by 10 % -- so the bulk
-    exchange is the default.
+    Step 2, three ways (`exchange`):
+      "copy" (default)  bulk peer-to-peer copies into the peers' receive buffers (torch symmetric memory)
+                        on a side stream, bracketed by two stream-ordered barriers: the copy engines move
+                        the masks over NVLink while the SMs run the kernels of the neighbouring chunks;
+      "all_to_all"      one all_to_all_single (NCCL) on the side stream -- its kernels take SMs from the
+                        persistent fused kernel in flight (2.8 ms per chunk on 8 GPUs); also the fallback
+                        where symmetric memory is not available;
+      "p2p"             ONE KERNEL WITH STEP 1: the sweep stores the mask words straight into the peers'
+                        receive buffers (whole 32-byte sectors); stores over NVLink slow the sweep by 10 %.
+    Measured on 8192^2, 8 GPUs (profiles/r02_summary.md).
     Chunks are double-buffered: the sweep (and exchange) of chunk k + 1 is enqueued before the fused
     kernels of chunk k, so the exchange hides behind them.
     With world == 1 the sweep writes straight into the receive buffer.  Nothing synchronises the host."""
 
-    def __init__(self, engine, bands, rank, world, group=None, budget_bytes=8 << 30, p2p=False):
+    def __init__(self, engine, bands, rank, world, group=None, budget_bytes=8 << 30, p2p=False, exchange=None):
         import torch
         self.torch = torch
         self.eng, self.bands, self.rank, self.world, self.group = engine, list(bands), int(rank), int(world), group
@@ -131,9 +134,14 @@ class ShardedShading:
         self.words = [engine.mask_words(n) for _, n in self.bands]       # uint32 per sub-step and band
         self.budget = int(budget_bytes)
         self.slots = [dict(send=None, recv=None, peers=None, ready=None) for _ in range(2)]
-        self.exchange = "none" if self.world == 1 else ("p2p" if p2p else "all_to_all")
+        # exchange: "all_to_all" (NCCL kernels), "p2p" (the sweep stores into the peers' buffers), "copy" (bulk
+        # peer-to-peer copies by the copy engines into the peers' buffers: no SM of the kernels in flight is taken)
+        self.exchange = "none" if self.world == 1 else (exchange or ("p2p" if p2p else "copy"))
+        if self.exchange not in ("none", "all_to_all", "p2p", "copy"):
+            raise ValueError("exchange must be all_to_all, p2p or copy")
         self.comm = torch.cuda.Stream() if self.world > 1 else None
         self.bytes_sent_last_run = 0
+        self.subs_last_scan = 0
         self._flag = torch.zeros(1, dtype=torch.int32, device="cuda") if self.world > 1 else None
         self._symm_failed = False
 
@@ -144,7 +152,7 @@ class ShardedShading:
         sl = self.slots[slot]
         if sl["recv"] is not None and sl["recv"].numel() >= n_words:
             return sl
-        if self.exchange == "p2p":
+        if self.exchange in ("p2p", "copy"):
             try:
                 import torch.distributed as dist
                 import torch.distributed._symmetric_memory as symm
@@ -153,6 +161,8 @@ class ShardedShading:
                 hdl = symm.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
                 sl["recv"], sl["peers"] = t, [int(p) for p in hdl.buffer_ptrs]
                 sl["hdl"] = hdl
+                # the peers' receive buffers as tensors (bulk copies of the "copy" exchange)
+                sl["peer_tensors"] = [hdl.get_buffer(q, (int(n_words),), torch.int32) for q in range(self.world)]
                 return sl
             except Exception as e:                                    # pragma: no cover  (needs several GPUs)
                 import sys
@@ -214,6 +224,7 @@ class ShardedShading:
             shares = split_even(s0, s1, world)
             a, b = shares[me]
             sl = self._recv(k % 2, recv_words)
+            self.subs_last_scan = b - a           # (last_sweep_ms() of the engine times the last scan only)
             if world == 1:
                 eng.shade_scan(a, b, [(self.bands[0][0], self.bands[0][1], sl["recv"].data_ptr())], sp)
             elif self.exchange == "p2p":
@@ -225,6 +236,35 @@ class ShardedShading:
                     eng.shade_scan(a, b, segs, sp)
                 self._barrier(stream)             # every rank's stores have landed
                 self.bytes_sent_last_run += 4 * (b - a) * (sum(self.words) - self.words[me])
+            elif self.exchange == "copy":
+                # sweep into the local send buffer (one segment per destination band), then bulk copies into
+                # the peers' receive buffers on the side stream: copy engines over NVLink, no kernel
+                in_split = [(b - a) * w for w in self.words]
+                send = self._send(k % 2, sum(in_split))
+                segs, off, offs = [], 0, []
+                for (r0, n), w in zip(self.bands, in_split):
+                    segs.append((r0, n, send.data_ptr() + 4 * off))
+                    offs.append(off)
+                    off += w
+                if k >= 2:
+                    self._barrier(stream)         # every rank has finished the fused kernels that read this slot
+                if b > a:
+                    eng.shade_scan(a, b, segs, sp)
+                swept = torch.cuda.Event()
+                swept.record(stream)
+                with torch.cuda.stream(self.comm):
+                    self.comm.wait_event(swept)
+                    for dq in range(world):
+                        q = (me + dq) % world     # start with myself, then round the ring: no two ranks hit one peer at once
+                        n_w = in_split[q]
+                        if n_w:
+                            dst0 = (a - s0) * self.words[q]
+                            sl["peer_tensors"][q][dst0:dst0 + n_w].copy_(send[offs[q]:offs[q] + n_w], non_blocking=True)
+                    self._barrier(self.comm)      # every rank's copies have landed
+                    done = torch.cuda.Event()
+                    done.record(self.comm)
+                sl["ready"] = done
+                self.bytes_sent_last_run += 4 * (sum(in_split) - in_split[me])
             else:
                 in_split = [(b - a) * w for w in self.words]                         # what I send to rank q
                 out_split = [(hi - lo) * self.words[me] for lo, hi in shares]        # what rank p sends me
@@ -253,7 +293,7 @@ class ShardedShading:
             if k + 1 < len(plan):
                 stage(k + 1)
             sl = staged.pop(k)
-            if self.exchange == "all_to_all":
+            if self.exchange in ("all_to_all", "copy"):
                 stream.wait_event(sl["ready"])
             if len(plan) > 1 and k == len(plan) - 1:
                 eng.defer_snow_total(False)
