@@ -191,3 +191,43 @@ def test_host_prepass_computed_insolation_and_errors():
     bad[3, _lib.F_RH] = 55.0                                                   # per cent instead of a fraction
     with pytest.raises(EnrgyError):
         host_prepass(case.dem, bad, **base)
+
+
+def test_extra_station_host_logic(tmp_path):
+    """add_station / add_cloud_transmissivity (BASELINE config C4): real-world coordinates -> cell units of
+    the model grid (cell centres), the station's own file -> the series table; argument checks."""
+    import csv
+    from enrgy_b200 import Energy, _lib
+    from enrgy_b200.forcing import build_station_series
+    from enrgy_b200.raster_utils import save_npy_raster
+    from enrgy_b200.synthetic import make_station_rows
+    case = make_case(40, 9, w=56, seed=3)
+    d = str(tmp_path)
+    dem = save_npy_raster(os.path.join(d, "dem.npy"), case.dem, case.geotransform)
+    e = Energy(dem, None, os.path.join(d, "out"), res=10)
+    ul_x, x_dist, _, ul_y, _, y_dist = case.geotransform
+    rows = make_station_rows(case, case.elev_aws + 80.0, seed=4)
+    path = os.path.join(d, "st.csv")
+    with open(path, "w", newline="") as f:
+        w = csv.DictWriter(f, fieldnames=list(rows[0]))
+        w.writeheader()
+        w.writerows(rows)
+    # the centre of cell (row 7, col 30) and a point a quarter of a cell off it
+    e.add_station(path, (ul_x + 30.5 * x_dist, ul_y + 7.5 * y_dist), case.elev_aws + 80.0)
+    e.add_station(path, (ul_x + 12.75 * x_dist, ul_y + 33.25 * y_dist), 512.0)
+    e.add_cloud_corr(0.2)
+    pos, series = e._station_setup(9)
+    assert np.allclose(pos, [(7.0, 30.0, case.elev_aws + 80.0), (32.75, 12.25, 512.0)], atol=1e-9)
+    want = build_station_series(rows, cloud_corr=0.2)
+    assert want.shape == (9, _lib.ST_COUNT) and np.array_equal(series[0], want)
+    assert np.all(want[:, _lib.ST_RH] <= 1.0) and np.all((want[:, _lib.ST_CLOUD] >= 0) & (want[:, _lib.ST_CLOUD] <= 1))
+    assert want[0, _lib.ST_T_AIR] == float(rows[0]["T_AIR"]) and want[3, _lib.ST_PRESSURE] == float(rows[3]["PRESSURE"])
+    with pytest.raises(ValueError):
+        e._station_setup(10)                       # another number of rows than the main AWS file
+    e.add_station(path, (ul_x, ul_y), 1.0)
+    with pytest.raises(ValueError):
+        e.add_station(path, (ul_x, ul_y), 1.0)     # a fourth one
+    with pytest.raises(ValueError):
+        e.add_cloud_transmissivity(-0.1)
+    e.add_cloud_transmissivity(0.7)
+    assert e.cloud_k == 0.7

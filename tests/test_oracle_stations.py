@@ -64,3 +64,29 @@ def test_station_blend_properties():
     w, D, V = O.station_fields(case.dem.astype(np.float64), P.oracle_config(case), case.geotransform, st2)
     assert np.allclose(w[0] + w[1], 1.0, atol=1e-15) and (w[0] >= 0).all() and (w[1] >= 0).all()
     assert np.unravel_index(np.argmax(w[1]), w[1].shape) == (35, 10)
+
+
+@pytest.mark.parametrize("f64", [False, True])
+def test_station_specification_is_frozen(f64):
+    """tests/golden_spec/stations_*.npz were written by the oracle itself (make_spec_golden.py): the
+    specification must not move under later edits."""
+    import json
+    import os
+    import sys
+    here = os.path.join(os.path.dirname(__file__), "golden_spec")
+    g = np.load(os.path.join(here, "stations_%s.npz" % ("f64" if f64 else "f32")), allow_pickle=False)
+    if str(g["numpy"]).split(".")[0] != np.__version__.split(".")[0]:
+        pytest.skip("fixture made with numpy %s" % g["numpy"])
+    sys.path.insert(0, here)
+    import make_spec_golden as M
+    rec = json.loads(str(g["recipe"]))
+    case = make_case(rec["n"], rec["n_steps"], seed=rec["seed"], w=rec["w"], calm_every=rec["calm_every"])
+    pot = P.random_insolation(case, rec["n_steps"])
+    r = P.run_oracle(case, pot, f64, stations=M.stations_of(case), cloud_k=0.8, cloud_corr=0.1, last_snowfall="20220525")
+    for k in ("swe", "total_snow", "total_ice"):
+        assert np.array_equal(r[k], g[k], equal_nan=True), k
+    for key in g.files:
+        if key.startswith("step"):
+            step, name = key.split("_", 1)
+            assert np.array_equal(r["rows"][int(step[4:])][name], g[key], equal_nan=True), key
+    assert r["stats_csv"] == str(g["stats_csv"])
