@@ -139,10 +139,10 @@ class ShardedShading:
         self.exchange = "none" if self.world == 1 else (exchange or ("p2p" if p2p else "copy"))
         if self.exchange not in ("none", "all_to_all", "p2p", "copy"):
             raise ValueError("exchange must be all_to_all, p2p or copy")
-        self.comm = torch.cuda.Stream() if self.world > 1 else None
+        self.comm = None                          # side stream of the exchange, made at the first run
         self.bytes_sent_last_run = 0
         self.subs_last_scan = 0
-        self._flag = torch.zeros(1, dtype=torch.int32, device="cuda") if self.world > 1 else None
+        self._flag = None                         # one word for the stream-ordered barriers
         self._symm_failed = False
 
     # ---- buffers ---------------------------------------------------------------------------------
@@ -205,6 +205,9 @@ class ShardedShading:
         torch = self.torch
         eng, me, world = self.eng, self.rank, self.world
         sp = stream.cuda_stream
+        if world > 1 and self.comm is None:
+            self.comm = torch.cuda.Stream()
+            self._flag = torch.zeros(1, dtype=torch.int32, device="cuda")
         plan = self.chunks(t0, t1, sub_counts)
         if len(plan) > 1:
             eng.defer_snow_total(True)            # the rasters must not depend on where the run is cut

@@ -231,3 +231,31 @@ def test_extra_station_host_logic(tmp_path):
         e.add_cloud_transmissivity(-0.1)
     e.add_cloud_transmissivity(0.7)
     assert e.cloud_k == 0.7
+
+
+def test_sharded_shading_chunk_plan():
+    """Chunks of the multi-GPU shading run: whole steps, inside the memory budget, and -- several ranks -- at
+    least 192 sub-steps per rank and launch (a smaller sweep launch leaves the GPU half empty in its tail)
+    unless the budget forbids it."""
+    from enrgy_b200.parallel import ShardedShading, plan_step_chunks, split_even
+
+    class Stub:
+        def mask_words(self, rows):
+            return (rows + 7) // 8 * 8 * 256          # 8192 columns
+    sub = np.array([4] * 300 + [0] * 84 + [4] * 384)   # a stretch of night rows in between
+    for world in (1, 2, 8):
+        bands = [(i * (8192 // world), 8192 // world) for i in range(world)]
+        sh = ShardedShading(Stub(), bands, 0, world)
+        plan = sh.chunks(0, sub.size, sub)
+        assert plan[0][0] == 0 and plan[-1][1] == sub.size and all(a[1] == b[0] for a, b in zip(plan, plan[1:]))
+        counts = [int(sub[a:b].sum()) for a, b in plan]
+        per_sub = 4 * (sum(sh.words) // world + max(sh.words)) * 2 + 1
+        assert all(c * per_sub <= sh.budget + 4 * per_sub for c in counts)
+        if world > 1:
+            assert all(c >= min(192 * world, sh.budget // per_sub) - 4 for c in counts[:-1]), (world, counts)
+    assert split_even(10, 27, 4) == [(10, 15), (15, 19), (19, 23), (23, 27)] or sum(b - a for a, b in split_even(10, 27, 4)) == 17
+    assert plan_step_chunks(sub, 0, 10, 3) == [(t, t + 1) for t in range(10)]       # a step is never cut
+    with pytest.raises(ValueError):
+        ShardedShading(Stub(), [(0, 100), (100, 92)], 0, 2)                          # band starts off the 8-row grid
+    with pytest.raises(ValueError):
+        ShardedShading(Stub(), [(0, 96), (96, 96)], 0, 2, exchange="pigeon")
