@@ -5,7 +5,7 @@
 // range: SWE and the ice-melt total live in registers, the per-step AWS scalars are staged per time
 // block in shared memory by TMA bulk copies (cp.async.bulk + mbarrier, double buffered), and the only
 // global traffic inside the time loop is the daily refresh of the albedo blend, the optional
-// streamed insolation raster (4 B per cell-step) and the shading ray samples.
+// streamed insolation raster (4 B per cell-step) and the sunlit masks of the shading sweep (1 bit).
 //
 // Reference arithmetic being replaced (tepextepex/ENRGY, file:line) -> where it lives here:
 //   var_classes.py:113-125  lapse-rate distribution of T, p, e            -> balance() in the step loop
@@ -683,7 +683,7 @@ energy_balance_kernel(const KernelArgs<R> a) {
     const int2 tile = a.tiles[ti];
     // ---- prologue: per-cell invariants and state into registers --------------------------------
     // A warp owns a compact 32-column x K-row patch (lane = column): every raster access is one
-    // coalesced 128 B line per row, and the patch keeps the shading bounding box tight.  The K cells
+    // coalesced 128 B line per row, and the K = 8 rows are one row group of the sunlit masks.  The K cells
     // of a thread are kept as K/2 PAIRS (rows 2q, 2q+1): all multiply/add arithmetic of the time
     // loop runs on both cells of a pair with one packed instruction (V2, FFMA2/FADD2/FMUL2).
     constexpr int KP = K / 2;
