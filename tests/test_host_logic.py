@@ -259,3 +259,19 @@ def test_sharded_shading_chunk_plan():
         ShardedShading(Stub(), [(0, 100), (100, 92)], 0, 2)                          # band starts off the 8-row grid
     with pytest.raises(ValueError):
         ShardedShading(Stub(), [(0, 96), (96, 96)], 0, 2, exchange="pigeon")
+
+
+def test_ensemble_members_and_sharding():
+    """Seeded member perturbations and their round-robin sharding over ranks."""
+    from enrgy_b200.ensemble import make_members, shard
+    a, b = make_members(64, seed=0), make_members(64, seed=0)
+    assert a == b and len(a) == 64
+    off = np.array([m["albedo_offset"] for m in a])
+    zm = np.array([m["zm"] for m in a])
+    assert abs(off.mean()) < 0.02 and 0.015 < off.std() < 0.045                 # N(0, 0.03)
+    assert (zm >= 3e-4).all() and (zm <= 3e-3).all()                            # log-uniform [3e-4, 3e-3]
+    assert all(abs(m["z_h_or_e"] - m["zm"] / 10.0) < 1e-18 for m in a)
+    assert make_members(4, seed=1) != make_members(4, seed=2)
+    parts = [shard(a, 8, r) for r in range(8)]
+    assert sorted(i for p in parts for i in p) == list(range(64)) and all(len(p) == 8 for p in parts)
+    assert shard(a[:5], 8, 7) == [] and shard(a[:5], 2, 1) == [1, 3]
