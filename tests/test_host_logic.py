@@ -275,3 +275,26 @@ def test_ensemble_members_and_sharding():
     parts = [shard(a, 8, r) for r in range(8)]
     assert sorted(i for p in parts for i in p) == list(range(64)) and all(len(p) == 8 for p in parts)
     assert shard(a[:5], 8, 7) == [] and shard(a[:5], 2, 1) == [1, 3]
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/enrgy_b200.h is the drop-in boundary: it must compile as C11 and as C++17 on its own, and the
+    calls INTEGRATION.md shows must match its prototypes."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "use.c"
+    src.write_text(
+        '#include <stddef.h>\n#include "enrgy_b200.h"\n'
+        "int f(enrgy_ctx* h, int n, const double* series, double* stats, float* a, float* b, float* c) {\n"
+        "  double row[3] = {1, 2, 3}, col[3] = {1, 2, 3}, elev[3] = {1, 2, 3}, off[8] = {0}, zm[8] = {0}, zhe[8] = {0}, tot[8][4];\n"
+        "  struct enrgy_params p; (void)p;\n"
+        "  if (enrgy_set_stations(h, 3, row, col, elev, series, 0.7) != ENRGY_OK) return 1;\n"
+        "  if (enrgy_set_insolation_aws(h, 0, n, series) != ENRGY_OK) return 1;\n"
+        "  enrgy_prepass(h); enrgy_run(h, 0, n, stats);\n"
+        "  if (enrgy_run_members(h, 8, off, zm, zhe, 0, n, NULL, &tot[0][0]) != ENRGY_OK) return (int)(size_t)enrgy_last_error();\n"
+        "  return enrgy_get_member_state(h, 3, 32, a, b, c);\n}\n")
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src)], check=True)
+    subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)], check=True)
